@@ -1,0 +1,278 @@
+/*
+ * lobstep.h -- C ABI of the B200-native batched limit-order-book step.
+ *
+ * This is the drop-in boundary for ONE hot path of JaxMARL-HFT: the batched
+ * limit-order-book environment step.  The reference has no FFI of its own (it
+ * is 100 % Python/JAX); the de-facto interface is the method set the trainer
+ * calls (all citations relative to /root/reference/gymnax_exchange):
+ *
+ *   lob_step_launch    <->  MARLEnv.step / step_env       jaxen/marl_env.py:776 / :212
+ *   lob_reset_launch   <->  MARLEnv.reset / reset_env     jaxen/marl_env.py:764 / :130
+ *   lob_replay_launch  <->  BaseLOBEnv.step_env           jaxen/base_env.py:189
+ *                           job.scan_through_entire_array jaxob/JaxOrderBookArrays.py:736
+ *                           (also the reset-state precompute, base_env.py:245-296)
+ *   lob_l2_launch      <->  job.get_L2_state              jaxob/JaxOrderBookArrays.py:1232
+ *   lob_replay_host    <->  the same replay through HOST buffers (bench e2e leg)
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / jax types.
+ *   - every *_launch takes DEVICE pointers and a cudaStream_t (as void*); it
+ *     validates on the host, enqueues on that stream, never synchronises and
+ *     never allocates.  Return 0 on success, a negative LOB_E_* otherwise;
+ *     lob_last_error() gives the text (thread local).
+ *   - re-entrant: no mutable globals; per-device constants arrive as buffers.
+ *   - int32 rows use the reference layouts verbatim:
+ *       order row  i32[6] = [price, qty, order_id, trader_id, time_s, time_ns]   jaxob_constants.py:38-44
+ *       trade row  i32[8] = [price, +-qty, passive_oid, aggr_oid, time_s, time_ns,
+ *                            passive_tid, aggr_tid]                               jaxob_constants.py:46-54
+ *       message    i32[8] = [type, side, qty, price, order_id, trader_id,
+ *                            time_s, time_ns]                                     jaxob_constants.py:84-92
+ *     empty rows are all -1.
+ *   - state leaves are updated IN PLACE (the XLA custom call would use
+ *     input_output_aliases); field order follows StatesandParams.py:14-122.
+ */
+#ifndef LOBSTEP_H_
+#define LOBSTEP_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LOB_ABI_VERSION 1
+#define LOB_MAX_AGENT_TYPES 4
+#define LOB_MAX_AGENT_I32 4  /* int32 state leaves per agent type */
+#define LOB_MAX_AGENT_F32 10 /* float32 state leaves per agent type */
+
+/* error codes */
+#define LOB_OK 0
+#define LOB_E_INVALID (-1)     /* bad config / shape */
+#define LOB_E_UNSUPPORTED (-2) /* valid in the reference, not built here (see DESIGN.md "next") */
+#define LOB_E_CUDA (-3)        /* CUDA runtime error at launch */
+
+/* ---- enums (values are part of the ABI) -------------------------------- */
+enum LobAgentKind { LOB_AGENT_MM = 0, LOB_AGENT_EXE = 1 };
+
+/* MarketMaking_EnvironmentConfig.action_space  jaxob_config.py:55 ; mm_env.py:161-178 */
+enum LobMMActionSpace { LOB_MM_ACT_FIXED_QUANTS = 0, LOB_MM_ACT_DIRECTIONAL = 1 };
+/* Execution_EnvironmentConfig.action_space     jaxob_config.py:157 ; exec_env.py:162-175 */
+enum LobEXEActionSpace { LOB_EXE_ACT_FIXED_QUANTS = 0, LOB_EXE_ACT_FIXED_QUANTS_COMPLEX = 1 };
+/* observation_space  mm_env.py:2767-2788 ; exec_env.py:179-186 */
+enum LobObsSpace { LOB_OBS_ENGINEERED = 0, LOB_OBS_BASIC = 1 };
+/* MM reward_function  mm_env.py:2489-2513 */
+enum LobMMReward {
+  LOB_MM_REW_PORTFOLIO_VALUE = 0, LOB_MM_REW_BUY_SELL_PNL = 1, LOB_MM_REW_COMPLEX = 2,
+  LOB_MM_REW_ZERO_INV = 3, LOB_MM_REW_SPOONER = 4, LOB_MM_REW_SPOONER_DAMPED = 5,
+  LOB_MM_REW_SPOONER_ASYM_DAMPED = 6, LOB_MM_REW_SPOONER_ASYM_DAMPED2 = 7,
+  LOB_MM_REW_SPOONER_SCALED = 8, LOB_MM_REW_DELTA_PORTFOLIO_VALUE = 9
+};
+/* EXE reward_function  exec_env.py:1735-1752 */
+enum LobEXEReward { LOB_EXE_REW_NORMAL = 0, LOB_EXE_REW_FINISH_FAST = 1, LOB_EXE_REW_SIMPLEST_CASE = 2 };
+/* reference_price / unwind_price  mm_env.py:2294-2303,2373-2396 ; exec_env.py:1564-1580 */
+enum LobRefPrice { LOB_REF_MID = 0, LOB_REF_MID_AVG = 1, LOB_REF_FAR_TOUCH = 2, LOB_REF_NEAR_TOUCH = 3 };
+/* inv_penalty  mm_env.py:2516-2536 */
+enum LobInvPenalty { LOB_INVPEN_NONE = 0, LOB_INVPEN_LINEAR = 1, LOB_INVPEN_QUADRATIC = 2,
+                     LOB_INVPEN_EXP4 = 3, LOB_INVPEN_THRESHOLD = 4 };
+/* Execution task  exec_env.py:220-223 */
+enum LobExeTask { LOB_TASK_RANDOM = 0, LOB_TASK_BUY = 1, LOB_TASK_SELL = 2 };
+
+/* ---- order book configuration: JAXLOB_Configuration  jaxob_config.py:12-30 */
+typedef struct LobBookConfig {
+  int32_t n_orders;              /* nOrders  : rows per book side */
+  int32_t n_trades;              /* nTrades  : rows of the trade log */
+  int32_t maxint;                /* cfg.maxint (2147483647) */
+  int32_t init_id;               /* cfg.init_id (-2) */
+  int32_t book_depth;            /* cfg.book_depth */
+  int32_t cancel_mode;           /* 0/1 supported (identical in the reference: job:94-139); 2/3 need JAX PRNG -> LOB_E_UNSUPPORTED */
+  int32_t type_4_interpretation; /* 0 IOC, 1 LIM, 2 MKT  jaxob_constants.py:70-74 */
+  int32_t check_book_fill;       /* job:395-401 / :484-490 */
+} LobBookConfig;
+
+/* ---- one agent type: MarketMaking_/Execution_EnvironmentConfig  jaxob_config.py:33-200 */
+typedef struct LobAgentTypeConfig {
+  int32_t kind;                  /* LobAgentKind */
+  int32_t n_agents;              /* number_of_agents_per_type[i] */
+  int32_t trader_id_start;       /* agent a has trader id trader_id_start - a   mm_env.py:193-195 */
+  int32_t action_space;
+  int32_t observation_space;
+  int32_t reward_function;
+  int32_t n_actions;
+  int32_t num_messages_by_agent;        /* cancels + actions */
+  int32_t num_action_messages_by_agent;
+  int32_t normalize;
+  int32_t time_delay_obs_act;
+  int32_t fixed_quant_value;
+  /* market making */
+  int32_t n_ticks_offset;
+  int32_t tenth_action_market_order;    /* tenth_action == "MarketOrder" */
+  int32_t sell_buy_all_option;          /* only 0 supported */
+  int32_t fixed_action_setting;
+  int32_t fixed_action;
+  int32_t auto_liquidate_threshold;
+  int32_t unwind_price_penalty;
+  int32_t inv_penalty;                  /* LobInvPenalty */
+  int32_t volume_traded_bonus_market_share; /* volume_traded_bonus == "market_share"  mm_env.py:2542 */
+  int32_t reference_price;              /* LobRefPrice */
+  int32_t unwind_price;                 /* LobRefPrice (mid / mid_avg / far_touch) */
+  int32_t clip_reward;
+  int32_t exclude_extreme_spreads;
+  /* execution */
+  int32_t task;                         /* LobExeTask */
+  int32_t task_size;
+  int32_t n_ticks_in_book;
+  int32_t larger_far_touch_quant;
+  int32_t doom_price_penalty;
+  /* python floats of the config: kept as double, narrowed to f32 where JAX's weak typing does */
+  double auto_liquidate_alpha;
+  double inv_penalty_lambda;
+  double inv_penalty_quadratic_factor;
+  double inv_penalty_threshold;
+  double reward_scaling_quo;
+  double inventoryPnL_eta;
+  double inventoryPnL_gamma;
+  double rebate_bps;
+  double unrealizedPnL_lambda;
+  double reward_lambda;
+} LobAgentTypeConfig;
+
+/* ---- the whole step: MultiAgentConfig  jaxob_config.py:205-250 */
+typedef struct LobStepConfig {
+  LobBookConfig book;
+  int32_t n_data_msg_per_step;   /* Nd */
+  int32_t tick_size;
+  int32_t ep_type_fixed_time;    /* 0 = "fixed_steps" (supported), 1 = "fixed_time" (LOB_E_UNSUPPORTED) */
+  int32_t episode_time;
+  int32_t order_id_counter_start;/* order_id_counter_start_when_resetting (-200) */
+  int32_t placeholder_order_id;  /* -198 */
+  int32_t artificial_trader_id_end_episode; /* -199 */
+  int32_t artificial_order_id_end_episode;  /* -199 */
+  int32_t shuffle_action_messages;
+  int32_t n_agent_types;
+  int32_t n_windows;             /* W: rows of the precomputed reset states */
+  int32_t _pad0;
+  int64_t n_messages;            /* M: rows of message_data */
+  LobAgentTypeConfig agent[LOB_MAX_AGENT_TYPES];
+} LobStepConfig;
+
+/* Derived sizes (marl_env.py:85-94): n_cancel = sum n_i*(num_messages-num_action_messages),
+ * n_action = sum n_i*num_action_messages, N = n_cancel + n_action + Nd. */
+int32_t lob_num_msgs_per_step(const LobStepConfig* cfg);
+int32_t lob_num_action_msgs(const LobStepConfig* cfg);
+int32_t lob_num_cancel_msgs(const LobStepConfig* cfg);
+int32_t lob_obs_dim(const LobStepConfig* cfg, int32_t agent_type);       /* mm_env.py:3195-3223 ; exec_env.py:2188-2202 */
+int32_t lob_info_i32_cols(const LobStepConfig* cfg, int32_t agent_type);
+int32_t lob_info_f32_cols(const LobStepConfig* cfg, int32_t agent_type);
+
+/* world info columns (marl_env.py:624-639) */
+#define LOB_WINFO_I32_COLS 11 /* window_index, step_counter, time_s, time_ns, order_id_counter, best_asks, best_bids,
+                                 current_step, ep_done_time, abort_episode, spread */
+#define LOB_WINFO_F32_COLS 4  /* end_mid_price, average_best_ask, average_best_bid, delta_time */
+/* MM info columns (mm_env.py:2695-2730) */
+#define LOB_MMINFO_I32_COLS 9  /* done, inventory, forced_unwind, posted_bid_price, posted_ask_price,
+                                  bid_distance_from_best, ask_distance_from_best, ask_quant, bid_quant */
+#define LOB_MMINFO_F32_COLS 15 /* reward, reward_portfolio_value, reward_spooner, end_of_ep_pv, reward_spooner_damped,
+                                  reward_spooner_asym_damped, reward_spooner_asym_damped2, reward_delta_pv, total_PnL,
+                                  delta_mid_price, market_share, buyPnL, invPnL, sellPnL, inventoryValue */
+/* EXE info columns (exec_env.py:1809-1829) */
+#define LOB_EXEINFO_I32_COLS 4 /* quant_left, done, doom_quant, is_sell_task */
+#define LOB_EXEINFO_F32_COLS 5 /* revenue_direction_normalised, vwap_rm, drift, advantage, reward */
+
+/* ---- buffers of one step call.  B = batch (vmap dim), N = msgs per step,
+ *      No/Nt = n_orders/n_trades, n_i = agents of type i, d_i = obs dim.   */
+typedef struct LobStepBuffers {
+  /* WorldState leaves, in/out in place (StatesandParams.py:14-36) */
+  int32_t* asks;             /* [B,No,6] ask_raw_orders */
+  int32_t* bids;             /* [B,No,6] bid_raw_orders */
+  int32_t* trades;           /* [B,Nt,8] */
+  int32_t* init_time;        /* [B,2] */
+  int32_t* window_index;     /* [B] */
+  int32_t* max_steps;        /* [B] max_steps_in_episode */
+  int32_t* start_index;      /* [B] */
+  int32_t* step_counter;     /* [B] */
+  int32_t* best_bids;        /* [B,N,2] */
+  int32_t* best_asks;        /* [B,N,2] */
+  int32_t* time;             /* [B,2] */
+  int32_t* order_id_counter; /* [B] */
+  float*   mid_price;        /* [B] */
+  float*   delta_time;       /* [B] */
+  /* agent state leaves per type, each [B,n_i], in/out in place (StatesandParams.py:48-74)
+   *   MM : i32 {posted_distance_bid, posted_distance_ask, inventory}
+   *        f32 {total_PnL, cash_balance}
+   *   EXE: i32 {task_to_execute, quant_executed, is_sell_task}
+   *        f32 {init_price, p_vwap, total_revenue, drift_return, advantage_return,
+   *             slippage_rm, price_adv_rm, price_drift_rm, vwap_rm, trade_duration} */
+  int32_t* agent_i32[LOB_MAX_AGENT_TYPES][LOB_MAX_AGENT_I32];
+  float*   agent_f32[LOB_MAX_AGENT_TYPES][LOB_MAX_AGENT_F32];
+  /* inputs */
+  const int32_t* actions[LOB_MAX_AGENT_TYPES]; /* [B,n_i] */
+  const int32_t* perm;             /* [B,n_action]  jax.random.permutation(shuffle_key, n_action)  marl_env.py:294-295 ; may be NULL when !shuffle */
+  const int32_t* reset_window;     /* [B] randint(world_key, 0, W) of the auto-reset  base_env.py:222-225 */
+  const int32_t* reset_is_sell;    /* [B,n_agent_types] randint(agent_key,0,2) per type (shared by its agents, marl_env.py:187) */
+  /* params (shared by the batch; expand_dims => no leading B) */
+  const int32_t* message_data;     /* [M,8] */
+  const int32_t* init_asks;        /* [W,No,6] init_states_array leaves (base_env.py:285-296) */
+  const int32_t* init_bids;        /* [W,No,6] */
+  const int32_t* init_trades;      /* [W,Nt,8] */
+  const int32_t* init_init_time;   /* [W,2] */
+  const int32_t* init_max_steps;   /* [W] */
+  const int32_t* init_start_index; /* [W] */
+  /* outputs */
+  float*   obs[LOB_MAX_AGENT_TYPES];         /* [B,n_i,d_i]  (reset obs where done_all) */
+  float*   reward[LOB_MAX_AGENT_TYPES];      /* [B,n_i] */
+  uint8_t* done_all;                         /* [B] dones["__all__"] */
+  uint8_t* done_agents[LOB_MAX_AGENT_TYPES]; /* [B,n_i] */
+  int32_t* info_world_i32;                   /* [B,LOB_WINFO_I32_COLS] */
+  float*   info_world_f32;                   /* [B,LOB_WINFO_F32_COLS] */
+  int32_t* info_agent_i32[LOB_MAX_AGENT_TYPES]; /* [B,n_i,Ki] */
+  float*   info_agent_f32[LOB_MAX_AGENT_TYPES]; /* [B,n_i,Kf] */
+} LobStepBuffers;
+
+/* ---- pure replay: every book b scans msgs[start[b] .. start[b]+n_msgs) -- */
+typedef struct LobReplayBuffers {
+  int32_t* asks;               /* [B,No,6] in/out */
+  int32_t* bids;               /* [B,No,6] in/out */
+  int32_t* trades;             /* [B,Nt,8] in/out (NOT re-initialised: base_env.py:208) */
+  const int32_t* msgs;         /* [M,8] */
+  const int64_t* start;        /* [B] first message of each book */
+  int64_t n_msgs_total;        /* M */
+  int32_t n_msgs;              /* T messages per book */
+  int32_t _pad0;
+  int32_t* best_out;           /* optional [B,4] = [best_ask, ask_vol, best_bid, bid_vol] after the scan (job:968), or NULL */
+} LobReplayBuffers;
+
+int  lob_abi_version(void);
+const char* lob_last_error(void);
+
+int lob_step_launch(const LobStepConfig* cfg, const LobStepBuffers* bufs, int64_t batch, void* cuda_stream);
+int lob_reset_launch(const LobStepConfig* cfg, const LobStepBuffers* bufs, int64_t batch, void* cuda_stream);
+int lob_replay_launch(const LobBookConfig* cfg, const LobReplayBuffers* bufs, int64_t n_books, void* cuda_stream);
+/* asks/bids [B,No,6] -> l2 [B,4*n_levels] = [ask_p,ask_q,bid_p,bid_q] x n_levels   job:1232-1264 */
+int lob_l2_launch(const LobBookConfig* cfg, const int32_t* asks, const int32_t* bids, int32_t* l2,
+                  int32_t n_levels, int64_t n_books, void* cuda_stream);
+
+/* Host-buffer replay (the end-to-end leg): copies books/msgs/start host->device, replays,
+ * copies books/trades back, synchronises the stream.  Device scratch is owned by the handle. */
+typedef struct LobHostReplay LobHostReplay;
+LobHostReplay* lob_host_replay_create(const LobBookConfig* cfg, int64_t max_books, int64_t max_msgs_total, int device);
+int  lob_host_replay_set_messages(LobHostReplay* h, const int32_t* msgs_host, int64_t n_msgs_total); /* the day tensor: resident once */
+int  lob_host_replay_run(LobHostReplay* h, int32_t* asks_host, int32_t* bids_host, int32_t* trades_host,
+                         const int64_t* start_host, int32_t n_msgs, int64_t n_books,
+                         int64_t* h2d_bytes, int64_t* d2h_bytes);
+void lob_host_replay_destroy(LobHostReplay* h);
+
+/* number of kernels this library launched on the calling thread since the last reset (bench "gpu_launches") */
+int64_t lob_launch_count(void);
+void    lob_launch_count_reset(void);
+
+/* sizeof() of the interface structs, so a binding can verify its mirror of this header */
+int64_t lob_sizeof_book_config(void);
+int64_t lob_sizeof_agent_type_config(void);
+int64_t lob_sizeof_step_config(void);
+int64_t lob_sizeof_step_buffers(void);
+int64_t lob_sizeof_replay_buffers(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LOBSTEP_H_ */

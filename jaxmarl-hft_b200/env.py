@@ -1,0 +1,277 @@
+"""Host-side mirror of the reference's environment API for the LOB step, natively batched.
+
+Reference call sites replaced (gymnax_exchange/jaxen):
+  ``MARLEnv(key, MultiAgentConfig)``                              marl_env.py:46
+  ``env.default_params``                                          marl_env.py:96-127, base_env.py:180-187
+  ``vmap(env.reset, (0, None))(keys, params)``                     marl_env.py:764, ippo_rnn_JAXMARL.py:571
+  ``vmap(env.step, (0, 0, 0, None))(keys, state, actions, params)`` marl_env.py:776, ippo_rnn_JAXMARL.py:616
+  ``BaseLOBEnv.step_env`` (pure book replay)                       base_env.py:189-216
+
+Differences that are deliberate: the batch is native (one launch steps every env: the leading ``B`` the trainer
+gets from ``vmap``), the state leaves are updated in place (donated), and the PRNG products the reference draws
+with ``jax.random`` inside the step (action-message permutation marl:294-295, reset window base:222-225,
+``is_sell_task`` exe:221) are drawn on the device by the host layer and handed to the kernel as buffers.
+
+The compute is ONLY the CUDA library (csrc/liblobstep.so, through include/lobstep.h); nothing here falls back to
+the CPU.
+"""
+import ctypes as C
+from dataclasses import dataclass
+from typing import Any, List
+
+import numpy as np
+
+from . import _lib, abi, lobster, states
+from .config import (Execution_EnvironmentConfig, MarketMaking_EnvironmentConfig, MultiAgentConfig,
+                     World_EnvironmentConfig, book_config, num_action_msgs, num_msgs_per_step, to_step_config)
+from .spaces import Box, Discrete
+
+
+# ---- state / params containers (field names of StatesandParams.py:14-122) ---------------------------------
+@dataclass
+class WorldState:
+    ask_raw_orders: Any
+    bid_raw_orders: Any
+    trades: Any
+    init_time: Any
+    window_index: Any
+    max_steps_in_episode: Any
+    start_index: Any
+    step_counter: Any
+    best_bids: Any
+    best_asks: Any
+    time: Any
+    order_id_counter: Any
+    mid_price: Any
+    delta_time: Any
+
+
+_WORLD_FIELDS = dict(ask_raw_orders="asks", bid_raw_orders="bids", trades="trades", init_time="init_time",
+                     window_index="window_index", max_steps_in_episode="max_steps", start_index="start_index",
+                     step_counter="step_counter", best_bids="best_bids", best_asks="best_asks", time="time",
+                     order_id_counter="order_id_counter", mid_price="mid_price", delta_time="delta_time")
+
+
+@dataclass
+class MultiAgentState:
+    """``world_state`` + one dict of leaves per agent type (MMEnvState / ExecEnvState fields).  ``arrays`` is the flat
+    buffer table the kernel works on (the leaves are views of it)."""
+    world_state: WorldState
+    agent_states: List[dict]
+    arrays: dict
+
+
+@dataclass
+class LoadedEnvParams:
+    message_data: Any
+    book_data: Any
+    init_states_array: dict
+
+
+@dataclass
+class MultiAgentParams:
+    loaded_params: LoadedEnvParams
+    agent_params: List[dict]
+
+
+def _state_view(cfg, arrays):
+    ws = WorldState(**{f: arrays[k] for f, k in _WORLD_FIELDS.items()})
+    agents = []
+    for t in range(cfg.n_agent_types):
+        li, lf = abi.state_leaves(cfg.agent[t].kind)
+        agents.append({n: arrays[f"a{t}_{n}"] for n in li + lf})
+    return MultiAgentState(world_state=ws, agent_states=agents, arrays=arrays)
+
+
+def build_reset_params(loaded: lobster.LoadedDay, world, replay_fn):
+    """base_env.py:298-333 ``_init_states``: one precomputed reset state per window.  ``replay_fn(asks, bids, trades,
+    msgs, start, n_msgs)`` scans the 2*depth initial limit orders of each window into an empty book, in place
+    (product: the CUDA replay kernel; tests: the oracle).  Returns the numpy params dict (states.PARAMS)."""
+    W = loaded.starts.shape[0]
+    No, Nt, depth = world.nOrders, world.nTrades, world.book_depth
+    first = loaded.msgs[loaded.starts]
+    init_msgs = lobster.init_messages_from_books(loaded.books, first, depth, world.init_id).reshape(W * 2 * depth, 8)
+    asks = np.full((W, No, 6), -1, np.int32)
+    bids = np.full((W, No, 6), -1, np.int32)
+    trades = np.full((W, Nt, 8), -1, np.int32)
+    start = (np.arange(W, dtype=np.int64) * 2 * depth)
+    asks, bids, trades = replay_fn(asks, bids, trades, np.ascontiguousarray(init_msgs), start, 2 * depth)
+    return {
+        "message_data": np.ascontiguousarray(loaded.msgs, np.int32),
+        "init_asks": asks, "init_bids": bids, "init_trades": trades,
+        "init_init_time": np.ascontiguousarray(first[:, 6:8], np.int32),                 # fixed_steps: base:288-291
+        "init_max_steps": (loaded.max_msgs // world.n_data_msg_per_step + 1).astype(np.int32),  # base:323-324
+        "init_start_index": loaded.starts.astype(np.int32),
+    }
+
+
+# ---- device-side replay -------------------------------------------------------------------------------------
+def replay_books(book_cfg: abi.LobBookConfig, asks, bids, trades, msgs, start, n_msgs, best_out=None):
+    """``job.scan_through_entire_array`` for every book (torch CUDA tensors, in place)."""
+    L = _lib.lib()
+    r = states.pack_replay(asks, bids, trades, msgs, start, n_msgs, best_out)
+    _lib.check(L.lob_replay_launch(C.byref(book_cfg), C.byref(r), asks.shape[0], _lib.current_stream_ptr()),
+               "lob_replay_launch")
+
+
+def l2_state(book_cfg: abi.LobBookConfig, asks, bids, n_levels):
+    """``job.get_L2_state`` for every book -> int32 [B, 4*n_levels]."""
+    import torch
+    L = _lib.lib()
+    out = torch.empty((asks.shape[0], 4 * n_levels), dtype=torch.int32, device=asks.device)
+    p = lambda t: C.cast(t.data_ptr(), abi.p_i32)
+    _lib.check(L.lob_l2_launch(C.byref(book_cfg), p(asks), p(bids), p(out), n_levels, asks.shape[0],
+                               _lib.current_stream_ptr()), "lob_l2_launch")
+    return out
+
+
+def _cuda_replay_fn(book_cfg, device):
+    import torch
+
+    def fn(asks, bids, trades, msgs, start, n_msgs):
+        ta, tb, tt = (torch.from_numpy(x).to(device) for x in (asks, bids, trades))
+        tm, ts = torch.from_numpy(msgs).to(device), torch.from_numpy(start).to(device)
+        replay_books(book_cfg, ta, tb, tt, tm, ts, n_msgs)
+        torch.cuda.synchronize(device)
+        return ta.cpu().numpy(), tb.cpu().numpy(), tt.cpu().numpy()
+    return fn
+
+
+class BaseLOBEnv:
+    """base_env.py:84-411: data window bookkeeping + the pure book replay (``step_env`` without agents)."""
+
+    def __init__(self, cfg: World_EnvironmentConfig, key=None, *, loaded=None, device="cuda", synth=None):
+        self.cfg = cfg
+        self.device = device
+        self.book_cfg = book_config(cfg)
+        self.n_data_msg_per_step = cfg.n_data_msg_per_step
+        if cfg.ep_type != "fixed_steps":
+            raise NotImplementedError("only ep_type='fixed_steps' is built")
+        self.loaded = loaded if loaded is not None else lobster.load_or_generate(cfg, **(synth or {}))
+        self.n_windows = int(self.loaded.starts.shape[0])
+        self.start_indeces, self.end_indeces = self.loaded.starts, self.loaded.ends
+        self.max_messages_in_episode_arr = self.loaded.max_msgs
+        self._params_np = build_reset_params(self.loaded, cfg, _cuda_replay_fn(self.book_cfg, device))
+        self._params_dev = None
+
+    def device_params(self):
+        """The whole day + reset states, resident in HBM once."""
+        if self._params_dev is None:
+            import torch
+            self._params_dev = {k: torch.from_numpy(v).to(self.device) for k, v in self._params_np.items()}
+        return self._params_dev
+
+    @property
+    def default_params(self) -> LoadedEnvParams:
+        p = self.device_params()
+        init = {k: p[k] for k in states.PARAMS if k.startswith("init_")}
+        return LoadedEnvParams(message_data=p["message_data"], book_data=self.loaded.books, init_states_array=init)
+
+    def replay(self, asks, bids, trades, start, n_msgs, best_out=None):
+        """base_env.py:189-216 for a batch of books: scan ``n_msgs`` data messages from ``start[b]``."""
+        replay_books(self.book_cfg, asks, bids, trades, self.device_params()["message_data"], start, n_msgs, best_out)
+
+
+class MARLEnv:
+    """marl_env.py:45-805, batched.  ``num_envs`` plays the role of the trainer's vmap width."""
+
+    def __init__(self, key, multi_agent_config: MultiAgentConfig, *, num_envs=1, loaded=None, device="cuda",
+                 synth=None, seed=0):
+        import torch
+        self.multi_agent_config = multi_agent_config
+        self.num_envs = int(num_envs)
+        self.device = torch.device(device)
+        self.num_agents = sum(multi_agent_config.number_of_agents_per_type)
+        self.base_env = BaseLOBEnv(multi_agent_config.world_config, key, loaded=loaded, device=device, synth=synth)
+        self.list_of_agents_configs = list(multi_agent_config.dict_of_agents_configs.values())
+        self.type_names = [c.short_name for c in self.list_of_agents_configs]
+        self.instance_list = self.list_of_agents_configs  # the trainer only takes len() / indexes alongside configs
+        self.cfg = to_step_config(multi_agent_config, self.base_env.n_windows, self.base_env.loaded.msgs.shape[0])
+        self.num_msgs_per_step = num_msgs_per_step(self.cfg)
+        self.num_action_msgs_per_step_by_all_agents = num_action_msgs(self.cfg)
+        self.action_spaces = [Discrete(c.n_actions) for c in self.list_of_agents_configs]
+        self.observation_spaces = [
+            Box(-1000 if isinstance(c, MarketMaking_EnvironmentConfig) else -10000,
+                1000 if isinstance(c, MarketMaking_EnvironmentConfig) else 10000,
+                (abi.obs_dim(self.cfg.agent[i].kind, self.cfg.agent[i].observation_space),), np.float32)
+            for i, c in enumerate(self.list_of_agents_configs)]
+        self._gen = torch.Generator(device=self.device)
+        self._gen.manual_seed(int(seed))
+        self._arrays = None
+
+    # -- API of the reference ------------------------------------------------------------------------------
+    def action_space(self):
+        return self.action_spaces
+
+    def observation_space(self):
+        return self.observation_spaces
+
+    @property
+    def default_params(self) -> MultiAgentParams:
+        agent_params = []
+        for t in range(self.cfg.n_agent_types):
+            a = self.cfg.agent[t]
+            agent_params.append({"trader_id": np.arange(a.trader_id_start, a.trader_id_start - a.n_agents, -1)})
+        return MultiAgentParams(loaded_params=self.base_env.default_params, agent_params=agent_params)
+
+    def _draw(self, arrays):
+        """The PRNG products of one step (see module docstring)."""
+        import torch
+        B, W = self.num_envs, self.cfg.n_windows
+        sel = self.multi_agent_config.world_config.window_selector
+        if sel == -1:
+            arrays["reset_window"].copy_(torch.randint(0, W, (B,), generator=self._gen, device=self.device,
+                                                       dtype=torch.int32))
+        else:
+            arrays["reset_window"].fill_(sel)
+        arrays["reset_is_sell"].copy_(torch.randint(0, 2, arrays["reset_is_sell"].shape, generator=self._gen,
+                                                    device=self.device, dtype=torch.int32))
+        n_act = self.num_action_msgs_per_step_by_all_agents
+        if n_act > 0:
+            r = torch.rand((B, n_act), generator=self._gen, device=self.device)
+            arrays["perm"].copy_(torch.argsort(r, dim=1).to(torch.int32))
+
+    def reset(self, key=None, params: MultiAgentParams = None, arrays=None):
+        """marl_env.py:764 -> (obs list [B,n_i,d_i], MultiAgentState)."""
+        if params is None:
+            raise ValueError("Params must be provided to reset the environment.")
+        L = _lib.lib()
+        if arrays is None:
+            arrays = states.alloc_torch(self.cfg, self.num_envs, self.device)
+            self._draw(arrays)
+        bufs = states.pack_buffers(self.cfg, arrays, self.base_env.device_params())
+        _lib.check(L.lob_reset_launch(C.byref(self.cfg), C.byref(bufs), self.num_envs, _lib.current_stream_ptr()),
+                   "lob_reset_launch")
+        obs = [arrays[f"obs{t}"] for t in range(self.cfg.n_agent_types)]
+        return obs, _state_view(self.cfg, arrays)
+
+    def step(self, key, state: MultiAgentState, actions, params: MultiAgentParams = None, draw=True):
+        """marl_env.py:776 -> (obs, state, rewards, dones, infos); ``state``'s buffers are donated."""
+        L = _lib.lib()
+        arrays = state.arrays
+        for t, a in enumerate(actions):
+            arrays[f"actions{t}"].copy_(a.reshape(arrays[f"actions{t}"].shape))
+        if draw:
+            self._draw(arrays)
+        bufs = states.pack_buffers(self.cfg, arrays, self.base_env.device_params())
+        _lib.check(L.lob_step_launch(C.byref(self.cfg), C.byref(bufs), self.num_envs, _lib.current_stream_ptr()),
+                   "lob_step_launch")
+        T = self.cfg.n_agent_types
+        obs = [arrays[f"obs{t}"] for t in range(T)]
+        rewards = [arrays[f"reward{t}"] for t in range(T)]
+        dones = {"__all__": arrays["done_all"].bool(), "agents": [arrays[f"done_agents{t}"].bool() for t in range(T)]}
+        return obs, _state_view(self.cfg, arrays), rewards, dones, self.unpack_info(arrays)
+
+    def unpack_info(self, arrays):
+        """Packed info columns -> the reference's dict keys (marl:624-639, mm:2695-2730, exe:1809-1829)."""
+        wi, wf = arrays["info_world_i32"], arrays["info_world_f32"]
+        world = {k: wi[:, j] for j, k in enumerate(abi.WINFO_I32) if k not in ("time_s", "time_ns")}
+        world["time"] = wi[:, 2:4]
+        world.update({k: wf[:, j] for j, k in enumerate(abi.WINFO_F32)})
+        agents = []
+        for t in range(self.cfg.n_agent_types):
+            ki, kf = abi.info_cols(self.cfg.agent[t].kind)
+            d = {k: arrays[f"info_i32_{t}"][..., j] for j, k in enumerate(ki)}
+            d.update({k: arrays[f"info_f32_{t}"][..., j] for j, k in enumerate(kf)})
+            agents.append(d)
+        return {"world": world, "agents": agents}

@@ -1,0 +1,126 @@
+"""Buffer table of one step call: names, shapes and dtypes of every leaf that crosses the C-ABI, and the packing of
+those arrays (numpy on the host, torch on the device) into ``LobStepBuffers`` pointers.
+
+Leaf order follows the reference's state pytrees (gymnax_exchange/jaxen/StatesandParams.py:14-122):
+``MultiAgentState = WorldState + [MMEnvState | ExecEnvState per agent type]``.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import abi
+from .config import num_action_msgs, num_msgs_per_step
+
+WORLD_I32 = ("asks", "bids", "trades", "init_time", "window_index", "max_steps", "start_index", "step_counter",
+             "best_bids", "best_asks", "time", "order_id_counter")
+WORLD_F32 = ("mid_price", "delta_time")
+PARAMS = ("message_data", "init_asks", "init_bids", "init_trades", "init_init_time", "init_max_steps",
+          "init_start_index")
+
+
+def leaf_specs(cfg: abi.LobStepConfig, batch: int):
+    """name -> (shape, dtype, role) for state ('s'), input ('i') and output ('o') leaves."""
+    B, No, Nt, N = batch, cfg.book.n_orders, cfg.book.n_trades, num_msgs_per_step(cfg)
+    T = cfg.n_agent_types
+    sp = {
+        "asks": ((B, No, 6), np.int32, "s"), "bids": ((B, No, 6), np.int32, "s"),
+        "trades": ((B, Nt, 8), np.int32, "s"), "init_time": ((B, 2), np.int32, "s"),
+        "window_index": ((B,), np.int32, "s"), "max_steps": ((B,), np.int32, "s"),
+        "start_index": ((B,), np.int32, "s"), "step_counter": ((B,), np.int32, "s"),
+        "best_bids": ((B, N, 2), np.int32, "s"), "best_asks": ((B, N, 2), np.int32, "s"),
+        "time": ((B, 2), np.int32, "s"), "order_id_counter": ((B,), np.int32, "s"),
+        "mid_price": ((B,), np.float32, "s"), "delta_time": ((B,), np.float32, "s"),
+        "perm": ((B, max(num_action_msgs(cfg), 1)), np.int32, "i"),
+        "reset_window": ((B,), np.int32, "i"), "reset_is_sell": ((B, max(T, 1)), np.int32, "i"),
+        "done_all": ((B,), np.uint8, "o"),
+        "info_world_i32": ((B, len(abi.WINFO_I32)), np.int32, "o"),
+        "info_world_f32": ((B, len(abi.WINFO_F32)), np.float32, "o"),
+    }
+    for t in range(T):
+        a = cfg.agent[t]
+        n = a.n_agents
+        li, lf = abi.state_leaves(a.kind)
+        for name in li:
+            sp[f"a{t}_{name}"] = ((B, n), np.int32, "s")
+        for name in lf:
+            sp[f"a{t}_{name}"] = ((B, n), np.float32, "s")
+        ki, kf = abi.info_cols(a.kind)
+        sp[f"actions{t}"] = ((B, n), np.int32, "i")
+        sp[f"obs{t}"] = ((B, n, abi.obs_dim(a.kind, a.observation_space)), np.float32, "o")
+        sp[f"reward{t}"] = ((B, n), np.float32, "o")
+        sp[f"done_agents{t}"] = ((B, n), np.uint8, "o")
+        sp[f"info_i32_{t}"] = ((B, n, len(ki)), np.int32, "o")
+        sp[f"info_f32_{t}"] = ((B, n, len(kf)), np.float32, "o")
+    return sp
+
+
+def state_names(cfg: abi.LobStepConfig):
+    return [k for k, v in leaf_specs(cfg, 1).items() if v[2] == "s"]
+
+
+def alloc_numpy(cfg: abi.LobStepConfig, batch: int):
+    out = {}
+    for k, (shape, dt, _) in leaf_specs(cfg, batch).items():
+        out[k] = np.zeros(shape, dt)
+    return out
+
+
+def alloc_torch(cfg: abi.LobStepConfig, batch: int, device):
+    import torch
+    tdt = {np.int32: torch.int32, np.float32: torch.float32, np.uint8: torch.uint8}
+    return {k: torch.zeros(shape, dtype=tdt[dt], device=device) for k, (shape, dt, _) in leaf_specs(cfg, batch).items()}
+
+
+def _ptr(a, ctype):
+    if a is None:
+        return C.cast(None, C.POINTER(ctype))
+    if isinstance(a, np.ndarray):
+        if not a.flags["C_CONTIGUOUS"]:
+            raise ValueError("buffers must be C-contiguous")
+        return C.cast(a.ctypes.data, C.POINTER(ctype))
+    if not a.is_contiguous():
+        raise ValueError("buffers must be contiguous")
+    return C.cast(a.data_ptr(), C.POINTER(ctype))
+
+
+def pack_buffers(cfg: abi.LobStepConfig, arrays: dict, params: dict) -> abi.LobStepBuffers:
+    """Raw pointers of ``arrays`` (leaf_specs names) and ``params`` (PARAMS names) -> LobStepBuffers.
+    The caller keeps the arrays alive for the duration of the call."""
+    b = abi.LobStepBuffers()
+    for name in WORLD_I32:
+        setattr(b, name, _ptr(arrays[name], C.c_int32))
+    for name in WORLD_F32:
+        setattr(b, name, _ptr(arrays[name], C.c_float))
+    for t in range(cfg.n_agent_types):
+        a = cfg.agent[t]
+        li, lf = abi.state_leaves(a.kind)
+        for j, name in enumerate(li):
+            b.agent_i32[t][j] = _ptr(arrays[f"a{t}_{name}"], C.c_int32)
+        for j, name in enumerate(lf):
+            b.agent_f32[t][j] = _ptr(arrays[f"a{t}_{name}"], C.c_float)
+        b.actions[t] = _ptr(arrays[f"actions{t}"], C.c_int32)
+        b.obs[t] = _ptr(arrays[f"obs{t}"], C.c_float)
+        b.reward[t] = _ptr(arrays[f"reward{t}"], C.c_float)
+        b.done_agents[t] = _ptr(arrays[f"done_agents{t}"], C.c_uint8)
+        b.info_agent_i32[t] = _ptr(arrays[f"info_i32_{t}"], C.c_int32)
+        b.info_agent_f32[t] = _ptr(arrays[f"info_f32_{t}"], C.c_float)
+    b.perm = _ptr(arrays["perm"], C.c_int32)
+    b.reset_window = _ptr(arrays["reset_window"], C.c_int32)
+    b.reset_is_sell = _ptr(arrays["reset_is_sell"], C.c_int32)
+    for name in PARAMS:
+        setattr(b, name, _ptr(params[name], C.c_int32))
+    b.done_all = _ptr(arrays["done_all"], C.c_uint8)
+    b.info_world_i32 = _ptr(arrays["info_world_i32"], C.c_int32)
+    b.info_world_f32 = _ptr(arrays["info_world_f32"], C.c_float)
+    return b
+
+
+def pack_replay(asks, bids, trades, msgs, start, n_msgs, best_out=None) -> abi.LobReplayBuffers:
+    r = abi.LobReplayBuffers()
+    r.asks, r.bids, r.trades = _ptr(asks, C.c_int32), _ptr(bids, C.c_int32), _ptr(trades, C.c_int32)
+    r.msgs = _ptr(msgs, C.c_int32)
+    r.start = _ptr(start, C.c_int64)
+    r.n_msgs_total = int(msgs.shape[0])
+    r.n_msgs = int(n_msgs)
+    r.best_out = _ptr(best_out, C.c_int32)
+    return r

@@ -1,0 +1,2 @@
+"""CPU oracle of the LOB step (TEST INFRASTRUCTURE).  Only tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs may import this package."""
