@@ -1,0 +1,391 @@
+#!/usr/bin/env python
+"""Benchmark of the LOB hot path on B200 (see DESIGN.md "Measurement").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference]
+
+Headline workload = BASELINE.json configs[1]: pure book replay (BaseLOBEnv.step_env / job.scan_through_entire_array)
+of a synthetic LOBSTER day, nOrders = nTrades = 100, 16384 independent books per GPU, each step = ONE launch that
+scans a 6400-message window (64 base-env steps of 100 messages) for every book.  The same run also times the
+multi-agent ``env.step`` (configs[3] shapes: 2_player_fq_fqc, 16384 envs per GPU) and reports it under "env_step".
+
+One JSON line on stdout (rank 0).  ``--impl reference`` times the CPU restatement of the reference (oracle/, OpenMP
+over books; the reference itself is JAX and cannot be installed offline) on a bounded sample of the same workload.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np  # noqa: E402
+
+WINDOW = 6400          # messages per book per replay step
+ND = 100               # data messages per base-env step
+DAY_EVENTS = 400_000
+DAY_SEED = 20220103
+METRIC = "lob_messages_per_sec"
+UNIT = "msgs/s"
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def _load_day(mac):
+    from jaxmarl_hft_b200 import lobster
+    cache = os.path.join(ROOT, ".cache")
+    return lobster.load_or_generate(mac.world_config, seed=DAY_SEED, n_events=DAY_EVENTS, cache_dir=cache)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md's clocks line)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def _dist():
+    ws = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return ws, rank, local
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
+def run_reference(args):
+    """The reference's algorithm on the host cores: oracle/lob_oracle.c (a restatement -- JAX is not installable
+    offline), OpenMP over books, all host threads, on a bounded sample of the replay workload."""
+    ws, rank, _ = _dist()
+    if rank != 0:
+        return
+    import helpers as H
+    from jaxmarl_hft_b200 import config as C, env as E
+    from oracle import lob_oracle
+    oracle = lob_oracle.load()
+    mac = H.load_mac("2_player_fq_fqc")
+    ld = _load_day(mac)
+    bc = C.book_config(mac.world_config)
+    params = E.build_reset_params(ld, mac.world_config, H.oracle_replay_fn(oracle, bc))
+    threads = oracle.max_threads()
+    B = args.ref_books
+    W = ld.starts.shape[0]
+    widx = np.arange(B) % W
+    asks, bids, trades = params["init_asks"][widx].copy(), params["init_bids"][widx].copy(), params["init_trades"][widx].copy()
+    M = ld.msgs.shape[0]
+    base = ld.starts[widx].astype(np.int64)
+    times = []
+    for k in range(args.warmup + args.steps):
+        start = (base + k * WINDOW) % (M - WINDOW)
+        t0 = time.perf_counter()
+        oracle.replay(bc, asks, bids, trades, ld.msgs, start, WINDOW, n_threads=threads)
+        dt = time.perf_counter() - t0
+        if k >= args.warmup:
+            times.append(dt)
+    total = sum(times)
+    value = B * WINDOW * len(times) / total
+    sample = f"{B} books x {WINDOW} msgs per step, {len(times)} steps, OpenMP over books"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+        "config": {"workload": "pure book replay, synthetic LOBSTER day, nOrders=100, nTrades=100 (BASELINE configs[1]), "
+                               "bounded sample", "books": B, "msgs_per_book_per_step": WINDOW},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# --------------------------------------------------------------------------------------------------- native arm
+def run_native(args):
+    import torch
+    import torch.distributed as dist
+    import helpers as H
+    from jaxmarl_hft_b200 import _lib, config as C, env as E, states
+
+    ws, rank, local = _dist()
+    if ws > 1:
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    torch.cuda.set_device(local)
+    dev = torch.device(f"cuda:{local}")
+    L = _lib.lib()          # raises when csrc/liblobstep.so is missing: there is no fallback
+    hbm_peak, peak_src = _peaks()
+
+    def barrier():
+        if ws > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if ws == 1:
+            return ms
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    mac = H.load_mac("2_player_fq_fqc")
+    ld = _load_day(mac)
+    bc = C.book_config(mac.world_config)
+    No, Nt = bc.n_orders, bc.n_trades
+    base_env = E.BaseLOBEnv(mac.world_config, loaded=ld, device=dev)   # reset states through the CUDA replay kernel
+    params_np = base_env._params_np
+    M, W = ld.msgs.shape[0], ld.starts.shape[0]
+    B = args.books
+    K, Wm = args.steps, args.warmup
+    # every rank replays its own shard of books: book g = rank * B + i starts in window g % W (no collective)
+    gidx = rank * B + np.arange(B)
+    widx = gidx % W
+    msgs_d = torch.from_numpy(ld.msgs).to(dev)
+    base = ld.starts[widx].astype(np.int64) + (gidx // W) % ND
+    starts_np = np.stack([(base + k * WINDOW) % (M - WINDOW) for k in range(Wm + K)])
+
+    def fresh_books():
+        return (torch.from_numpy(params_np["init_asks"][widx]).to(dev), torch.from_numpy(params_np["init_bids"][widx]).to(dev),
+                torch.from_numpy(params_np["init_trades"][widx]).to(dev))
+
+    # ---- (1) replay, inputs resident in HBM ----
+    asks, bids, trades = fresh_books()
+    starts_d = torch.from_numpy(starts_np).to(dev)
+    for k in range(Wm):
+        E.replay_books(bc, asks, bids, trades, msgs_d, starts_d[k], WINDOW)
+    sampler = ClockSampler(local)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    L.lob_launch_count_reset()
+    barrier()
+    if rank == 0:
+        sampler.start()
+    t_begin.record()
+    for k in range(K):
+        ev[k][0].record()
+        E.replay_books(bc, asks, bids, trades, msgs_d, starts_d[Wm + k], WINDOW)
+        ev[k][1].record()
+    t_end.record()
+    barrier()
+    launches = int(L.lob_launch_count())
+    clocks = sampler.stop() if rank == 0 else None
+    total_ms = max_over_ranks(t_begin.elapsed_time(t_end))
+    kern_ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
+    value = ws * B * WINDOW * K / (total_ms * 1e-3)
+    bytes_per_launch = B * (2 * (2 * No * 24) + 2 * Nt * 32 + 32 * WINDOW + 8)
+    achieved = bytes_per_launch / (kern_ms * 1e-3) / 1e9
+
+    # ---- (2) replay end to end through the public API: per step the inputs (start offsets) come from pinned host
+    #          memory and the result (best bid/ask + quantities per book) is read back to the host ----
+    asks, bids, trades = fresh_books()
+    starts_h = torch.from_numpy(starts_np).pin_memory()
+    start_dev = torch.empty(B, dtype=torch.int64, device=dev)
+    best_dev = torch.empty((B, 4), dtype=torch.int32, device=dev)
+    best_host = torch.empty((B, 4), dtype=torch.int32).pin_memory()
+
+    def e2e_step(k):
+        start_dev.copy_(starts_h[k], non_blocking=True)
+        base_env.replay(asks, bids, trades, start_dev, WINDOW, best_out=best_dev)
+        best_host.copy_(best_dev, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    for k in range(Wm):
+        e2e_step(k)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for k in range(K):
+        e2e_step(Wm + k)
+    e1.record()
+    barrier()
+    e2e_ms = max_over_ranks(e0.elapsed_time(e1))
+    e2e_value = ws * B * WINDOW * K / (e2e_ms * 1e-3)
+    del asks, bids, trades
+
+    # ---- (3) multi-agent env.step (2_player_fq_fqc), same batch per GPU ----
+    env = E.MARLEnv(None, mac, num_envs=args.envs, loaded=ld, device=dev, seed=1234 + rank)
+    envp = env.default_params
+    obs, state = env.reset(None, envp)
+    T = env.cfg.n_agent_types
+    n_act_space = [env.action_spaces[t].n for t in range(T)]
+    g = torch.Generator(device=dev); g.manual_seed(99 + rank)
+    n_i = [env.cfg.agent[t].n_agents for t in range(T)]
+    acts_d = [[torch.randint(0, n_act_space[t], (args.envs, n_i[t]), generator=g, device=dev, dtype=torch.int32)
+               for t in range(T)] for _ in range(4)]
+    N = env.num_msgs_per_step
+    for k in range(Wm):
+        env.step(None, state, acts_d[k % 4], envp)
+    barrier()
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    bufs = states.pack_buffers(env.cfg, state.arrays, env.base_env.device_params())
+    stream = _lib.current_stream_ptr()
+    L.lob_launch_count_reset()
+    s0.record()
+    for k in range(K):   # kernel-only: PRNG products and actions of the previous draw stay resident
+        sev[k][0].record()
+        _lib.check(L.lob_step_launch(ctypes.byref(env.cfg), ctypes.byref(bufs), args.envs, stream), "lob_step_launch")
+        sev[k][1].record()
+    s1.record()
+    barrier()
+    step_launches = int(L.lob_launch_count())
+    step_ms = max_over_ranks(s0.elapsed_time(s1))
+    step_kern_ms = float(np.mean([a.elapsed_time(b) for a, b in sev]))
+    step_value = ws * args.envs * K / (step_ms * 1e-3)
+    # algorithmic bytes per env-step: books in+out, data slice in, trades out, per-message bests out,
+    # scalars / agent state / actions / perm in+out, obs / reward / done / info out
+    n_mm = sum(env.cfg.agent[t].n_agents for t in range(T) if env.cfg.agent[t].kind == 0)
+    n_ex = sum(env.cfg.agent[t].n_agents for t in range(T) if env.cfg.agent[t].kind == 1)
+    n_ag = n_mm + n_ex
+    S_r = 64 + 20 * n_mm + 52 * n_ex + 4 * n_ag + 4 * env.num_action_msgs_per_step_by_all_agents
+    d_obs = sum(env.cfg.agent[t].n_agents * env.observation_spaces[t].shape[0] for t in range(T))
+    S_w = 64 + 20 * n_mm + 52 * n_ex + 4 * d_obs + 4 * n_ag + n_ag + 1 + 4 * (15 + 24 * n_mm + 9 * n_ex)
+    step_bytes = (2 * No * 24 + ND * 32 + S_r) + (2 * No * 24 + Nt * 32 + 2 * N * 8 + S_w)
+    step_achieved = step_bytes * args.envs / (step_kern_ms * 1e-3) / 1e9
+    # env.step end to end through MARLEnv.step: actions from pinned host memory, PRNG draws, obs/reward/done to host
+    acts_h = [[a.cpu().pin_memory() for a in row] for row in acts_d]
+    acts_in = [torch.empty_like(a) for a in acts_d[0]]
+    outs_h = None
+
+    def env_e2e(k):
+        nonlocal outs_h
+        for t in range(T):
+            acts_in[t].copy_(acts_h[k % 4][t], non_blocking=True)
+        o, st, r, d, info = env.step(None, state, acts_in, envp)
+        outs = list(o) + list(r) + [state.arrays["done_all"]]
+        if outs_h is None:
+            outs_h = [torch.empty(x.shape, dtype=x.dtype).pin_memory() for x in outs]
+        for h, x in zip(outs_h, outs):
+            h.copy_(x, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    for k in range(Wm):
+        env_e2e(k)
+    barrier()
+    q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    q0.record()
+    for k in range(K):
+        env_e2e(k)
+    q1.record()
+    barrier()
+    step_e2e_ms = max_over_ranks(q0.elapsed_time(q1))
+    step_e2e_value = ws * args.envs * K / (step_e2e_ms * 1e-3)
+    step_h2d = sum(a.numel() * 4 for a in acts_in)
+    step_d2h = sum(h.numel() * h.element_size() for h in outs_h)
+
+    # ---- (4) CPU baseline beside it (rank 0, N=1): the oracle on a bounded sample of the replay workload ----
+    cpu = None
+    if rank == 0 and ws == 1 and not args.no_cpu:
+        from oracle import lob_oracle
+        oracle = lob_oracle.load()
+        threads = oracle.max_threads()
+        cb = args.ref_books
+        cw = np.arange(cb) % W
+        ca, cbid, ct = params_np["init_asks"][cw].copy(), params_np["init_bids"][cw].copy(), params_np["init_trades"][cw].copy()
+        cstart = ld.starts[cw].astype(np.int64)
+        oracle.replay(bc, ca.copy(), cbid.copy(), ct.copy(), ld.msgs, cstart, 200, n_threads=threads)  # warm the threads
+        t0 = time.perf_counter()
+        reps = 0
+        while True:
+            oracle.replay(bc, ca, cbid, ct, ld.msgs, (cstart + reps * WINDOW) % (M - WINDOW), WINDOW, n_threads=threads)
+            reps += 1
+            if time.perf_counter() - t0 > args.cpu_seconds or reps >= 50:
+                break
+        dt = time.perf_counter() - t0
+        cpu = {"value": cb * WINDOW * reps / dt, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": f"{cb} books x {WINDOW} msgs x {reps} passes ({dt:.1f} s), oracle/lob_oracle.c, OpenMP over books"}
+
+    if rank == 0:
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": ws, "steps": K, "warmup": Wm,
+            "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "int32", "data": "synthetic",
+            "config": {"workload": "pure book replay (job.scan_through_entire_array), synthetic LOBSTER day, nOrders=100, "
+                                   "nTrades=100, BASELINE configs[1]",
+                       "books_per_gpu": B, "msgs_per_book_per_step": WINDOW, "day_msgs": int(M),
+                       "l2_policy": f"inputs larger than L2: {B * (2 * No * 24 + Nt * 32) / 1e6:.0f} MB of book state per GPU"},
+            "base_env_steps_per_sec": value / ND,
+            "roofline": {"bound": "hbm", "kernel": "lob_replay_kernel", "achieved": achieved, "peak": hbm_peak,
+                         "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": bytes_per_launch, "kernel_ms": kern_ms},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * 8, "d2h_bytes_per_step": B * 16,
+                    "api": "BaseLOBEnv.replay: start offsets from pinned host memory, best bid/ask per book read back; "
+                           "book state stays device-resident as in the reference"},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "env_step": {"metric": "env_steps_per_sec", "value": step_value, "unit": "env-steps/s",
+                         "msgs_per_sec": step_value * N, "ms_per_step": step_ms / K,
+                         "config": {"workload": "MARLEnv.step 2_player_fq_fqc (MM fixed_quants + EXE fixed_quants_complex), "
+                                                "BASELINE configs[3] shapes", "envs_per_gpu": args.envs, "msgs_per_env_step": N},
+                         "roofline": {"bound": "hbm", "kernel": "lob_step_kernel", "achieved": step_achieved,
+                                      "peak": hbm_peak, "unit": "GB/s", "frac": step_achieved / hbm_peak, "traffic": None,
+                                      "algorithmic_bytes_per_env_step": step_bytes, "kernel_ms": step_kern_ms},
+                         "e2e": {"value": step_e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": step_h2d,
+                                 "d2h_bytes_per_step": step_d2h},
+                         "gpu_launches": step_launches},
+        }
+        if cpu is not None:
+            out["cpu_baseline"] = cpu
+        print(json.dumps(out))
+    if ws > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--books", type=int, default=16384, help="books per GPU (replay workload)")
+    ap.add_argument("--envs", type=int, default=16384, help="environments per GPU (env.step workload)")
+    ap.add_argument("--ref-books", type=int, default=256, help="books in the CPU sample")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "native" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_native(args)
+
+
+if __name__ == "__main__":
+    main()

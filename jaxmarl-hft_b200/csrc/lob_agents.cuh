@@ -1,0 +1,597 @@
+// lob_agents.cuh -- agent-side device code of the LOB step: action -> order messages, cancel messages,
+// netting filter, rewards, state update, observations.  Warp-cooperative: reductions over the book / the
+// trade log use all 32 lanes, the scalar arithmetic is executed redundantly (warp-uniform).
+//
+// Restated from the reference (gymnax_exchange/jaxen): mm = mm_env.py, exe = exec_env.py, job =
+// ../jaxob/JaxOrderBookArrays.py.  float32 throughout (jax_enable_x64 = False); the file is compiled with
+// -fmad=false so that a*b+c is two roundings as in XLA.  Float reductions over the trade log are summed
+// left-to-right over the NON-ZERO terms in row order, which equals a plain left-to-right sum.
+#pragma once
+#include <math.h>
+#include "lob_book.cuh"
+
+namespace lob {
+
+// ---- JAX scalar semantics ---------------------------------------------------------------------------------
+__device__ __forceinline__ int ifloordiv(int a, int b) {  // jnp.floor_divide on int32
+  int q = a / b, r = a % b;
+  int sa = (a > 0) - (a < 0), sb = (b > 0) - (b < 0);
+  if (sa != sb && r != 0) q -= 1;
+  return q;
+}
+__device__ __forceinline__ float fsignf(float x) { return (x > 0.f) ? 1.f : ((x < 0.f) ? -1.f : x); }
+__device__ __forceinline__ float ffloordiv(float x1, float x2) {  // jax._src.numpy.ufuncs._float_divmod
+  float mod = fmodf(x1, x2);
+  float div = (x1 - mod) / x2;
+  if (mod != 0.f && fsignf(x2) != fsignf(mod)) div = div - 1.f;
+  return roundf(div);
+}
+__device__ __forceinline__ float jmaxf(float a, float b) { return (a != a || b != b) ? NAN : (a > b ? a : b); }
+__device__ __forceinline__ float jminf(float a, float b) { return (a != a || b != b) ? NAN : (a < b ? a : b); }
+__device__ __forceinline__ int f2i(float x) { return (int)x; }
+__device__ __forceinline__ int clamp_index(int a, int n) { if (a < 0) a += n; return max(0, min(a, n - 1)); }
+__device__ __forceinline__ int isign(int a) { return (a > 0) - (a < 0); }
+
+// Left-to-right float sum of term(r), r = 0..n-1, skipping exact zeros (x + 0.0f == x).
+template <class F>
+__device__ __forceinline__ float ordered_sum(int n, F term) {
+  float acc = 0.f;
+  const int lane = lane_id();
+  for (int base = 0; base < n; base += 32) {
+    const int r = base + lane;
+    const float t = (r < n) ? term(r) : 0.f;
+    unsigned m = __ballot_sync(kFull, t != 0.f);
+    while (m) {
+      const int j = __ffs(m) - 1;
+      acc = acc + __shfl_sync(kFull, t, j);
+      m &= m - 1;
+    }
+  }
+  return acc;
+}
+template <class F>
+__device__ __forceinline__ int int_sum(int n, F term) {
+  int acc = 0;
+  for (int r = lane_id(); r < n; r += 32) acc += term(r);
+  return wsum(acc);
+}
+
+// One trade row classified against a trader id (job:895-904, mm:2214-2243)
+struct TradeRow {
+  int p, q, ts;
+  bool agent, buy, sell, pass_buy, pass_sell;
+};
+__device__ __forceinline__ TradeRow classify(const int* tr, int nt, int r, int tid) {
+  TradeRow o;
+  const bool valid = tr[r] >= 0;  // trades[:,0] >= 0
+  const int p = valid ? tr[r] : 0, q = valid ? tr[nt + r] : 0, ts = valid ? tr[4 * nt + r] : 0;
+  const int ptid = valid ? tr[6 * nt + r] : 0, atid = valid ? tr[7 * nt + r] : 0;
+  const bool m2 = (tid == ptid) || (tid == atid);
+  // agentTrades rows that are not the agent's are all-zero: tid == 0 never holds for those unless tid is 0
+  const int aq = m2 ? q : 0, aptid = m2 ? ptid : 0, aatid = m2 ? atid : 0;
+  o.agent = m2;
+  o.p = p; o.q = q; o.ts = ts;
+  o.buy = ((aq >= 0) && (tid == aptid)) || ((aq < 0) && (tid == aatid));
+  o.sell = ((aq < 0) && (tid == aptid)) || ((aq >= 0) && (tid == aatid));
+  o.pass_buy = (aq >= 0) && (tid == aptid);
+  o.pass_sell = (aq < 0) && (tid == aptid);
+  return o;
+}
+
+// job:886-889 add_trade for the reward only: overwrite the first row holding a -1 (else the last row); returns the
+// row and the saved field (lane k < 8 keeps field k) so that `restore_trade` can undo it.
+__device__ __forceinline__ int insert_fictional(int* tr, int nt, const int (&row)[8], int& saved) {
+  const int lane = lane_id();
+  int first = kBig;
+  for (int r = lane; r < nt; r += 32) {
+    bool any = false;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) any |= tr[k * nt + r] == -1;
+    if (any) first = min(first, r);
+  }
+  first = wmin(first);
+  const int e = (first == kBig) ? nt - 1 : first;
+  __syncwarp();
+  if (lane < 8) { saved = tr[lane * nt + e]; tr[lane * nt + e] = row[lane]; }
+  __syncwarp();
+  return e;
+}
+__device__ __forceinline__ void restore_trade(int* tr, int nt, int e, int saved) {
+  __syncwarp();
+  if (lane_id() < 8) tr[lane_id() * nt + e] = saved;
+  __syncwarp();
+}
+
+// job:827-853 getCancelMsgs: the k-th (k = 0..size-1) row of `side` whose trader id is `agent`
+template <int SLOTS>
+__device__ __forceinline__ void cancel_msgs(const Book<SLOTS>& bk, int s, int agent, int size, int side_sign, int t,
+                                            int tns, int* out /* smem [size][8] */) {
+  const int lane = lane_id();
+  int prev = -1;
+  for (int k = 0; k < size; ++k) {
+    int idx = kBig;
+#pragma unroll
+    for (int j = SLOTS - 1; j >= 0; --j) { int r = j * 32 + lane; if (r < bk.no && r > prev && bk.F(s, F_TID)[r] == agent) idx = r; }
+    idx = wmin(idx);
+    int q = 0, p = 0, o = 0, ti = 0;
+    if (idx != kBig) { q = bk.F(s, F_Q)[idx]; p = bk.F(s, F_P)[idx]; o = bk.F(s, F_OID)[idx]; ti = bk.F(s, F_TID)[idx]; prev = idx; }
+    else prev = bk.no;  // nothing further: zeros from the appended row
+    if (lane == 0) {
+      int* m = out + k * 8;
+      m[0] = 2; m[1] = side_sign; m[2] = q; m[3] = p; m[4] = o; m[5] = ti; m[6] = t; m[7] = tns;
+    }
+  }
+  __syncwarp();
+}
+
+// mm:520-582 == exe:413-475 _filter_messages; one lane, k <= 16
+__device__ __forceinline__ void filter_messages(int* act, int ka, int* cnl, int kc) {
+  bool a_mask[16], c_mask[16];
+  int a_i[16], c_i[16], a[16], cq[16], rel[16];
+  for (int i = 0; i < ka; ++i) a_mask[i] = false;
+  for (int j = 0; j < kc; ++j) c_mask[j] = false;
+  for (int i = 0; i < ka; ++i)
+    for (int j = 0; j < kc; ++j)
+      if (cnl[j * 8 + 3] == act[i * 8 + 3] && act[i * 8 + 3] != 0) { a_mask[i] = true; c_mask[j] = true; }
+  int na = 0, nc = 0;
+  for (int i = 0; i < ka; ++i) if (a_mask[i]) a_i[na++] = i;
+  for (int j = 0; j < kc; ++j) if (c_mask[j]) c_i[nc++] = j;
+  for (int k = 0; k < ka; ++k) a[k] = (k < na) ? act[a_i[k] * 8 + 2] : 0;
+  for (int k = 0; k < kc; ++k) cq[k] = (k < nc) ? cnl[c_i[k] * 8 + 2] : 0;
+  for (int k = 0; k < ka; ++k) rel[k] = (cq[k] >= a[k]) ? a[k] : 0;
+  int rt = 0, rf = na;
+  for (int i = 0; i < ka; ++i) { int rank = a_mask[i] ? rt++ : rf++; act[i * 8 + 2] -= rel[rank]; }
+  for (int i = 0; i < ka; ++i)
+    if (act[i * 8 + 2] == 0)
+      for (int k = 0; k < 8; ++k) act[i * 8 + k] = 0;
+  rt = 0; rf = nc;
+  for (int j = 0; j < kc; ++j) { int rank = c_mask[j] ? rt++ : rf++; cnl[j * 8 + 2] -= rel[rank]; }
+}
+
+// Old-world scalars every agent function needs (warp-uniform)
+struct WorldIn {
+  int time0, time1, init_time0, step_counter, max_steps;
+  int old_ba_last, old_bb_last;   // world_state.best_asks[-1,0] / best_bids[-1,0]
+  float mid_price;
+  bool extreme_spread;            // any((ba-bb)/((ba+bb)/2) > 0.1) over the OLD per-message bests (mm:2545-2553)
+};
+
+struct MMOut {  // what the MM action leaves for the info / state update
+  int posted_bid_price, posted_ask_price, bid_dist, ask_dist, bid_quant, ask_quant;
+};
+
+// mm:1869-1913 get_messages (fixed_quants mm:970-1118 / directional mm:1810-1865).  act/cnl are shared memory.
+template <int SLOTS>
+__device__ __forceinline__ MMOut mm_get_messages(const Book<SLOTS>& bk, const LobStepConfig& c, const LobAgentTypeConfig& ac,
+                                                 int action, const WorldIn& w, int inventory, int tid, int* act, int* cnl) {
+  const int lane = lane_id();
+  const int tick = c.tick_size;
+  MMOut o;
+  int best_ask = 0, best_bid = 0;
+  bool empty_book = false;
+  if (ac.action_space == LOB_MM_ACT_FIXED_QUANTS) {
+    // mm:979-985 best prices excluding own orders
+    int mn = bk.maxint, mx = INT32_MIN;
+#pragma unroll
+    for (int k = 0; k < SLOTS; ++k) {
+      int r = k * 32 + lane;
+      if (r < bk.no) {
+        int pa = (bk.F(ASK, F_TID)[r] != tid) ? bk.F(ASK, F_P)[r] : -1;
+        int pb = (bk.F(BID, F_TID)[r] != tid) ? bk.F(BID, F_P)[r] : -1;
+        mn = min(mn, pa == -1 ? bk.maxint : pa);
+        mx = max(mx, pb);
+      }
+    }
+    mn = wmin(mn); mx = wmax(mx);
+    best_ask = (mn == bk.maxint) ? -1 : mn;
+    best_bid = mx;
+    empty_book = (best_ask == -1) || (best_bid == -1);
+    best_ask = ifloordiv(best_ask, tick) * tick;
+    best_bid = ifloordiv(best_bid, tick) * tick;
+    if (empty_book) { best_bid = w.old_bb_last; best_ask = w.old_ba_last; }
+  }
+  const int sz = ac.num_messages_by_agent / 4;
+  cancel_msgs(bk, BID, tid, sz, 1, w.time0, w.time1, cnl);
+  cancel_msgs(bk, ASK, tid, sz, -1, w.time0, w.time1, cnl + sz * 8);
+
+  int types[2] = {1, 1}, sides[2] = {1, -1}, quants[2], prices[2];
+  if (ac.action_space == LOB_MM_ACT_FIXED_QUANTS) {
+    if (ac.fixed_action_setting) action = ac.fixed_action;
+    const int ai = clamp_index(action, 10);
+    // bid/ask offset tables mm:1012-1015
+    const float bid_offset = (float)((0x0152043210u >> (4 * ai)) & 0xf);   // {0,1,2,3,4,0,2,5,1,0}
+    const float ask_offset = (float)((0x0510243210u >> (4 * ai)) & 0xf);   // {0,1,2,3,4,2,0,1,5,0}
+    const int unit = (ai == 9) ? 0 : 1;
+    float half_spread_prev = jmaxf((float)(best_ask - best_bid) / 2.0f, (float)((double)tick / 2.0));
+    float half_spread = (ffloordiv(half_spread_prev, (float)tick) + 1.0f) * (float)tick;
+    int bid_quant = unit * ac.fixed_quant_value, ask_quant = unit * ac.fixed_quant_value;
+    if (empty_book) { bid_quant = 0; ask_quant = 0; }
+    float bid_price_f = (float)best_bid - bid_offset * half_spread;
+    float ask_price_f = (float)best_ask + ask_offset * half_spread;
+    bid_price_f = ffloordiv(jmaxf(bid_price_f, 0.0f), (float)tick) * (float)tick;
+    const int bid_price = f2i(bid_price_f);
+    ask_price_f = ffloordiv(jmaxf((float)(bid_price + tick), ask_price_f), (float)tick) * (float)tick;
+    const int ask_price = f2i(ask_price_f);
+    quants[0] = bid_quant; quants[1] = ask_quant; prices[0] = bid_price; prices[1] = ask_price;
+    bool use_liq = (ac.tenth_action_market_order && action == 9);
+    if (ac.auto_liquidate_threshold != 0 && abs(inventory) > ac.auto_liquidate_threshold) use_liq = true;
+    if (use_liq) {  // mm:1073-1094
+      types[0] = 4; types[1] = 4; sides[0] = -1; sides[1] = 1;
+      quants[0] = f2i((float)ac.auto_liquidate_alpha * (float)max(-inventory, 0));
+      quants[1] = f2i((float)ac.auto_liquidate_alpha * (float)max(inventory, 0));
+      prices[0] = f2i((float)best_ask + half_spread * 10.0f);
+      prices[1] = f2i((float)best_bid - half_spread * 10.0f);
+    }
+    o.posted_bid_price = bid_price; o.posted_ask_price = ask_price;
+    o.bid_dist = best_bid - bid_price; o.ask_dist = ask_price - best_ask;
+    o.bid_quant = bid_quant; o.ask_quant = ask_quant;
+  } else {  // directional_trading
+    const int ba = ifloordiv(w.old_ba_last, tick) * tick, bb = ifloordiv(w.old_bb_last, tick) * tick;
+    const int ai = clamp_index(action, 3);
+    quants[0] = (ai == 1) ? ac.fixed_quant_value : 0;
+    quants[1] = (ai == 2) ? ac.fixed_quant_value : 0;
+    prices[0] = ba; prices[1] = bb;
+    o.posted_bid_price = 0; o.posted_ask_price = 0; o.bid_dist = 0; o.ask_dist = 0;
+    o.bid_quant = quants[0]; o.ask_quant = quants[1];
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      int* m = act + k * 8;
+      m[0] = types[k]; m[1] = sides[k]; m[2] = quants[k]; m[3] = prices[k]; m[4] = c.placeholder_order_id; m[5] = tid;
+      m[6] = w.time0 + ac.time_delay_obs_act; m[7] = w.time1 + ac.time_delay_obs_act;
+    }
+    filter_messages(act, ac.num_action_messages_by_agent, cnl, 2 * sz);
+  }
+  __syncwarp();
+  return o;
+}
+
+// exe:1229-1273 get_messages (fixed_quants exe:623-724 / fixed_quants_complex exe:838-932)
+template <int SLOTS>
+__device__ __forceinline__ void exe_get_messages(const Book<SLOTS>& bk, const LobStepConfig& c, const LobAgentTypeConfig& ac,
+                                                 int action, const WorldIn& w, int task_to_execute, int quant_executed,
+                                                 int is_sell, int tid, int* act, int* cnl) {
+  const int tick = c.tick_size;
+  const int best_ask = ifloordiv(w.old_ba_last, tick) * tick, best_bid = ifloordiv(w.old_bb_last, tick) * tick;
+  int lv[4];
+  if (is_sell) {
+    lv[0] = best_bid;
+    lv[1] = f2i(ceilf(ffloordiv((float)(best_bid + best_ask) / 2.0f, (float)tick)) * (float)tick);
+    lv[2] = best_ask;
+    lv[3] = best_ask + tick * ac.n_ticks_in_book;
+  } else {
+    lv[0] = best_ask;
+    lv[1] = ifloordiv(ifloordiv(best_bid + best_ask, 2), tick) * tick;
+    lv[2] = best_bid;
+    lv[3] = best_bid - tick * ac.n_ticks_in_book;
+  }
+  int q[4] = {0, 0, 0, 0};
+  int first0 = 1;  // quant_array[1][0]
+  if (ac.action_space == LOB_EXE_ACT_FIXED_QUANTS_COMPLEX) {
+    const int ai = clamp_index(action, 13);
+    const int mult = (ai >= 9) ? 5 : (ai >= 5) ? 2 : 1;
+    if (ai > 0) {
+      const int col = (ai - 1) & 3;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) if (k == col) q[k] = mult;
+    }
+  } else {
+    const int ai = clamp_index(action, 5);
+    if (ac.larger_far_touch_quant) first0 = 10;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) if (ai == k + 1) q[k] = (k == 0 && ac.larger_far_touch_quant) ? 10 : 1;
+  }
+  int total = 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { q[k] *= ac.fixed_quant_value; total += q[k]; }
+  const int quant_left = task_to_execute - quant_executed;
+  if (!(total <= quant_left)) {
+    q[0] = f2i(floorf((float)(first0 * quant_left)));
+    q[1] = f2i(floorf((float)(0 * quant_left))); q[2] = q[1]; q[3] = q[1];
+  }
+  const int side = 1 - is_sell * 2;
+  const int sz = ac.num_messages_by_agent / 2;
+  if (is_sell) cancel_msgs(bk, ASK, tid, sz, side, w.time0, w.time1, cnl);
+  else cancel_msgs(bk, BID, tid, sz, side, w.time0, w.time1, cnl);
+  if (lane_id() == 0) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      int* m = act + k * 8;
+      m[0] = 1; m[1] = side; m[2] = q[k]; m[3] = lv[k]; m[4] = c.placeholder_order_id; m[5] = tid;
+      m[6] = w.time0 + ac.time_delay_obs_act; m[7] = w.time1 + ac.time_delay_obs_act;
+    }
+    filter_messages(act, ac.num_action_messages_by_agent, cnl, sz);
+  }
+  __syncwarp();
+}
+
+// Per-step market summary the rewards need (from the scan)
+struct StepOut {
+  int ba_last, bb_last;      // new best ask / bid price after the last message (forward filled)
+  float avg_mid;             // mean_i (bb_i + ba_i) / 2
+  bool ep_done;
+};
+
+struct MMState { int posted_distance_bid, posted_distance_ask, inventory; float total_PnL, cash_balance; };
+struct MMReward {
+  float reward_scaled, reward, reward_portfolio_value, end_of_ep_pv, reward_spooner, reward_spooner_damped,
+      reward_spooner_asym_damped, reward_spooner_asym_damped2, reward_delta_pv, market_share, inventoryValue,
+      delta_mid_price, buyPnL, sellPnL, invPnL, PnL, cash_balance;
+  int forced_unwind, end_inventory;
+};
+
+// mm:2247-2673 get_reward
+__device__ __forceinline__ MMReward mm_get_reward(int* tr, int nt, const LobStepConfig& c, const LobAgentTypeConfig& ac,
+                                                  const WorldIn& w, const StepOut& so, const MMState& st, int tid) {
+  MMReward R;
+  const int tick = c.tick_size;
+  const float tickf = (float)tick;
+  int buyQ = int_sum(nt, [&](int r) { TradeRow t = classify(tr, nt, r, tid); return (t.agent && t.buy) ? abs(t.q) : 0; });
+  int sellQ = int_sum(nt, [&](int r) { TradeRow t = classify(tr, nt, r, tid); return (t.agent && t.sell) ? abs(t.q) : 0; });
+  const int inv_before = st.inventory + buyQ - sellQ;
+  const float last_mid = (float)(so.bb_last + so.ba_last) / 2.0f;
+  int penalty = ac.unwind_price_penalty * tick;
+  penalty = (inv_before > 0) ? penalty : -penalty;
+  int unwind_price;
+  if (ac.unwind_price == LOB_REF_MID_AVG) unwind_price = f2i(so.avg_mid - (float)penalty);
+  else if (ac.unwind_price == LOB_REF_MID) unwind_price = f2i(last_mid - (float)penalty);
+  else unwind_price = ((inv_before > 0) ? so.bb_last : so.ba_last) - penalty;
+  const bool fict = so.ep_done && abs(inv_before) > 0;
+  int saved = 0, frow = 0;
+  if (fict) {
+    const int row[8] = {unwind_price, isign(inv_before) * abs(inv_before), c.artificial_order_id_end_episode,
+                        c.placeholder_order_id, 0, 0, c.artificial_trader_id_end_episode, tid};
+    frow = insert_fictional(tr, nt, row, saved);
+  }
+  R.forced_unwind = inv_before * (so.ep_done ? 1 : 0);
+
+  const float income = ordered_sum(nt, [&](int r) { TradeRow t = classify(tr, nt, r, tid);
+    return (t.agent && t.sell) ? (float)t.p / tickf * (float)abs(t.q) : 0.f; });
+  const float outgoing = ordered_sum(nt, [&](int r) { TradeRow t = classify(tr, nt, r, tid);
+    return (t.agent && t.buy) ? (float)t.p / tickf * (float)abs(t.q) : 0.f; });
+  buyQ = int_sum(nt, [&](int r) { TradeRow t = classify(tr, nt, r, tid); return (t.agent && t.buy) ? abs(t.q) : 0; });
+  sellQ = int_sum(nt, [&](int r) { TradeRow t = classify(tr, nt, r, tid); return (t.agent && t.sell) ? abs(t.q) : 0; });
+  const int otherQ = int_sum(nt, [&](int r) { TradeRow t = classify(tr, nt, r, tid); return t.agent ? 0 : abs(t.q); });
+  const int new_inventory = st.inventory + buyQ - sellQ;
+  const float rb = ordered_sum(nt, [&](int r) { TradeRow t = classify(tr, nt, r, tid);
+    return (t.agent && t.pass_buy) ? (float)t.p / tickf * (float)abs(t.q) : 0.f; });
+  const float rs = ordered_sum(nt, [&](int r) { TradeRow t = classify(tr, nt, r, tid);
+    return (t.agent && t.pass_sell) ? (float)t.p / tickf * (float)abs(t.q) : 0.f; });
+  const float rebate_income = (rb + rs) * (float)(ac.rebate_bps / 10000.0);
+
+  const bool ref_is_int = (ac.reference_price == LOB_REF_FAR_TOUCH || ac.reference_price == LOB_REF_NEAR_TOUCH);
+  float ref_f = (ac.reference_price == LOB_REF_MID_AVG) ? so.avg_mid : last_mid;
+  int ref_buy_i = 0, ref_sell_i = 0, reference_i = 0;
+  if (ac.reference_price == LOB_REF_FAR_TOUCH) { ref_buy_i = so.ba_last; ref_sell_i = so.bb_last; }
+  else if (ac.reference_price == LOB_REF_NEAR_TOUCH) { ref_buy_i = so.bb_last; ref_sell_i = so.ba_last; }
+  reference_i = (new_inventory > 0) ? ref_buy_i : ref_sell_i;
+
+  const float PnL = income - outgoing + rebate_income;
+  const float new_cash = st.cash_balance + PnL;
+  const float inventoryValue = ref_is_int ? (float)(new_inventory * reference_i) / tickf
+                                          : ((float)new_inventory * ref_f) / tickf;
+  const float netWorth = new_cash + inventoryValue;
+  const int traded = buyQ + sellQ;
+  const float market_share = (float)traded / (float)(traded + otherQ);
+  const float InvPnL = ((float)st.inventory * (last_mid - w.mid_price)) / tickf;
+  const float buyPnL = ordered_sum(nt, [&](int r) { TradeRow t = classify(tr, nt, r, tid);
+    if (!(t.agent && t.buy)) return 0.f;   // rows that are not buys contribute (ref - 0)/tick * 0 == 0
+    const float d = ref_is_int ? (float)(ref_buy_i - t.p) : (ref_f - (float)t.p);
+    return d / tickf * (float)abs(t.q); });
+  const float sellPnL = ordered_sum(nt, [&](int r) { TradeRow t = classify(tr, nt, r, tid);
+    if (!(t.agent && t.sell)) return 0.f;
+    const float d = ref_is_int ? (float)(t.p - ref_sell_i) : ((float)t.p - ref_f);
+    return d / tickf * (float)abs(t.q); });
+  const float eta = (float)ac.inventoryPnL_eta, gamma = (float)ac.inventoryPnL_gamma;
+  R.reward_spooner = buyPnL + sellPnL + rebate_income + InvPnL;
+  R.reward_spooner_damped = buyPnL + sellPnL + rebate_income + InvPnL - (eta * InvPnL);
+  R.reward_spooner_asym_damped = buyPnL + sellPnL + rebate_income + InvPnL - jmaxf(0.f, eta * InvPnL);
+  R.reward_spooner_asym_damped2 = buyPnL + sellPnL + rebate_income + gamma * (InvPnL - jmaxf(0.f, eta * InvPnL));
+  const float reward_spooner_scaled =
+      buyPnL + sellPnL + rebate_income + eta * (InvPnL - (float)(1.0 - ac.inventoryPnL_eta) * jmaxf(0.f, InvPnL));
+  float reward_complex = 0.f;
+  if (ac.reward_function == LOB_MM_REW_COMPLEX) {  // mm:2437-2450
+    const int inv_change = buyQ - sellQ;
+    float avg_buy = 0.f, avg_sell = 0.f;
+    if (buyQ > 0) avg_buy = ordered_sum(nt, [&](int r) { TradeRow t = classify(tr, nt, r, tid);
+      return (t.agent && t.buy) ? (float)t.p / (float)buyQ * (float)abs(t.q) : 0.f; });
+    if (sellQ > 0) avg_sell = ordered_sum(nt, [&](int r) { TradeRow t = classify(tr, nt, r, tid);
+      return (t.agent && t.sell) ? (float)t.p / (float)sellQ * (float)abs(t.q) : 0.f; });
+    const float realized = (float)min(buyQ, sellQ) * (avg_sell - avg_buy);
+    const float unrealized = (inv_change > 0) ? (float)inv_change * (so.avg_mid - avg_buy)
+                                              : (float)abs(inv_change) * (avg_sell - so.avg_mid);
+    reward_complex = realized + (float)ac.unrealizedPnL_lambda * unrealized + eta * jminf(InvPnL, InvPnL * eta);
+  }
+  if (fict) restore_trade(tr, nt, frow, saved);
+
+  R.reward_portfolio_value = ref_is_int ? (float)new_inventory * ((float)reference_i / tickf) + new_cash
+                                        : (float)new_inventory * (ref_f / tickf) + new_cash;
+  float old_ref_over_tick;
+  if (!ref_is_int) old_ref_over_tick = w.mid_price / tickf;
+  else if (ac.reference_price == LOB_REF_FAR_TOUCH)
+    old_ref_over_tick = (float)((st.inventory > 0) ? w.old_ba_last : w.old_bb_last) / tickf;
+  else
+    old_ref_over_tick = (float)((st.inventory > 0) ? w.old_bb_last : w.old_ba_last) / tickf;
+  const float old_netWorth = old_ref_over_tick * (float)st.inventory + st.cash_balance;
+  R.reward_delta_pv = netWorth - old_netWorth;
+
+  float reward;
+  switch (ac.reward_function) {
+    case LOB_MM_REW_PORTFOLIO_VALUE: reward = R.reward_portfolio_value; break;
+    case LOB_MM_REW_BUY_SELL_PNL: reward = buyPnL + sellPnL; break;
+    case LOB_MM_REW_COMPLEX: reward = reward_complex; break;
+    case LOB_MM_REW_ZERO_INV: reward = (float)(-abs(new_inventory)); break;
+    case LOB_MM_REW_SPOONER: reward = R.reward_spooner; break;
+    case LOB_MM_REW_SPOONER_DAMPED: reward = R.reward_spooner_damped; break;
+    case LOB_MM_REW_SPOONER_ASYM_DAMPED: reward = R.reward_spooner_asym_damped; break;
+    case LOB_MM_REW_SPOONER_ASYM_DAMPED2: reward = R.reward_spooner_asym_damped2; break;
+    case LOB_MM_REW_SPOONER_SCALED: reward = reward_spooner_scaled; break;
+    default: reward = R.reward_delta_pv; break;
+  }
+  const float lam = (float)ac.inv_penalty_lambda;
+  switch (ac.inv_penalty) {
+    case LOB_INVPEN_NONE: reward = reward + (float)(ac.inv_penalty_lambda * 0.0); break;
+    case LOB_INVPEN_LINEAR: reward = reward + lam * (float)(-abs(new_inventory)); break;
+    case LOB_INVPEN_QUADRATIC:
+      reward = reward + lam * ((float)(-(new_inventory * new_inventory)) / (float)ac.inv_penalty_quadratic_factor); break;
+    case LOB_INVPEN_EXP4: reward = reward + lam * (-1.0f * expf((float)(new_inventory * 4))); break;
+    default: {
+      const float pen = ((float)abs(new_inventory) > (float)ac.inv_penalty_threshold)
+                            ? -1.0f * ((float)(new_inventory * new_inventory) / (float)ac.inv_penalty_quadratic_factor)
+                            : 0.0f;
+      reward = reward + lam * pen;
+    }
+  }
+  if (ac.clip_reward) reward = jmaxf(-10000.f, jminf(reward, 10000.f));
+  if (ac.volume_traded_bonus_market_share) reward = reward + fabsf(reward) * market_share;
+  if (ac.exclude_extreme_spreads && w.extreme_spread) reward = 0.0f;
+  R.reward = reward;
+  R.end_of_ep_pv = R.reward_portfolio_value * (float)(so.ep_done ? 1 : 0);
+  R.market_share = market_share;
+  R.inventoryValue = inventoryValue;
+  R.delta_mid_price = last_mid - w.mid_price;
+  R.buyPnL = buyPnL; R.sellPnL = sellPnL; R.invPnL = InvPnL; R.PnL = PnL;
+  R.cash_balance = new_cash; R.end_inventory = new_inventory;
+  R.reward_scaled = reward / (float)ac.reward_scaling_quo;
+  return R;
+}
+
+// mm:2963-3154 observation (fixed_steps), alphabetical key order
+__device__ __forceinline__ void mm_write_obs(const LobAgentTypeConfig& ac, float* obs, int inventory, float mid_price, int ba,
+                                             int bb, int qa, int qb, int step_counter, bool zero) {
+  if (lane_id() != 0) return;
+  const bool nz = ac.normalize;
+  const int spread = abs(ba - bb);
+  if (ac.observation_space == LOB_OBS_BASIC) {
+    obs[0] = zero ? 0.f : (nz ? (float)inventory / 10.0f : (float)inventory);
+    obs[1] = zero ? 0.f : (nz ? (float)spread / 1e4f : (float)spread);
+    return;
+  }
+  float v[8];
+  v[0] = nz ? (float)inventory / 10.0f : (float)inventory;
+  v[1] = nz ? mid_price / 1e6f : mid_price;
+  v[2] = nz ? (float)ba / 1e6f : (float)ba;
+  v[3] = nz ? (float)bb / 1e6f : (float)bb;
+  v[4] = nz ? (float)qa / 1000.0f : (float)qa;
+  v[5] = nz ? (float)qb / 1000.0f : (float)qb;
+  v[6] = nz ? (float)spread / 1e4f : (float)spread;
+  v[7] = nz ? (float)step_counter / 10.0f : (float)step_counter;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) obs[k] = zero ? 0.f : v[k];
+}
+
+struct EXEState {
+  int task_to_execute, quant_executed, is_sell_task;
+  float init_price, p_vwap, total_revenue, drift_return, advantage_return, slippage_rm, price_adv_rm, price_drift_rm,
+      vwap_rm, trade_duration;
+};
+struct EXEReward {
+  float reward_scaled, reward, slippage_rm, price_adv_rm, price_drift_rm, p_vwap, vwap_rm, advantage, drift, slippage,
+      trade_duration;
+  int agentQuant, qp_agent, doom_quant, quant_left;
+};
+
+__device__ __forceinline__ float rolling_mean(float old_mean, float nv, int step) {
+  return (old_mean * (float)step + nv) / (float)(step + 1);
+}
+
+// exe:1511-1758 get_reward
+__device__ __forceinline__ EXEReward exe_get_reward(int* tr, int nt, const LobStepConfig& c, const LobAgentTypeConfig& ac,
+                                                    const WorldIn& w, const StepOut& so, const EXEState& st, int tid) {
+  EXEReward R;
+  const int tick = c.tick_size;
+  const float tickf = (float)tick;
+  const int qsum = int_sum(nt, [&](int r) { TradeRow t = classify(tr, nt, r, tid); return t.agent ? t.q : 0; });
+  const int quant_left0 = st.task_to_execute - (st.quant_executed + abs(qsum));
+  const int penalty = ac.doom_price_penalty * tick;
+  const int side_sign = st.is_sell_task * 2 - 1;
+  int reference_price;
+  if (ac.reference_price == LOB_REF_MID) {
+    const float x = st.is_sell_task ? (so.avg_mid - (float)penalty) : (so.avg_mid + (float)penalty);
+    reference_price = f2i(ffloordiv(x, tickf) * tickf);
+  } else {
+    const int x = st.is_sell_task ? (so.bb_last - penalty) : (so.ba_last + penalty);
+    reference_price = ifloordiv(x, tick) * tick;
+  }
+  const bool fict = so.ep_done && quant_left0 > 0;
+  int saved = 0, frow = 0;
+  if (fict) {
+    const int row[8] = {reference_price, side_sign * abs(quant_left0), c.artificial_order_id_end_episode,
+                        c.placeholder_order_id, 0, 0, c.artificial_trader_id_end_episode, tid};
+    frow = insert_fictional(tr, nt, row, saved);
+  }
+  R.doom_quant = (so.ep_done ? 1 : 0) * quant_left0;
+  const int agentQ = int_sum(nt, [&](int r) { TradeRow t = classify(tr, nt, r, tid); return t.agent ? abs(t.q) : 0; });
+  const int otherQ = int_sum(nt, [&](int r) { TradeRow t = classify(tr, nt, r, tid); return t.agent ? 0 : abs(t.q); });
+  float P_vwap;
+  if (otherQ == 0) P_vwap = ffloordiv(so.avg_mid, tickf);
+  else P_vwap = ordered_sum(nt, [&](int r) { TradeRow t = classify(tr, nt, r, tid);
+    return t.agent ? 0.f : (float)ifloordiv(t.p, tick) * ((float)abs(t.q) / (float)otherQ); });
+  const int ds = isign(st.is_sell_task * 2 - 1);
+  const int QP = int_sum(nt, [&](int r) { TradeRow t = classify(tr, nt, r, tid); return t.agent ? ifloordiv(t.p, tick) * abs(t.q) : 0; });
+  const float advantage = (float)ds * ((float)QP - P_vwap * (float)agentQ);
+  const float drift = (float)(ds * agentQ) * (P_vwap - ffloordiv(st.init_price, tickf));
+  const float denom = (float)agentQ + 1e-9f;
+  const float price_adv = advantage / denom, price_drift = drift / denom;
+  const float slippage = advantage + drift;
+  R.vwap_rm = rolling_mean(st.vwap_rm, P_vwap, w.step_counter);
+  R.price_adv_rm = rolling_mean(st.price_adv_rm, price_adv, w.step_counter);
+  R.slippage_rm = rolling_mean(st.slippage_rm, slippage, w.step_counter);
+  R.price_drift_rm = rolling_mean(st.price_drift_rm, price_drift, w.step_counter);
+  const float reward = advantage + (float)ac.reward_lambda * drift;
+  const float tds = ordered_sum(nt, [&](int r) { TradeRow t = classify(tr, nt, r, tid);
+    return t.agent ? (float)abs(t.q) / (float)st.task_to_execute * (float)(t.ts - w.init_time0) : 0.f; });
+  R.trade_duration = st.trade_duration + tds;
+  R.quant_left = st.task_to_execute - st.quant_executed - agentQ;
+  R.reward = reward; R.agentQuant = agentQ; R.qp_agent = QP; R.p_vwap = P_vwap;
+  R.advantage = advantage; R.drift = drift; R.slippage = slippage;
+  R.reward_scaled = reward / (float)ac.reward_scaling_quo;
+  if (ac.reward_function == LOB_EXE_REW_FINISH_FAST) R.reward_scaled = (float)(-abs(R.quant_left)) / (float)ac.reward_scaling_quo;
+  if (ac.reward_function == LOB_EXE_REW_SIMPLEST_CASE) {
+    const float r = ordered_sum(nt, [&](int rr) { TradeRow t = classify(tr, nt, rr, tid);
+      if (!t.agent) return 0.f;   // |q| == 0 for rows that are not the agent's
+      float slip = (float)t.p - st.init_price;
+      if (!st.is_sell_task) slip = -slip;
+      return slip * (float)abs(t.q); });
+    R.reward_scaled = r / (float)ac.reward_scaling_quo;
+  }
+  if (fict) restore_trade(tr, nt, frow, saved);
+  return R;
+}
+
+// exe:1879-1906 / exe:1913-2079 (fixed_steps), alphabetical key order
+__device__ __forceinline__ void exe_write_obs(const LobAgentTypeConfig& ac, float* obs, const EXEState& st, int ba, int bb,
+                                              int ask_vol, int bid_vol, int step_counter, int max_steps, bool zero) {
+  if (lane_id() != 0) return;
+  const bool nz = ac.normalize;
+  const float ts = (float)ac.task_size;
+  const int rem = st.task_to_execute - st.quant_executed;
+  if (ac.observation_space == LOB_OBS_BASIC) {
+    obs[0] = zero ? 0.f : (nz ? (float)(ba - 1550000) / 1e3f : (float)ba);
+    obs[1] = zero ? 0.f : (nz ? (float)(bb - 1550000) / 1e3f : (float)bb);
+    obs[2] = zero ? 0.f : (nz ? (float)rem / ts : (float)rem);
+    return;
+  }
+  const int p_aggr = st.is_sell_task ? bb : ba, p_pass = st.is_sell_task ? ba : bb;
+  const int q_aggr = st.is_sell_task ? bid_vol : ask_vol, q_pass = st.is_sell_task ? ask_vol : bid_vol;
+  const float ratio = (max_steps == 0) ? 0.f : 1.0f - (float)step_counter / (float)max_steps;
+  const int spread = abs(p_aggr - p_pass);
+  float v[12];
+  v[0] = nz ? (float)st.quant_executed / ts : (float)st.quant_executed;
+  v[1] = nz ? st.init_price / 1e7f : st.init_price;
+  v[2] = nz ? (float)st.is_sell_task / 1.0f : (float)st.is_sell_task;
+  v[3] = nz ? ((float)p_aggr - st.init_price) / 1e5f : (float)p_aggr;
+  v[4] = nz ? ((float)p_pass - st.init_price) / 1e5f : (float)p_pass;
+  v[5] = nz ? (float)q_aggr / 1000.0f : (float)q_aggr;
+  v[6] = nz ? (float)q_pass / 1000.0f : (float)q_pass;
+  v[7] = nz ? (float)rem / ts : (float)rem;
+  v[8] = nz ? ratio / 1.0f : ratio;
+  v[9] = nz ? (float)spread / 1e4f : (float)spread;
+  v[10] = nz ? (float)step_counter / 30.0f : (float)step_counter;
+  v[11] = nz ? (float)st.task_to_execute / ts : (float)st.task_to_execute;
+#pragma unroll
+  for (int k = 0; k < 12; ++k) obs[k] = zero ? 0.f : v[k];
+}
+
+}  // namespace lob

@@ -1,0 +1,63 @@
+// lob_inst.cu -- kernel instantiations + launch wrappers for ONE book-capacity class: LOB_SLOTS rows per lane
+// (n_orders <= 32 * LOB_SLOTS).  Compiled once per value of LOB_SLOTS (1, 2, 4, 8, 16) by build.py.
+#ifndef LOB_SLOTS
+#error "compile with -DLOB_SLOTS=<1|2|4|8|16>"
+#endif
+#include "lob_launch.cuh"
+
+namespace lobhost {
+
+template <int S>
+int launch_replay(const LobBookConfig* cfg, const LobReplayBuffers* bufs, int64_t n_books, cudaStream_t st, const DevInfo& d) {
+  const lob::WarpLayout L = lob::make_layout(cfg->n_orders, cfg->n_trades, 2 * lob::kReplayChunk * 8, 0);
+  const size_t smem = (size_t)L.words * 4 * lob::kWarps;
+  int per_sm = 1;
+  int rc = prepare(lob::lob_replay_kernel<S>, smem, d, &per_sm);
+  if (rc) return rc;
+  lob::lob_replay_kernel<S><<<grid_for(n_books, d.sms, per_sm), lob::kWarps * 32, smem, st>>>(*cfg, *bufs, n_books, L);
+  return launched("lob_replay_kernel");
+}
+
+template <int S>
+int launch_step(const LobStepConfig* c, const LobStepBuffers* b, int64_t batch, cudaStream_t st, const DevInfo& d) {
+  const int N = lob_num_msgs_per_step(c), n_act = lob_num_action_msgs(c), n_cnl = lob_num_cancel_msgs(c);
+  const lob::WarpLayout L = lob::make_layout(c->book.n_orders, c->book.n_trades, N * 8, n_act);
+  if (((n_cnl + n_act) * 8) % 4 != 0) return fail(LOB_E_INVALID, "internal: data slice misaligned");
+  const size_t smem = (size_t)L.words * 4 * lob::kWarps;
+  int per_sm = 1;
+  int rc = prepare(lob::lob_step_kernel<S>, smem, d, &per_sm);
+  if (rc) return rc;
+  int need_extreme = 0;
+  for (int t = 0; t < c->n_agent_types; ++t)
+    if (c->agent[t].kind == LOB_AGENT_MM && c->agent[t].exclude_extreme_spreads) need_extreme = 1;
+  lob::lob_step_kernel<S><<<grid_for(batch, d.sms, per_sm), lob::kWarps * 32, smem, st>>>(*c, *b, batch, L, N, n_act, n_cnl,
+                                                                                      need_extreme);
+  return launched("lob_step_kernel");
+}
+
+template <int S>
+int launch_reset(const LobStepConfig* c, const LobStepBuffers* b, int64_t batch, cudaStream_t st, const DevInfo& d) {
+  const int N = lob_num_msgs_per_step(c);
+  const lob::WarpLayout L = lob::make_layout(c->book.n_orders, c->book.n_trades, 0, 0);
+  const size_t smem = (size_t)L.words * 4 * lob::kWarps;
+  int per_sm = 1;
+  int rc = prepare(lob::lob_reset_kernel<S>, smem, d, &per_sm);
+  if (rc) return rc;
+  lob::lob_reset_kernel<S><<<grid_for(batch, d.sms, per_sm), lob::kWarps * 32, smem, st>>>(*c, *b, batch, L, N);
+  return launched("lob_reset_kernel");
+}
+
+
+template <int S>
+int launch_l2(const LobBookConfig* cfg, const int32_t* asks, const int32_t* bids, int32_t* l2, int32_t n_levels,
+              int64_t n_books, cudaStream_t st, const DevInfo& d) {
+  lob::lob_l2_kernel<S><<<grid_for(n_books, d.sms, 8), lob::kWarps * 32, 0, st>>>(*cfg, asks, bids, l2, n_levels, n_books);
+  return launched("lob_l2_kernel");
+}
+
+template int launch_replay<LOB_SLOTS>(const LobBookConfig*, const LobReplayBuffers*, int64_t, cudaStream_t, const DevInfo&);
+template int launch_step<LOB_SLOTS>(const LobStepConfig*, const LobStepBuffers*, int64_t, cudaStream_t, const DevInfo&);
+template int launch_reset<LOB_SLOTS>(const LobStepConfig*, const LobStepBuffers*, int64_t, cudaStream_t, const DevInfo&);
+template int launch_l2<LOB_SLOTS>(const LobBookConfig*, const int32_t*, const int32_t*, int32_t*, int32_t, int64_t, cudaStream_t, const DevInfo&);
+
+}  // namespace lobhost

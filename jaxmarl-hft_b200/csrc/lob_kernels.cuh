@@ -1,0 +1,554 @@
+// lob_kernels.cuh -- the sm_100a kernels of the LOB step: replay, step (+fused auto-reset), reset, L2 snapshot.
+//
+// Work decomposition: one WARP owns one environment for the whole call; a CTA is kWarps independent warps, the grid
+// is persistent (a multiple of the SM count) and every warp walks the batch with a grid stride.  Per warp, shared
+// memory holds both book sides (struct-of-arrays), the trade log, the step's message list and a few agent scalars;
+// the data-message slice is staged from HBM by the bulk-copy engine (cp.async.bulk -> UBLKCP, completion on an
+// mbarrier) while the warp transposes the books in and builds the agent messages.  Nothing inside a step
+// synchronises across warps.
+//
+// Reference call sites restated (gymnax_exchange/jaxen): marl_env.py:211-709 step_env, :775-804 auto-reset,
+// :129-207 reset_env, base_env.py:189-234,339-369; jaxob/JaxOrderBookArrays.py:736-823 scans, :1232-1264 L2.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "lob_agents.cuh"
+
+namespace lob {
+
+constexpr int kWarps = 4;            // warps (= environments in flight) per CTA
+constexpr int kReplayChunk = 64;     // messages per staged chunk of the replay kernel (2 KB)
+constexpr int kMaxAgents = 32;       // agents per environment, all types
+
+// ---- bulk-copy engine + mbarrier (PTX) ----------------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, unsigned bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+// generic-proxy accesses of a buffer -> ordered before the async proxy overwrites it
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ---- shared-memory layout of one warp (in 32-bit words) -----------------------------------------------------
+struct WarpLayout {
+  int book;      // 12 * no
+  int trades;    // 8 * nt
+  int msgs;      // step: N * 8 ; replay: 2 * kReplayChunk * 8      (16-byte aligned)
+  int act;       // step: n_act * 8
+  int scratch;   // step: kMaxAgents * 8
+  int bar;       // 2 mbarriers (4 words, 8-byte aligned)
+  int words;     // per-warp total, multiple of 4
+};
+__host__ __device__ inline WarpLayout make_layout(int no, int nt, int msg_words, int n_act) {
+  WarpLayout L;
+  int o = 0;
+  L.book = o; o += 12 * no;
+  o = (o + 3) & ~3;
+  L.trades = o; o += 8 * nt;
+  o = (o + 3) & ~3;
+  L.msgs = o; o += msg_words;
+  o = (o + 3) & ~3;
+  L.act = o; o += n_act * 8;
+  L.scratch = o; o += kMaxAgents * 8;
+  o = (o + 3) & ~3;
+  L.bar = o; o += 4;
+  L.words = (o + 3) & ~3;
+  return L;
+}
+
+// ================================================================================================ replay ====
+// base_env.py:189-216 / job:736-756: book b scans msgs[start[b] .. start[b]+T); the trade log persists.
+template <int SLOTS>
+__global__ void __launch_bounds__(kWarps * 32)
+lob_replay_kernel(const __grid_constant__ LobBookConfig cfg, const __grid_constant__ LobReplayBuffers B,
+                  long long n_books, WarpLayout L) {
+  extern __shared__ __align__(128) int smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int* ws = smem + warp * L.words;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(ws + L.bar);
+  int* mbuf = ws + L.msgs;
+  if (lane == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); }
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncwarp();
+  unsigned phase[2] = {0u, 0u};
+
+  Book<SLOTS> bk;
+  bk.init(cfg, ws + L.book, ws + L.trades);
+  const int no = cfg.n_orders, nt = cfg.n_trades;
+  const long long stride = (long long)gridDim.x * kWarps;
+  for (long long b = (long long)blockIdx.x * kWarps + warp; b < n_books; b += stride) {
+    long long st = B.start[b];
+    long long avail = B.n_msgs_total - st;
+    int T = B.n_msgs;
+    if (st < 0 || avail <= 0) T = 0; else if (avail < T) T = (int)avail;
+    const int* src = B.msgs + st * 8;
+    const int nch = (T + kReplayChunk - 1) / kReplayChunk;
+    if (nch > 0 && lane == 0) {
+      const int n0 = min(T, kReplayChunk);
+      fence_async_smem();
+      mbar_expect_tx(&bar[0], n0 * 32);
+      bulk_g2s(mbuf, src, n0 * 32, &bar[0]);
+    }
+    bk.load_side(ASK, B.asks + b * no * 6);
+    bk.load_side(BID, B.bids + b * no * 6);
+    bk.load_trades(B.trades + b * nt * 8);
+    __syncwarp();
+    bk.scan_side_flags(ASK);
+    bk.scan_side_flags(BID);
+    bk.scan_trade_flags();
+    for (int c = 0; c < nch; ++c) {
+      const int cur = c & 1;
+      if (c + 1 < nch) {  // prefetch the next chunk into the other buffer (all lanes are done reading it)
+        __syncwarp();
+        if (lane == 0) {
+          const int n1 = min(T - (c + 1) * kReplayChunk, kReplayChunk);
+          fence_async_smem();
+          mbar_expect_tx(&bar[cur ^ 1], n1 * 32);
+          bulk_g2s(mbuf + (cur ^ 1) * kReplayChunk * 8, src + (long long)(c + 1) * kReplayChunk * 8, n1 * 32,
+                   &bar[cur ^ 1]);
+        }
+      }
+      mbar_wait(&bar[cur], phase[cur]);
+      phase[cur] ^= 1u;
+      const int n = min(T - c * kReplayChunk, kReplayChunk);
+      const int4* m4 = reinterpret_cast<const int4*>(mbuf + cur * kReplayChunk * 8);
+      for (int i = 0; i < n; ++i) bk.process(m4[2 * i], m4[2 * i + 1]);
+    }
+    __syncwarp();
+    if (B.best_out) {
+      bk.recompute(ASK);
+      bk.recompute(BID);
+      if (lane == 0) {
+        int4 o = make_int4(bk.bestp[ASK], bk.bestq[ASK], bk.bestp[BID], bk.bestq[BID]);
+        *reinterpret_cast<int4*>(B.best_out + b * 4) = o;
+      }
+    }
+    bk.store_side(ASK, B.asks + b * no * 6);
+    bk.store_side(BID, B.bids + b * no * 6);
+    bk.store_trades(B.trades + b * nt * 8);
+    __syncwarp();
+  }
+}
+
+// ================================================================================================== step ====
+struct AgentIdx { int t, a; };
+
+__device__ __forceinline__ void load_mm_state(const LobStepBuffers& b, int t, long long idx, MMState& s) {
+  s.posted_distance_bid = b.agent_i32[t][0][idx];
+  s.posted_distance_ask = b.agent_i32[t][1][idx];
+  s.inventory = b.agent_i32[t][2][idx];
+  s.total_PnL = b.agent_f32[t][0][idx];
+  s.cash_balance = b.agent_f32[t][1][idx];
+}
+__device__ __forceinline__ void store_mm_state(const LobStepBuffers& b, int t, long long idx, const MMState& s) {
+  b.agent_i32[t][0][idx] = s.posted_distance_bid;
+  b.agent_i32[t][1][idx] = s.posted_distance_ask;
+  b.agent_i32[t][2][idx] = s.inventory;
+  b.agent_f32[t][0][idx] = s.total_PnL;
+  b.agent_f32[t][1][idx] = s.cash_balance;
+}
+__device__ __forceinline__ void load_exe_state(const LobStepBuffers& b, int t, long long idx, EXEState& s) {
+  s.task_to_execute = b.agent_i32[t][0][idx];
+  s.quant_executed = b.agent_i32[t][1][idx];
+  s.is_sell_task = b.agent_i32[t][2][idx];
+  float* const* f = b.agent_f32[t];
+  s.init_price = f[0][idx]; s.p_vwap = f[1][idx]; s.total_revenue = f[2][idx]; s.drift_return = f[3][idx];
+  s.advantage_return = f[4][idx]; s.slippage_rm = f[5][idx]; s.price_adv_rm = f[6][idx];
+  s.price_drift_rm = f[7][idx]; s.vwap_rm = f[8][idx]; s.trade_duration = f[9][idx];
+}
+__device__ __forceinline__ void store_exe_state(const LobStepBuffers& b, int t, long long idx, const EXEState& s) {
+  b.agent_i32[t][0][idx] = s.task_to_execute;
+  b.agent_i32[t][1][idx] = s.quant_executed;
+  b.agent_i32[t][2][idx] = s.is_sell_task;
+  float* const* f = b.agent_f32[t];
+  f[0][idx] = s.init_price; f[1][idx] = s.p_vwap; f[2][idx] = s.total_revenue; f[3][idx] = s.drift_return;
+  f[4][idx] = s.advantage_return; f[5][idx] = s.slippage_rm; f[6][idx] = s.price_adv_rm;
+  f[7][idx] = s.price_drift_rm; f[8][idx] = s.vwap_rm; f[9][idx] = s.trade_duration;
+}
+
+__device__ __forceinline__ int obs_dim_of(const LobAgentTypeConfig& a) {
+  if (a.kind == LOB_AGENT_MM) return a.observation_space == LOB_OBS_BASIC ? 2 : 8;
+  return a.observation_space == LOB_OBS_BASIC ? 3 : 12;
+}
+
+// marl_env.py:130-207 reset_env for env e: the precomputed state of window reset_window[e] replaces every leaf.
+// The book / trade log are left in shared memory (the caller stores them); everything else is written here.
+template <int SLOTS>
+__device__ __forceinline__ void reset_env(const LobStepConfig& c, const LobStepBuffers& b, long long e, Book<SLOTS>& bk,
+                                          int N) {
+  const int lane = lane_id();
+  const int no = c.book.n_orders, nt = c.book.n_trades, T = c.n_agent_types;
+  int wdx = b.reset_window[e];
+  if (wdx < 0) wdx += c.n_windows;
+  wdx = max(0, min(wdx, c.n_windows - 1));
+  __syncwarp();
+  bk.load_side(ASK, b.init_asks + (long long)wdx * no * 6);
+  bk.load_side(BID, b.init_bids + (long long)wdx * no * 6);
+  bk.load_trades(b.init_trades + (long long)wdx * nt * 8);
+  __syncwarp();
+  bk.recompute(ASK);   // marl:157 get_best_bid_and_ask_inclQuants
+  bk.recompute(BID);
+  const int ap = bk.bestp[ASK], aq = bk.bestq[ASK], bp = bk.bestp[BID], bq = bk.bestq[BID];
+  int2* ga = reinterpret_cast<int2*>(b.best_asks + e * N * 2);
+  int2* gb = reinterpret_cast<int2*>(b.best_bids + e * N * 2);
+  for (int i = lane; i < N; i += 32) { ga[i] = make_int2(ap, aq); gb[i] = make_int2(bp, bq); }   // marl:158-159
+  const float mid = (float)(bp + ap) / 2.0f;   // marl:160
+  const int it0 = b.init_init_time[wdx * 2], it1 = b.init_init_time[wdx * 2 + 1];
+  const int max_steps = b.init_max_steps[wdx];
+  if (lane == 0) {
+    b.init_time[e * 2] = it0; b.init_time[e * 2 + 1] = it1;
+    b.window_index[e] = wdx; b.max_steps[e] = max_steps;
+    b.start_index[e] = b.init_start_index[wdx]; b.step_counter[e] = 0;
+    b.time[e * 2] = it0; b.time[e * 2 + 1] = it1;
+    b.order_id_counter[e] = c.order_id_counter_start;
+    b.mid_price[e] = mid; b.delta_time[e] = 0.0f;
+  }
+  const int qa = bk.volume(ASK), qb = bk.volume(BID);
+  for (int t = 0; t < T; ++t) {
+    const LobAgentTypeConfig& ac = c.agent[t];
+    const int d = obs_dim_of(ac);
+    for (int a = 0; a < ac.n_agents; ++a) {
+      const long long idx = e * ac.n_agents + a;
+      if (ac.kind == LOB_AGENT_MM) {   // mm:417-459
+        MMState s = {0, 0, 0, 0.f, 0.f};
+        if (lane == 0) store_mm_state(b, t, idx, s);
+        mm_write_obs(ac, b.obs[t] + idx * d, 0, mid, ap, bp, qa, qb, 0, false);
+      } else {                          // exe:210-266
+        EXEState s = {};
+        s.is_sell_task = (ac.task == LOB_TASK_RANDOM) ? b.reset_is_sell[e * T + t] : (ac.task == LOB_TASK_BUY ? 0 : 1);
+        s.init_price = mid;
+        s.task_to_execute = ac.task_size;
+        s.p_vwap = mid / (float)c.tick_size;
+        if (lane == 0) store_exe_state(b, t, idx, s);
+        exe_write_obs(ac, b.obs[t] + idx * d, s, ap, bp, qa, qb, 0, max_steps, false);
+      }
+    }
+  }
+}
+
+template <int SLOTS>
+__global__ void __launch_bounds__(kWarps * 32)
+lob_step_kernel(const __grid_constant__ LobStepConfig c, const __grid_constant__ LobStepBuffers b, long long batch,
+                WarpLayout L, int N, int n_act, int n_cnl, int need_extreme) {
+  extern __shared__ __align__(128) int smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int* ws = smem + warp * L.words;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(ws + L.bar);
+  int* msgs = ws + L.msgs;
+  int* act_all = ws + L.act;
+  int* scr = ws + L.scratch;
+  if (lane == 0) mbar_init(&bar[0], 1);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncwarp();
+  unsigned phase = 0u;
+
+  Book<SLOTS> bk;
+  bk.init(c.book, ws + L.book, ws + L.trades);
+  const int no = c.book.n_orders, nt = c.book.n_trades, Nd = c.n_data_msg_per_step, T = c.n_agent_types;
+  const int tick = c.tick_size;
+  const long long stride = (long long)gridDim.x * kWarps;
+  for (long long e = (long long)blockIdx.x * kWarps + warp; e < batch; e += stride) {
+    // ---- old world state (the reward sees it: marl:462) ----
+    WorldIn w;
+    w.time0 = b.time[e * 2]; w.time1 = b.time[e * 2 + 1];
+    w.init_time0 = b.init_time[e * 2];
+    w.step_counter = b.step_counter[e];
+    w.max_steps = b.max_steps[e];
+    w.mid_price = b.mid_price[e];
+    w.old_ba_last = b.best_asks[(e * N + N - 1) * 2];
+    w.old_bb_last = b.best_bids[(e * N + N - 1) * 2];
+    const int start_index = b.start_index[e];
+    const int oid_counter = b.order_id_counter[e];
+    const int window_index = b.window_index[e];
+
+    // ---- (B) base:339-369 data messages: dynamic_slice clamps the start; staged by the bulk-copy engine ----
+    {
+      long long off = (long long)(int)(start_index + Nd * w.step_counter);
+      if (off > c.n_messages - Nd) off = c.n_messages - Nd;
+      if (off < 0) off = 0;
+      __syncwarp();
+      if (lane == 0) {
+        fence_async_smem();
+        mbar_expect_tx(&bar[0], Nd * 32);
+        bulk_g2s(msgs + (n_cnl + n_act) * 8, b.message_data + off * 8, Nd * 32, &bar[0]);
+      }
+    }
+    bk.load_side(ASK, b.asks + e * no * 6);
+    bk.load_side(BID, b.bids + e * no * 6);
+    w.extreme_spread = false;
+    if (need_extreme) {   // mm:2545-2553 over the OLD per-message bests
+      bool any = false;
+      for (int i = lane; i < N; i += 32) {
+        const int a = b.best_asks[(e * N + i) * 2], bb = b.best_bids[(e * N + i) * 2];
+        const float mid = (float)(a + bb) / 2.0f;
+        any |= ((float)(a - bb) / mid > 0.1f);
+      }
+      w.extreme_spread = __any_sync(kFull, any);
+    }
+    __syncwarp();
+    bk.scan_side_flags(ASK);
+    bk.scan_side_flags(BID);
+
+    // ---- (C) marl:254-315 agent messages: [cancels | permuted actions | data] ----
+    {
+      int ci = 0, ai = 0, flat = 0;
+      for (int t = 0; t < T; ++t) {
+        const LobAgentTypeConfig& ac = c.agent[t];
+        const int kc = ac.num_messages_by_agent - ac.num_action_messages_by_agent, ka = ac.num_action_messages_by_agent;
+        for (int a = 0; a < ac.n_agents; ++a, ++flat) {
+          const long long idx = e * ac.n_agents + a;
+          const int tid = ac.trader_id_start - a;
+          const int action = b.actions[t][idx];
+          if (ac.kind == LOB_AGENT_MM) {
+            const int inventory = b.agent_i32[t][2][idx];
+            MMOut o = mm_get_messages(bk, c, ac, action, w, inventory, tid, act_all + ai * 8, msgs + ci * 8);
+            if (lane == 0) {
+              int* s = scr + flat * 8;
+              s[0] = o.posted_bid_price; s[1] = o.posted_ask_price; s[2] = o.bid_dist; s[3] = o.ask_dist;
+              s[4] = o.bid_quant; s[5] = o.ask_quant;
+            }
+          } else {
+            exe_get_messages(bk, c, ac, action, w, b.agent_i32[t][0][idx], b.agent_i32[t][1][idx],
+                             b.agent_i32[t][2][idx], tid, act_all + ai * 8, msgs + ci * 8);
+          }
+          ci += kc; ai += ka;
+        }
+      }
+      __syncwarp();
+      for (int i = lane; i < n_act; i += 32) act_all[i * 8 + 4] = oid_counter - i;   // marl:285-289
+      __syncwarp();
+      for (int j = lane; j < n_act * 8; j += 32) {   // marl:293-295 permutation(key, x) == x[perm]
+        const int i = j >> 3, k = j & 7;
+        int src = i;
+        if (c.shuffle_action_messages && b.perm) src = max(0, min(b.perm[e * n_act + i], n_act - 1));
+        msgs[(n_cnl + i) * 8 + k] = act_all[src * 8 + k];
+      }
+    }
+    bk.fill_trades_empty();
+    mbar_wait(&bar[0], phase);
+    phase ^= 1u;
+    __syncwarp();
+
+    // ---- (D) marl:348-364 the scan, with the per-message best bid/ask (job:792-823) and the forward fill ----
+    float avg_sum = 0.f, sum_a = 0.f, sum_b = 0.f;
+    int prev_a = w.old_ba_last, prev_b = w.old_bb_last;
+    bool abort_episode = false;
+    {
+      const int4* m4 = reinterpret_cast<const int4*>(msgs);
+      int2* gq = reinterpret_cast<int2*>((lane == 0 ? b.best_asks : b.best_bids) + e * N * 2);
+      for (int i = 0; i < N; ++i) {
+        bk.process(m4[2 * i], m4[2 * i + 1]);
+        bk.ensure(ASK);
+        bk.ensure(BID);
+        int ap = bk.bestp[ASK], aq = bk.bestq[ASK], bp = bk.bestp[BID], bq = bk.bestq[BID];
+        abort_episode |= (ap == -1) | (bp == -1);
+        if (ap == -1) { ap = prev_a; aq = 0; }      // marl:723-749 _ffill_best_prices, online
+        if (bp == -1) { bp = prev_b; bq = 0; }
+        prev_a = ap; prev_b = bp;
+        avg_sum += (float)(bp + ap) / 2.0f;
+        sum_a += (float)ap; sum_b += (float)bp;
+        if (lane < 2) gq[i] = (lane == 0) ? make_int2(ap, aq) : make_int2(bp, bq);
+      }
+    }
+    __syncwarp();
+    const int ft0 = msgs[(N - 1) * 8 + 6], ft1 = msgs[(N - 1) * 8 + 7];   // marl:419
+    StepOut so;
+    so.ba_last = prev_a; so.bb_last = prev_b;
+    so.avg_mid = avg_sum / (float)N;
+    so.ep_done = (w.max_steps - w.step_counter - 1) <= 1;                   // marl:717-718
+
+    // ---- (F) new world state marl:489-515 ----
+    const int new_step = w.step_counter + 1;
+    const float new_mid = (float)(so.bb_last + so.ba_last) / 2.0f;
+    const float new_dt = (float)ft0 + (float)ft1 / 1e9f - (float)w.time0 - (float)w.time1 / 1e9f;
+    const int new_oid_counter = oid_counter - n_act;
+    const int vol_a = bk.volume(ASK), vol_b = bk.volume(BID);
+
+    // ---- (E)+(G)+(I)+(J)+(K) per agent: reward, state, done, info, obs ----
+    {
+      int flat = 0;
+      for (int t = 0; t < T; ++t) {
+        const LobAgentTypeConfig& ac = c.agent[t];
+        const int d = obs_dim_of(ac);
+        for (int a = 0; a < ac.n_agents; ++a, ++flat) {
+          const long long idx = e * ac.n_agents + a;
+          const int tid = ac.trader_id_start - a;
+          float* obs = b.obs[t] + idx * d;
+          if (ac.kind == LOB_AGENT_MM) {
+            MMState s; load_mm_state(b, t, idx, s);
+            const MMReward R = mm_get_reward(bk.tr, nt, c, ac, w, so, s, tid);
+            const int* x = scr + flat * 8;
+            MMState ns;   // mm:2677-2736
+            ns.posted_distance_bid = x[2]; ns.posted_distance_ask = x[3];
+            ns.inventory = R.end_inventory;
+            ns.total_PnL = s.total_PnL + R.PnL;
+            ns.cash_balance = R.cash_balance;
+            if (lane == 0) {
+              b.reward[t][idx] = R.reward_scaled;
+              b.done_agents[t][idx] = 0;
+              if (!so.ep_done) store_mm_state(b, t, idx, ns);
+              int* ii = b.info_agent_i32[t] + idx * LOB_MMINFO_I32_COLS;
+              float* fi = b.info_agent_f32[t] + idx * LOB_MMINFO_F32_COLS;
+              ii[0] = 0; ii[1] = ns.inventory; ii[2] = R.forced_unwind; ii[3] = x[0]; ii[4] = x[1]; ii[5] = x[2];
+              ii[6] = x[3]; ii[7] = x[5]; ii[8] = x[4];
+              fi[0] = R.reward; fi[1] = R.reward_portfolio_value; fi[2] = R.reward_spooner; fi[3] = R.end_of_ep_pv;
+              fi[4] = R.reward_spooner_damped; fi[5] = R.reward_spooner_asym_damped;
+              fi[6] = R.reward_spooner_asym_damped2; fi[7] = R.reward_delta_pv; fi[8] = ns.total_PnL;
+              fi[9] = R.delta_mid_price; fi[10] = R.market_share; fi[11] = R.buyPnL; fi[12] = R.invPnL;
+              fi[13] = R.sellPnL; fi[14] = R.inventoryValue;
+            }
+            if (!so.ep_done)
+              mm_write_obs(ac, obs, ns.inventory, new_mid, so.ba_last, so.bb_last, vol_a, vol_b, new_step, false);
+          } else {
+            EXEState s; load_exe_state(b, t, idx, s);
+            const EXEReward R = exe_get_reward(bk.tr, nt, c, ac, w, so, s, tid);
+            EXEState ns = s;   // exe:1771-1839
+            ns.quant_executed = s.quant_executed + R.agentQuant;
+            ns.p_vwap = R.p_vwap;
+            ns.total_revenue = s.total_revenue + (float)R.qp_agent;
+            ns.drift_return = s.drift_return + R.drift;
+            ns.advantage_return = s.advantage_return + R.advantage;
+            ns.slippage_rm = R.slippage_rm; ns.price_adv_rm = R.price_adv_rm;
+            ns.price_drift_rm = R.price_drift_rm; ns.vwap_rm = R.vwap_rm;
+            ns.trade_duration = R.trade_duration;
+            const bool done = (ns.task_to_execute - ns.quant_executed) <= 0;   // exe:270-272
+            if (lane == 0) {
+              b.reward[t][idx] = R.reward_scaled;
+              b.done_agents[t][idx] = done ? 1 : 0;
+              if (!so.ep_done) store_exe_state(b, t, idx, ns);
+              int* ii = b.info_agent_i32[t] + idx * LOB_EXEINFO_I32_COLS;
+              float* fi = b.info_agent_f32[t] + idx * LOB_EXEINFO_F32_COLS;
+              ii[0] = R.quant_left; ii[1] = done ? 1 : 0; ii[2] = R.doom_quant; ii[3] = ns.is_sell_task;
+              fi[0] = R.slippage; fi[1] = ns.vwap_rm; fi[2] = R.drift; fi[3] = R.advantage; fi[4] = R.reward;
+            }
+            if (!so.ep_done)   // marl:690-698: a finished agent observes zeros until the episode ends
+              exe_write_obs(ac, obs, ns, so.ba_last, so.bb_last, vol_a, vol_b, new_step, w.max_steps, done);
+          }
+        }
+      }
+    }
+    // ---- world info marl:618-639 ----
+    if (lane == 0) {
+      b.done_all[e] = so.ep_done ? 1 : 0;
+      int* wi = b.info_world_i32 + e * LOB_WINFO_I32_COLS;
+      float* wf = b.info_world_f32 + e * LOB_WINFO_F32_COLS;
+      wi[0] = window_index; wi[1] = new_step; wi[2] = ft0; wi[3] = ft1; wi[4] = new_oid_counter;
+      wi[5] = so.ba_last; wi[6] = so.bb_last; wi[7] = new_step; wi[8] = so.ep_done ? 1 : 0;
+      wi[9] = abort_episode ? 1 : 0; wi[10] = so.ba_last - so.bb_last;
+      wf[0] = new_mid; wf[1] = sum_a / (float)N; wf[2] = sum_b / (float)N; wf[3] = new_dt;
+    }
+    if (so.ep_done) {   // marl:787-803 auto-reset, fused: the reset state is only touched when the episode ended
+      reset_env(c, b, e, bk, N);
+    } else if (lane == 0) {
+      b.step_counter[e] = new_step;
+      b.time[e * 2] = ft0; b.time[e * 2 + 1] = ft1;
+      b.order_id_counter[e] = new_oid_counter;
+      b.mid_price[e] = new_mid;
+      b.delta_time[e] = new_dt;
+    }
+    __syncwarp();
+    bk.store_side(ASK, b.asks + e * no * 6);
+    bk.store_side(BID, b.bids + e * no * 6);
+    bk.store_trades(b.trades + e * nt * 8);
+    __syncwarp();
+  }
+  (void)tick;
+}
+
+// ================================================================================================= reset ====
+template <int SLOTS>
+__global__ void __launch_bounds__(kWarps * 32)
+lob_reset_kernel(const __grid_constant__ LobStepConfig c, const __grid_constant__ LobStepBuffers b, long long batch,
+                 WarpLayout L, int N) {
+  extern __shared__ __align__(128) int smem[];
+  const int warp = threadIdx.x >> 5;
+  int* ws = smem + warp * L.words;
+  Book<SLOTS> bk;
+  bk.init(c.book, ws + L.book, ws + L.trades);
+  const int no = c.book.n_orders, nt = c.book.n_trades;
+  const long long stride = (long long)gridDim.x * kWarps;
+  for (long long e = (long long)blockIdx.x * kWarps + warp; e < batch; e += stride) {
+    reset_env(c, b, e, bk, N);
+    __syncwarp();
+    bk.store_side(ASK, b.asks + e * no * 6);
+    bk.store_side(BID, b.bids + e * no * 6);
+    bk.store_trades(b.trades + e * nt * 8);
+    __syncwarp();
+  }
+}
+
+// ==================================================================================================== L2 ====
+// job:1232-1264 get_L2_state: n_levels best distinct prices per side and the volume at each.
+template <int SLOTS>
+__global__ void __launch_bounds__(kWarps * 32)
+lob_l2_kernel(const __grid_constant__ LobBookConfig cfg, const int* __restrict__ asks, const int* __restrict__ bids,
+              int* __restrict__ l2, int n_levels, long long n_books) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int no = cfg.n_orders, maxint = cfg.maxint;
+  const long long stride = (long long)gridDim.x * kWarps;
+  for (long long b = (long long)blockIdx.x * kWarps + warp; b < n_books; b += stride) {
+    int pa[SLOTS], qa[SLOTS], pb[SLOTS], qb[SLOTS];
+#pragma unroll
+    for (int k = 0; k < SLOTS; ++k) {
+      const int r = k * 32 + lane;
+      const bool in = r < no;
+      const int2 a = in ? *reinterpret_cast<const int2*>(asks + (b * no + r) * 6) : make_int2(-1, 0);
+      const int2 d = in ? *reinterpret_cast<const int2*>(bids + (b * no + r) * 6) : make_int2(0, 0);
+      pa[k] = a.x; qa[k] = a.y; pb[k] = d.x; qb[k] = d.y;
+    }
+    long long last_a = -((long long)1 << 40);  // ascending distinct values of (p == -1 ? maxint : p)
+    long long last_b = (long long)1 << 40;     // descending distinct bid prices (a -1 row is a price like any other)
+    for (int lv = 0; lv < n_levels; ++lv) {
+      int ca = INT32_MAX, fa = 0, cb = INT32_MIN, fb = 0;
+#pragma unroll
+      for (int k = 0; k < SLOTS; ++k) {
+        const int r = k * 32 + lane;
+        if (r < no) {
+          const int v = (pa[k] == -1) ? maxint : pa[k];
+          if ((long long)v > last_a) { ca = min(ca, v); fa = 1; }
+          if ((long long)pb[k] < last_b) { cb = max(cb, pb[k]); fb = 1; }
+        }
+      }
+      ca = wmin(ca); cb = wmax(cb);
+      fa = __any_sync(kFull, fa); fb = __any_sync(kFull, fb);
+      int ask_p = fa ? ca : -1, bid_p = fb ? cb : -1;   // unique(..., fill_value=-1) / -unique(-p, fill_value=1)
+      if (fa) last_a = ca; else last_a = (long long)1 << 40;
+      if (fb) last_b = cb; else last_b = -((long long)1 << 40);
+      if (ask_p == -1) ask_p = maxint;
+      if (bid_p == -1) bid_p = -maxint;
+      int va = 0, vb = 0;
+#pragma unroll
+      for (int k = 0; k < SLOTS; ++k) {
+        const int r = k * 32 + lane;
+        if (r < no) { if (pa[k] == ask_p) va += qa[k]; if (pb[k] == bid_p) vb += qb[k]; }
+      }
+      va = wsum(va); vb = wsum(vb);
+      if (lane == 0) {
+        int4 o = make_int4(ask_p, max(va, 0), bid_p, max(vb, 0));
+        *reinterpret_cast<int4*>(l2 + (b * n_levels + lv) * 4) = o;
+      }
+    }
+  }
+}
+
+}  // namespace lob

@@ -1,0 +1,60 @@
+// lob_launch.cuh -- host-side launch helpers shared by lobstep.cu (the C ABI) and lob_inst.cu (one translation unit
+// per SLOTS value, so the kernel instantiations compile in parallel).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+
+#include "../../include/lobstep.h"
+#include "lob_kernels.cuh"
+
+namespace lobhost {
+
+char* err_buf();            // thread-local message buffer (512 bytes), defined in lobstep.cu
+void count_launch();        // thread-local launch counter, defined in lobstep.cu
+
+inline int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(err_buf(), 512, fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+struct DevInfo { int sms; int max_smem_optin; };
+
+// persistent grid: a multiple of the SM count, capped by the work
+inline int grid_for(long long n_items, int sms, int ctas_per_sm) {
+  long long ctas_needed = (n_items + lob::kWarps - 1) / lob::kWarps;
+  long long cap = (long long)sms * ctas_per_sm;
+  long long g = ctas_needed < cap ? ctas_needed : cap;
+  return (int)(g < 1 ? 1 : g);
+}
+
+template <typename K>
+int prepare(K kernel, size_t smem_bytes, const DevInfo& d, int* ctas_per_sm) {
+  if ((int)smem_bytes > d.max_smem_optin)
+    return fail(LOB_E_INVALID, "configuration needs %zu B of shared memory per CTA (device limit %d)", smem_bytes,
+                d.max_smem_optin);
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+  if (e != cudaSuccess) return fail(LOB_E_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+  int n = 0;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, lob::kWarps * 32, smem_bytes);
+  if (e != cudaSuccess) return fail(LOB_E_CUDA, "occupancy query: %s", cudaGetErrorString(e));
+  *ctas_per_sm = n < 1 ? 1 : n;
+  return LOB_OK;
+}
+
+inline int launched(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(LOB_E_CUDA, "%s: %s", what, cudaGetErrorString(e));
+  count_launch();
+  return LOB_OK;
+}
+
+template <int S> int launch_replay(const LobBookConfig* cfg, const LobReplayBuffers* bufs, int64_t n_books, cudaStream_t st, const DevInfo& d);
+template <int S> int launch_step(const LobStepConfig* c, const LobStepBuffers* b, int64_t batch, cudaStream_t st, const DevInfo& d);
+template <int S> int launch_reset(const LobStepConfig* c, const LobStepBuffers* b, int64_t batch, cudaStream_t st, const DevInfo& d);
+template <int S> int launch_l2(const LobBookConfig* cfg, const int32_t* asks, const int32_t* bids, int32_t* l2, int32_t n_levels, int64_t n_books, cudaStream_t st, const DevInfo& d);
+
+}  // namespace lobhost

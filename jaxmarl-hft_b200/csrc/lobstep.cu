@@ -1,0 +1,330 @@
+// lobstep.cu -- the C ABI of include/lobstep.h: host-side validation + kernel launches.  No torch / jax types, no
+// allocation and no synchronisation in the *_launch entry points (the host-replay handle owns its own scratch).
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/lobstep.h"
+#include "lob_launch.cuh"
+
+namespace lobhost {
+static thread_local char g_err[512] = "";
+static thread_local int64_t g_launches = 0;
+char* err_buf() { return g_err; }
+void count_launch() { ++g_launches; }
+}  // namespace lobhost
+
+using namespace lobhost;
+
+namespace {
+
+int device_info(DevInfo* d) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return fail(LOB_E_CUDA, "cudaGetDevice: %s", cudaGetErrorString(e));
+  // cheap attribute queries; cached per device
+  static thread_local int cached_dev = -1;
+  static thread_local DevInfo cached;
+  if (cached_dev != dev) {
+    if ((e = cudaDeviceGetAttribute(&cached.sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess ||
+        (e = cudaDeviceGetAttribute(&cached.max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev)) != cudaSuccess)
+      return fail(LOB_E_CUDA, "cudaDeviceGetAttribute: %s", cudaGetErrorString(e));
+    cached_dev = dev;
+  }
+  *d = cached;
+  return LOB_OK;
+}
+
+int check_book(const LobBookConfig* c) {
+  if (!c) return fail(LOB_E_INVALID, "null book config");
+  if (c->n_orders < 1 || c->n_orders > 512) return fail(LOB_E_INVALID, "n_orders=%d outside [1,512]", c->n_orders);
+  if (c->n_trades < 1 || c->n_trades > 4096) return fail(LOB_E_INVALID, "n_trades=%d outside [1,4096]", c->n_trades);
+  if (c->cancel_mode < 0 || c->cancel_mode > 3) return fail(LOB_E_INVALID, "cancel_mode=%d", c->cancel_mode);
+  if (c->cancel_mode > 1)
+    return fail(LOB_E_UNSUPPORTED, "cancel_mode %d draws jax.random.choice per message (job:142-164): not built",
+                c->cancel_mode);
+  if (c->type_4_interpretation < 0 || c->type_4_interpretation > 2)
+    return fail(LOB_E_INVALID, "type_4_interpretation=%d", c->type_4_interpretation);
+  return LOB_OK;
+}
+
+int check_step_cfg(const LobStepConfig* c) {
+  if (!c) return fail(LOB_E_INVALID, "null step config");
+  int rc = check_book(&c->book);
+  if (rc) return rc;
+  if (c->n_agent_types < 0 || c->n_agent_types > LOB_MAX_AGENT_TYPES)
+    return fail(LOB_E_INVALID, "n_agent_types=%d", c->n_agent_types);
+  if (c->ep_type_fixed_time) return fail(LOB_E_UNSUPPORTED, "ep_type 'fixed_time' is not built (base:358-368)");
+  if (c->n_data_msg_per_step < 1) return fail(LOB_E_INVALID, "n_data_msg_per_step=%d", c->n_data_msg_per_step);
+  if (c->tick_size < 1) return fail(LOB_E_INVALID, "tick_size=%d", c->tick_size);
+  if (c->n_windows < 1) return fail(LOB_E_INVALID, "n_windows=%d", c->n_windows);
+  if (c->n_messages < c->n_data_msg_per_step) return fail(LOB_E_INVALID, "n_messages < n_data_msg_per_step");
+  int total = 0;
+  for (int t = 0; t < c->n_agent_types; ++t) {
+    const LobAgentTypeConfig* a = &c->agent[t];
+    if (a->kind != LOB_AGENT_MM && a->kind != LOB_AGENT_EXE) return fail(LOB_E_INVALID, "agent[%d].kind=%d", t, a->kind);
+    if (a->n_agents < 0) return fail(LOB_E_INVALID, "agent[%d].n_agents=%d", t, a->n_agents);
+    total += a->n_agents;
+    const int ka = a->num_action_messages_by_agent, kc = a->num_messages_by_agent - ka;
+    if (kc != ka || ka < 1 || ka > 16)
+      return fail(LOB_E_INVALID, "agent[%d]: cancel (%d) and action (%d) message counts must match and be in [1,16]", t, kc, ka);
+    if (a->kind == LOB_AGENT_MM) {
+      if (a->action_space != LOB_MM_ACT_FIXED_QUANTS && a->action_space != LOB_MM_ACT_DIRECTIONAL)
+        return fail(LOB_E_UNSUPPORTED, "agent[%d]: MM action space %d is not built", t, a->action_space);
+      if (ka != 2) return fail(LOB_E_INVALID, "agent[%d]: MM action spaces built here post 2 messages", t);
+      if (a->sell_buy_all_option) return fail(LOB_E_UNSUPPORTED, "agent[%d]: sell_buy_all_option is not built", t);
+      if (a->reward_function < 0 || a->reward_function > LOB_MM_REW_DELTA_PORTFOLIO_VALUE)
+        return fail(LOB_E_INVALID, "agent[%d].reward_function=%d", t, a->reward_function);
+    } else {
+      if (a->action_space != LOB_EXE_ACT_FIXED_QUANTS && a->action_space != LOB_EXE_ACT_FIXED_QUANTS_COMPLEX)
+        return fail(LOB_E_UNSUPPORTED, "agent[%d]: EXE action space %d is not built", t, a->action_space);
+      if (ka != 4) return fail(LOB_E_INVALID, "agent[%d]: EXE action spaces built here post 4 messages", t);
+      if (a->reward_function < 0 || a->reward_function > LOB_EXE_REW_SIMPLEST_CASE)
+        return fail(LOB_E_INVALID, "agent[%d].reward_function=%d", t, a->reward_function);
+      if (a->reference_price != LOB_REF_MID && a->reference_price != LOB_REF_FAR_TOUCH)
+        return fail(LOB_E_INVALID, "agent[%d]: EXE reference_price must be mid or far_touch", t);
+    }
+    if (a->observation_space != LOB_OBS_ENGINEERED && a->observation_space != LOB_OBS_BASIC)
+      return fail(LOB_E_UNSUPPORTED, "agent[%d]: observation space %d is not built", t, a->observation_space);
+  }
+  if (total > lob::kMaxAgents) return fail(LOB_E_INVALID, "%d agents per environment (max %d)", total, lob::kMaxAgents);
+  return LOB_OK;
+}
+
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+int check_step_bufs(const LobStepConfig* c, const LobStepBuffers* b, bool step) {
+  if (!b) return fail(LOB_E_INVALID, "null buffers");
+#define REQ(f) if (!b->f) return fail(LOB_E_INVALID, "buffer '" #f "' is null")
+  REQ(asks); REQ(bids); REQ(trades); REQ(init_time); REQ(window_index); REQ(max_steps); REQ(start_index);
+  REQ(step_counter); REQ(best_bids); REQ(best_asks); REQ(time); REQ(order_id_counter); REQ(mid_price); REQ(delta_time);
+  REQ(reset_window); REQ(init_asks); REQ(init_bids); REQ(init_trades); REQ(init_init_time); REQ(init_max_steps);
+  REQ(init_start_index);
+  if (step) { REQ(message_data); REQ(done_all); REQ(info_world_i32); REQ(info_world_f32); }
+#undef REQ
+  if (step && !aligned16(b->message_data)) return fail(LOB_E_INVALID, "message_data must be 16-byte aligned");
+  if (!aligned16(b->asks) || !aligned16(b->bids) || !aligned16(b->trades) || !aligned16(b->best_asks) ||
+      !aligned16(b->best_bids))
+    return fail(LOB_E_INVALID, "book / trade / best-price buffers must be 16-byte aligned");
+  bool any_exe_random = false;
+  for (int t = 0; t < c->n_agent_types; ++t) {
+    const LobAgentTypeConfig* a = &c->agent[t];
+    const int ni = 3, nf = a->kind == LOB_AGENT_MM ? 2 : 10;
+    for (int j = 0; j < ni; ++j) if (!b->agent_i32[t][j]) return fail(LOB_E_INVALID, "agent_i32[%d][%d] is null", t, j);
+    for (int j = 0; j < nf; ++j) if (!b->agent_f32[t][j]) return fail(LOB_E_INVALID, "agent_f32[%d][%d] is null", t, j);
+    if (!b->obs[t]) return fail(LOB_E_INVALID, "obs[%d] is null", t);
+    if (step && (!b->actions[t] || !b->reward[t] || !b->done_agents[t] || !b->info_agent_i32[t] || !b->info_agent_f32[t]))
+      return fail(LOB_E_INVALID, "step buffers of agent type %d are incomplete", t);
+    if (a->kind == LOB_AGENT_EXE && a->task == LOB_TASK_RANDOM) any_exe_random = true;
+  }
+  if (any_exe_random && !b->reset_is_sell) return fail(LOB_E_INVALID, "buffer 'reset_is_sell' is null");
+  return LOB_OK;
+}
+
+int slots_for(int n_orders) {
+  int s = (n_orders + 31) / 32;
+  int p = 1;
+  while (p < s) p <<= 1;
+  return p;
+}
+
+#define DISPATCH_SLOTS(slots, CALL)                                   \
+  switch (slots) {                                                    \
+    case 1: { constexpr int S = 1; CALL; } break;                     \
+    case 2: { constexpr int S = 2; CALL; } break;                     \
+    case 4: { constexpr int S = 4; CALL; } break;                     \
+    case 8: { constexpr int S = 8; CALL; } break;                     \
+    default: { constexpr int S = 16; CALL; } break;                   \
+  }
+
+}  // namespace
+
+extern "C" {
+
+int lob_abi_version(void) { return LOB_ABI_VERSION; }
+const char* lob_last_error(void) { return g_err; }
+int64_t lob_launch_count(void) { return g_launches; }
+void lob_launch_count_reset(void) { g_launches = 0; }
+
+int64_t lob_sizeof_book_config(void) { return (int64_t)sizeof(LobBookConfig); }
+int64_t lob_sizeof_agent_type_config(void) { return (int64_t)sizeof(LobAgentTypeConfig); }
+int64_t lob_sizeof_step_config(void) { return (int64_t)sizeof(LobStepConfig); }
+int64_t lob_sizeof_step_buffers(void) { return (int64_t)sizeof(LobStepBuffers); }
+int64_t lob_sizeof_replay_buffers(void) { return (int64_t)sizeof(LobReplayBuffers); }
+
+/* marl_env.py:85-94 */
+int32_t lob_num_action_msgs(const LobStepConfig* c) {
+  int32_t n = 0;
+  for (int t = 0; t < c->n_agent_types; ++t) n += c->agent[t].n_agents * c->agent[t].num_action_messages_by_agent;
+  return n;
+}
+int32_t lob_num_cancel_msgs(const LobStepConfig* c) {
+  int32_t n = 0;
+  for (int t = 0; t < c->n_agent_types; ++t)
+    n += c->agent[t].n_agents * (c->agent[t].num_messages_by_agent - c->agent[t].num_action_messages_by_agent);
+  return n;
+}
+int32_t lob_num_msgs_per_step(const LobStepConfig* c) {
+  return c->n_data_msg_per_step + lob_num_action_msgs(c) + lob_num_cancel_msgs(c);
+}
+/* mm_env.py:3195-3223 ; exec_env.py:2188-2202 (fixed_steps) */
+int32_t lob_obs_dim(const LobStepConfig* c, int32_t t) {
+  const LobAgentTypeConfig* a = &c->agent[t];
+  if (a->kind == LOB_AGENT_MM) return a->observation_space == LOB_OBS_BASIC ? 2 : 8;
+  return a->observation_space == LOB_OBS_BASIC ? 3 : 12;
+}
+int32_t lob_info_i32_cols(const LobStepConfig* c, int32_t t) {
+  return c->agent[t].kind == LOB_AGENT_MM ? LOB_MMINFO_I32_COLS : LOB_EXEINFO_I32_COLS;
+}
+int32_t lob_info_f32_cols(const LobStepConfig* c, int32_t t) {
+  return c->agent[t].kind == LOB_AGENT_MM ? LOB_MMINFO_F32_COLS : LOB_EXEINFO_F32_COLS;
+}
+
+int lob_replay_launch(const LobBookConfig* cfg, const LobReplayBuffers* bufs, int64_t n_books, void* cuda_stream) {
+  int rc = check_book(cfg);
+  if (rc) return rc;
+  if (!bufs || !bufs->asks || !bufs->bids || !bufs->trades || !bufs->start)
+    return fail(LOB_E_INVALID, "replay buffers are incomplete");
+  if (bufs->n_msgs < 0 || bufs->n_msgs_total < 0) return fail(LOB_E_INVALID, "negative message count");
+  if (bufs->n_msgs > 0 && !bufs->msgs) return fail(LOB_E_INVALID, "replay buffer 'msgs' is null");
+  if (!aligned16(bufs->msgs) || !aligned16(bufs->asks) || !aligned16(bufs->bids) || !aligned16(bufs->trades) ||
+      (bufs->best_out && !aligned16(bufs->best_out)))
+    return fail(LOB_E_INVALID, "replay buffers must be 16-byte aligned");
+  if (n_books < 0) return fail(LOB_E_INVALID, "n_books=%lld", (long long)n_books);
+  if (n_books == 0) return LOB_OK;
+  DevInfo d;
+  if ((rc = device_info(&d))) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  DISPATCH_SLOTS(slots_for(cfg->n_orders), rc = launch_replay<S>(cfg, bufs, n_books, st, d));
+  return rc;
+}
+
+int lob_step_launch(const LobStepConfig* cfg, const LobStepBuffers* bufs, int64_t batch, void* cuda_stream) {
+  int rc = check_step_cfg(cfg);
+  if (rc) return rc;
+  if ((rc = check_step_bufs(cfg, bufs, true))) return rc;
+  if (batch < 0) return fail(LOB_E_INVALID, "batch=%lld", (long long)batch);
+  if (batch == 0) return LOB_OK;
+  DevInfo d;
+  if ((rc = device_info(&d))) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  DISPATCH_SLOTS(slots_for(cfg->book.n_orders), rc = launch_step<S>(cfg, bufs, batch, st, d));
+  return rc;
+}
+
+int lob_reset_launch(const LobStepConfig* cfg, const LobStepBuffers* bufs, int64_t batch, void* cuda_stream) {
+  int rc = check_step_cfg(cfg);
+  if (rc) return rc;
+  if ((rc = check_step_bufs(cfg, bufs, false))) return rc;
+  if (batch < 0) return fail(LOB_E_INVALID, "batch=%lld", (long long)batch);
+  if (batch == 0) return LOB_OK;
+  DevInfo d;
+  if ((rc = device_info(&d))) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  DISPATCH_SLOTS(slots_for(cfg->book.n_orders), rc = launch_reset<S>(cfg, bufs, batch, st, d));
+  return rc;
+}
+
+int lob_l2_launch(const LobBookConfig* cfg, const int32_t* asks, const int32_t* bids, int32_t* l2, int32_t n_levels,
+                  int64_t n_books, void* cuda_stream) {
+  int rc = check_book(cfg);
+  if (rc) return rc;
+  if (!asks || !bids || !l2) return fail(LOB_E_INVALID, "L2 buffers are incomplete");
+  if (n_levels < 1 || n_levels > cfg->n_orders) return fail(LOB_E_INVALID, "n_levels=%d", n_levels);
+  if (!aligned16(l2) || (reinterpret_cast<uintptr_t>(asks) & 7u) || (reinterpret_cast<uintptr_t>(bids) & 7u))
+    return fail(LOB_E_INVALID, "L2 buffers are misaligned");
+  if (n_books < 0) return fail(LOB_E_INVALID, "n_books=%lld", (long long)n_books);
+  if (n_books == 0) return LOB_OK;
+  DevInfo d;
+  if ((rc = device_info(&d))) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  DISPATCH_SLOTS(slots_for(cfg->n_orders), rc = launch_l2<S>(cfg, asks, bids, l2, n_levels, n_books, st, d));
+  return rc;
+}
+
+/* ---- host-buffer replay: the end-to-end leg (H2D + replay + D2H inside one call) ---- */
+struct LobHostReplay {
+  LobBookConfig cfg;
+  int64_t max_books, max_msgs;
+  int device;
+  cudaStream_t stream;
+  int32_t *d_asks, *d_bids, *d_trades, *d_msgs;
+  int64_t* d_start;
+  int64_t n_msgs_resident;
+};
+
+LobHostReplay* lob_host_replay_create(const LobBookConfig* cfg, int64_t max_books, int64_t max_msgs_total, int device) {
+  if (check_book(cfg)) return nullptr;
+  if (max_books < 1 || max_msgs_total < 1) { fail(LOB_E_INVALID, "host replay: empty capacity"); return nullptr; }
+  if (cudaSetDevice(device) != cudaSuccess) { fail(LOB_E_CUDA, "cudaSetDevice(%d) failed", device); return nullptr; }
+  LobHostReplay* h = new LobHostReplay();
+  memset(h, 0, sizeof(*h));
+  h->cfg = *cfg; h->max_books = max_books; h->max_msgs = max_msgs_total; h->device = device;
+  const size_t side = (size_t)max_books * cfg->n_orders * 6 * 4, tr = (size_t)max_books * cfg->n_trades * 8 * 4;
+  cudaError_t e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaMalloc(&h->d_asks, side);
+  if (e == cudaSuccess) e = cudaMalloc(&h->d_bids, side);
+  if (e == cudaSuccess) e = cudaMalloc(&h->d_trades, tr);
+  if (e == cudaSuccess) e = cudaMalloc(&h->d_msgs, (size_t)max_msgs_total * 32);
+  if (e == cudaSuccess) e = cudaMalloc(&h->d_start, (size_t)max_books * 8);
+  if (e != cudaSuccess) {
+    fail(LOB_E_CUDA, "host replay allocation: %s", cudaGetErrorString(e));
+    lob_host_replay_destroy(h);
+    return nullptr;
+  }
+  return h;
+}
+
+int lob_host_replay_set_messages(LobHostReplay* h, const int32_t* msgs_host, int64_t n_msgs_total) {
+  if (!h || !msgs_host) return fail(LOB_E_INVALID, "host replay: null argument");
+  if (n_msgs_total < 0 || n_msgs_total > h->max_msgs) return fail(LOB_E_INVALID, "host replay: %lld messages exceed capacity", (long long)n_msgs_total);
+  cudaSetDevice(h->device);
+  cudaError_t e = cudaMemcpyAsync(h->d_msgs, msgs_host, (size_t)n_msgs_total * 32, cudaMemcpyHostToDevice, h->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  if (e != cudaSuccess) return fail(LOB_E_CUDA, "host replay set_messages: %s", cudaGetErrorString(e));
+  h->n_msgs_resident = n_msgs_total;
+  return LOB_OK;
+}
+
+int lob_host_replay_run(LobHostReplay* h, int32_t* asks_host, int32_t* bids_host, int32_t* trades_host,
+                        const int64_t* start_host, int32_t n_msgs, int64_t n_books, int64_t* h2d_bytes,
+                        int64_t* d2h_bytes) {
+  if (!h || !asks_host || !bids_host || !trades_host || !start_host) return fail(LOB_E_INVALID, "host replay: null argument");
+  if (n_books < 0 || n_books > h->max_books) return fail(LOB_E_INVALID, "host replay: %lld books exceed capacity", (long long)n_books);
+  cudaSetDevice(h->device);
+  const size_t side = (size_t)n_books * h->cfg.n_orders * 6 * 4, tr = (size_t)n_books * h->cfg.n_trades * 8 * 4;
+  cudaError_t e = cudaMemcpyAsync(h->d_asks, asks_host, side, cudaMemcpyHostToDevice, h->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(h->d_bids, bids_host, side, cudaMemcpyHostToDevice, h->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(h->d_trades, trades_host, tr, cudaMemcpyHostToDevice, h->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(h->d_start, start_host, (size_t)n_books * 8, cudaMemcpyHostToDevice, h->stream);
+  if (e != cudaSuccess) return fail(LOB_E_CUDA, "host replay H2D: %s", cudaGetErrorString(e));
+  LobReplayBuffers r;
+  memset(&r, 0, sizeof(r));
+  r.asks = h->d_asks; r.bids = h->d_bids; r.trades = h->d_trades; r.msgs = h->d_msgs; r.start = h->d_start;
+  r.n_msgs_total = h->n_msgs_resident; r.n_msgs = n_msgs; r.best_out = nullptr;
+  int rc = lob_replay_launch(&h->cfg, &r, n_books, h->stream);
+  if (rc) return rc;
+  e = cudaMemcpyAsync(asks_host, h->d_asks, side, cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(bids_host, h->d_bids, side, cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(trades_host, h->d_trades, tr, cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  if (e != cudaSuccess) return fail(LOB_E_CUDA, "host replay D2H: %s", cudaGetErrorString(e));
+  if (h2d_bytes) *h2d_bytes = (int64_t)(2 * side + tr + (size_t)n_books * 8);
+  if (d2h_bytes) *d2h_bytes = (int64_t)(2 * side + tr);
+  return LOB_OK;
+}
+
+void lob_host_replay_destroy(LobHostReplay* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  if (h->d_asks) cudaFree(h->d_asks);
+  if (h->d_bids) cudaFree(h->d_bids);
+  if (h->d_trades) cudaFree(h->d_trades);
+  if (h->d_msgs) cudaFree(h->d_msgs);
+  if (h->d_start) cudaFree(h->d_start);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+}  // extern "C"

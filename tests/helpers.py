@@ -106,3 +106,85 @@ def to_numpy(arrays):
 def empty_book(n_orders=100, n_trades=100):
     return (np.full((n_orders, 6), -1, np.int32), np.full((n_orders, 6), -1, np.int32),
             np.full((n_trades, 8), -1, np.int32))
+
+
+# ---- CUDA side (only imported by -m gpu tests) ----------------------------------------------------------------
+class CudaEnv:
+    """The same buffer table on cuda:0, stepped by csrc/liblobstep.so through the C ABI (lob_*_launch)."""
+
+    def __init__(self, mac, loaded, num_envs, params_np, device="cuda:0"):
+        import torch
+        from jaxmarl_hft_b200 import _lib
+        self.torch, self._lib, self.L = torch, _lib, _lib.lib()
+        self.mac, self.B, self.device = mac, num_envs, torch.device(device)
+        self.cfg = C.to_step_config(mac, loaded.starts.shape[0], loaded.msgs.shape[0])
+        self.params = {k: torch.from_numpy(np.ascontiguousarray(v)).to(self.device) for k, v in params_np.items()}
+        self.arrays = states.alloc_torch(self.cfg, num_envs, self.device)
+
+    def load(self, arrays_np):
+        for k, v in arrays_np.items():
+            self.arrays[k].copy_(self.torch.from_numpy(v))
+
+    def set_inputs(self, arrays_np):
+        for k, v in arrays_np.items():
+            if k.startswith("actions") or k in ("perm", "reset_window", "reset_is_sell"):
+                self.arrays[k].copy_(self.torch.from_numpy(v))
+
+    def _bufs(self):
+        return states.pack_buffers(self.cfg, self.arrays, self.params)
+
+    def reset(self):
+        import ctypes
+        bufs = self._bufs()
+        self._lib.check(self.L.lob_reset_launch(ctypes.byref(self.cfg), ctypes.byref(bufs), self.B,
+                                                self._lib.current_stream_ptr()), "lob_reset_launch")
+
+    def step(self):
+        import ctypes
+        bufs = self._bufs()
+        self._lib.check(self.L.lob_step_launch(ctypes.byref(self.cfg), ctypes.byref(bufs), self.B,
+                                               self._lib.current_stream_ptr()), "lob_step_launch")
+
+    def numpy(self):
+        self.torch.cuda.synchronize()
+        return to_numpy(self.arrays)
+
+
+def cuda_replay(book_cfg, asks, bids, trades, msgs, start, n_msgs, want_best=False, device="cuda:0"):
+    """numpy in -> numpy out through lob_replay_launch."""
+    import torch
+    from jaxmarl_hft_b200 import env as E2
+    dev = torch.device(device)
+    ta, tb, tt = (torch.from_numpy(np.ascontiguousarray(x)).to(dev) for x in (asks, bids, trades))
+    tm = torch.from_numpy(np.ascontiguousarray(msgs, np.int32)).to(dev)
+    ts = torch.from_numpy(np.ascontiguousarray(start, np.int64)).to(dev)
+    best = torch.zeros((asks.shape[0], 4), dtype=torch.int32, device=dev) if want_best else None
+    E2.replay_books(book_cfg, ta, tb, tt, tm, ts, n_msgs, best)
+    torch.cuda.synchronize()
+    out = (ta.cpu().numpy(), tb.cpu().numpy(), tt.cpu().numpy())
+    return out + ((best.cpu().numpy(),) if want_best else ())
+
+
+def random_messages(rng, n, book_cfg, price_lo=99_000, price_hi=101_000, tick=100, id_pool=400, weird=0.02):
+    """A raw message stream that exercises every branch of job:556-637: limits on both sides (many crossing),
+    cancels of known / unknown ids, type-4 executions, no-ops, and a few malformed (type, side) pairs."""
+    m = np.zeros((n, 8), np.int32)
+    t = rng.choice([1, 2, 3, 4, 0], size=n, p=[0.5, 0.2, 0.1, 0.18, 0.02])
+    side = rng.choice([-1, 1], size=n)
+    side[t == 0] = 0
+    m[:, 0], m[:, 1] = t, side
+    m[:, 2] = rng.integers(1, 300, size=n)
+    m[:, 3] = rng.integers(price_lo // tick, price_hi // tick, size=n) * tick
+    m[:, 4] = rng.integers(1, id_pool, size=n)          # small id pool: cancels hit live orders often
+    m[:, 5] = m[:, 4]
+    init_rows = rng.random(n) < 0.05                    # orders carrying the INITID (get_init_id_match job:121)
+    m[init_rows, 4] = book_cfg.init_id
+    m[init_rows, 5] = book_cfg.init_id - rng.integers(0, 2 * book_cfg.book_depth, size=init_rows.sum())
+    ts = 34200 + np.cumsum(rng.integers(0, 2, size=n))
+    m[:, 6] = ts
+    m[:, 7] = rng.integers(0, 1_000_000_000, size=n)
+    bad = rng.random(n) < weird                         # unexpected combos dispatch to ask_lim (quirk Q8)
+    m[bad, 0] = rng.choice([0, 1, 5, 7], size=bad.sum())
+    m[bad, 1] = rng.choice([0, -1, 1, 2], size=bad.sum())
+    m[t == 0, 2:] = 0
+    return m

@@ -1,0 +1,210 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle, on a B200.
+
+Integer / byte leaves: bit-exact.  float32 leaves: rel 1e-5 (the tolerance BASELINE.json's north_star states); the
+kernel and the oracle both sum float reductions left-to-right, so in practice they agree far tighter."""
+import ctypes
+
+import numpy as np
+import pytest
+
+import helpers as H
+from jaxmarl_hft_b200 import abi, config as C, env as E, lobster, states
+
+pytestmark = pytest.mark.gpu
+
+
+def _book_cfg(no=100, nt=100, **kw):
+    w = C.World_EnvironmentConfig(nOrders=no, nTrades=nt, **kw)
+    return C.book_config(w)
+
+
+@pytest.mark.parametrize("no,nt,t4,fill", [(100, 100, 0, True), (32, 16, 0, True), (20, 8, 1, True), (100, 50, 2, True),
+                                           (64, 100, 0, False), (200, 128, 0, True), (512, 256, 0, True), (7, 3, 0, True)])
+def test_replay_random_streams_bit_exact(oracle, no, nt, t4, fill):
+    """job.scan_through_entire_array on adversarial random streams, including books that overflow (eviction, the
+    last-row quirks Q1/Q2/Q5) and trade logs that overflow (Q3)."""
+    rng = np.random.default_rng(no * 1000 + nt)
+    bc = _book_cfg(no, nt, type_4_interpretation=t4, check_book_fill=fill)
+    B, T = 64, 700
+    msgs = H.random_messages(rng, B * T, bc, price_lo=99_000, price_hi=100_600 if no < 64 else 101_500)
+    start = (np.arange(B, dtype=np.int64) * T)
+    a0 = np.full((B, no, 6), -1, np.int32); b0 = a0.copy(); t0 = np.full((B, nt, 8), -1, np.int32)
+    ra, rb, rt = a0.copy(), b0.copy(), t0.copy()
+    rbest = np.zeros((B, 4), np.int32)
+    oracle.replay(bc, ra, rb, rt, msgs, start, T, best_out=rbest)
+    ga, gb, gt, gbest = H.cuda_replay(bc, a0, b0, t0, msgs, start, T, want_best=True)
+    np.testing.assert_array_equal(ga, ra); np.testing.assert_array_equal(gb, rb)
+    np.testing.assert_array_equal(gt, rt); np.testing.assert_array_equal(gbest, rbest)
+    assert (rt[:, :, 0] >= 0).any() and (ra[:, :, 0] >= 0).any()
+
+
+def test_replay_ragged_and_empty(oracle):
+    """Zero messages, one message, a non-multiple of the staging chunk, windows ending at the array end."""
+    rng = np.random.default_rng(3)
+    bc = _book_cfg()
+    msgs = H.random_messages(rng, 5000, bc)
+    for T in (0, 1, 63, 64, 65, 129):
+        B = 9
+        start = rng.integers(0, 5000 - T + 1, size=B).astype(np.int64)
+        start[-1] = 5000 - T
+        a0 = np.full((B, 100, 6), -1, np.int32); b0 = a0.copy(); t0 = np.full((B, 100, 8), -1, np.int32)
+        ra, rb, rt = a0.copy(), b0.copy(), t0.copy()
+        oracle.replay(bc, ra, rb, rt, msgs, start, T)
+        ga, gb, gt = H.cuda_replay(bc, a0, b0, t0, msgs, start, T)
+        np.testing.assert_array_equal(ga, ra); np.testing.assert_array_equal(gb, rb); np.testing.assert_array_equal(gt, rt)
+
+
+def test_replay_synthetic_day_and_l2(oracle):
+    """Config #2 at test size: windows of the synthetic LOBSTER day replayed from their reset states; then L2."""
+    mac = H.load_mac("2_player_fq_fqc")
+    day = H.small_day(n_events=30000)
+    ld = H.load_for(mac, day)
+    bc = C.book_config(mac.world_config)
+    params = E.build_reset_params(ld, mac.world_config, H.oracle_replay_fn(oracle, bc))
+    W = ld.starts.shape[0]
+    B = 48
+    widx = np.arange(B) % W
+    a0, b0, t0 = params["init_asks"][widx].copy(), params["init_bids"][widx].copy(), params["init_trades"][widx].copy()
+    start = ld.starts[widx].astype(np.int64) + (np.arange(B) // W) * 100
+    T = 6400
+    ra, rb, rt = a0.copy(), b0.copy(), t0.copy()
+    oracle.replay(bc, ra, rb, rt, ld.msgs, start, T)
+    ga, gb, gt = H.cuda_replay(bc, a0, b0, t0, ld.msgs, start, T)
+    np.testing.assert_array_equal(ga, ra); np.testing.assert_array_equal(gb, rb); np.testing.assert_array_equal(gt, rt)
+    import torch
+    l2 = E.l2_state(bc, torch.from_numpy(ga).cuda(), torch.from_numpy(gb).cuda(), 10).cpu().numpy()
+    np.testing.assert_array_equal(l2, oracle.l2(bc, ra, rb, 10))
+    # reset-state precompute through the CUDA replay == through the oracle (base_env.py:245-296)
+    p2 = E.build_reset_params(ld, mac.world_config, E._cuda_replay_fn(bc, "cuda:0"))
+    for k in params:
+        np.testing.assert_array_equal(p2[k], params[k], err_msg=k)
+
+
+def test_l2_on_sparse_and_empty_books(oracle):
+    rng = np.random.default_rng(8)
+    bc = _book_cfg(100, 100)
+    B = 32
+    asks = np.full((B, 100, 6), -1, np.int32); bids = asks.copy()
+    for b in range(B):
+        for side in (asks, bids):
+            n = int(rng.integers(0, 12)) if b % 3 else 0
+            rows = rng.choice(100, size=n, replace=False)
+            side[b, rows, 0] = rng.integers(990, 1010, size=n) * 100
+            side[b, rows, 1] = rng.integers(1, 500, size=n)
+            side[b, rows, 2:] = 5
+    import torch
+    for n_levels in (1, 5, 10, 20):
+        got = E.l2_state(bc, torch.from_numpy(asks).cuda(), torch.from_numpy(bids).cuda(), n_levels).cpu().numpy()
+        np.testing.assert_array_equal(got, oracle.l2(bc, asks, bids, n_levels))
+
+
+def _rollout_parity(oracle, mac, day, B, steps, seed, stress_actions=False):
+    ld = H.load_for(mac, day)
+    ref = H.OracleEnv(oracle, mac, ld, B)
+    gpu = H.CudaEnv(mac, ld, B, ref.params)
+    rng = np.random.default_rng(seed)
+    H.draw_prng(rng, ref.cfg, ref.arrays)
+    gpu.set_inputs(ref.arrays)
+    ref.reset(); gpu.reset()
+    H.assert_arrays_match(ref.arrays, gpu.numpy(), ref.cfg)
+    n_done = 0
+    for s in range(steps):
+        H.draw_prng(rng, ref.cfg, ref.arrays)
+        H.draw_actions(rng, ref.cfg, ref.arrays)
+        if stress_actions and s % 7 == 3:   # out-of-range actions: jnp gather wraps once, then clamps
+            for t in range(ref.cfg.n_agent_types):
+                ref.arrays[f"actions{t}"][::5] = rng.integers(-3, 40, size=ref.arrays[f"actions{t}"][::5].shape)
+        gpu.set_inputs(ref.arrays)
+        ref.step(n_threads=8); gpu.step()
+        try:
+            H.assert_arrays_match(ref.arrays, gpu.numpy(), ref.cfg)
+        except AssertionError as e:
+            raise AssertionError(f"step {s}: {e}") from None
+        n_done += int(ref.arrays["done_all"].sum())
+    return ref, n_done
+
+
+def test_step_2_player_rollout_with_auto_reset(oracle):
+    """BASELINE config #1 shapes (2_player_fq_fqc: MM fixed_quants + EXE fixed_quants_complex), 70 steps so every env
+    crosses an episode boundary (done on the 64th step, quirk Q14) and the fused auto-reset is exercised."""
+    mac = H.load_mac("2_player_fq_fqc")
+    ref, n_done = _rollout_parity(oracle, mac, H.small_day(n_events=30000), B=96, steps=70, seed=1, stress_actions=True)
+    assert n_done == 96
+    assert (ref.arrays["info_i32_1"][..., 0] >= 0).all()
+
+
+def test_step_exec_only(oracle):
+    """BASELINE config #3 shapes: single execution agent, fixed_quants_complex."""
+    mac = H.load_mac("exec_longrun_fixed_quants_complex")
+    _rollout_parity(oracle, mac, H.small_day(n_events=30000), B=64, steps=40, seed=2)
+
+
+def test_step_hetero_deep_book(oracle):
+    """BASELINE config #5 shapes: 3 MM + 2 EXE + 2 directional, 512-row book sides, 256-row trade log."""
+    mac = H.load_mac("hetero_deep_book")
+    _rollout_parity(oracle, mac, H.small_day(n_events=30000), B=24, steps=30, seed=3)
+
+
+def test_step_stress_day_capacity(oracle):
+    """A day whose flow overfills a small book: eviction, last-row cancels and trade-log overflow inside env.step."""
+    mac = H.load_mac("2_player_fq_fqc", nOrders=40, nTrades=24)
+    _rollout_parity(oracle, mac, H.small_day(seed=9, n_events=30000, stress=True), B=48, steps=66, seed=4)
+
+
+@pytest.mark.parametrize("reward", ["portfolio_value", "buy_sell_pnl", "complex", "zero_inv", "spooner",
+                                    "spooner_damped", "spooner_asym_damped", "spooner_scaled",
+                                    "delta_portfolio_value"])
+def test_step_mm_reward_variants(oracle, reward):
+    import dataclasses
+    mac = H.load_mac("2_player_fq_fqc")
+    agents = dict(mac.dict_of_agents_configs)
+    mm = agents["MarketMaking"]
+    agents["MarketMaking"] = dataclasses.replace(
+        mm, reward_function=reward, observation_space="engineered", inv_penalty="quadratic",
+        reference_price="far_touch" if reward in ("spooner", "portfolio_value") else "mid_avg",
+        unwind_price="far_touch" if reward == "complex" else "mid_avg", clip_reward=True, exclude_extreme_spreads=True,
+        volume_traded_bonus="market_share")
+    exe = agents["Execution"]
+    agents["Execution"] = dataclasses.replace(exe, action_space="fixed_quants", observation_space="basic",
+                                              reference_price="far_touch", task="sell", reward_lambda=0.5)
+    mac2 = H.with_agents(mac, agents, [2, 2])
+    _rollout_parity(oracle, mac2, H.small_day(n_events=30000), B=32, steps=66, seed=5)
+
+
+def test_full_size_properties():
+    """BASELINE config #2 at full size (16384 books): size-independent properties instead of an oracle run --
+    (i) determinism, (ii) replay(T1) then replay(T2) == replay(T1+T2) (scan composition), (iii) book invariants."""
+    import torch
+    mac = H.load_mac("2_player_fq_fqc")
+    ld = H.load_for(mac, H.small_day(n_events=30000))
+    bc = C.book_config(mac.world_config)
+    params = E.build_reset_params(ld, mac.world_config, E._cuda_replay_fn(bc, "cuda:0"))
+    B, W = 16384, ld.starts.shape[0]
+    widx = np.arange(B) % W
+    dev = torch.device("cuda:0")
+    msgs = torch.from_numpy(ld.msgs).to(dev)
+    start = torch.from_numpy(ld.starts[widx].astype(np.int64) + (np.arange(B) // W) % 3000).to(dev)
+
+    def run(splits):
+        a = torch.from_numpy(params["init_asks"][widx]).to(dev)
+        b = torch.from_numpy(params["init_bids"][widx]).to(dev)
+        t = torch.from_numpy(params["init_trades"][widx]).to(dev)
+        off = 0
+        for n in splits:
+            E.replay_books(bc, a, b, t, msgs, start + off, n)
+            off += n
+        torch.cuda.synchronize()
+        return a, b, t
+
+    a1, b1, t1 = run([2000])
+    a2, b2, t2 = run([2000])
+    a3, b3, t3 = run([700, 1237, 63])
+    for x, y in ((a1, a2), (b1, b2), (t1, t2), (a1, a3), (b1, b3), (t1, t3)):
+        assert torch.equal(x, y)
+    # invariants of reference-made books: a row is either all -1 or has qty > 0; the book is never crossed
+    for side in (a1, b1):
+        blank = (side == -1).all(dim=2)
+        assert bool((blank | (side[:, :, 1] > 0)).all())
+    best_ask = torch.where(a1[:, :, 0] == -1, torch.full_like(a1[:, :, 0], 2**31 - 1), a1[:, :, 0]).min(dim=1).values
+    best_bid = b1[:, :, 0].max(dim=1).values
+    assert bool((best_bid < best_ask).all())
