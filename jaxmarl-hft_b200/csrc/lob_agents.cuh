@@ -1,11 +1,16 @@
 // lob_agents.cuh -- agent-side device code of the LOB step: action -> order messages, cancel messages,
 // netting filter, rewards, state update, observations.  Warp-cooperative: reductions over the book / the
-// trade log use all 32 lanes, the scalar arithmetic is executed redundantly (warp-uniform).
+// trade log use all 32 lanes, the scalar arithmetic is executed redundantly (warp-uniform).  Everything here runs
+// once per agent per step (not per message), so it is written for SMALL CODE: __noinline__ functions, rolled loops,
+// one fused pass over the trade log per reward.
 //
 // Restated from the reference (gymnax_exchange/jaxen): mm = mm_env.py, exe = exec_env.py, job =
 // ../jaxob/JaxOrderBookArrays.py.  float32 throughout (jax_enable_x64 = False); the file is compiled with
-// -fmad=false so that a*b+c is two roundings as in XLA.  Float reductions over the trade log are summed
-// left-to-right over the NON-ZERO terms in row order, which equals a plain left-to-right sum.
+// -fmad=false so that a*b+c is two roundings as in XLA.
+//
+// Float reductions over the trade log: XLA leaves the order of a reduction unspecified, so this path (and the CPU
+// oracle, bit for bit) fixes one: row r is accumulated by lane r % 32 in increasing r, then the 32 partial sums are
+// combined by a butterfly (xor 16, 8, 4, 2, 1).
 #pragma once
 #include <math.h>
 #include "lob_book.cuh"
@@ -20,7 +25,7 @@ __device__ __forceinline__ int ifloordiv(int a, int b) {  // jnp.floor_divide on
   return q;
 }
 __device__ __forceinline__ float fsignf(float x) { return (x > 0.f) ? 1.f : ((x < 0.f) ? -1.f : x); }
-__device__ __forceinline__ float ffloordiv(float x1, float x2) {  // jax._src.numpy.ufuncs._float_divmod
+static __device__ __noinline__ float ffloordiv(float x1, float x2) {  // jax._src.numpy.ufuncs._float_divmod
   float mod = fmodf(x1, x2);
   float div = (x1 - mod) / x2;
   if (mod != 0.f && fsignf(x2) != fsignf(mod)) div = div - 1.f;
@@ -32,28 +37,11 @@ __device__ __forceinline__ int f2i(float x) { return (int)x; }
 __device__ __forceinline__ int clamp_index(int a, int n) { if (a < 0) a += n; return max(0, min(a, n - 1)); }
 __device__ __forceinline__ int isign(int a) { return (a > 0) - (a < 0); }
 
-// Left-to-right float sum of term(r), r = 0..n-1, skipping exact zeros (x + 0.0f == x).
-template <class F>
-__device__ __forceinline__ float ordered_sum(int n, F term) {
-  float acc = 0.f;
-  const int lane = lane_id();
-  for (int base = 0; base < n; base += 32) {
-    const int r = base + lane;
-    const float t = (r < n) ? term(r) : 0.f;
-    unsigned m = __ballot_sync(kFull, t != 0.f);
-    while (m) {
-      const int j = __ffs(m) - 1;
-      acc = acc + __shfl_sync(kFull, t, j);
-      m &= m - 1;
-    }
-  }
-  return acc;
-}
-template <class F>
-__device__ __forceinline__ int int_sum(int n, F term) {
-  int acc = 0;
-  for (int r = lane_id(); r < n; r += 32) acc += term(r);
-  return wsum(acc);
+// butterfly combine of the 32 per-lane partial sums (see the header note)
+__device__ __forceinline__ float wsumf(float v) {
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) v = v + __shfl_xor_sync(kFull, v, off);
+  return v;
 }
 
 // One trade row classified against a trader id (job:895-904, mm:2214-2243)
@@ -61,11 +49,12 @@ struct TradeRow {
   int p, q, ts;
   bool agent, buy, sell, pass_buy, pass_sell;
 };
-__device__ __forceinline__ TradeRow classify(const int* tr, int nt, int r, int tid) {
+__device__ __forceinline__ TradeRow classify(const int* tr, int r, int tid) {
   TradeRow o;
-  const bool valid = tr[r] >= 0;  // trades[:,0] >= 0
-  const int p = valid ? tr[r] : 0, q = valid ? tr[nt + r] : 0, ts = valid ? tr[4 * nt + r] : 0;
-  const int ptid = valid ? tr[6 * nt + r] : 0, atid = valid ? tr[7 * nt + r] : 0;
+  const int4 a = reinterpret_cast<const int4*>(tr)[2 * r], b = reinterpret_cast<const int4*>(tr)[2 * r + 1];
+  const bool valid = a.x >= 0;  // trades[:,0] >= 0
+  const int p = valid ? a.x : 0, q = valid ? a.y : 0, ts = valid ? b.x : 0;
+  const int ptid = valid ? b.z : 0, atid = valid ? b.w : 0;
   const bool m2 = (tid == ptid) || (tid == atid);
   // agentTrades rows that are not the agent's are all-zero: tid == 0 never holds for those unless tid is 0
   const int aq = m2 ? q : 0, aptid = m2 ? ptid : 0, aatid = m2 ? atid : 0;
@@ -79,72 +68,93 @@ __device__ __forceinline__ TradeRow classify(const int* tr, int nt, int r, int t
 }
 
 // job:886-889 add_trade for the reward only: overwrite the first row holding a -1 (else the last row); returns the
-// row and the saved field (lane k < 8 keeps field k) so that `restore_trade` can undo it.
-__device__ __forceinline__ int insert_fictional(int* tr, int nt, const int (&row)[8], int& saved) {
+// row; lane k < 8 keeps field k in `saved` so that `restore_trade` can undo it.
+static __device__ __noinline__ int insert_fictional(int* tr, int nt, int4 lo, int4 hi, int* saved) {
   const int lane = lane_id();
   int first = kBig;
+#pragma unroll 1
   for (int r = lane; r < nt; r += 32) {
-    bool any = false;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) any |= tr[k * nt + r] == -1;
+    const int4 a = reinterpret_cast<const int4*>(tr)[2 * r], b = reinterpret_cast<const int4*>(tr)[2 * r + 1];
+    const bool any = (a.x == -1) | (a.y == -1) | (a.z == -1) | (a.w == -1) | (b.x == -1) | (b.y == -1) | (b.z == -1) | (b.w == -1);
     if (any) first = min(first, r);
   }
   first = wmin(first);
   const int e = (first == kBig) ? nt - 1 : first;
   __syncwarp();
-  if (lane < 8) { saved = tr[lane * nt + e]; tr[lane * nt + e] = row[lane]; }
+  if (lane < 8) *saved = tr[e * 8 + lane];
+  __syncwarp();
+  if (lane == 0) {
+    reinterpret_cast<int4*>(tr)[2 * e] = lo;
+    reinterpret_cast<int4*>(tr)[2 * e + 1] = hi;
+  }
   __syncwarp();
   return e;
 }
-__device__ __forceinline__ void restore_trade(int* tr, int nt, int e, int saved) {
+__device__ __forceinline__ void restore_trade(int* tr, int e, int saved) {
   __syncwarp();
-  if (lane_id() < 8) tr[lane_id() * nt + e] = saved;
+  if (lane_id() < 8) tr[e * 8 + lane_id()] = saved;
   __syncwarp();
 }
 
 // job:827-853 getCancelMsgs: the k-th (k = 0..size-1) row of `side` whose trader id is `agent`
-template <int SLOTS>
-__device__ __forceinline__ void cancel_msgs(const Book<SLOTS>& bk, int s, int agent, int size, int side_sign, int t,
-                                            int tns, int* out /* smem [size][8] */) {
+static __device__ __noinline__ void cancel_msgs(BookCtx bk, int s, int agent, int size, int side_sign, int t, int tns,
+                                               int* out /* smem [size][8] */) {
   const int lane = lane_id();
   int prev = -1;
+#pragma unroll 1
   for (int k = 0; k < size; ++k) {
     int idx = kBig;
-#pragma unroll
-    for (int j = SLOTS - 1; j >= 0; --j) { int r = j * 32 + lane; if (r < bk.no && r > prev && bk.F(s, F_TID)[r] == agent) idx = r; }
+#pragma unroll 1
+    for (int r = lane; r < bk.no; r += 32)
+      if (r > prev && rowp(bk, s, r)[F_TID] == agent) idx = min(idx, r);
     idx = wmin(idx);
     int q = 0, p = 0, o = 0, ti = 0;
-    if (idx != kBig) { q = bk.F(s, F_Q)[idx]; p = bk.F(s, F_P)[idx]; o = bk.F(s, F_OID)[idx]; ti = bk.F(s, F_TID)[idx]; prev = idx; }
+    if (idx != kBig) { const int* rw = rowp(bk, s, idx); q = rw[F_Q]; p = rw[F_P]; o = rw[F_OID]; ti = rw[F_TID]; prev = idx; }
     else prev = bk.no;  // nothing further: zeros from the appended row
     if (lane == 0) {
-      int* m = out + k * 8;
-      m[0] = 2; m[1] = side_sign; m[2] = q; m[3] = p; m[4] = o; m[5] = ti; m[6] = t; m[7] = tns;
+      int4* m = reinterpret_cast<int4*>(out + k * 8);
+      m[0] = make_int4(2, side_sign, q, p);
+      m[1] = make_int4(o, ti, t, tns);
     }
   }
   __syncwarp();
 }
 
 // mm:520-582 == exe:413-475 _filter_messages; one lane, k <= 16
-__device__ __forceinline__ void filter_messages(int* act, int ka, int* cnl, int kc) {
+static __device__ __noinline__ void filter_messages(int* act, int ka, int* cnl, int kc) {
   bool a_mask[16], c_mask[16];
   int a_i[16], c_i[16], a[16], cq[16], rel[16];
+#pragma unroll 1
   for (int i = 0; i < ka; ++i) a_mask[i] = false;
+#pragma unroll 1
   for (int j = 0; j < kc; ++j) c_mask[j] = false;
+#pragma unroll 1
   for (int i = 0; i < ka; ++i)
+#pragma unroll 1
     for (int j = 0; j < kc; ++j)
       if (cnl[j * 8 + 3] == act[i * 8 + 3] && act[i * 8 + 3] != 0) { a_mask[i] = true; c_mask[j] = true; }
   int na = 0, nc = 0;
+#pragma unroll 1
   for (int i = 0; i < ka; ++i) if (a_mask[i]) a_i[na++] = i;
+#pragma unroll 1
   for (int j = 0; j < kc; ++j) if (c_mask[j]) c_i[nc++] = j;
+#pragma unroll 1
   for (int k = 0; k < ka; ++k) a[k] = (k < na) ? act[a_i[k] * 8 + 2] : 0;
+#pragma unroll 1
   for (int k = 0; k < kc; ++k) cq[k] = (k < nc) ? cnl[c_i[k] * 8 + 2] : 0;
+#pragma unroll 1
   for (int k = 0; k < ka; ++k) rel[k] = (cq[k] >= a[k]) ? a[k] : 0;
   int rt = 0, rf = na;
+#pragma unroll 1
   for (int i = 0; i < ka; ++i) { int rank = a_mask[i] ? rt++ : rf++; act[i * 8 + 2] -= rel[rank]; }
+#pragma unroll 1
   for (int i = 0; i < ka; ++i)
-    if (act[i * 8 + 2] == 0)
-      for (int k = 0; k < 8; ++k) act[i * 8 + k] = 0;
+    if (act[i * 8 + 2] == 0) {
+      reinterpret_cast<int4*>(act + i * 8)[0] = make_int4(0, 0, 0, 0);
+      reinterpret_cast<int4*>(act + i * 8)[1] = make_int4(0, 0, 0, 0);
+    }
   rt = 0; rf = nc;
+#pragma unroll 1
   for (int j = 0; j < kc; ++j) { int rank = c_mask[j] ? rt++ : rf++; cnl[j * 8 + 2] -= rel[rank]; }
 }
 
@@ -161,9 +171,9 @@ struct MMOut {  // what the MM action leaves for the info / state update
 };
 
 // mm:1869-1913 get_messages (fixed_quants mm:970-1118 / directional mm:1810-1865).  act/cnl are shared memory.
-template <int SLOTS>
-__device__ __forceinline__ MMOut mm_get_messages(const Book<SLOTS>& bk, const LobStepConfig& c, const LobAgentTypeConfig& ac,
-                                                 int action, const WorldIn& w, int inventory, int tid, int* act, int* cnl) {
+static __device__ __noinline__ MMOut mm_get_messages(BookCtx bk, const LobStepConfig& c, const LobAgentTypeConfig& ac,
+                                                     int action, const WorldIn& w, int inventory, int tid, int* act,
+                                                     int* cnl) {
   const int lane = lane_id();
   const int tick = c.tick_size;
   MMOut o;
@@ -172,15 +182,14 @@ __device__ __forceinline__ MMOut mm_get_messages(const Book<SLOTS>& bk, const Lo
   if (ac.action_space == LOB_MM_ACT_FIXED_QUANTS) {
     // mm:979-985 best prices excluding own orders
     int mn = bk.maxint, mx = INT32_MIN;
-#pragma unroll
-    for (int k = 0; k < SLOTS; ++k) {
-      int r = k * 32 + lane;
-      if (r < bk.no) {
-        int pa = (bk.F(ASK, F_TID)[r] != tid) ? bk.F(ASK, F_P)[r] : -1;
-        int pb = (bk.F(BID, F_TID)[r] != tid) ? bk.F(BID, F_P)[r] : -1;
-        mn = min(mn, pa == -1 ? bk.maxint : pa);
-        mx = max(mx, pb);
-      }
+#pragma unroll 1
+    for (int r = lane; r < bk.no; r += 32) {
+      const int* ra = rowp(bk, ASK, r);
+      const int* rb = rowp(bk, BID, r);
+      const int pa = (ra[F_TID] != tid) ? ra[F_P] : -1;
+      const int pb = (rb[F_TID] != tid) ? rb[F_P] : -1;
+      mn = min(mn, pa == -1 ? bk.maxint : pa);
+      mx = max(mx, pb);
     }
     mn = wmin(mn); mx = wmax(mx);
     best_ask = (mn == bk.maxint) ? -1 : mn;
@@ -199,18 +208,19 @@ __device__ __forceinline__ MMOut mm_get_messages(const Book<SLOTS>& bk, const Lo
     if (ac.fixed_action_setting) action = ac.fixed_action;
     const int ai = clamp_index(action, 10);
     // bid/ask offset tables mm:1012-1015
-    const float bid_offset = (float)((0x0152043210u >> (4 * ai)) & 0xf);   // {0,1,2,3,4,0,2,5,1,0}
-    const float ask_offset = (float)((0x0510243210u >> (4 * ai)) & 0xf);   // {0,1,2,3,4,2,0,1,5,0}
+    const float bid_offset = (float)((0x0152043210ull >> (4 * ai)) & 0xf);   // {0,1,2,3,4,0,2,5,1,0}
+    const float ask_offset = (float)((0x0510243210ull >> (4 * ai)) & 0xf);   // {0,1,2,3,4,2,0,1,5,0}
     const int unit = (ai == 9) ? 0 : 1;
+    const float tickf = (float)tick;
     float half_spread_prev = jmaxf((float)(best_ask - best_bid) / 2.0f, (float)((double)tick / 2.0));
-    float half_spread = (ffloordiv(half_spread_prev, (float)tick) + 1.0f) * (float)tick;
+    float half_spread = (ffloordiv(half_spread_prev, tickf) + 1.0f) * tickf;
     int bid_quant = unit * ac.fixed_quant_value, ask_quant = unit * ac.fixed_quant_value;
     if (empty_book) { bid_quant = 0; ask_quant = 0; }
     float bid_price_f = (float)best_bid - bid_offset * half_spread;
     float ask_price_f = (float)best_ask + ask_offset * half_spread;
-    bid_price_f = ffloordiv(jmaxf(bid_price_f, 0.0f), (float)tick) * (float)tick;
+    bid_price_f = ffloordiv(jmaxf(bid_price_f, 0.0f), tickf) * tickf;
     const int bid_price = f2i(bid_price_f);
-    ask_price_f = ffloordiv(jmaxf((float)(bid_price + tick), ask_price_f), (float)tick) * (float)tick;
+    ask_price_f = ffloordiv(jmaxf((float)(bid_price + tick), ask_price_f), tickf) * tickf;
     const int ask_price = f2i(ask_price_f);
     quants[0] = bid_quant; quants[1] = ask_quant; prices[0] = bid_price; prices[1] = ask_price;
     bool use_liq = (ac.tenth_action_market_order && action == 9);
@@ -237,9 +247,9 @@ __device__ __forceinline__ MMOut mm_get_messages(const Book<SLOTS>& bk, const Lo
   if (lane == 0) {
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
-      int* m = act + k * 8;
-      m[0] = types[k]; m[1] = sides[k]; m[2] = quants[k]; m[3] = prices[k]; m[4] = c.placeholder_order_id; m[5] = tid;
-      m[6] = w.time0 + ac.time_delay_obs_act; m[7] = w.time1 + ac.time_delay_obs_act;
+      int4* m = reinterpret_cast<int4*>(act + k * 8);
+      m[0] = make_int4(types[k], sides[k], quants[k], prices[k]);
+      m[1] = make_int4(c.placeholder_order_id, tid, w.time0 + ac.time_delay_obs_act, w.time1 + ac.time_delay_obs_act);
     }
     filter_messages(act, ac.num_action_messages_by_agent, cnl, 2 * sz);
   }
@@ -248,10 +258,9 @@ __device__ __forceinline__ MMOut mm_get_messages(const Book<SLOTS>& bk, const Lo
 }
 
 // exe:1229-1273 get_messages (fixed_quants exe:623-724 / fixed_quants_complex exe:838-932)
-template <int SLOTS>
-__device__ __forceinline__ void exe_get_messages(const Book<SLOTS>& bk, const LobStepConfig& c, const LobAgentTypeConfig& ac,
-                                                 int action, const WorldIn& w, int task_to_execute, int quant_executed,
-                                                 int is_sell, int tid, int* act, int* cnl) {
+static __device__ __noinline__ void exe_get_messages(BookCtx bk, const LobStepConfig& c, const LobAgentTypeConfig& ac,
+                                                     int action, const WorldIn& w, int task_to_execute,
+                                                     int quant_executed, int is_sell, int tid, int* act, int* cnl) {
   const int tick = c.tick_size;
   const int best_ask = ifloordiv(w.old_ba_last, tick) * tick, best_bid = ifloordiv(w.old_bb_last, tick) * tick;
   int lv[4];
@@ -292,14 +301,13 @@ __device__ __forceinline__ void exe_get_messages(const Book<SLOTS>& bk, const Lo
   }
   const int side = 1 - is_sell * 2;
   const int sz = ac.num_messages_by_agent / 2;
-  if (is_sell) cancel_msgs(bk, ASK, tid, sz, side, w.time0, w.time1, cnl);
-  else cancel_msgs(bk, BID, tid, sz, side, w.time0, w.time1, cnl);
+  cancel_msgs(bk, is_sell ? ASK : BID, tid, sz, side, w.time0, w.time1, cnl);
   if (lane_id() == 0) {
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      int* m = act + k * 8;
-      m[0] = 1; m[1] = side; m[2] = q[k]; m[3] = lv[k]; m[4] = c.placeholder_order_id; m[5] = tid;
-      m[6] = w.time0 + ac.time_delay_obs_act; m[7] = w.time1 + ac.time_delay_obs_act;
+      int4* m = reinterpret_cast<int4*>(act + k * 8);
+      m[0] = make_int4(1, side, q[k], lv[k]);
+      m[1] = make_int4(c.placeholder_order_id, tid, w.time0 + ac.time_delay_obs_act, w.time1 + ac.time_delay_obs_act);
     }
     filter_messages(act, ac.num_action_messages_by_agent, cnl, sz);
   }
@@ -321,68 +329,96 @@ struct MMReward {
   int forced_unwind, end_inventory;
 };
 
+// One fused pass over the trade log for the MM reward (mm:2214-2243 masks + the sums of mm:2318-2417)
+struct MMSums {
+  int buyQ, sellQ, otherQ;
+  float income, outgoing, rebate_buy, rebate_sell, buyPnL, sellPnL;
+};
+static __device__ __noinline__ MMSums mm_trade_sums(const int* tr, int nt, int tid, float tickf, bool ref_is_int,
+                                                    int ref_buy_i, int ref_sell_i, float ref_f) {
+  MMSums s = {0, 0, 0, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+  for (int r = lane_id(); r < nt; r += 32) {
+    const TradeRow t = classify(tr, r, tid);
+    const int aq = abs(t.q);
+    const float fq = (float)aq;
+    const float pq = (float)t.p / tickf * fq;
+    const bool buy = t.agent && t.buy, sell = t.agent && t.sell;
+    s.buyQ += buy ? aq : 0;
+    s.sellQ += sell ? aq : 0;
+    s.otherQ += t.agent ? 0 : aq;
+    s.outgoing = s.outgoing + (buy ? pq : 0.f);
+    s.income = s.income + (sell ? pq : 0.f);
+    s.rebate_buy = s.rebate_buy + ((t.agent && t.pass_buy) ? pq : 0.f);
+    s.rebate_sell = s.rebate_sell + ((t.agent && t.pass_sell) ? pq : 0.f);
+    // rows that are not buys contribute (ref - 0)/tick * 0 == 0 (mm:2416-2417)
+    const float db = ref_is_int ? (float)(ref_buy_i - t.p) : (ref_f - (float)t.p);
+    const float ds = ref_is_int ? (float)(t.p - ref_sell_i) : ((float)t.p - ref_f);
+    s.buyPnL = s.buyPnL + (buy ? db / tickf * fq : 0.f);
+    s.sellPnL = s.sellPnL + (sell ? ds / tickf * fq : 0.f);
+  }
+  s.buyQ = wsum(s.buyQ); s.sellQ = wsum(s.sellQ); s.otherQ = wsum(s.otherQ);
+  s.income = wsumf(s.income); s.outgoing = wsumf(s.outgoing);
+  s.rebate_buy = wsumf(s.rebate_buy); s.rebate_sell = wsumf(s.rebate_sell);
+  s.buyPnL = wsumf(s.buyPnL); s.sellPnL = wsumf(s.sellPnL);
+  return s;
+}
+// mm:2441-2442: sum_r p_r / Q * |q_r| over the agent's buys (want_buy) or sells
+static __device__ __noinline__ float mm_avg_price(const int* tr, int nt, int tid, bool want_buy, int Q) {
+  float acc = 0.f;
+#pragma unroll 1
+  for (int r = lane_id(); r < nt; r += 32) {
+    const TradeRow t = classify(tr, r, tid);
+    const bool hit = t.agent && (want_buy ? t.buy : t.sell);
+    acc = acc + (hit ? (float)t.p / (float)Q * (float)abs(t.q) : 0.f);
+  }
+  return wsumf(acc);
+}
+
 // mm:2247-2673 get_reward
-__device__ __forceinline__ MMReward mm_get_reward(int* tr, int nt, const LobStepConfig& c, const LobAgentTypeConfig& ac,
-                                                  const WorldIn& w, const StepOut& so, const MMState& st, int tid) {
+static __device__ __noinline__ MMReward mm_get_reward(int* tr, int nt, const LobStepConfig& c, const LobAgentTypeConfig& ac,
+                                                      const WorldIn& w, const StepOut& so, const MMState& st, int tid) {
   MMReward R;
   const int tick = c.tick_size;
   const float tickf = (float)tick;
-  int buyQ = int_sum(nt, [&](int r) { TradeRow t = classify(tr, nt, r, tid); return (t.agent && t.buy) ? abs(t.q) : 0; });
-  int sellQ = int_sum(nt, [&](int r) { TradeRow t = classify(tr, nt, r, tid); return (t.agent && t.sell) ? abs(t.q) : 0; });
-  const int inv_before = st.inventory + buyQ - sellQ;
   const float last_mid = (float)(so.bb_last + so.ba_last) / 2.0f;
-  int penalty = ac.unwind_price_penalty * tick;
-  penalty = (inv_before > 0) ? penalty : -penalty;
-  int unwind_price;
-  if (ac.unwind_price == LOB_REF_MID_AVG) unwind_price = f2i(so.avg_mid - (float)penalty);
-  else if (ac.unwind_price == LOB_REF_MID) unwind_price = f2i(last_mid - (float)penalty);
-  else unwind_price = ((inv_before > 0) ? so.bb_last : so.ba_last) - penalty;
-  const bool fict = so.ep_done && abs(inv_before) > 0;
-  int saved = 0, frow = 0;
-  if (fict) {
-    const int row[8] = {unwind_price, isign(inv_before) * abs(inv_before), c.artificial_order_id_end_episode,
-                        c.placeholder_order_id, 0, 0, c.artificial_trader_id_end_episode, tid};
-    frow = insert_fictional(tr, nt, row, saved);
-  }
-  R.forced_unwind = inv_before * (so.ep_done ? 1 : 0);
-
-  const float income = ordered_sum(nt, [&](int r) { TradeRow t = classify(tr, nt, r, tid);
-    return (t.agent && t.sell) ? (float)t.p / tickf * (float)abs(t.q) : 0.f; });
-  const float outgoing = ordered_sum(nt, [&](int r) { TradeRow t = classify(tr, nt, r, tid);
-    return (t.agent && t.buy) ? (float)t.p / tickf * (float)abs(t.q) : 0.f; });
-  buyQ = int_sum(nt, [&](int r) { TradeRow t = classify(tr, nt, r, tid); return (t.agent && t.buy) ? abs(t.q) : 0; });
-  sellQ = int_sum(nt, [&](int r) { TradeRow t = classify(tr, nt, r, tid); return (t.agent && t.sell) ? abs(t.q) : 0; });
-  const int otherQ = int_sum(nt, [&](int r) { TradeRow t = classify(tr, nt, r, tid); return t.agent ? 0 : abs(t.q); });
-  const int new_inventory = st.inventory + buyQ - sellQ;
-  const float rb = ordered_sum(nt, [&](int r) { TradeRow t = classify(tr, nt, r, tid);
-    return (t.agent && t.pass_buy) ? (float)t.p / tickf * (float)abs(t.q) : 0.f; });
-  const float rs = ordered_sum(nt, [&](int r) { TradeRow t = classify(tr, nt, r, tid);
-    return (t.agent && t.pass_sell) ? (float)t.p / tickf * (float)abs(t.q) : 0.f; });
-  const float rebate_income = (rb + rs) * (float)(ac.rebate_bps / 10000.0);
-
   const bool ref_is_int = (ac.reference_price == LOB_REF_FAR_TOUCH || ac.reference_price == LOB_REF_NEAR_TOUCH);
-  float ref_f = (ac.reference_price == LOB_REF_MID_AVG) ? so.avg_mid : last_mid;
-  int ref_buy_i = 0, ref_sell_i = 0, reference_i = 0;
+  const float ref_f = (ac.reference_price == LOB_REF_MID_AVG) ? so.avg_mid : last_mid;
+  int ref_buy_i = 0, ref_sell_i = 0;
   if (ac.reference_price == LOB_REF_FAR_TOUCH) { ref_buy_i = so.ba_last; ref_sell_i = so.bb_last; }
   else if (ac.reference_price == LOB_REF_NEAR_TOUCH) { ref_buy_i = so.bb_last; ref_sell_i = so.ba_last; }
-  reference_i = (new_inventory > 0) ? ref_buy_i : ref_sell_i;
 
-  const float PnL = income - outgoing + rebate_income;
+  MMSums s = mm_trade_sums(tr, nt, tid, tickf, ref_is_int, ref_buy_i, ref_sell_i, ref_f);
+  const int inv_before = st.inventory + s.buyQ - s.sellQ;
+  R.forced_unwind = inv_before * (so.ep_done ? 1 : 0);
+  const bool fict = so.ep_done && abs(inv_before) > 0;
+  int saved = 0, frow = 0;
+  if (fict) {   // mm:2294-2316 the inventory is unwound by a fictional trade at the unwind price
+    int penalty = ac.unwind_price_penalty * tick;
+    penalty = (inv_before > 0) ? penalty : -penalty;
+    int unwind_price;
+    if (ac.unwind_price == LOB_REF_MID_AVG) unwind_price = f2i(so.avg_mid - (float)penalty);
+    else if (ac.unwind_price == LOB_REF_MID) unwind_price = f2i(last_mid - (float)penalty);
+    else unwind_price = ((inv_before > 0) ? so.bb_last : so.ba_last) - penalty;
+    frow = insert_fictional(tr, nt,
+                            make_int4(unwind_price, isign(inv_before) * abs(inv_before), c.artificial_order_id_end_episode,
+                                      c.placeholder_order_id),
+                            make_int4(0, 0, c.artificial_trader_id_end_episode, tid), &saved);
+    s = mm_trade_sums(tr, nt, tid, tickf, ref_is_int, ref_buy_i, ref_sell_i, ref_f);
+  }
+  const int buyQ = s.buyQ, sellQ = s.sellQ;
+  const int new_inventory = st.inventory + buyQ - sellQ;
+  const float rebate_income = (s.rebate_buy + s.rebate_sell) * (float)(ac.rebate_bps / 10000.0);
+  const int reference_i = (new_inventory > 0) ? ref_buy_i : ref_sell_i;
+  const float PnL = s.income - s.outgoing + rebate_income;
   const float new_cash = st.cash_balance + PnL;
   const float inventoryValue = ref_is_int ? (float)(new_inventory * reference_i) / tickf
                                           : ((float)new_inventory * ref_f) / tickf;
   const float netWorth = new_cash + inventoryValue;
   const int traded = buyQ + sellQ;
-  const float market_share = (float)traded / (float)(traded + otherQ);
+  const float market_share = (float)traded / (float)(traded + s.otherQ);
   const float InvPnL = ((float)st.inventory * (last_mid - w.mid_price)) / tickf;
-  const float buyPnL = ordered_sum(nt, [&](int r) { TradeRow t = classify(tr, nt, r, tid);
-    if (!(t.agent && t.buy)) return 0.f;   // rows that are not buys contribute (ref - 0)/tick * 0 == 0
-    const float d = ref_is_int ? (float)(ref_buy_i - t.p) : (ref_f - (float)t.p);
-    return d / tickf * (float)abs(t.q); });
-  const float sellPnL = ordered_sum(nt, [&](int r) { TradeRow t = classify(tr, nt, r, tid);
-    if (!(t.agent && t.sell)) return 0.f;
-    const float d = ref_is_int ? (float)(t.p - ref_sell_i) : ((float)t.p - ref_f);
-    return d / tickf * (float)abs(t.q); });
+  const float buyPnL = s.buyPnL, sellPnL = s.sellPnL;
   const float eta = (float)ac.inventoryPnL_eta, gamma = (float)ac.inventoryPnL_gamma;
   R.reward_spooner = buyPnL + sellPnL + rebate_income + InvPnL;
   R.reward_spooner_damped = buyPnL + sellPnL + rebate_income + InvPnL - (eta * InvPnL);
@@ -393,17 +429,14 @@ __device__ __forceinline__ MMReward mm_get_reward(int* tr, int nt, const LobStep
   float reward_complex = 0.f;
   if (ac.reward_function == LOB_MM_REW_COMPLEX) {  // mm:2437-2450
     const int inv_change = buyQ - sellQ;
-    float avg_buy = 0.f, avg_sell = 0.f;
-    if (buyQ > 0) avg_buy = ordered_sum(nt, [&](int r) { TradeRow t = classify(tr, nt, r, tid);
-      return (t.agent && t.buy) ? (float)t.p / (float)buyQ * (float)abs(t.q) : 0.f; });
-    if (sellQ > 0) avg_sell = ordered_sum(nt, [&](int r) { TradeRow t = classify(tr, nt, r, tid);
-      return (t.agent && t.sell) ? (float)t.p / (float)sellQ * (float)abs(t.q) : 0.f; });
+    const float avg_buy = (buyQ > 0) ? mm_avg_price(tr, nt, tid, true, buyQ) : 0.f;
+    const float avg_sell = (sellQ > 0) ? mm_avg_price(tr, nt, tid, false, sellQ) : 0.f;
     const float realized = (float)min(buyQ, sellQ) * (avg_sell - avg_buy);
     const float unrealized = (inv_change > 0) ? (float)inv_change * (so.avg_mid - avg_buy)
                                               : (float)abs(inv_change) * (avg_sell - so.avg_mid);
     reward_complex = realized + (float)ac.unrealizedPnL_lambda * unrealized + eta * jminf(InvPnL, InvPnL * eta);
   }
-  if (fict) restore_trade(tr, nt, frow, saved);
+  if (fict) restore_trade(tr, frow, saved);
 
   R.reward_portfolio_value = ref_is_int ? (float)new_inventory * ((float)reference_i / tickf) + new_cash
                                         : (float)new_inventory * (ref_f / tickf) + new_cash;
@@ -458,8 +491,8 @@ __device__ __forceinline__ MMReward mm_get_reward(int* tr, int nt, const LobStep
 }
 
 // mm:2963-3154 observation (fixed_steps), alphabetical key order
-__device__ __forceinline__ void mm_write_obs(const LobAgentTypeConfig& ac, float* obs, int inventory, float mid_price, int ba,
-                                             int bb, int qa, int qb, int step_counter, bool zero) {
+static __device__ __noinline__ void mm_write_obs(const LobAgentTypeConfig& ac, float* obs, int inventory, float mid_price,
+                                                 int ba, int bb, int qa, int qb, int step_counter, bool zero) {
   if (lane_id() != 0) return;
   const bool nz = ac.normalize;
   const int spread = abs(ba - bb);
@@ -496,40 +529,76 @@ __device__ __forceinline__ float rolling_mean(float old_mean, float nv, int step
   return (old_mean * (float)step + nv) / (float)(step + 1);
 }
 
+// One fused pass over the trade log for the EXE reward (job:895-904 masks + the sums of exe:1527-1712)
+struct EXESums {
+  int qsum, agentQ, otherQ, QP;
+  float tds, simplest;
+};
+static __device__ __noinline__ EXESums exe_trade_sums(const int* tr, int nt, int tid, int tick, int task_to_execute,
+                                                      int init_time0, float init_price, int is_sell) {
+  EXESums s = {0, 0, 0, 0, 0.f, 0.f};
+#pragma unroll 1
+  for (int r = lane_id(); r < nt; r += 32) {
+    const TradeRow t = classify(tr, r, tid);
+    const int aq = abs(t.q);
+    s.qsum += t.agent ? t.q : 0;
+    s.agentQ += t.agent ? aq : 0;
+    s.otherQ += t.agent ? 0 : aq;
+    s.QP += t.agent ? ifloordiv(t.p, tick) * aq : 0;
+    s.tds = s.tds + (t.agent ? (float)aq / (float)task_to_execute * (float)(t.ts - init_time0) : 0.f);
+    float slip = (float)t.p - init_price;   // exe:1744-1752 (|q| == 0 for rows that are not the agent's)
+    if (!is_sell) slip = -slip;
+    s.simplest = s.simplest + (t.agent ? slip * (float)aq : 0.f);
+  }
+  s.qsum = wsum(s.qsum); s.agentQ = wsum(s.agentQ); s.otherQ = wsum(s.otherQ); s.QP = wsum(s.QP);
+  s.tds = wsumf(s.tds); s.simplest = wsumf(s.simplest);
+  return s;
+}
+// exe:1630-1632: sum_r (p_r // tick) * (|q_r| / otherQ) over the OTHER traders' trades
+static __device__ __noinline__ float exe_vwap(const int* tr, int nt, int tid, int tick, int otherQ) {
+  float acc = 0.f;
+#pragma unroll 1
+  for (int r = lane_id(); r < nt; r += 32) {
+    const TradeRow t = classify(tr, r, tid);
+    acc = acc + (t.agent ? 0.f : (float)ifloordiv(t.p, tick) * ((float)abs(t.q) / (float)otherQ));
+  }
+  return wsumf(acc);
+}
+
 // exe:1511-1758 get_reward
-__device__ __forceinline__ EXEReward exe_get_reward(int* tr, int nt, const LobStepConfig& c, const LobAgentTypeConfig& ac,
-                                                    const WorldIn& w, const StepOut& so, const EXEState& st, int tid) {
+static __device__ __noinline__ EXEReward exe_get_reward(int* tr, int nt, const LobStepConfig& c, const LobAgentTypeConfig& ac,
+                                                        const WorldIn& w, const StepOut& so, const EXEState& st, int tid) {
   EXEReward R;
   const int tick = c.tick_size;
   const float tickf = (float)tick;
-  const int qsum = int_sum(nt, [&](int r) { TradeRow t = classify(tr, nt, r, tid); return t.agent ? t.q : 0; });
-  const int quant_left0 = st.task_to_execute - (st.quant_executed + abs(qsum));
-  const int penalty = ac.doom_price_penalty * tick;
-  const int side_sign = st.is_sell_task * 2 - 1;
-  int reference_price;
-  if (ac.reference_price == LOB_REF_MID) {
-    const float x = st.is_sell_task ? (so.avg_mid - (float)penalty) : (so.avg_mid + (float)penalty);
-    reference_price = f2i(ffloordiv(x, tickf) * tickf);
-  } else {
-    const int x = st.is_sell_task ? (so.bb_last - penalty) : (so.ba_last + penalty);
-    reference_price = ifloordiv(x, tick) * tick;
-  }
+  EXESums s = exe_trade_sums(tr, nt, tid, tick, st.task_to_execute, w.init_time0, st.init_price, st.is_sell_task);
+  const int quant_left0 = st.task_to_execute - (st.quant_executed + abs(s.qsum));
+  R.doom_quant = (so.ep_done ? 1 : 0) * quant_left0;
   const bool fict = so.ep_done && quant_left0 > 0;
   int saved = 0, frow = 0;
-  if (fict) {
-    const int row[8] = {reference_price, side_sign * abs(quant_left0), c.artificial_order_id_end_episode,
-                        c.placeholder_order_id, 0, 0, c.artificial_trader_id_end_episode, tid};
-    frow = insert_fictional(tr, nt, row, saved);
+  if (fict) {   // exe:1564-1588 the remainder is executed by a fictional trade at the doom price
+    const int penalty = ac.doom_price_penalty * tick;
+    const int side_sign = st.is_sell_task * 2 - 1;
+    int reference_price;
+    if (ac.reference_price == LOB_REF_MID) {
+      const float x = st.is_sell_task ? (so.avg_mid - (float)penalty) : (so.avg_mid + (float)penalty);
+      reference_price = f2i(ffloordiv(x, tickf) * tickf);
+    } else {
+      const int x = st.is_sell_task ? (so.bb_last - penalty) : (so.ba_last + penalty);
+      reference_price = ifloordiv(x, tick) * tick;
+    }
+    frow = insert_fictional(tr, nt,
+                            make_int4(reference_price, side_sign * abs(quant_left0), c.artificial_order_id_end_episode,
+                                      c.placeholder_order_id),
+                            make_int4(0, 0, c.artificial_trader_id_end_episode, tid), &saved);
+    s = exe_trade_sums(tr, nt, tid, tick, st.task_to_execute, w.init_time0, st.init_price, st.is_sell_task);
   }
-  R.doom_quant = (so.ep_done ? 1 : 0) * quant_left0;
-  const int agentQ = int_sum(nt, [&](int r) { TradeRow t = classify(tr, nt, r, tid); return t.agent ? abs(t.q) : 0; });
-  const int otherQ = int_sum(nt, [&](int r) { TradeRow t = classify(tr, nt, r, tid); return t.agent ? 0 : abs(t.q); });
+  const int agentQ = s.agentQ, otherQ = s.otherQ, QP = s.QP;
   float P_vwap;
   if (otherQ == 0) P_vwap = ffloordiv(so.avg_mid, tickf);
-  else P_vwap = ordered_sum(nt, [&](int r) { TradeRow t = classify(tr, nt, r, tid);
-    return t.agent ? 0.f : (float)ifloordiv(t.p, tick) * ((float)abs(t.q) / (float)otherQ); });
+  else P_vwap = exe_vwap(tr, nt, tid, tick, otherQ);
+  if (fict) restore_trade(tr, frow, saved);
   const int ds = isign(st.is_sell_task * 2 - 1);
-  const int QP = int_sum(nt, [&](int r) { TradeRow t = classify(tr, nt, r, tid); return t.agent ? ifloordiv(t.p, tick) * abs(t.q) : 0; });
   const float advantage = (float)ds * ((float)QP - P_vwap * (float)agentQ);
   const float drift = (float)(ds * agentQ) * (P_vwap - ffloordiv(st.init_price, tickf));
   const float denom = (float)agentQ + 1e-9f;
@@ -540,29 +609,19 @@ __device__ __forceinline__ EXEReward exe_get_reward(int* tr, int nt, const LobSt
   R.slippage_rm = rolling_mean(st.slippage_rm, slippage, w.step_counter);
   R.price_drift_rm = rolling_mean(st.price_drift_rm, price_drift, w.step_counter);
   const float reward = advantage + (float)ac.reward_lambda * drift;
-  const float tds = ordered_sum(nt, [&](int r) { TradeRow t = classify(tr, nt, r, tid);
-    return t.agent ? (float)abs(t.q) / (float)st.task_to_execute * (float)(t.ts - w.init_time0) : 0.f; });
-  R.trade_duration = st.trade_duration + tds;
+  R.trade_duration = st.trade_duration + s.tds;
   R.quant_left = st.task_to_execute - st.quant_executed - agentQ;
   R.reward = reward; R.agentQuant = agentQ; R.qp_agent = QP; R.p_vwap = P_vwap;
   R.advantage = advantage; R.drift = drift; R.slippage = slippage;
   R.reward_scaled = reward / (float)ac.reward_scaling_quo;
   if (ac.reward_function == LOB_EXE_REW_FINISH_FAST) R.reward_scaled = (float)(-abs(R.quant_left)) / (float)ac.reward_scaling_quo;
-  if (ac.reward_function == LOB_EXE_REW_SIMPLEST_CASE) {
-    const float r = ordered_sum(nt, [&](int rr) { TradeRow t = classify(tr, nt, rr, tid);
-      if (!t.agent) return 0.f;   // |q| == 0 for rows that are not the agent's
-      float slip = (float)t.p - st.init_price;
-      if (!st.is_sell_task) slip = -slip;
-      return slip * (float)abs(t.q); });
-    R.reward_scaled = r / (float)ac.reward_scaling_quo;
-  }
-  if (fict) restore_trade(tr, nt, frow, saved);
+  if (ac.reward_function == LOB_EXE_REW_SIMPLEST_CASE) R.reward_scaled = s.simplest / (float)ac.reward_scaling_quo;
   return R;
 }
 
 // exe:1879-1906 / exe:1913-2079 (fixed_steps), alphabetical key order
-__device__ __forceinline__ void exe_write_obs(const LobAgentTypeConfig& ac, float* obs, const EXEState& st, int ba, int bb,
-                                              int ask_vol, int bid_vol, int step_counter, int max_steps, bool zero) {
+static __device__ __noinline__ void exe_write_obs(const LobAgentTypeConfig& ac, float* obs, const EXEState& st, int ba, int bb,
+                                                  int ask_vol, int bid_vol, int step_counter, int max_steps, bool zero) {
   if (lane_id() != 0) return;
   const bool nz = ac.normalize;
   const float ts = (float)ac.task_size;

@@ -1,11 +1,20 @@
 // lob_book.cuh -- warp-cooperative fixed-capacity limit order book for sm_100a.
 //
-// One warp owns one environment.  Both book sides live in shared memory as struct-of-arrays
-// (field-major: price[], qty[], oid[], tid[], ts[], tns[]), row r is touched by lane r % 32, so a
-// field scan is SLOTS conflict-free LDS per lane followed by one REDUX (redux.sync min/max/add).
-// The per-side best price, the quantity and row count at that price, the number of rows with a
-// negative price and a per-lane bitmask of rows holding a -1 are carried in registers and updated
-// incrementally; a side is rescanned only when an update cannot be expressed incrementally.
+// One warp owns one environment.  Both book sides and the trade log live in shared memory in the SAME row layout as
+// in HBM (order row = 6 ints, trade row = 8 ints), so they are moved by the bulk-copy engine without a transpose.
+// Row r of a side belongs to lane r % 32 (slot r / 32); a field scan is SLOTS loads per lane (64-bit loads at a
+// 24-byte stride are bank-conflict free) followed by one REDUX.  Each side is padded to SLOTS*32 rows with blank
+// (-1) rows, so scans need no bounds checks.
+//
+// Two tiers:
+//   * FAST paths (inlined, small): the cases that make up a real message flow on books the reference itself produced
+//     -- a limit order that rests in a blank row, a cancel that hits its order id, a match against the best level --
+//     driven by register-resident summaries (per-lane blank-row bitmask, per-side best price / quantity / order
+//     count, count of negative-price rows, next trade row) that are updated incrementally;
+//   * GENERIC path (g_* functions, __noinline__): a literal restatement of the reference's array algorithm with full
+//     scans, used for everything else (unmatched cancels and the -1 index wrap, full books and eviction, zero
+//     remainders into a full side, rows holding stray -1 fields or non-positive quantities, MKT interpretation, ...).
+//     After a generic call the summaries are rebuilt from shared memory.
 //
 // Semantics restated from the reference (gymnax_exchange/jaxob/JaxOrderBookArrays.py, "job"):
 //   add_order job:63-83, _removeZeroNegQuant :86-90, cancel_order :94-117, get_init_id_match :121-139,
@@ -32,328 +41,449 @@ struct Msg {
   int type, side, qty, price, oid, tid, ts, tns;
 };
 
-// Per-warp book context.  Everything except `anyneg` is warp-uniform.
-template <int SLOTS>
-struct Book {
-  int* base;            // shared memory, F(side, field)[row] = base[(side * 6 + field) * no + row]
-  int* tr;              // shared memory trades, field-major: tr[field * nt + row]
+// What the generic functions need, passed BY VALUE (all warp-uniform) so that no book state has its address taken.
+struct BookCtx {
+  int* rows;   // shared memory: row r of side s at rows + (s * nrows + r) * 6
+  int* tr;     // shared memory trade log, row r at tr + r * 8
+  int nrows;   // rows allocated per side (SLOTS * 32 >= no)
   int no, nt;
   int maxint, init_id, init_lo, t4, check_fill;
-  unsigned anyneg[2];   // PER LANE: bit s <-> row s*32+lane holds a -1 in some field
-  int nneg[2];          // rows with price < 0
-  int bestp[2], bestq[2], bestn[2];
-  bool valid[2];        // best* caches valid
-  bool unclean[2];      // side may hold rows with qty <= 0 that are not all -1 (never true for reference-made states)
-  int ntr;              // next trade row (first row whose time_s column is -1) when tr_contig
-  bool tr_contig;
+};
+__device__ __forceinline__ int* rowp(const BookCtx& c, int s, int r) { return c.rows + (s * c.nrows + r) * 6; }
 
-  __device__ __forceinline__ void init(const LobBookConfig& c, int* smem_book, int* smem_trades) {
-    no = c.n_orders; nt = c.n_trades;
-    maxint = c.maxint; init_id = c.init_id; init_lo = c.init_id - 2 * c.book_depth;
-    t4 = c.type_4_interpretation; check_fill = c.check_book_fill;
-    base = smem_book;
-    tr = smem_trades;
-  }
-  __device__ __forceinline__ int* F(int s, int k) const { return base + (s * 6 + k) * no; }
+struct Best { int p, q, n; };
 
-  // ---- global <-> shared, coalesced (AoS rows in HBM, field-major in smem) ----
-  __device__ __forceinline__ void load_side(int s, const int* __restrict__ g) {
-    const int lane = lane_id();
-    const int total = no * 6;
-    for (int i = lane; i < total; i += 32) {
-      int v = g[i];
-      int r = i / 6, k = i - r * 6;
-      F(s, k)[r] = v;
+// =============================================================================== generic (literal) path ========
+// job:86-90
+static __device__ __noinline__ void g_remove_zero_neg(BookCtx c, int s) {
+  for (int r = lane_id(); r < c.no; r += 32) {
+    int* p = rowp(c, s, r);
+    if (p[F_Q] <= 0) {
+      int2* q = reinterpret_cast<int2*>(p);
+      q[0] = make_int2(-1, -1); q[1] = make_int2(-1, -1); q[2] = make_int2(-1, -1);
     }
+  }
+  __syncwarp();
+}
+// job:73 jnp.where(orderside == -1, size=1, fill_value=-1)[0]: first row (row-major) holding a -1, else kBig
+static __device__ __noinline__ int g_first_flagged(BookCtx c, int s) {
+  int f = kBig;
+  for (int r = lane_id(); r < c.no; r += 32) {
+    const int* p = rowp(c, s, r);
+    const bool any = (p[0] == -1) | (p[1] == -1) | (p[2] == -1) | (p[3] == -1) | (p[4] == -1) | (p[5] == -1);
+    if (any) f = min(f, r);
+  }
+  return wmin(f);
+}
+// job:63-83 add_order
+static __device__ __noinline__ void g_add(BookCtx c, int s, Msg m) {
+  int r = g_first_flagged(c, s);
+  if (r == kBig) r = c.no - 1;   // .at[-1]: the LAST row is overwritten (quirk Q1)
+  __syncwarp();
+  if (lane_id() == 0) {
+    int* p = rowp(c, s, r);
+    p[F_P] = m.price; p[F_Q] = max(0, m.qty); p[F_OID] = m.oid; p[F_TID] = m.tid; p[F_TS] = m.ts; p[F_TNS] = m.tns;
+  }
+  __syncwarp();
+  g_remove_zero_neg(c, s);
+}
+// job:94-139 cancel_order + get_init_id_match (cancel_mode 0/1)
+static __device__ __noinline__ void g_cancel(BookCtx c, int s, Msg m) {
+  int idx = kBig;
+  for (int r = lane_id(); r < c.no; r += 32)
+    if (rowp(c, s, r)[F_OID] == m.oid) idx = min(idx, r);
+  idx = wmin(idx);
+  if (idx == kBig) {
+    for (int r = lane_id(); r < c.no; r += 32) {
+      const int* p = rowp(c, s, r);
+      if (p[F_P] == m.price && p[F_OID] <= c.init_id && p[F_OID] >= c.init_lo && p[F_Q] >= m.qty) idx = min(idx, r);
+    }
+    idx = wmin(idx);
+    if (idx == kBig) idx = c.no - 1;   // JAX normalises index -1: the LAST row loses quantity (quirk Q2)
+  }
+  __syncwarp();
+  if (lane_id() == 0) rowp(c, s, idx)[F_Q] -= m.qty;
+  __syncwarp();
+  g_remove_zero_neg(c, s);
+}
+// job:242-268 price-time priority, literal (also for degenerate inputs)
+static __device__ __noinline__ int g_top(BookCtx c, int s) {
+  const int lane = lane_id();
+  int ext = (s == BID) ? INT32_MIN : c.maxint;
+  for (int r = lane; r < c.no; r += 32) {
+    const int p = rowp(c, s, r)[F_P];
+    ext = (s == BID) ? max(ext, p) : min(ext, p == -1 ? c.maxint : p);
+  }
+  ext = (s == BID) ? wmax(ext) : wmin(ext);
+  int mt = c.maxint;
+  for (int r = lane; r < c.no; r += 32) {
+    const int* p = rowp(c, s, r);
+    mt = min(mt, p[F_P] == ext ? p[F_TS] : c.maxint);
+  }
+  mt = wmin(mt);
+  int mn = c.maxint;
+  for (int r = lane; r < c.no; r += 32) {
+    const int* p = rowp(c, s, r);
+    const int t = p[F_P] == ext ? p[F_TS] : c.maxint;
+    mn = min(mn, t == mt ? p[F_TNS] : c.maxint);
+  }
+  mn = wmin(mn);
+  int idx = kBig;
+  for (int r = lane; r < c.no; r += 32) {
+    const int* p = rowp(c, s, r);
+    const int t = p[F_P] == ext ? p[F_TS] : c.maxint;
+    const int n = t == mt ? p[F_TNS] : c.maxint;
+    if (n == mn) idx = min(idx, r);
+  }
+  idx = wmin(idx);
+  return idx == kBig ? c.no - 1 : idx;
+}
+// job:173-220 + 285-331: the while loop of _match_against_{bid,ask}_orders; returns the remaining quantity
+static __device__ __noinline__ int g_match(BookCtx c, int opp, Msg m, int qtm) {
+  const int lane = lane_id();
+  int top = g_top(c, opp);
+  while (true) {
+    int* o = rowp(c, opp, top);
+    const int tp = o[F_P];
+    const bool cross = (opp == BID) ? (tp >= m.price) : (tp <= m.price);
+    if (!(cross && qtm > 0 && tp != -1)) break;
+    const int oq = o[F_Q], ooid = o[F_OID], otid = o[F_TID];
+    const int newq = max(0, oq - qtm);
+    qtm = qtm - oq;
+    int e = kBig;   // job:205: first trade row whose column 4 (time_s) is -1, else the last row (quirk Q3)
+    for (int r = lane; r < c.nt; r += 32)
+      if (c.tr[r * 8 + 4] == -1) e = min(e, r);
+    e = wmin(e);
+    if (e == kBig) e = c.nt - 1;
+    __syncwarp();
+    if (lane == 0) {
+      int* t = c.tr + e * 8;
+      t[0] = tp; t[1] = -m.side * (oq - newq); t[2] = ooid; t[3] = m.oid; t[4] = m.ts; t[5] = m.tns; t[6] = otid; t[7] = m.tid;
+      o[F_Q] = newq;
+    }
+    __syncwarp();
+    g_remove_zero_neg(c, opp);
+    top = g_top(c, opp);
+  }
+  return qtm;
+}
+// job:395-401 / 484-490: no row with a negative price -> blank every row at the worst price
+static __device__ __noinline__ void g_evict(BookCtx c, int s) {
+  const int lane = lane_id();
+  int w = (s == BID) ? INT32_MAX : INT32_MIN;
+  bool neg = false;
+  for (int r = lane; r < c.no; r += 32) {
+    const int p = rowp(c, s, r)[F_P];
+    neg |= p < 0;
+    w = (s == BID) ? min(w, p) : max(w, p);
+  }
+  if (__any_sync(kFull, neg)) return;
+  w = (s == BID) ? wmin(w) : wmax(w);
+  for (int r = lane; r < c.no; r += 32) {
+    int* p = rowp(c, s, r);
+    if (p[F_P] == w) {
+      int2* q = reinterpret_cast<int2*>(p);
+      q[0] = make_int2(-1, -1); q[1] = make_int2(-1, -1); q[2] = make_int2(-1, -1);
+    }
+  }
+  __syncwarp();
+}
+// job:358-420 bid_lim (own = BID) / job:447-508 ask_lim (own = ASK)
+static __device__ __noinline__ void g_limit(BookCtx c, int own, Msg m) {
+  const int opp = 1 - own;
+  if (own == ASK && c.t4 == 2) m.price = 0;              // job:471-472
+  const int qtm = g_match(c, opp, m, m.qty);
+  if (own == BID && c.t4 == 2) m.price = c.maxint;       // job:391-392
+  m.qty = qtm;
+  if (c.check_fill) g_evict(c, own);
+  if (m.type == 4 && c.t4 != 1) return;                  // job:415-418 / 503-506: IOC remainder dropped, eviction kept
+  g_add(c, own, m);
+}
+// job:556-637 cond_type_side (GENERAL_EXCHANGE)
+static __device__ __noinline__ void g_process(BookCtx c, Msg m) {
+  const int s = m.side, t = m.type;
+  const bool lim = (t == 1) | (t == 4), cnl = (t == 2) | (t == 3);
+  if (s == 1 && lim) g_limit(c, BID, m);
+  else if (s == -1 && cnl) g_cancel(c, ASK, m);
+  else if (s == 1 && cnl) g_cancel(c, BID, m);
+  else if (s == 0 && t == 0) { /* doNothing */ }
+  else g_limit(c, ASK, m);                               // index 0 is also the lax.switch target of every other (type, side)
+}
+// job:933-984: best price, quantity at it, rows at it
+static __device__ __noinline__ Best g_best(BookCtx c, int s) {
+  const int lane = lane_id();
+  int bp;
+  if (s == ASK) {
+    int mn = c.maxint;
+    for (int r = lane; r < c.no; r += 32) { const int p = rowp(c, ASK, r)[F_P]; mn = min(mn, p == -1 ? c.maxint : p); }
+    mn = wmin(mn);
+    bp = (mn == c.maxint) ? -1 : mn;
+  } else {
+    int mx = INT32_MIN;
+    for (int r = lane; r < c.no; r += 32) mx = max(mx, rowp(c, BID, r)[F_P]);
+    bp = wmax(mx);
+  }
+  int q = 0, n = 0;
+  for (int r = lane; r < c.no; r += 32) {
+    const int2 pq = *reinterpret_cast<const int2*>(rowp(c, s, r));
+    if (pq.x == bp) { q += pq.y; n += 1; }
+  }
+  Best b;
+  b.p = bp; b.q = wsum(q); b.n = wsum(n);
+  return b;
+}
+// job:920-930 get_volume
+static __device__ __noinline__ int g_volume(BookCtx c, int s) {
+  int v = 0;
+  for (int r = lane_id(); r < c.no; r += 32) {
+    const int2 pq = *reinterpret_cast<const int2*>(rowp(c, s, r));
+    if (pq.x != -1) v += pq.y;
+  }
+  return wsum(v);
+}
+
+// ======================================================================================= fast path =============
+template <int SLOTS>
+struct Book {
+  static constexpr int kRows = SLOTS * 32;
+  BookCtx c;
+  unsigned flag[2];   // PER LANE: bit k <-> row k*32+lane holds a -1 in some field (padding rows are never flagged)
+  int nneg[2];        // rows with price < 0
+  int bestp[2], bestq[2], bestn[2];
+  bool valid[2];      // best* caches valid
+  bool odd[2];        // side holds rows the fast paths do not model: a non-blank row with qty <= 0 or with a -1 field
+  int ntr;            // next trade row: first row whose time_s column is -1
+  bool tr_odd;        // the rows after ntr are not all free -> the trade slot must be searched (generic path)
+
+  __device__ __forceinline__ void init(const LobBookConfig& cfg, int* smem_book, int* smem_trades) {
+    c.rows = smem_book; c.tr = smem_trades; c.nrows = kRows;
+    c.no = cfg.n_orders; c.nt = cfg.n_trades;
+    c.maxint = cfg.maxint; c.init_id = cfg.init_id; c.init_lo = cfg.init_id - 2 * cfg.book_depth;
+    c.t4 = cfg.type_4_interpretation; c.check_fill = cfg.check_book_fill;
+    // padding rows [no, kRows) of both sides are blank for the whole kernel
+    for (int i = lane_id(); i < 2 * kRows * 6; i += 32) smem_book[i] = -1;
+    __syncwarp();
+  }
+  __device__ __forceinline__ int* row(int s, int r) const { return c.rows + (s * kRows + r) * 6; }
+  __device__ __forceinline__ int* side_base(int s) const { return c.rows + s * kRows * 6; }
+
+  // ---- plain (non-bulk) global <-> shared copies: same layout on both sides ----
+  __device__ __forceinline__ void load_side(int s, const int* __restrict__ g) {
+    const int2* g2 = reinterpret_cast<const int2*>(g);
+    int2* d = reinterpret_cast<int2*>(side_base(s));
+    for (int i = lane_id(); i < c.no * 3; i += 32) d[i] = g2[i];
   }
   __device__ __forceinline__ void store_side(int s, int* __restrict__ g) const {
-    const int lane = lane_id();
-    const int total = no * 6;
-    for (int i = lane; i < total; i += 32) {
-      int r = i / 6, k = i - r * 6;
-      g[i] = F(s, k)[r];
-    }
+    int2* g2 = reinterpret_cast<int2*>(g);
+    const int2* d = reinterpret_cast<const int2*>(side_base(s));
+    for (int i = lane_id(); i < c.no * 3; i += 32) g2[i] = d[i];
   }
   __device__ __forceinline__ void load_trades(const int* __restrict__ g) {
-    const int lane = lane_id();
-    for (int i = lane; i < nt * 8; i += 32) { int r = i >> 3, k = i & 7; tr[k * nt + r] = g[i]; }
-  }
-  __device__ __forceinline__ void fill_trades_empty() {
-    const int lane = lane_id();
-    for (int i = lane; i < nt * 8; i += 32) tr[i] = -1;
-    ntr = 0; tr_contig = true;
+    const int4* g4 = reinterpret_cast<const int4*>(g);
+    int4* d = reinterpret_cast<int4*>(c.tr);
+    for (int i = lane_id(); i < c.nt * 2; i += 32) d[i] = g4[i];
   }
   __device__ __forceinline__ void store_trades(int* __restrict__ g) const {
-    const int lane = lane_id();
-    for (int i = lane; i < nt * 8; i += 32) { int r = i >> 3, k = i & 7; g[i] = tr[k * nt + r]; }
+    int4* g4 = reinterpret_cast<int4*>(g);
+    const int4* d = reinterpret_cast<const int4*>(c.tr);
+    for (int i = lane_id(); i < c.nt * 2; i += 32) g4[i] = d[i];
+  }
+  __device__ __forceinline__ void fill_trades_empty() {
+    int4* d = reinterpret_cast<int4*>(c.tr);
+    for (int i = lane_id(); i < c.nt * 2; i += 32) d[i] = make_int4(-1, -1, -1, -1);
+    ntr = 0; tr_odd = false;
   }
 
-  // ---- derive the register-resident summaries from shared memory (after a load) ----
-  __device__ __forceinline__ void scan_side_flags(int s) {
+  // ---- derive the register-resident summaries from shared memory ----
+  __device__ __forceinline__ void scan_side(int s) {
     const int lane = lane_id();
-    unsigned m = 0; int neg = 0; int dirty = 0;
+    unsigned m = 0; int neg = 0; bool od = false;
 #pragma unroll
     for (int k = 0; k < SLOTS; ++k) {
-      int r = k * 32 + lane;
-      if (r < no) {
-        int p = F(s, F_P)[r], q = F(s, F_Q)[r], o = F(s, F_OID)[r], t = F(s, F_TID)[r], a = F(s, F_TS)[r], b = F(s, F_TNS)[r];
-        bool any = (p == -1) | (q == -1) | (o == -1) | (t == -1) | (a == -1) | (b == -1);
-        bool all = (p == -1) & (q == -1) & (o == -1) & (t == -1) & (a == -1) & (b == -1);
+      const int r = k * 32 + lane;
+      if (r < c.no) {
+        const int2* p = reinterpret_cast<const int2*>(row(s, r));
+        const int2 a = p[0], b = p[1], d = p[2];
+        const bool any = (a.x == -1) | (a.y == -1) | (b.x == -1) | (b.y == -1) | (d.x == -1) | (d.y == -1);
+        const bool all = (a.x == -1) & (a.y == -1) & (b.x == -1) & (b.y == -1) & (d.x == -1) & (d.y == -1);
         if (any) m |= 1u << k;
-        neg += (p < 0);
-        dirty |= (q <= 0) & !all;
+        neg += (a.x < 0);
+        od |= (!all) & (any | (a.y <= 0));
       }
     }
-    anyneg[s] = m;
+    flag[s] = m;
     nneg[s] = wsum(neg);
-    unclean[s] = __any_sync(kFull, dirty);
+    odd[s] = __any_sync(kFull, od);
     valid[s] = false;
   }
-  __device__ __forceinline__ void scan_trade_flags() {
-    // ntr = first row with time_s == -1; contiguous iff every later row is also -1 there
+  __device__ __forceinline__ void scan_trades() {
+    // ntr = first row with time_s == -1; tr_odd iff some later row is filled there
     const int lane = lane_id();
     int first = kBig, last_filled = -1;
-    for (int r = lane; r < nt; r += 32) {
-      if (tr[4 * nt + r] == -1) first = min(first, r); else last_filled = max(last_filled, r);
+    for (int r = lane; r < c.nt; r += 32) {
+      if (c.tr[r * 8 + 4] == -1) first = min(first, r); else last_filled = max(last_filled, r);
     }
     first = wmin(first); last_filled = wmax(last_filled);
-    ntr = (first == kBig) ? nt : first;
-    tr_contig = last_filled < ntr;
+    ntr = (first == kBig) ? c.nt : first;
+    tr_odd = last_filled >= ntr;
   }
+  __device__ __forceinline__ void rescan() { scan_side(ASK); scan_side(BID); scan_trades(); }
 
-  // job:933-984: best price, quantity at it, rows at it
   __device__ __forceinline__ void recompute(int s) {
-    const int lane = lane_id();
-    int bp;
-    if (s == ASK) {
-      int mn = maxint;
-#pragma unroll
-      for (int k = 0; k < SLOTS; ++k) { int r = k * 32 + lane; if (r < no) { int p = F(ASK, F_P)[r]; mn = min(mn, p == -1 ? maxint : p); } }
-      mn = wmin(mn);
-      bp = (mn == maxint) ? -1 : mn;
-    } else {
-      int mx = INT32_MIN;
-#pragma unroll
-      for (int k = 0; k < SLOTS; ++k) { int r = k * 32 + lane; if (r < no) mx = max(mx, F(BID, F_P)[r]); }
-      bp = wmax(mx);
-    }
-    int q = 0, n = 0;
-#pragma unroll
-    for (int k = 0; k < SLOTS; ++k) { int r = k * 32 + lane; if (r < no && F(s, F_P)[r] == bp) { q += F(s, F_Q)[r]; n += 1; } }
-    bestp[s] = bp; bestq[s] = wsum(q); bestn[s] = wsum(n); valid[s] = true;
+    const Best b = g_best(c, s);
+    bestp[s] = b.p; bestq[s] = b.q; bestn[s] = b.n; valid[s] = true;
   }
   __device__ __forceinline__ void ensure(int s) { if (!valid[s]) recompute(s); }
+  __device__ __forceinline__ int volume(int s) const { return g_volume(c, s); }
 
-  // job:73 first row (row-major) holding a -1, else kBig
-  __device__ __forceinline__ int first_anyneg(int s) const {
-    unsigned m = anyneg[s];
+  // first flagged row (== first blank row when !odd), else kBig
+  __device__ __forceinline__ int first_flagged(int s) const {
+    const unsigned m = flag[s];
     return wmin(m ? (__ffs(m) - 1) * 32 + lane_id() : kBig);
   }
 
-  __device__ __forceinline__ void set_flag(int s, int r, bool any) {
-    if (lane_id() == (r & 31)) { unsigned b = 1u << (r >> 5); anyneg[s] = any ? (anyneg[s] | b) : (anyneg[s] & ~b); }
-  }
-
-  // blank one row (all fields -1) and keep the summaries exact
-  __device__ __forceinline__ void blank_row(int s, int r, int rp, int rq) {
+  // blank one LIVE row (price rp != -1, quantity rq) and keep the summaries exact
+  template <int S>
+  __device__ __forceinline__ void blank_live(int r, int rp, int rq) {
     if (lane_id() == (r & 31)) {
-#pragma unroll
-      for (int k = 0; k < 6; ++k) F(s, k)[r] = -1;
+      int2* p = reinterpret_cast<int2*>(row(S, r));
+      p[0] = make_int2(-1, -1); p[1] = make_int2(-1, -1); p[2] = make_int2(-1, -1);
+      flag[S] |= 1u << (r >> 5);
     }
-    set_flag(s, r, true);
-    nneg[s] += (rp >= 0);
-    if (valid[s]) {
-      if (bestp[s] == -1) valid[s] = false;
-      else if (rp == bestp[s]) { bestq[s] -= rq; bestn[s] -= 1; if (bestn[s] <= 0) valid[s] = false; }
+    nneg[S] += (rp >= 0);
+    if (valid[S] && rp == bestp[S]) {
+      bestq[S] -= rq; bestn[S] -= 1;
+      if (bestn[S] <= 0) valid[S] = false;
     }
-    __syncwarp();
   }
 
-  // job:86-90 after an op that changed row r of side s (rp/rq = its current price/qty)
-  __device__ __forceinline__ void finish_side(int s, int r, int rp, int rq) {
-    if (unclean[s]) {  // generic pass, only for states the reference itself never produces
-      const int lane = lane_id();
+  // job:285-331 against the cached best level of side OPP; returns the remaining quantity
+  template <int OPP>
+  __device__ __forceinline__ int match(const Msg& m, int qtm) {
+    const int lane = lane_id();
+    while (true) {
+      ensure(OPP);
+      const int tp = bestp[OPP];
+      const bool cross = (OPP == BID) ? (tp >= m.price) : (tp <= m.price);
+      if (!(cross && qtm > 0 && tp != -1)) break;
+      int top = kBig;
+      if (bestn[OPP] == 1) {
 #pragma unroll
-      for (int k = 0; k < SLOTS; ++k) {
-        int rr = k * 32 + lane;
-        if (rr < no && F(s, F_Q)[rr] <= 0) {
+        for (int k = SLOTS - 1; k >= 0; --k) { const int r = k * 32 + lane; if (row(OPP, r)[F_P] == tp) top = r; }
+        top = wmin(top);
+      } else {   // job:242-268: min time_s, then min time_ns, then lowest row
+        int t[SLOTS], n[SLOTS];
+        int mt = c.maxint;
 #pragma unroll
-          for (int j = 0; j < 6; ++j) F(s, j)[rr] = -1;
+        for (int k = 0; k < SLOTS; ++k) {
+          const int* p = row(OPP, k * 32 + lane);
+          const int2 tt = *reinterpret_cast<const int2*>(p + F_TS);
+          t[k] = (p[F_P] == tp) ? tt.x : c.maxint;
+          n[k] = tt.y;
+          mt = min(mt, t[k]);
         }
+        mt = wmin(mt);
+        if (mt == c.maxint) { top = g_top(c, OPP); }   // degenerate timestamps: literal search
+        else {
+          int mn = c.maxint;
+#pragma unroll
+          for (int k = 0; k < SLOTS; ++k) { n[k] = (t[k] == mt) ? n[k] : c.maxint; mn = min(mn, n[k]); }
+          mn = wmin(mn);
+#pragma unroll
+          for (int k = SLOTS - 1; k >= 0; --k) if (n[k] == mn) top = k * 32 + lane;
+          top = wmin(top);
+          if (top >= c.no) top = g_top(c, OPP);
+        }
+      }
+      const int* o = row(OPP, top);
+      const int2 pq = *reinterpret_cast<const int2*>(o);
+      const int2 ot = *reinterpret_cast<const int2*>(o + F_OID);
+      const int oq = pq.y;
+      const int newq = max(0, oq - qtm);
+      qtm = qtm - oq;
+      const int e = (ntr < c.nt) ? ntr : c.nt - 1;        // job:205 (quirk Q3)
+      if (lane == 0) {
+        int4* t4p = reinterpret_cast<int4*>(c.tr + e * 8);
+        t4p[0] = make_int4(tp, -m.side * (oq - newq), ot.x, m.oid);
+        t4p[1] = make_int4(m.ts, m.tns, ot.y, m.tid);
+      }
+      if (ntr < c.nt && m.ts != -1) ntr += 1;
+      if (newq > 0) {
+        if (lane == (top & 31)) row(OPP, top)[F_Q] = newq;
+        bestq[OPP] += newq - oq;
+      } else {
+        blank_live<OPP>(top, tp, oq);
       }
       __syncwarp();
-      scan_side_flags(s);
-      unclean[s] = false;
+    }
+    return qtm;
+  }
+
+  __device__ __forceinline__ void generic(const Msg& m) {
+    __syncwarp();
+    g_process(c, m);
+    rescan();
+  }
+
+  // job:358-420 bid_lim (OWN = BID) / job:447-508 ask_lim (OWN = ASK)
+  template <int OWN>
+  __device__ __forceinline__ void limit(const Msg& m) {
+    constexpr int OPP = 1 - OWN;
+    const int qtm = match<OPP>(m, m.qty);
+    if (c.check_fill && nneg[OWN] == 0) {   // job:395-401: full side -> the worst price level is evicted
+      g_evict(c, OWN);
+      scan_side(OWN);
+    }
+    if (m.type == 4 && c.t4 != 1) return;   // IOC remainder dropped, eviction kept
+    const int q = max(0, qtm);
+    const int r = first_flagged(OWN);
+    if (q == 0 && r != kBig && !odd[OWN]) return;   // written into a blank row and blanked again (job:83): no-op
+    const bool neg1 = (m.price == -1) | (m.oid == -1) | (m.tid == -1) | (m.ts == -1) | (m.tns == -1);
+    if (q == 0 || r == kBig || odd[OWN] || neg1 || m.price <= 0) {
+      Msg a = m;
+      a.qty = qtm;
+      __syncwarp();
+      g_add(c, OWN, a);
+      scan_side(OWN);
       return;
     }
-    if (rq <= 0) blank_row(s, r, rp, rq);
-  }
-
-  // job:242-268 price-time priority among rows at `price` (literal restatement, also for degenerate inputs)
-  __device__ __forceinline__ int top_idx(int s, int price) const {
-    const int lane = lane_id();
-    int t[SLOTS], n[SLOTS];
-    int mt = maxint;
-#pragma unroll
-    for (int k = 0; k < SLOTS; ++k) {
-      int r = k * 32 + lane;
-      bool in = r < no;
-      int p = in ? F(s, F_P)[r] : 0;
-      t[k] = (in && p == price) ? F(s, F_TS)[r] : maxint;
-      n[k] = in ? F(s, F_TNS)[r] : maxint;
-      if (in) mt = min(mt, t[k]);
+    if (lane_id() == (r & 31)) {            // the blank row r takes the order
+      int2* p = reinterpret_cast<int2*>(row(OWN, r));
+      p[0] = make_int2(m.price, q); p[1] = make_int2(m.oid, m.tid); p[2] = make_int2(m.ts, m.tns);
+      flag[OWN] &= ~(1u << (r >> 5));
     }
-    mt = wmin(mt);
-    int mn = maxint;
-#pragma unroll
-    for (int k = 0; k < SLOTS; ++k) {
-      int r = k * 32 + lane;
-      n[k] = (r < no && t[k] == mt) ? n[k] : maxint;
-      if (r < no) mn = min(mn, n[k]);
-    }
-    mn = wmin(mn);
-    int idx = kBig;
-#pragma unroll
-    for (int k = SLOTS - 1; k >= 0; --k) { int r = k * 32 + lane; if (r < no && n[k] == mn) idx = r; }
-    idx = wmin(idx);
-    return idx == kBig ? no - 1 : idx;
-  }
-
-  // job:173-220 one match against row `top` of side `s` (its price is `tp`)
-  __device__ __forceinline__ void match_one(int s, int top, int tp, int& qtm, const Msg& m) {
-    const int oq = F(s, F_Q)[top], ooid = F(s, F_OID)[top], otid = F(s, F_TID)[top];
-    const int newq = max(0, oq - qtm);
-    qtm = qtm - oq;
-    // job:205: first trade row whose column 4 (time_s) is -1, else the last row
-    int e;
-    if (tr_contig) e = (ntr < nt) ? ntr : nt - 1;
-    else {
-      int first = kBig;
-      for (int r = lane_id(); r < nt; r += 32) if (tr[4 * nt + r] == -1) first = min(first, r);
-      first = wmin(first);
-      e = (first == kBig) ? nt - 1 : first;
-    }
-    const int lane = lane_id();
-    if (lane < 8) {
-      int v = lane == 0 ? tp : lane == 1 ? -m.side * (oq - newq) : lane == 2 ? ooid : lane == 3 ? m.oid
-            : lane == 4 ? m.ts : lane == 5 ? m.tns : lane == 6 ? otid : m.tid;
-      tr[lane * nt + e] = v;
-    }
-    if (tr_contig && ntr < nt && m.ts != -1) ntr += 1;
-    __syncwarp();
-    if (lane == (top & 31)) F(s, F_Q)[top] = newq;
-    if (valid[s]) { if (bestp[s] == -1) valid[s] = false; else if (tp == bestp[s]) bestq[s] += newq - oq; }
-    __syncwarp();
-    finish_side(s, top, tp, newq);
-  }
-
-  // job:285-331: incoming order on side `own` crosses the opposite side while prices overlap
-  __device__ __forceinline__ void match_against(int opp, int& qtm, int price, const Msg& m) {
-    ensure(opp);
-    while (true) {
-      const int tp = bestp[opp];  // == price of the reference's top order (or -1)
-      const bool cross = (opp == BID) ? (tp >= price) : (tp <= price);
-      if (!(cross && qtm > 0 && tp != -1)) break;
-      const int top = top_idx(opp, tp);
-      match_one(opp, top, tp, qtm, m);
-      ensure(opp);
+    nneg[OWN] -= 1;
+    if (valid[OWN]) {
+      const int bp = bestp[OWN];
+      const bool better = (bp == -1) | ((OWN == ASK) ? (m.price < bp) : (m.price > bp));
+      if (better) { bestp[OWN] = m.price; bestq[OWN] = q; bestn[OWN] = 1; }
+      else if (m.price == bp) { bestq[OWN] += q; bestn[OWN] += 1; }
     }
   }
 
-  // job:395-401 / 484-490
-  __device__ __forceinline__ void evict_if_full(int s) {
-    if (nneg[s] != 0) return;
-    const int lane = lane_id();
-    int w = (s == BID) ? INT32_MAX : INT32_MIN;
-#pragma unroll
-    for (int k = 0; k < SLOTS; ++k) { int r = k * 32 + lane; if (r < no) { int p = F(s, F_P)[r]; w = (s == BID) ? min(w, p) : max(w, p); } }
-    w = (s == BID) ? wmin(w) : wmax(w);
-#pragma unroll
-    for (int k = 0; k < SLOTS; ++k) {
-      int r = k * 32 + lane;
-      if (r < no && F(s, F_P)[r] == w) {
-#pragma unroll
-        for (int j = 0; j < 6; ++j) F(s, j)[r] = -1;
-      }
-    }
-    __syncwarp();
-    scan_side_flags(s);  // rare path: rebuild every summary
-  }
-
-  // job:63-83 add_order
-  __device__ __forceinline__ void add_order(int s, const Msg& m) {
-    int r = first_anyneg(s);
-    const bool into_flagged = r != kBig;
-    if (!into_flagged) r = no - 1;
-    const int q = max(0, m.qty);
-    const int oldp = F(s, F_P)[r];
-    const int oldq = F(s, F_Q)[r];
-    const bool old_blank = into_flagged && oldp == -1 && oldq == -1;  // reference-made states: a flagged row is an empty row
-    if (q == 0 && old_blank && !unclean[s]) {
-      // zero remainder written into an empty row and blanked again (job:83): a no-op when the row is all -1
-      const bool all_blank = (F(s, F_OID)[r] == -1) & (F(s, F_TID)[r] == -1) & (F(s, F_TS)[r] == -1) & (F(s, F_TNS)[r] == -1);
-      if (all_blank) return;
-    }
-    __syncwarp();
-    if (lane_id() == (r & 31)) {
-      F(s, F_P)[r] = m.price; F(s, F_Q)[r] = q; F(s, F_OID)[r] = m.oid;
-      F(s, F_TID)[r] = m.tid; F(s, F_TS)[r] = m.ts; F(s, F_TNS)[r] = m.tns;
-    }
-    const bool any = (m.price == -1) | (q == -1) | (m.oid == -1) | (m.tid == -1) | (m.ts == -1) | (m.tns == -1);
-    set_flag(s, r, any);
-    nneg[s] += (m.price < 0) - (oldp < 0);
-    if (valid[s]) {
-      const int bp = bestp[s];
-      if (!old_blank || m.price < 0 || bp == -1) valid[s] = false;
-      else {
-        const bool better = (s == ASK) ? (m.price < bp) : (m.price > bp);
-        if (better) { bestp[s] = m.price; bestq[s] = q; bestn[s] = 1; }
-        else if (m.price == bp) { bestq[s] += q; bestn[s] += 1; }
-      }
-    }
-    __syncwarp();
-    finish_side(s, r, m.price, q);
-  }
-
-  // job:358-420 bid_lim (own = BID) / job:447-508 ask_lim (own = ASK)
-  __device__ __forceinline__ void limit_order(int own, Msg m) {
-    const int opp = 1 - own;
-    if (own == ASK && t4 == 2) m.price = 0;            // job:471-472
-    int qtm = m.qty;
-    match_against(opp, qtm, m.price, m);
-    if (own == BID && t4 == 2) m.price = maxint;       // job:391-392
-    m.qty = qtm;
-    if (check_fill) evict_if_full(own);
-    if (m.type == 4 && t4 != 1) return;                // job:415-418 / 503-506: IOC remainder dropped, eviction kept
-    add_order(own, m);
-  }
-
-  // job:94-139 cancel_order (+ get_init_id_match)
-  __device__ __forceinline__ void cancel_order(int s, const Msg& m) {
+  // job:94-139 cancel_order, order-id hit on a live row; anything else is generic
+  template <int S>
+  __device__ __forceinline__ void cancel(const Msg& m) {
     const int lane = lane_id();
     int idx = kBig;
 #pragma unroll
-    for (int k = SLOTS - 1; k >= 0; --k) { int r = k * 32 + lane; if (r < no && F(s, F_OID)[r] == m.oid) idx = r; }
+    for (int k = SLOTS - 1; k >= 0; --k) { const int r = k * 32 + lane; if (row(S, r)[F_OID] == m.oid) idx = r; }
     idx = wmin(idx);
-    if (idx == kBig) {
-#pragma unroll
-      for (int k = SLOTS - 1; k >= 0; --k) {
-        int r = k * 32 + lane;
-        if (r < no) {
-          int o = F(s, F_OID)[r];
-          if (F(s, F_P)[r] == m.price && o <= init_id && o >= init_lo && F(s, F_Q)[r] >= m.qty) idx = r;
-        }
-      }
-      idx = wmin(idx);
-      if (idx == kBig) idx = no - 1;                   // JAX normalises index -1: the LAST row loses quantity
+    int2 pq = make_int2(-1, -1);
+    if (idx < c.no) pq = *reinterpret_cast<const int2*>(row(S, idx));
+    if (idx >= c.no || pq.x == -1) {        // no such order (or a blank row "matched" oid -1): literal search
+      __syncwarp();
+      g_cancel(c, S, m);
+      scan_side(S);
+      return;
     }
-    const int rp = F(s, F_P)[idx], oq = F(s, F_Q)[idx];
-    const int nq = oq - m.qty;
-    __syncwarp();
-    if (lane == (idx & 31)) F(s, F_Q)[idx] = nq;
-    if (valid[s]) { if (bestp[s] == -1) valid[s] = false; else if (rp == bestp[s]) bestq[s] += nq - oq; }
-    __syncwarp();
-    finish_side(s, idx, rp, nq);
+    const int nq = pq.y - m.qty;
+    if (nq > 0) {
+      if (lane == (idx & 31)) row(S, idx)[F_Q] = nq;
+      if (valid[S] && pq.x == bestp[S]) bestq[S] -= m.qty;
+    } else {
+      blank_live<S>(idx, pq.x, pq.y);
+    }
   }
 
   // job:556-637 cond_type_side (GENERAL_EXCHANGE)
@@ -362,21 +492,14 @@ struct Book {
     m.type = lo.x; m.side = (lo.x == 4) ? -lo.y : lo.y; m.qty = lo.z; m.price = lo.w;
     m.oid = hi.x; m.tid = hi.y; m.ts = hi.z; m.tns = hi.w;
     const int s = m.side, t = m.type;
+    if (s == 0 && t == 0) return;                          // doNothing
+    if (odd[ASK] | odd[BID] | tr_odd | (c.t4 == 2)) { generic(m); return; }
     const bool lim = (t == 1) | (t == 4), cnl = (t == 2) | (t == 3);
-    if (s == 1 && lim) limit_order(BID, m);
-    else if (s == -1 && cnl) cancel_order(ASK, m);
-    else if (s == 1 && cnl) cancel_order(BID, m);
-    else if (s == 0 && t == 0) { /* doNothing */ }
-    else limit_order(ASK, m);                          // index 0 is also the lax.switch target of every other (type, side)
-  }
-
-  // job:920-930 get_volume
-  __device__ __forceinline__ int volume(int s) const {
-    const int lane = lane_id();
-    int v = 0;
-#pragma unroll
-    for (int k = 0; k < SLOTS; ++k) { int r = k * 32 + lane; if (r < no && F(s, F_P)[r] != -1) v += F(s, F_Q)[r]; }
-    return wsum(v);
+    if (cnl & (s == -1)) cancel<ASK>(m);
+    else if (cnl & (s == 1)) cancel<BID>(m);
+    else if (lim & (s == 1)) limit<BID>(m);
+    else limit<ASK>(m);                                    // index 0 is also the lax.switch target of every other (type, side)
+    __syncwarp();
   }
 };
 

@@ -46,12 +46,22 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
                "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
-// generic-proxy accesses of a buffer -> ordered before the async proxy overwrites it
+__device__ __forceinline__ void bulk_s2g(void* dst_gmem, const void* src_smem, unsigned bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// the issuing thread's bulk stores have finished READING shared memory (the buffer may be overwritten)
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// ... and have fully completed (before the kernel exits)
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// generic-proxy accesses of a buffer -> ordered before the async proxy reads / overwrites it
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // ---- shared-memory layout of one warp (in 32-bit words) -----------------------------------------------------
 struct WarpLayout {
-  int book;      // 12 * no
+  int book;      // 2 sides * nrows * 6 (nrows = SLOTS * 32, padded with blank rows)
   int trades;    // 8 * nt
   int msgs;      // step: N * 8 ; replay: 2 * kReplayChunk * 8      (16-byte aligned)
   int act;       // step: n_act * 8
@@ -59,10 +69,10 @@ struct WarpLayout {
   int bar;       // 2 mbarriers (4 words, 8-byte aligned)
   int words;     // per-warp total, multiple of 4
 };
-__host__ __device__ inline WarpLayout make_layout(int no, int nt, int msg_words, int n_act) {
+__host__ __device__ inline WarpLayout make_layout(int nrows, int nt, int msg_words, int n_act) {
   WarpLayout L;
   int o = 0;
-  L.book = o; o += 12 * no;
+  L.book = o; o += 12 * nrows;
   o = (o + 3) & ~3;
   L.trades = o; o += 8 * nt;
   o = (o + 3) & ~3;
@@ -89,12 +99,13 @@ lob_replay_kernel(const __grid_constant__ LobBookConfig cfg, const __grid_consta
   int* mbuf = ws + L.msgs;
   if (lane == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); }
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  __syncwarp();
-  unsigned phase[2] = {0u, 0u};
+  unsigned ph0 = 0u, ph1 = 0u;
 
   Book<SLOTS> bk;
   bk.init(cfg, ws + L.book, ws + L.trades);
   const int no = cfg.n_orders, nt = cfg.n_trades;
+  const bool bulk_books = (no & 1) == 0;   // a side is no*24 bytes: 16-byte granular iff no is even
+  const unsigned side_bytes = (unsigned)no * 24u, tr_bytes = (unsigned)nt * 32u;
   const long long stride = (long long)gridDim.x * kWarps;
   for (long long b = (long long)blockIdx.x * kWarps + warp; b < n_books; b += stride) {
     long long st = B.start[b];
@@ -103,51 +114,63 @@ lob_replay_kernel(const __grid_constant__ LobBookConfig cfg, const __grid_consta
     if (st < 0 || avail <= 0) T = 0; else if (avail < T) T = (int)avail;
     const int* src = B.msgs + st * 8;
     const int nch = (T + kReplayChunk - 1) / kReplayChunk;
-    if (nch > 0 && lane == 0) {
-      const int n0 = min(T, kReplayChunk);
+    // ---- stage book + trade log + first message chunk: one mbarrier phase ----
+    if (lane == 0) {
+      bulk_wait_read();          // the previous book's bulk stores have drained this warp's buffers
       fence_async_smem();
-      mbar_expect_tx(&bar[0], n0 * 32);
-      bulk_g2s(mbuf, src, n0 * 32, &bar[0]);
+      const unsigned n0 = (unsigned)min(T, kReplayChunk) * 32u;
+      mbar_expect_tx(&bar[0], (bulk_books ? 2u * side_bytes : 0u) + tr_bytes + n0);
+      if (bulk_books) {
+        bulk_g2s(bk.side_base(ASK), B.asks + b * no * 6, side_bytes, &bar[0]);
+        bulk_g2s(bk.side_base(BID), B.bids + b * no * 6, side_bytes, &bar[0]);
+      }
+      bulk_g2s(bk.c.tr, B.trades + b * nt * 8, tr_bytes, &bar[0]);
+      if (n0) bulk_g2s(mbuf, src, n0, &bar[0]);
     }
-    bk.load_side(ASK, B.asks + b * no * 6);
-    bk.load_side(BID, B.bids + b * no * 6);
-    bk.load_trades(B.trades + b * nt * 8);
     __syncwarp();
-    bk.scan_side_flags(ASK);
-    bk.scan_side_flags(BID);
-    bk.scan_trade_flags();
+    if (!bulk_books) { bk.load_side(ASK, B.asks + b * no * 6); bk.load_side(BID, B.bids + b * no * 6); }
+    mbar_wait(&bar[0], ph0);
+    ph0 ^= 1u;
+    __syncwarp();
+    bk.rescan();
     for (int c = 0; c < nch; ++c) {
       const int cur = c & 1;
       if (c + 1 < nch) {  // prefetch the next chunk into the other buffer (all lanes are done reading it)
         __syncwarp();
         if (lane == 0) {
-          const int n1 = min(T - (c + 1) * kReplayChunk, kReplayChunk);
+          const unsigned n1 = (unsigned)min(T - (c + 1) * kReplayChunk, kReplayChunk) * 32u;
           fence_async_smem();
-          mbar_expect_tx(&bar[cur ^ 1], n1 * 32);
-          bulk_g2s(mbuf + (cur ^ 1) * kReplayChunk * 8, src + (long long)(c + 1) * kReplayChunk * 8, n1 * 32,
-                   &bar[cur ^ 1]);
+          mbar_expect_tx(&bar[cur ^ 1], n1);
+          bulk_g2s(mbuf + (cur ^ 1) * kReplayChunk * 8, src + (long long)(c + 1) * kReplayChunk * 8, n1, &bar[cur ^ 1]);
         }
       }
-      mbar_wait(&bar[cur], phase[cur]);
-      phase[cur] ^= 1u;
+      if (c > 0) {   // chunk 0 arrived with the book
+        if (cur) { mbar_wait(&bar[1], ph1); ph1 ^= 1u; } else { mbar_wait(&bar[0], ph0); ph0 ^= 1u; }
+      }
       const int n = min(T - c * kReplayChunk, kReplayChunk);
       const int4* m4 = reinterpret_cast<const int4*>(mbuf + cur * kReplayChunk * 8);
+#pragma unroll 1
       for (int i = 0; i < n; ++i) bk.process(m4[2 * i], m4[2 * i + 1]);
     }
     __syncwarp();
     if (B.best_out) {
-      bk.recompute(ASK);
-      bk.recompute(BID);
-      if (lane == 0) {
-        int4 o = make_int4(bk.bestp[ASK], bk.bestq[ASK], bk.bestp[BID], bk.bestq[BID]);
-        *reinterpret_cast<int4*>(B.best_out + b * 4) = o;
-      }
+      const Best a = g_best(bk.c, ASK), d = g_best(bk.c, BID);
+      if (lane == 0) *reinterpret_cast<int4*>(B.best_out + b * 4) = make_int4(a.p, a.q, d.p, d.q);
     }
-    bk.store_side(ASK, B.asks + b * no * 6);
-    bk.store_side(BID, B.bids + b * no * 6);
-    bk.store_trades(B.trades + b * nt * 8);
+    // ---- write back: same layout in HBM, so the bulk-copy engine does it ----
+    if (!bulk_books) { bk.store_side(ASK, B.asks + b * no * 6); bk.store_side(BID, B.bids + b * no * 6); }
+    fence_async_smem();
     __syncwarp();
+    if (lane == 0) {
+      if (bulk_books) {
+        bulk_s2g(B.asks + b * no * 6, bk.side_base(ASK), side_bytes);
+        bulk_s2g(B.bids + b * no * 6, bk.side_base(BID), side_bytes);
+      }
+      bulk_s2g(B.trades + b * nt * 8, bk.c.tr, tr_bytes);
+      bulk_commit();
+    }
   }
+  if (lane == 0) bulk_wait_all();
 }
 
 // ================================================================================================== step ====
@@ -194,7 +217,7 @@ __device__ __forceinline__ int obs_dim_of(const LobAgentTypeConfig& a) {
 // marl_env.py:130-207 reset_env for env e: the precomputed state of window reset_window[e] replaces every leaf.
 // The book / trade log are left in shared memory (the caller stores them); everything else is written here.
 template <int SLOTS>
-__device__ __forceinline__ void reset_env(const LobStepConfig& c, const LobStepBuffers& b, long long e, Book<SLOTS>& bk,
+__device__ __noinline__ void reset_env(const LobStepConfig& c, const LobStepBuffers& b, long long e, Book<SLOTS>& bk,
                                           int N) {
   const int lane = lane_id();
   const int no = c.book.n_orders, nt = c.book.n_trades, T = c.n_agent_types;
@@ -206,9 +229,8 @@ __device__ __forceinline__ void reset_env(const LobStepConfig& c, const LobStepB
   bk.load_side(BID, b.init_bids + (long long)wdx * no * 6);
   bk.load_trades(b.init_trades + (long long)wdx * nt * 8);
   __syncwarp();
-  bk.recompute(ASK);   // marl:157 get_best_bid_and_ask_inclQuants
-  bk.recompute(BID);
-  const int ap = bk.bestp[ASK], aq = bk.bestq[ASK], bp = bk.bestp[BID], bq = bk.bestq[BID];
+  const Best ba = g_best(bk.c, ASK), bb = g_best(bk.c, BID);   // marl:157 get_best_bid_and_ask_inclQuants
+  const int ap = ba.p, aq = ba.q, bp = bb.p, bq = bb.q;
   int2* ga = reinterpret_cast<int2*>(b.best_asks + e * N * 2);
   int2* gb = reinterpret_cast<int2*>(b.best_bids + e * N * 2);
   for (int i = lane; i < N; i += 32) { ga[i] = make_int2(ap, aq); gb[i] = make_int2(bp, bq); }   // marl:158-159
@@ -259,13 +281,13 @@ lob_step_kernel(const __grid_constant__ LobStepConfig c, const __grid_constant__
   int* scr = ws + L.scratch;
   if (lane == 0) mbar_init(&bar[0], 1);
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  __syncwarp();
   unsigned phase = 0u;
 
   Book<SLOTS> bk;
   bk.init(c.book, ws + L.book, ws + L.trades);
   const int no = c.book.n_orders, nt = c.book.n_trades, Nd = c.n_data_msg_per_step, T = c.n_agent_types;
-  const int tick = c.tick_size;
+  const bool bulk_books = (no & 1) == 0;   // a side is no*24 bytes: 16-byte granular iff no is even
+  const unsigned side_bytes = (unsigned)no * 24u, tr_bytes = (unsigned)nt * 32u;
   const long long stride = (long long)gridDim.x * kWarps;
   for (long long e = (long long)blockIdx.x * kWarps + warp; e < batch; e += stride) {
     // ---- old world state (the reward sees it: marl:462) ----
@@ -281,20 +303,26 @@ lob_step_kernel(const __grid_constant__ LobStepConfig c, const __grid_constant__
     const int oid_counter = b.order_id_counter[e];
     const int window_index = b.window_index[e];
 
-    // ---- (B) base:339-369 data messages: dynamic_slice clamps the start; staged by the bulk-copy engine ----
+    // ---- stage both book sides and (B) the data-message slice (base:339-369; dynamic_slice clamps the start) with
+    //      the bulk-copy engine: one mbarrier phase ----
     {
       long long off = (long long)(int)(start_index + Nd * w.step_counter);
       if (off > c.n_messages - Nd) off = c.n_messages - Nd;
       if (off < 0) off = 0;
-      __syncwarp();
       if (lane == 0) {
+        bulk_wait_read();        // the previous env's bulk stores have drained this warp's buffers
         fence_async_smem();
-        mbar_expect_tx(&bar[0], Nd * 32);
-        bulk_g2s(msgs + (n_cnl + n_act) * 8, b.message_data + off * 8, Nd * 32, &bar[0]);
+        mbar_expect_tx(&bar[0], (bulk_books ? 2u * side_bytes : 0u) + (unsigned)Nd * 32u);
+        if (bulk_books) {
+          bulk_g2s(bk.side_base(ASK), b.asks + e * no * 6, side_bytes, &bar[0]);
+          bulk_g2s(bk.side_base(BID), b.bids + e * no * 6, side_bytes, &bar[0]);
+        }
+        bulk_g2s(msgs + (n_cnl + n_act) * 8, b.message_data + off * 8, (unsigned)Nd * 32u, &bar[0]);
       }
+      __syncwarp();
     }
-    bk.load_side(ASK, b.asks + e * no * 6);
-    bk.load_side(BID, b.bids + e * no * 6);
+    if (!bulk_books) { bk.load_side(ASK, b.asks + e * no * 6); bk.load_side(BID, b.bids + e * no * 6); }
+    bk.fill_trades_empty();      // marl:348: the trade log is re-initialised every step
     w.extreme_spread = false;
     if (need_extreme) {   // mm:2545-2553 over the OLD per-message bests
       bool any = false;
@@ -305,9 +333,11 @@ lob_step_kernel(const __grid_constant__ LobStepConfig c, const __grid_constant__
       }
       w.extreme_spread = __any_sync(kFull, any);
     }
+    mbar_wait(&bar[0], phase);
+    phase ^= 1u;
     __syncwarp();
-    bk.scan_side_flags(ASK);
-    bk.scan_side_flags(BID);
+    bk.scan_side(ASK);
+    bk.scan_side(BID);
 
     // ---- (C) marl:254-315 agent messages: [cancels | permuted actions | data] ----
     {
@@ -321,14 +351,14 @@ lob_step_kernel(const __grid_constant__ LobStepConfig c, const __grid_constant__
           const int action = b.actions[t][idx];
           if (ac.kind == LOB_AGENT_MM) {
             const int inventory = b.agent_i32[t][2][idx];
-            MMOut o = mm_get_messages(bk, c, ac, action, w, inventory, tid, act_all + ai * 8, msgs + ci * 8);
+            MMOut o = mm_get_messages(bk.c, c, ac, action, w, inventory, tid, act_all + ai * 8, msgs + ci * 8);
             if (lane == 0) {
               int* s = scr + flat * 8;
               s[0] = o.posted_bid_price; s[1] = o.posted_ask_price; s[2] = o.bid_dist; s[3] = o.ask_dist;
               s[4] = o.bid_quant; s[5] = o.ask_quant;
             }
           } else {
-            exe_get_messages(bk, c, ac, action, w, b.agent_i32[t][0][idx], b.agent_i32[t][1][idx],
+            exe_get_messages(bk.c, c, ac, action, w, b.agent_i32[t][0][idx], b.agent_i32[t][1][idx],
                              b.agent_i32[t][2][idx], tid, act_all + ai * 8, msgs + ci * 8);
           }
           ci += kc; ai += ka;
@@ -344,9 +374,6 @@ lob_step_kernel(const __grid_constant__ LobStepConfig c, const __grid_constant__
         msgs[(n_cnl + i) * 8 + k] = act_all[src * 8 + k];
       }
     }
-    bk.fill_trades_empty();
-    mbar_wait(&bar[0], phase);
-    phase ^= 1u;
     __syncwarp();
 
     // ---- (D) marl:348-364 the scan, with the per-message best bid/ask (job:792-823) and the forward fill ----
@@ -356,6 +383,7 @@ lob_step_kernel(const __grid_constant__ LobStepConfig c, const __grid_constant__
     {
       const int4* m4 = reinterpret_cast<const int4*>(msgs);
       int2* gq = reinterpret_cast<int2*>((lane == 0 ? b.best_asks : b.best_bids) + e * N * 2);
+#pragma unroll 1
       for (int i = 0; i < N; ++i) {
         bk.process(m4[2 * i], m4[2 * i + 1]);
         bk.ensure(ASK);
@@ -396,7 +424,7 @@ lob_step_kernel(const __grid_constant__ LobStepConfig c, const __grid_constant__
           float* obs = b.obs[t] + idx * d;
           if (ac.kind == LOB_AGENT_MM) {
             MMState s; load_mm_state(b, t, idx, s);
-            const MMReward R = mm_get_reward(bk.tr, nt, c, ac, w, so, s, tid);
+            const MMReward R = mm_get_reward(bk.c.tr, nt, c, ac, w, so, s, tid);
             const int* x = scr + flat * 8;
             MMState ns;   // mm:2677-2736
             ns.posted_distance_bid = x[2]; ns.posted_distance_ask = x[3];
@@ -421,7 +449,7 @@ lob_step_kernel(const __grid_constant__ LobStepConfig c, const __grid_constant__
               mm_write_obs(ac, obs, ns.inventory, new_mid, so.ba_last, so.bb_last, vol_a, vol_b, new_step, false);
           } else {
             EXEState s; load_exe_state(b, t, idx, s);
-            const EXEReward R = exe_get_reward(bk.tr, nt, c, ac, w, so, s, tid);
+            const EXEReward R = exe_get_reward(bk.c.tr, nt, c, ac, w, so, s, tid);
             EXEState ns = s;   // exe:1771-1839
             ns.quant_executed = s.quant_executed + R.agentQuant;
             ns.p_vwap = R.p_vwap;
@@ -467,12 +495,20 @@ lob_step_kernel(const __grid_constant__ LobStepConfig c, const __grid_constant__
       b.delta_time[e] = new_dt;
     }
     __syncwarp();
-    bk.store_side(ASK, b.asks + e * no * 6);
-    bk.store_side(BID, b.bids + e * no * 6);
-    bk.store_trades(b.trades + e * nt * 8);
+    // ---- write back: same layout in HBM, so the bulk-copy engine does it ----
+    if (!bulk_books) { bk.store_side(ASK, b.asks + e * no * 6); bk.store_side(BID, b.bids + e * no * 6); }
+    fence_async_smem();
     __syncwarp();
+    if (lane == 0) {
+      if (bulk_books) {
+        bulk_s2g(b.asks + e * no * 6, bk.side_base(ASK), side_bytes);
+        bulk_s2g(b.bids + e * no * 6, bk.side_base(BID), side_bytes);
+      }
+      bulk_s2g(b.trades + e * nt * 8, bk.c.tr, tr_bytes);
+      bulk_commit();
+    }
   }
-  (void)tick;
+  if (lane == 0) bulk_wait_all();
 }
 
 // ================================================================================================= reset ====
