@@ -44,7 +44,7 @@ struct Msg {
 // What the generic functions need, passed BY VALUE (all warp-uniform) so that no book state has its address taken.
 struct BookCtx {
   int* rows;   // shared memory: row r of side s at rows + (s * nrows + r) * 6
-  int* tr;     // shared memory trade log, row r at tr + r * 8
+  int* tr;     // trade log of the current environment (worked on in place in global memory), row r at tr + r * 8
   int nrows;   // rows allocated per side (SLOTS * 32 >= no)
   int no, nt;
   int maxint, init_id, init_lo, t4, check_fill;
@@ -56,6 +56,7 @@ struct Best { int p, q, n; };
 // =============================================================================== generic (literal) path ========
 // job:86-90
 static __device__ __noinline__ void g_remove_zero_neg(BookCtx c, int s) {
+  _Pragma("unroll 1")
   for (int r = lane_id(); r < c.no; r += 32) {
     int* p = rowp(c, s, r);
     if (p[F_Q] <= 0) {
@@ -68,6 +69,7 @@ static __device__ __noinline__ void g_remove_zero_neg(BookCtx c, int s) {
 // job:73 jnp.where(orderside == -1, size=1, fill_value=-1)[0]: first row (row-major) holding a -1, else kBig
 static __device__ __noinline__ int g_first_flagged(BookCtx c, int s) {
   int f = kBig;
+  _Pragma("unroll 1")
   for (int r = lane_id(); r < c.no; r += 32) {
     const int* p = rowp(c, s, r);
     const bool any = (p[0] == -1) | (p[1] == -1) | (p[2] == -1) | (p[3] == -1) | (p[4] == -1) | (p[5] == -1);
@@ -90,10 +92,12 @@ static __device__ __noinline__ void g_add(BookCtx c, int s, Msg m) {
 // job:94-139 cancel_order + get_init_id_match (cancel_mode 0/1)
 static __device__ __noinline__ void g_cancel(BookCtx c, int s, Msg m) {
   int idx = kBig;
+  _Pragma("unroll 1")
   for (int r = lane_id(); r < c.no; r += 32)
     if (rowp(c, s, r)[F_OID] == m.oid) idx = min(idx, r);
   idx = wmin(idx);
   if (idx == kBig) {
+    _Pragma("unroll 1")
     for (int r = lane_id(); r < c.no; r += 32) {
       const int* p = rowp(c, s, r);
       if (p[F_P] == m.price && p[F_OID] <= c.init_id && p[F_OID] >= c.init_lo && p[F_Q] >= m.qty) idx = min(idx, r);
@@ -110,18 +114,21 @@ static __device__ __noinline__ void g_cancel(BookCtx c, int s, Msg m) {
 static __device__ __noinline__ int g_top(BookCtx c, int s) {
   const int lane = lane_id();
   int ext = (s == BID) ? INT32_MIN : c.maxint;
+  _Pragma("unroll 1")
   for (int r = lane; r < c.no; r += 32) {
     const int p = rowp(c, s, r)[F_P];
     ext = (s == BID) ? max(ext, p) : min(ext, p == -1 ? c.maxint : p);
   }
   ext = (s == BID) ? wmax(ext) : wmin(ext);
   int mt = c.maxint;
+  _Pragma("unroll 1")
   for (int r = lane; r < c.no; r += 32) {
     const int* p = rowp(c, s, r);
     mt = min(mt, p[F_P] == ext ? p[F_TS] : c.maxint);
   }
   mt = wmin(mt);
   int mn = c.maxint;
+  _Pragma("unroll 1")
   for (int r = lane; r < c.no; r += 32) {
     const int* p = rowp(c, s, r);
     const int t = p[F_P] == ext ? p[F_TS] : c.maxint;
@@ -129,6 +136,7 @@ static __device__ __noinline__ int g_top(BookCtx c, int s) {
   }
   mn = wmin(mn);
   int idx = kBig;
+  _Pragma("unroll 1")
   for (int r = lane; r < c.no; r += 32) {
     const int* p = rowp(c, s, r);
     const int t = p[F_P] == ext ? p[F_TS] : c.maxint;
@@ -151,6 +159,7 @@ static __device__ __noinline__ int g_match(BookCtx c, int opp, Msg m, int qtm) {
     const int newq = max(0, oq - qtm);
     qtm = qtm - oq;
     int e = kBig;   // job:205: first trade row whose column 4 (time_s) is -1, else the last row (quirk Q3)
+    _Pragma("unroll 1")
     for (int r = lane; r < c.nt; r += 32)
       if (c.tr[r * 8 + 4] == -1) e = min(e, r);
     e = wmin(e);
@@ -172,6 +181,7 @@ static __device__ __noinline__ void g_evict(BookCtx c, int s) {
   const int lane = lane_id();
   int w = (s == BID) ? INT32_MAX : INT32_MIN;
   bool neg = false;
+  _Pragma("unroll 1")
   for (int r = lane; r < c.no; r += 32) {
     const int p = rowp(c, s, r)[F_P];
     neg |= p < 0;
@@ -179,6 +189,7 @@ static __device__ __noinline__ void g_evict(BookCtx c, int s) {
   }
   if (__any_sync(kFull, neg)) return;
   w = (s == BID) ? wmin(w) : wmax(w);
+  _Pragma("unroll 1")
   for (int r = lane; r < c.no; r += 32) {
     int* p = rowp(c, s, r);
     if (p[F_P] == w) {
@@ -215,15 +226,18 @@ static __device__ __noinline__ Best g_best(BookCtx c, int s) {
   int bp;
   if (s == ASK) {
     int mn = c.maxint;
+    _Pragma("unroll 1")
     for (int r = lane; r < c.no; r += 32) { const int p = rowp(c, ASK, r)[F_P]; mn = min(mn, p == -1 ? c.maxint : p); }
     mn = wmin(mn);
     bp = (mn == c.maxint) ? -1 : mn;
   } else {
     int mx = INT32_MIN;
+    _Pragma("unroll 1")
     for (int r = lane; r < c.no; r += 32) mx = max(mx, rowp(c, BID, r)[F_P]);
     bp = wmax(mx);
   }
   int q = 0, n = 0;
+  _Pragma("unroll 1")
   for (int r = lane; r < c.no; r += 32) {
     const int2 pq = *reinterpret_cast<const int2*>(rowp(c, s, r));
     if (pq.x == bp) { q += pq.y; n += 1; }
@@ -235,11 +249,47 @@ static __device__ __noinline__ Best g_best(BookCtx c, int s) {
 // job:920-930 get_volume
 static __device__ __noinline__ int g_volume(BookCtx c, int s) {
   int v = 0;
+  _Pragma("unroll 1")
   for (int r = lane_id(); r < c.no; r += 32) {
     const int2 pq = *reinterpret_cast<const int2*>(rowp(c, s, r));
     if (pq.x != -1) v += pq.y;
   }
   return wsum(v);
+}
+
+// Summaries of one side rebuilt from shared memory: per-lane flag mask (bit k <-> row k*32+lane holds a -1), number of
+// rows with a negative price, and whether the side holds rows the fast paths do not model.
+struct SideScan { unsigned flag; int nneg; int odd; };
+static __device__ __noinline__ SideScan g_scan_side(BookCtx c, int s) {
+  const int lane = lane_id();
+  unsigned m = 0; int neg = 0; bool od = false;
+  _Pragma("unroll 1")
+  for (int r = lane, k = 0; r < c.no; r += 32, ++k) {
+    const int2* p = reinterpret_cast<const int2*>(rowp(c, s, r));
+    const int2 a = p[0], b = p[1], d = p[2];
+    const bool any = (a.x == -1) | (a.y == -1) | (b.x == -1) | (b.y == -1) | (d.x == -1) | (d.y == -1);
+    const bool all = (a.x == -1) & (a.y == -1) & (b.x == -1) & (b.y == -1) & (d.x == -1) & (d.y == -1);
+    if (any) m |= 1u << k;
+    neg += (a.x < 0);
+    od |= (!all) & (any | (a.y <= 0));
+  }
+  SideScan r;
+  r.flag = m; r.nneg = wsum(neg); r.odd = __any_sync(kFull, od) ? 1 : 0;
+  return r;
+}
+// first trade row whose time_s column is -1 (nt if none) and whether a later row is filled there
+struct TradeScan { int ntr; int odd; };
+static __device__ __noinline__ TradeScan g_scan_trades(BookCtx c) {
+  int first = kBig, last_filled = -1;
+  _Pragma("unroll 1")
+  for (int r = lane_id(); r < c.nt; r += 32) {
+    if (c.tr[r * 8 + 4] == -1) first = min(first, r); else last_filled = max(last_filled, r);
+  }
+  first = wmin(first); last_filled = wmax(last_filled);
+  TradeScan t;
+  t.ntr = (first == kBig) ? c.nt : first;
+  t.odd = last_filled >= t.ntr ? 1 : 0;
+  return t;
 }
 
 // ======================================================================================= fast path =============
@@ -255,8 +305,8 @@ struct Book {
   int ntr;            // next trade row: first row whose time_s column is -1
   bool tr_odd;        // the rows after ntr are not all free -> the trade slot must be searched (generic path)
 
-  __device__ __forceinline__ void init(const LobBookConfig& cfg, int* smem_book, int* smem_trades) {
-    c.rows = smem_book; c.tr = smem_trades; c.nrows = kRows;
+  __device__ __forceinline__ void init(const LobBookConfig& cfg, int* smem_book) {
+    c.rows = smem_book; c.tr = nullptr; c.nrows = kRows;
     c.no = cfg.n_orders; c.nt = cfg.n_trades;
     c.maxint = cfg.maxint; c.init_id = cfg.init_id; c.init_lo = cfg.init_id - 2 * cfg.book_depth;
     c.t4 = cfg.type_4_interpretation; c.check_fill = cfg.check_book_fill;
@@ -296,36 +346,12 @@ struct Book {
 
   // ---- derive the register-resident summaries from shared memory ----
   __device__ __forceinline__ void scan_side(int s) {
-    const int lane = lane_id();
-    unsigned m = 0; int neg = 0; bool od = false;
-#pragma unroll
-    for (int k = 0; k < SLOTS; ++k) {
-      const int r = k * 32 + lane;
-      if (r < c.no) {
-        const int2* p = reinterpret_cast<const int2*>(row(s, r));
-        const int2 a = p[0], b = p[1], d = p[2];
-        const bool any = (a.x == -1) | (a.y == -1) | (b.x == -1) | (b.y == -1) | (d.x == -1) | (d.y == -1);
-        const bool all = (a.x == -1) & (a.y == -1) & (b.x == -1) & (b.y == -1) & (d.x == -1) & (d.y == -1);
-        if (any) m |= 1u << k;
-        neg += (a.x < 0);
-        od |= (!all) & (any | (a.y <= 0));
-      }
-    }
-    flag[s] = m;
-    nneg[s] = wsum(neg);
-    odd[s] = __any_sync(kFull, od);
-    valid[s] = false;
+    const SideScan r = g_scan_side(c, s);
+    flag[s] = r.flag; nneg[s] = r.nneg; odd[s] = r.odd != 0; valid[s] = false;
   }
   __device__ __forceinline__ void scan_trades() {
-    // ntr = first row with time_s == -1; tr_odd iff some later row is filled there
-    const int lane = lane_id();
-    int first = kBig, last_filled = -1;
-    for (int r = lane; r < c.nt; r += 32) {
-      if (c.tr[r * 8 + 4] == -1) first = min(first, r); else last_filled = max(last_filled, r);
-    }
-    first = wmin(first); last_filled = wmax(last_filled);
-    ntr = (first == kBig) ? c.nt : first;
-    tr_odd = last_filled >= ntr;
+    const TradeScan t = g_scan_trades(c);
+    ntr = t.ntr; tr_odd = t.odd != 0;
   }
   __device__ __forceinline__ void rescan() { scan_side(ASK); scan_side(BID); scan_trades(); }
 

@@ -9,7 +9,7 @@ namespace lobhost {
 
 template <int S>
 int launch_replay(const LobBookConfig* cfg, const LobReplayBuffers* bufs, int64_t n_books, cudaStream_t st, const DevInfo& d) {
-  const lob::WarpLayout L = lob::make_layout(S * 32, cfg->n_trades, 2 * lob::kReplayChunk * 8, 0);
+  const lob::WarpLayout L = lob::make_layout(S * 32, 2 * lob::kReplayChunk * 8, 0);
   const size_t smem = (size_t)L.words * 4 * lob::kWarps;
   int per_sm = 1;
   int rc = prepare(lob::lob_replay_kernel<S>, smem, d, &per_sm);
@@ -21,7 +21,7 @@ int launch_replay(const LobBookConfig* cfg, const LobReplayBuffers* bufs, int64_
 template <int S>
 int launch_step(const LobStepConfig* c, const LobStepBuffers* b, int64_t batch, cudaStream_t st, const DevInfo& d) {
   const int N = lob_num_msgs_per_step(c), n_act = lob_num_action_msgs(c), n_cnl = lob_num_cancel_msgs(c);
-  const lob::WarpLayout L = lob::make_layout(S * 32, c->book.n_trades, N * 8, n_act);
+  const lob::WarpLayout L = lob::make_layout(S * 32, N * 8, n_act);
   if (((n_cnl + n_act) * 8) % 4 != 0) return fail(LOB_E_INVALID, "internal: data slice misaligned");
   const size_t smem = (size_t)L.words * 4 * lob::kWarps;
   int per_sm = 1;
@@ -38,7 +38,7 @@ int launch_step(const LobStepConfig* c, const LobStepBuffers* b, int64_t batch, 
 template <int S>
 int launch_reset(const LobStepConfig* c, const LobStepBuffers* b, int64_t batch, cudaStream_t st, const DevInfo& d) {
   const int N = lob_num_msgs_per_step(c);
-  const lob::WarpLayout L = lob::make_layout(S * 32, c->book.n_trades, 0, 0);
+  const lob::WarpLayout L = lob::make_layout(S * 32, 0, 0);
   const size_t smem = (size_t)L.words * 4 * lob::kWarps;
   int per_sm = 1;
   int rc = prepare(lob::lob_reset_kernel<S>, smem, d, &per_sm);

@@ -17,8 +17,8 @@
 namespace lob {
 
 constexpr int kWarps = 4;            // warps (= environments in flight) per CTA
-constexpr int kReplayChunk = 64;     // messages per staged chunk of the replay kernel (2 KB)
-constexpr int kMaxAgents = 32;       // agents per environment, all types
+constexpr int kReplayChunk = 32;     // messages per staged chunk of the replay kernel (1 KB, double buffered)
+constexpr int kMaxAgents = 16;       // agents per environment, all types
 
 // ---- bulk-copy engine + mbarrier (PTX) ----------------------------------------------------------------------
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -62,19 +62,16 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 // ---- shared-memory layout of one warp (in 32-bit words) -----------------------------------------------------
 struct WarpLayout {
   int book;      // 2 sides * nrows * 6 (nrows = SLOTS * 32, padded with blank rows)
-  int trades;    // 8 * nt
   int msgs;      // step: N * 8 ; replay: 2 * kReplayChunk * 8      (16-byte aligned)
   int act;       // step: n_act * 8
   int scratch;   // step: kMaxAgents * 8
   int bar;       // 2 mbarriers (4 words, 8-byte aligned)
   int words;     // per-warp total, multiple of 4
 };
-__host__ __device__ inline WarpLayout make_layout(int nrows, int nt, int msg_words, int n_act) {
+__host__ __device__ inline WarpLayout make_layout(int nrows, int msg_words, int n_act) {
   WarpLayout L;
   int o = 0;
   L.book = o; o += 12 * nrows;
-  o = (o + 3) & ~3;
-  L.trades = o; o += 8 * nt;
   o = (o + 3) & ~3;
   L.msgs = o; o += msg_words;
   o = (o + 3) & ~3;
@@ -89,7 +86,7 @@ __host__ __device__ inline WarpLayout make_layout(int nrows, int nt, int msg_wor
 // ================================================================================================ replay ====
 // base_env.py:189-216 / job:736-756: book b scans msgs[start[b] .. start[b]+T); the trade log persists.
 template <int SLOTS>
-__global__ void __launch_bounds__(kWarps * 32)
+__global__ void __launch_bounds__(kWarps * 32, (SLOTS <= 4 ? 6 : SLOTS == 8 ? 3 : 1))
 lob_replay_kernel(const __grid_constant__ LobBookConfig cfg, const __grid_constant__ LobReplayBuffers B,
                   long long n_books, WarpLayout L) {
   extern __shared__ __align__(128) int smem[];
@@ -102,10 +99,10 @@ lob_replay_kernel(const __grid_constant__ LobBookConfig cfg, const __grid_consta
   unsigned ph0 = 0u, ph1 = 0u;
 
   Book<SLOTS> bk;
-  bk.init(cfg, ws + L.book, ws + L.trades);
+  bk.init(cfg, ws + L.book);
   const int no = cfg.n_orders, nt = cfg.n_trades;
   const bool bulk_books = (no & 1) == 0;   // a side is no*24 bytes: 16-byte granular iff no is even
-  const unsigned side_bytes = (unsigned)no * 24u, tr_bytes = (unsigned)nt * 32u;
+  const unsigned side_bytes = (unsigned)no * 24u;
   const long long stride = (long long)gridDim.x * kWarps;
   for (long long b = (long long)blockIdx.x * kWarps + warp; b < n_books; b += stride) {
     long long st = B.start[b];
@@ -119,15 +116,15 @@ lob_replay_kernel(const __grid_constant__ LobBookConfig cfg, const __grid_consta
       bulk_wait_read();          // the previous book's bulk stores have drained this warp's buffers
       fence_async_smem();
       const unsigned n0 = (unsigned)min(T, kReplayChunk) * 32u;
-      mbar_expect_tx(&bar[0], (bulk_books ? 2u * side_bytes : 0u) + tr_bytes + n0);
+      mbar_expect_tx(&bar[0], (bulk_books ? 2u * side_bytes : 0u) + n0);
       if (bulk_books) {
         bulk_g2s(bk.side_base(ASK), B.asks + b * no * 6, side_bytes, &bar[0]);
         bulk_g2s(bk.side_base(BID), B.bids + b * no * 6, side_bytes, &bar[0]);
       }
-      bulk_g2s(bk.c.tr, B.trades + b * nt * 8, tr_bytes, &bar[0]);
       if (n0) bulk_g2s(mbuf, src, n0, &bar[0]);
     }
     __syncwarp();
+    bk.c.tr = B.trades + b * nt * 8;   // the trade log is worked on in place (HBM / L2): a row is one 32-byte sector
     if (!bulk_books) { bk.load_side(ASK, B.asks + b * no * 6); bk.load_side(BID, B.bids + b * no * 6); }
     mbar_wait(&bar[0], ph0);
     ph0 ^= 1u;
@@ -166,7 +163,6 @@ lob_replay_kernel(const __grid_constant__ LobBookConfig cfg, const __grid_consta
         bulk_s2g(B.asks + b * no * 6, bk.side_base(ASK), side_bytes);
         bulk_s2g(B.bids + b * no * 6, bk.side_base(BID), side_bytes);
       }
-      bulk_s2g(B.trades + b * nt * 8, bk.c.tr, tr_bytes);
       bulk_commit();
     }
   }
@@ -227,7 +223,8 @@ __device__ __noinline__ void reset_env(const LobStepConfig& c, const LobStepBuff
   __syncwarp();
   bk.load_side(ASK, b.init_asks + (long long)wdx * no * 6);
   bk.load_side(BID, b.init_bids + (long long)wdx * no * 6);
-  bk.load_trades(b.init_trades + (long long)wdx * nt * 8);
+  bk.c.tr = b.trades + e * nt * 8;
+  bk.load_trades(b.init_trades + (long long)wdx * nt * 8);   // straight into the state buffer
   __syncwarp();
   const Best ba = g_best(bk.c, ASK), bb = g_best(bk.c, BID);   // marl:157 get_best_bid_and_ask_inclQuants
   const int ap = ba.p, aq = ba.q, bp = bb.p, bq = bb.q;
@@ -269,7 +266,7 @@ __device__ __noinline__ void reset_env(const LobStepConfig& c, const LobStepBuff
 }
 
 template <int SLOTS>
-__global__ void __launch_bounds__(kWarps * 32)
+__global__ void __launch_bounds__(kWarps * 32, (SLOTS <= 4 ? 5 : SLOTS == 8 ? 3 : 1))
 lob_step_kernel(const __grid_constant__ LobStepConfig c, const __grid_constant__ LobStepBuffers b, long long batch,
                 WarpLayout L, int N, int n_act, int n_cnl, int need_extreme) {
   extern __shared__ __align__(128) int smem[];
@@ -284,10 +281,10 @@ lob_step_kernel(const __grid_constant__ LobStepConfig c, const __grid_constant__
   unsigned phase = 0u;
 
   Book<SLOTS> bk;
-  bk.init(c.book, ws + L.book, ws + L.trades);
+  bk.init(c.book, ws + L.book);
   const int no = c.book.n_orders, nt = c.book.n_trades, Nd = c.n_data_msg_per_step, T = c.n_agent_types;
   const bool bulk_books = (no & 1) == 0;   // a side is no*24 bytes: 16-byte granular iff no is even
-  const unsigned side_bytes = (unsigned)no * 24u, tr_bytes = (unsigned)nt * 32u;
+  const unsigned side_bytes = (unsigned)no * 24u;
   const long long stride = (long long)gridDim.x * kWarps;
   for (long long e = (long long)blockIdx.x * kWarps + warp; e < batch; e += stride) {
     // ---- old world state (the reward sees it: marl:462) ----
@@ -322,7 +319,8 @@ lob_step_kernel(const __grid_constant__ LobStepConfig c, const __grid_constant__
       __syncwarp();
     }
     if (!bulk_books) { bk.load_side(ASK, b.asks + e * no * 6); bk.load_side(BID, b.bids + e * no * 6); }
-    bk.fill_trades_empty();      // marl:348: the trade log is re-initialised every step
+    bk.c.tr = b.trades + e * nt * 8;   // the trade log is worked on in place (HBM / L2): a row is one 32-byte sector
+    bk.fill_trades_empty();            // marl:348: the trade log is re-initialised every step
     w.extreme_spread = false;
     if (need_extreme) {   // mm:2545-2553 over the OLD per-message bests
       bool any = false;
@@ -504,7 +502,6 @@ lob_step_kernel(const __grid_constant__ LobStepConfig c, const __grid_constant__
         bulk_s2g(b.asks + e * no * 6, bk.side_base(ASK), side_bytes);
         bulk_s2g(b.bids + e * no * 6, bk.side_base(BID), side_bytes);
       }
-      bulk_s2g(b.trades + e * nt * 8, bk.c.tr, tr_bytes);
       bulk_commit();
     }
   }
@@ -520,7 +517,7 @@ lob_reset_kernel(const __grid_constant__ LobStepConfig c, const __grid_constant_
   const int warp = threadIdx.x >> 5;
   int* ws = smem + warp * L.words;
   Book<SLOTS> bk;
-  bk.init(c.book, ws + L.book, ws + L.trades);
+  bk.init(c.book, ws + L.book);
   const int no = c.book.n_orders, nt = c.book.n_trades;
   const long long stride = (long long)gridDim.x * kWarps;
   for (long long e = (long long)blockIdx.x * kWarps + warp; e < batch; e += stride) {
@@ -528,7 +525,6 @@ lob_reset_kernel(const __grid_constant__ LobStepConfig c, const __grid_constant_
     __syncwarp();
     bk.store_side(ASK, b.asks + e * no * 6);
     bk.store_side(BID, b.bids + e * no * 6);
-    bk.store_trades(b.trades + e * nt * 8);
     __syncwarp();
   }
 }

@@ -27,8 +27,12 @@
  *   - python scalars are weakly typed (float scalar (+) int32 array -> float32);
  *   - float32 `//` is jnp.floor_divide == round((x - fmod(x,y)) / y) with the
  *     sign fix-up of jax._src.numpy.ufuncs._float_divmod;
- *   - float reductions: XLA leaves the order unspecified; this oracle sums
- *     left-to-right in row order.
+ *   - float reductions: XLA leaves the order unspecified.  Reductions over the
+ *     trade log use ONE fixed order, shared bit for bit with the CUDA path:
+ *     row r is accumulated into partial sum r % 32 in increasing r, then the
+ *     32 partial sums are combined by a butterfly (xor 16, 8, 4, 2, 1) --
+ *     wsumf() below.  The per-message mid-price / best-price means are summed
+ *     left-to-right in message order.
  * Compile: gcc -O2 -fwrapv -ffp-contract=off -fno-fast-math (see Makefile).
  */
 #include <math.h>
@@ -77,6 +81,19 @@ static inline float jmaxf(float a, float b) { return (a != a || b != b) ? NAN : 
 static inline float jminf(float a, float b) { return (a != a || b != b) ? NAN : (a < b ? a : b); }
 /* convert_element_type f32 -> s32 truncates toward zero */
 static inline int32_t f2i(float x) { return (int32_t)x; }
+
+/* The fixed reduction order of float sums over the trade log (see the header): 32 interleaved partial sums, then a
+ * butterfly.  term[r] is the r-th addend. */
+static float wsumf(const float* term, int n) {
+  float acc[32], nxt[32];
+  for (int l = 0; l < 32; ++l) acc[l] = 0.f;
+  for (int r = 0; r < n; ++r) acc[r & 31] = acc[r & 31] + term[r];
+  for (int off = 16; off > 0; off >>= 1) {
+    for (int l = 0; l < 32; ++l) nxt[l] = acc[l] + acc[l ^ off];
+    for (int l = 0; l < 32; ++l) acc[l] = nxt[l];
+  }
+  return acc[0];
+}
 
 /* --------------------------------------------------------- order book core */
 
@@ -553,17 +570,16 @@ static int32_t sum_abs_q(const int32_t* t, int nt) {
   for (int r = 0; r < nt; ++r) s += iabs32(t[r * 8 + 1]);
   return s;
 }
-/* sum_r( f32(p)/tick * |q| ), left to right */
-static float sum_pq_over_tick(const int32_t* t, int nt, int32_t tick) {
-  float s = 0.f;
-  for (int r = 0; r < nt; ++r) s += (float)t[r * 8 + 0] / (float)tick * (float)iabs32(t[r * 8 + 1]);
-  return s;
+/* sum_r( f32(p)/tick * |q| ) in the wsumf order; ft = scratch [nt] */
+static float sum_pq_over_tick(const int32_t* t, int nt, int32_t tick, float* ft) {
+  for (int r = 0; r < nt; ++r) ft[r] = (float)t[r * 8 + 0] / (float)tick * (float)iabs32(t[r * 8 + 1]);
+  return wsumf(ft, nt);
 }
 
 /* mm:2247-2673 get_reward */
 static float mm_get_reward(const LobStepConfig* c, const LobAgentTypeConfig* ac, const World* w /* OLD world */,
                            const MMState* st, int32_t tid, const int32_t* trades_in, const int32_t* bestasks,
-                           const int32_t* bestbids, int ep_done, int32_t* tmp /* 6*Nt*8 */, MMExtras* ex) {
+                           const int32_t* bestbids, int ep_done, int32_t* tmp /* 6*Nt*8 + 2*Nt */, MMExtras* ex) {
   const int nt = c->book.n_trades, N = lob_num_msgs_per_step(c);
   const int32_t tick = c->tick_size;
   const float tickf = (float)tick;
@@ -595,12 +611,13 @@ static float mm_get_reward(const LobStepConfig* c, const LobAgentTypeConfig* ac,
 
   extract_agent_trade_stats(trades, nt, tid, &s);
   float mid_price_end = (float)(bb_last + ba_last) / 2.0f;
-  float income = sum_pq_over_tick(s.agent_sells, nt, tick);
-  float outgoing = sum_pq_over_tick(s.agent_buys, nt, tick);
+  float* ft = (float*)(tmp + 6 * nt * 8); /* [2*nt] float scratch */
+  float income = sum_pq_over_tick(s.agent_sells, nt, tick, ft);
+  float outgoing = sum_pq_over_tick(s.agent_buys, nt, tick, ft);
   buyQuant = sum_abs_q(s.agent_buys, nt);
   sellQuant = sum_abs_q(s.agent_sells, nt);
   int32_t new_inventory = st->inventory + buyQuant - sellQuant;
-  float rebate_value = sum_pq_over_tick(s.pass_buys, nt, tick) + sum_pq_over_tick(s.pass_sells, nt, tick);
+  float rebate_value = sum_pq_over_tick(s.pass_buys, nt, tick, ft) + sum_pq_over_tick(s.pass_sells, nt, tick, ft);
   float rebate_income = rebate_value * (float)(ac->rebate_bps / 10000.0);
 
   /* reference prices mm:2373-2396: float32 for mid / mid_avg, int32 for touch prices */
@@ -622,13 +639,13 @@ static float mm_get_reward(const LobStepConfig* c, const LobAgentTypeConfig* ac,
   float market_share = (float)TradedVolume / (float)(TradedVolume + other_exec_quants);
 
   float InventoryPnL = ((float)st->inventory * (mid_price_end - w->mid_price)) / tickf; /* mm:2414 */
-  float buyPnL = 0.f, sellPnL = 0.f;
   for (int r = 0; r < nt; ++r) { /* mm:2416-2417 */
     float db = ref_is_int ? (float)(ref_buy_i - s.agent_buys[r * 8]) : (ref_buy_f - (float)s.agent_buys[r * 8]);
     float ds = ref_is_int ? (float)(s.agent_sells[r * 8] - ref_sell_i) : ((float)s.agent_sells[r * 8] - ref_sell_f);
-    buyPnL += db / tickf * (float)iabs32(s.agent_buys[r * 8 + 1]);
-    sellPnL += ds / tickf * (float)iabs32(s.agent_sells[r * 8 + 1]);
+    ft[r] = db / tickf * (float)iabs32(s.agent_buys[r * 8 + 1]);
+    ft[nt + r] = ds / tickf * (float)iabs32(s.agent_sells[r * 8 + 1]);
   }
+  float buyPnL = wsumf(ft, nt), sellPnL = wsumf(ft + nt, nt);
   const float eta = (float)ac->inventoryPnL_eta, gamma = (float)ac->inventoryPnL_gamma;
   float reward_spooner = buyPnL + sellPnL + rebate_income + InventoryPnL;
   float reward_spooner_damped = buyPnL + sellPnL + rebate_income + InventoryPnL - (eta * InventoryPnL);
@@ -642,10 +659,14 @@ static float mm_get_reward(const LobStepConfig* c, const LobAgentTypeConfig* ac,
   /* complex reward mm:2437-2450 */
   int32_t inventory_change = buyQuant - sellQuant;
   float avg_buy_price = 0.f, avg_sell_price = 0.f;
-  if (buyQuant > 0) for (int r = 0; r < nt; ++r)
-    avg_buy_price += (float)s.agent_buys[r * 8] / (float)buyQuant * (float)iabs32(s.agent_buys[r * 8 + 1]);
-  if (sellQuant > 0) for (int r = 0; r < nt; ++r)
-    avg_sell_price += (float)s.agent_sells[r * 8] / (float)sellQuant * (float)iabs32(s.agent_sells[r * 8 + 1]);
+  if (buyQuant > 0) {
+    for (int r = 0; r < nt; ++r) ft[r] = (float)s.agent_buys[r * 8] / (float)buyQuant * (float)iabs32(s.agent_buys[r * 8 + 1]);
+    avg_buy_price = wsumf(ft, nt);
+  }
+  if (sellQuant > 0) {
+    for (int r = 0; r < nt; ++r) ft[r] = (float)s.agent_sells[r * 8] / (float)sellQuant * (float)iabs32(s.agent_sells[r * 8 + 1]);
+    avg_sell_price = wsumf(ft, nt);
+  }
   float approx_realized_pnl = (float)imin32(buyQuant, sellQuant) * (avg_sell_price - avg_buy_price);
   float approx_unrealized_pnl = (inventory_change > 0) ? (float)inventory_change * (averageMidprice - avg_buy_price)
                                                         : (float)iabs32(inventory_change) * (avg_sell_price - averageMidprice);
@@ -823,11 +844,12 @@ static inline float rolling_mean(float old_mean, float new_value, int32_t step) 
 /* exe:1511-1758 get_reward */
 static float exe_get_reward(const LobStepConfig* c, const LobAgentTypeConfig* ac, const World* w /* OLD */,
                             const EXEState* st, int32_t tid, const int32_t* trades_in, const int32_t* bestasks,
-                            const int32_t* bestbids, int ep_done, int32_t* tmp /* 3*Nt*8 */, EXEExtras* ex) {
+                            const int32_t* bestbids, int ep_done, int32_t* tmp /* 6*Nt*8 + 2*Nt */, EXEExtras* ex) {
   const int nt = c->book.n_trades, N = lob_num_msgs_per_step(c);
   const int32_t tick = c->tick_size;
   const float tickf = (float)tick;
   int32_t *trades = tmp, *agent = tmp + nt * 8, *other = tmp + 2 * nt * 8;
+  float* ft = (float*)(tmp + 6 * nt * 8); /* [2*nt] float scratch */
   memcpy(trades, trades_in, sizeof(int32_t) * nt * 8);
   get_agent_trades(trades, nt, tid, agent, other);
   int32_t qsum = 0;
@@ -858,10 +880,10 @@ static float exe_get_reward(const LobStepConfig* c, const LobAgentTypeConfig* ac
   int32_t agentQuant = sum_abs_q(agent, nt), otherQuant = sum_abs_q(other, nt);
   float P_vwap;
   if (otherQuant == 0) P_vwap = ffloordiv(averageMidprice, tickf); /* exe:1629 */
-  else {
-    P_vwap = 0.f; /* exe:1630-1632 */
+  else { /* exe:1630-1632 */
     for (int r = 0; r < nt; ++r)
-      P_vwap += (float)ifloordiv(other[r * 8], tick) * ((float)iabs32(other[r * 8 + 1]) / (float)otherQuant);
+      ft[r] = (float)ifloordiv(other[r * 8], tick) * ((float)iabs32(other[r * 8 + 1]) / (float)otherQuant);
+    P_vwap = wsumf(ft, nt);
   }
   int32_t direction_switch = isign32(st->is_sell_task * 2 - 1);
   int32_t QP_agent = 0;
@@ -876,10 +898,9 @@ static float exe_get_reward(const LobStepConfig* c, const LobAgentTypeConfig* ac
   ex->slippage_rm = rolling_mean(st->slippage_rm, slippage, w->step_counter);
   ex->price_drift_rm = rolling_mean(st->price_drift_rm, price_drift, w->step_counter);
   float reward = advantage + (float)ac->reward_lambda * drift;
-  float tds = 0.f; /* exe:1710-1712 */
-  for (int r = 0; r < nt; ++r)
-    tds += (float)iabs32(agent[r * 8 + 1]) / (float)st->task_to_execute * (float)(agent[r * 8 + 4] - w->init_time[0]);
-  ex->trade_duration = st->trade_duration + tds;
+  for (int r = 0; r < nt; ++r) /* exe:1710-1712; rows that are not the agent's contribute 0/task * (0 - t0) == 0 */
+    ft[r] = (float)iabs32(agent[r * 8 + 1]) / (float)st->task_to_execute * (float)(agent[r * 8 + 4] - w->init_time[0]);
+  ex->trade_duration = st->trade_duration + wsumf(ft, nt);
   int32_t quant_left2 = st->task_to_execute - st->quant_executed - agentQuant;
   ex->reward = reward;
   ex->agentQuant = agentQuant;
@@ -893,13 +914,12 @@ static float exe_get_reward(const LobStepConfig* c, const LobAgentTypeConfig* ac
   float reward_scaled = reward / (float)ac->reward_scaling_quo;
   if (ac->reward_function == LOB_EXE_REW_FINISH_FAST) reward_scaled = (float)(-iabs32(quant_left2)) / (float)ac->reward_scaling_quo;
   if (ac->reward_function == LOB_EXE_REW_SIMPLEST_CASE) { /* exe:1744-1752 */
-    float r = 0.f;
     for (int k = 0; k < nt; ++k) {
       float slip = (float)agent[k * 8] - st->init_price;
       if (!st->is_sell_task) slip = -slip;
-      r += slip * (float)iabs32(agent[k * 8 + 1]);
+      ft[k] = slip * (float)iabs32(agent[k * 8 + 1]);
     }
-    reward_scaled = r / (float)ac->reward_scaling_quo;
+    reward_scaled = wsumf(ft, nt) / (float)ac->reward_scaling_quo;
   }
   return reward_scaled;
 }
@@ -1078,7 +1098,7 @@ static void step_one(const LobStepConfig* c, const LobStepBuffers* b, int64_t e,
   int32_t* old_bids = ws;        ws += no * 6;
   int32_t* old_bestasks = ws;    ws += N * 2;
   int32_t* old_bestbids = ws;    ws += N * 2;
-  int32_t* rtmp = ws;            ws += 6 * nt * 8;
+  int32_t* rtmp = ws;            ws += 6 * nt * 8 + 2 * nt;
 
   World w; /* OLD world state (the reward sees it: marl:462) */
   w.asks = old_asks; w.bids = old_bids; w.trades = NULL;
@@ -1268,7 +1288,7 @@ static void step_one(const LobStepConfig* c, const LobStepBuffers* b, int64_t e,
 
 static size_t step_ws_words(const LobStepConfig* c) {
   const int no = c->book.n_orders, nt = c->book.n_trades, N = lob_num_msgs_per_step(c), n_act = lob_num_action_msgs(c);
-  return (size_t)N * 8 + (size_t)(n_act + 1) * 8 + (size_t)no * 6 * 3 + (size_t)N * 2 * 4 + (size_t)6 * nt * 8 + 64;
+  return (size_t)N * 8 + (size_t)(n_act + 1) * 8 + (size_t)no * 6 * 3 + (size_t)N * 2 * 4 + (size_t)6 * nt * 8 + (size_t)2 * nt + 64;
 }
 
 static int check_cfg(const LobStepConfig* c) {

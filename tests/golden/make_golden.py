@@ -1,0 +1,196 @@
+#!/usr/bin/env python
+"""Generate golden vectors by executing the UNMODIFIED reference sources (/root/reference/gymnax_exchange) under the
+NumPy-backed JAX emulation in tests/golden/jaxshim (jax / jaxlib are not installable offline).
+
+    python tests/golden/make_golden.py            # writes tests/golden/*.npz
+
+For each case it builds the reference's own ``MARLEnv`` from the reference's own env JSON (paths / stock pointed at a
+synthetic LOBSTER CSV pair written by our generator and read by the reference's own pandas loader), then runs
+``vmap(env.reset)`` and ``vmap(env.step)`` exactly as the trainer does (ippo_rnn_JAXMARL.py:571,616) with recorded
+random actions, and dumps per step: every state leaf, obs, rewards, dones, the info dicts, and the PRNG products the
+reference drew inside the step (action-message permutation, reset window, is_sell_task) so that the oracle / CUDA path
+receive the same draws as inputs.  Also dumps job.scan_through_entire_array cases (pure replay) and get_L2_state.
+
+This script needs /root/reference; the tests that consume the .npz files do not.
+"""
+import dataclasses
+import os
+import sys
+import tempfile
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REFERENCE = "/root/reference"
+sys.path.insert(0, os.path.join(HERE, "jaxshim"))
+sys.path.insert(0, REFERENCE)
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np  # noqa: E402
+
+import jax  # noqa: E402  (the shim)
+import jax.numpy as jnp  # noqa: E402
+
+assert getattr(jax, "SHIM", False), "this script must import the NumPy-backed jax shim"
+
+import jaxmarl_hft_b200  # noqa: E402,F401
+from jaxmarl_hft_b200 import lobster  # noqa: E402
+
+
+def _np(x):
+    return np.asarray(x.view(np.ndarray) if isinstance(x, np.ndarray) else x)
+
+
+def write_day(tmp, seed, n_events, stress):
+    day = lobster.generate_day(seed=seed, n_events=n_events, stress=stress)
+    lobster.write_lobster_csv(day, os.path.join(tmp, "data", "rawLOBSTER", "GOOG", "2022"))
+    return day
+
+
+def reference_config(json_name, tmp, **world_overrides):
+    from gymnax_exchange.jaxob.config_io import load_config_from_file
+    from gymnax_exchange.jaxob.jaxob_config import MultiAgentConfig
+    mac = load_config_from_file(os.path.join(REFERENCE, "config", "env_configs", json_name))
+    world = dataclasses.replace(mac.world_config, dataPath=os.path.join(tmp, "data"), alphatradePath=os.path.join(tmp, "at"),
+                                stock="GOOG", timePeriod="2022", use_pickles_for_init=False, **world_overrides)
+    return MultiAgentConfig(world_config=world, dict_of_agents_configs=mac.dict_of_agents_configs,
+                            number_of_agents_per_type=mac.number_of_agents_per_type)
+
+
+def flatten_state(state, n_types, kinds):
+    """MultiAgentState (batched) -> dict of numpy arrays with the leaf names of jaxmarl_hft_b200.states."""
+    w = state.world_state
+    out = {
+        "asks": _np(w.ask_raw_orders), "bids": _np(w.bid_raw_orders), "trades": _np(w.trades),
+        "init_time": _np(w.init_time), "window_index": _np(w.window_index), "max_steps": _np(w.max_steps_in_episode),
+        "start_index": _np(w.start_index), "step_counter": _np(w.step_counter), "best_bids": _np(w.best_bids),
+        "best_asks": _np(w.best_asks), "time": _np(w.time), "order_id_counter": _np(w.order_id_counter),
+        "mid_price": _np(w.mid_price), "delta_time": _np(w.delta_time),
+    }
+    for t in range(n_types):
+        a = state.agent_states[t]
+        for f in dataclasses.fields(a):
+            out[f"a{t}_{f.name}"] = _np(getattr(a, f.name))
+    return out
+
+
+def collect_prng(trace, B, n_act, n_types):
+    """Split the recorded draws of ONE vmapped call into per-env arrays.  Under the shim a vmapped call runs env by env,
+    so the trace is B consecutive groups."""
+    perms, windows, sells = [], [], []
+    for fn, caller, key, args, res in trace:
+        if fn == "permutation":
+            perms.append(np.asarray(res, np.int32))
+        elif fn == "randint" and caller.startswith("reset_env") and args[2] != 2:
+            windows.append(int(res))
+        elif fn == "randint":
+            sells.append(int(res))
+    return perms, windows, sells
+
+
+def run_env_case(name, json_name, seed, B, steps, n_events=30000, stress=False, out_dir=HERE, **world_overrides):
+    from gymnax_exchange.jaxen.marl_env import MARLEnv
+    import jax.random as jr
+    with tempfile.TemporaryDirectory() as tmp:
+        write_day(tmp, seed=5 if not stress else 9, n_events=n_events, stress=stress)
+        mac = reference_config(json_name, tmp, **world_overrides)
+        env = MARLEnv(jr.PRNGKey(seed), mac)
+        params = env.default_params
+        n_types = len(env.instance_list)
+        n_per = list(mac.number_of_agents_per_type)
+        rng = np.random.default_rng(seed)
+        key = jr.PRNGKey(seed + 1)
+        key, k_reset = jr.split(key)
+        reset_keys = jr.split(k_reset, B)
+        jr.TRACE.clear()
+        obs, state = jax.vmap(env.reset, in_axes=(0, None))(reset_keys, params)
+        reset_trace = list(jr.TRACE)
+        record = {"B": np.int64(B), "steps": np.int64(steps), "json": np.array(json_name),
+                  "day_seed": np.int64(5 if not stress else 9), "n_events": np.int64(n_events), "stress": np.int64(stress),
+                  "world_overrides": np.array(repr(sorted(world_overrides.items())))}
+        # reset draws: per env one window randint (base_env.reset_env) + one is_sell randint per EXE type
+        rw, rs = [], []
+        for fn, caller, k, args, res in reset_trace:
+            if fn != "randint":
+                continue
+            (rw if "reset_env" in caller and args[2] == env.n_windows and len(rw) * 1 <= len(rs) * 10 + len(rw) else rs)
+        record["reset_trace"] = np.array([f"{fn}|{caller}|{args}|{np.asarray(res).tolist()}" for fn, caller, k, args, res in reset_trace])
+        st0 = flatten_state(state, n_types, None)
+        for k2, v in st0.items():
+            record[f"reset/state/{k2}"] = v
+        for t in range(n_types):
+            record[f"reset/obs{t}"] = _np(obs[t])
+        for s in range(steps):
+            key, k_step, k_act = jr.split(key, 3)
+            step_keys = jr.split(k_step, B)
+            actions = []
+            for t in range(n_types):
+                n_a = env.action_spaces[t].n
+                a = rng.integers(0, n_a, size=(B, n_per[t])).astype(np.int32)
+                if s % 9 == 4:
+                    a[::3] = rng.integers(-2, n_a + 3, size=a[::3].shape)   # out-of-range actions (gather wrap + clamp)
+                actions.append(a)
+            # the trainer squeezes single-agent types (marl_env.py:265-266 handles both)
+            jax_actions = [jnp.asarray(a[:, 0] if a.shape[1] == 1 else a) for a in actions]
+            jr.TRACE.clear()
+            obs, state, rewards, dones, info = jax.vmap(env.step, in_axes=(0, 0, 0, None))(step_keys, state, jax_actions, params)
+            trace = list(jr.TRACE)
+            record[f"step{s}/trace"] = np.array([f"{fn}|{caller}|{args}|{np.asarray(res).tolist()}" for fn, caller, k, args, res in trace])
+            for t in range(n_types):
+                record[f"step{s}/actions{t}"] = actions[t]
+                record[f"step{s}/obs{t}"] = _np(obs[t])
+                record[f"step{s}/reward{t}"] = _np(rewards[t])
+                record[f"step{s}/done_agents{t}"] = _np(dones["agents"][t])
+                for k2, v in info["agents"][t].items():
+                    record[f"step{s}/info{t}/{k2}"] = _np(v)
+            record[f"step{s}/done_all"] = _np(dones["__all__"])
+            for k2, v in info["world"].items():
+                record[f"step{s}/winfo/{k2}"] = _np(v)
+            for k2, v in flatten_state(state, n_types, None).items():
+                record[f"step{s}/state/{k2}"] = v
+        record["n_windows"] = np.int64(env.n_windows)
+        record["type_names"] = np.array(env.type_names)
+        path = os.path.join(out_dir, f"{name}.npz")
+        np.savez_compressed(path, **record)
+        print("wrote", path, os.path.getsize(path) // 1024, "KiB")
+
+
+def run_replay_case(name, seed, B, T, no, nt, t4, fill, out_dir=HERE):
+    """job.scan_through_entire_array_save_bidask on adversarial random streams + job.get_L2_state of the result."""
+    import helpers as H
+    from gymnax_exchange.jaxob import JaxOrderBookArrays as job
+    from gymnax_exchange.jaxob.jaxob_config import JAXLOB_Configuration
+    from jaxmarl_hft_b200 import config as C
+    import jax.random as jr
+    cfg = JAXLOB_Configuration(nOrders=no, nTrades=nt, type_4_interpretation=t4, check_book_fill=fill)
+    bc = C.book_config(C.World_EnvironmentConfig(nOrders=no, nTrades=nt, type_4_interpretation=t4, check_book_fill=fill))
+    rng = np.random.default_rng(seed)
+    msgs = H.random_messages(rng, B * T, bc, price_lo=99_000, price_hi=100_600 if no < 64 else 101_500)
+    rec = {"msgs": msgs, "B": np.int64(B), "T": np.int64(T), "no": np.int64(no), "nt": np.int64(nt), "t4": np.int64(t4),
+           "fill": np.int64(fill)}
+    A, Bd, Tr, BA, BB, L2 = [], [], [], [], [], []
+    for b in range(B):
+        asks = job.init_orderside(no)
+        bids = job.init_orderside(no)
+        trades = (jnp.ones((nt, 8)) * -1).astype(jnp.int32)
+        (asks, bids, trades), (ba, bb) = job.scan_through_entire_array_save_bidask(
+            cfg, jr.PRNGKey(0), jnp.asarray(msgs[b * T:(b + 1) * T]), (asks, bids, trades), T)
+        A.append(_np(asks)); Bd.append(_np(bids)); Tr.append(_np(trades)); BA.append(_np(ba)); BB.append(_np(bb))
+        L2.append(_np(job.get_L2_state(asks, bids, 10, cfg)))
+    rec.update(asks=np.stack(A), bids=np.stack(Bd), trades=np.stack(Tr), best_asks=np.stack(BA), best_bids=np.stack(BB),
+               l2=np.stack(L2))
+    path = os.path.join(out_dir, f"{name}.npz")
+    np.savez_compressed(path, **rec)
+    print("wrote", path, os.path.getsize(path) // 1024, "KiB")
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["replay", "env"]
+    if "replay" in which:
+        run_replay_case("replay_100", seed=11, B=6, T=500, no=100, nt=100, t4=0, fill=True)
+        run_replay_case("replay_small_full", seed=12, B=6, T=400, no=20, nt=8, t4=0, fill=True)
+        run_replay_case("replay_t4lim_nofill", seed=13, B=4, T=300, no=24, nt=16, t4=1, fill=False)
+        run_replay_case("replay_mkt", seed=14, B=4, T=300, no=32, nt=16, t4=2, fill=True)
+    if "env" in which:
+        run_env_case("env_2player", "2_player_fq_fqc.json", seed=3, B=3, steps=68)
+        run_env_case("env_exec", "exec_longrun_fixed_quants_complex.json", seed=4, B=2, steps=20)
