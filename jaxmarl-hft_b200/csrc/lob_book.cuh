@@ -271,7 +271,7 @@ static __device__ __noinline__ SideScan g_scan_side(BookCtx c, int s) {
     const bool all = (a.x == -1) & (a.y == -1) & (b.x == -1) & (b.y == -1) & (d.x == -1) & (d.y == -1);
     if (any) m |= 1u << k;
     neg += (a.x < 0);
-    od |= (!all) & (any | (a.y <= 0));
+    od |= (!all) & (any | (a.y <= 0) | (a.x < 0));
   }
   SideScan r;
   r.flag = m; r.nneg = wsum(neg); r.odd = __any_sync(kFull, od) ? 1 : 0;
@@ -301,7 +301,7 @@ struct Book {
   int nneg[2];        // rows with price < 0
   int bestp[2], bestq[2], bestn[2];
   bool valid[2];      // best* caches valid
-  bool odd[2];        // side holds rows the fast paths do not model: a non-blank row with qty <= 0 or with a -1 field
+  bool odd[2];        // side holds rows the fast paths do not model: a non-blank row with qty <= 0, a -1 field or price < 0
   int ntr;            // next trade row: first row whose time_s column is -1
   bool tr_odd;        // the rows after ntr are not all free -> the trade slot must be searched (generic path)
 
@@ -355,8 +355,30 @@ struct Book {
   }
   __device__ __forceinline__ void rescan() { scan_side(ASK); scan_side(BID); scan_trades(); }
 
+  // job:933-984 on a side without odd rows: live prices are >= 0, every other row (blank or padding) has price -1
+  static __device__ __noinline__ Best best_scan(const int* side_rows, int is_bid, int maxint, int n_blank) {
+    const int lane = lane_id();
+    int2 pq[SLOTS];
+    int ext = is_bid ? -1 : maxint;
+#pragma unroll
+    for (int k = 0; k < SLOTS; ++k) {
+      pq[k] = *reinterpret_cast<const int2*>(side_rows + (k * 32 + lane) * 6);
+      ext = is_bid ? max(ext, pq[k].x) : min(ext, pq[k].x == -1 ? maxint : pq[k].x);
+    }
+    ext = is_bid ? wmax(ext) : wmin(ext);
+    Best b;
+    if (ext == (is_bid ? -1 : maxint)) {   // empty side: best price -1, "quantity" = sum of the blank rows' -1 (quirk Q7)
+      b.p = -1; b.q = -n_blank; b.n = n_blank;
+      return b;
+    }
+    int q = 0, n = 0;
+#pragma unroll
+    for (int k = 0; k < SLOTS; ++k) if (pq[k].x == ext) { q += pq[k].y; n += 1; }
+    b.p = ext; b.q = wsum(q); b.n = wsum(n);
+    return b;
+  }
   __device__ __forceinline__ void recompute(int s) {
-    const Best b = g_best(c, s);
+    const Best b = odd[s] ? g_best(c, s) : best_scan(side_base(s), s == BID, c.maxint, nneg[s]);
     bestp[s] = b.p; bestq[s] = b.q; bestn[s] = b.n; valid[s] = true;
   }
   __device__ __forceinline__ void ensure(int s) { if (!valid[s]) recompute(s); }
@@ -487,7 +509,8 @@ struct Book {
     }
   }
 
-  // job:94-139 cancel_order, order-id hit on a live row; anything else is generic
+  // job:94-139 cancel_order: order-id hit, else the initial-order match by price (job:121-139), else the LAST row
+  // (JAX normalises the index -1: quirk Q2)
   template <int S>
   __device__ __forceinline__ void cancel(const Msg& m) {
     const int lane = lane_id();
@@ -495,9 +518,21 @@ struct Book {
 #pragma unroll
     for (int k = SLOTS - 1; k >= 0; --k) { const int r = k * 32 + lane; if (row(S, r)[F_OID] == m.oid) idx = r; }
     idx = wmin(idx);
-    int2 pq = make_int2(-1, -1);
-    if (idx < c.no) pq = *reinterpret_cast<const int2*>(row(S, idx));
-    if (idx >= c.no || pq.x == -1) {        // no such order (or a blank row "matched" oid -1): literal search
+    if (idx >= c.no) {   // no such order id (padding rows carry -1 and are not rows of the book)
+      int j = kBig;
+#pragma unroll
+      for (int k = SLOTS - 1; k >= 0; --k) {
+        const int* p = row(S, k * 32 + lane);
+        const int2 pq = *reinterpret_cast<const int2*>(p);
+        const int o = p[F_OID];
+        if (pq.x == m.price && o <= c.init_id && o >= c.init_lo && pq.y >= m.qty) j = k * 32 + lane;
+      }
+      j = wmin(j);
+      idx = (j < c.no) ? j : c.no - 1;
+    }
+    const int2 pq = *reinterpret_cast<const int2*>(row(S, idx));
+    if (pq.x == -1) {        // a blank row takes the cancel: qty = -1 - q stays <= 0 and the row is blanked again
+      if (m.qty >= 0) return;
       __syncwarp();
       g_cancel(c, S, m);
       scan_side(S);

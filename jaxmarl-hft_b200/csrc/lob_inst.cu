@@ -23,15 +23,27 @@ int launch_step(const LobStepConfig* c, const LobStepBuffers* b, int64_t batch, 
   const int N = lob_num_msgs_per_step(c), n_act = lob_num_action_msgs(c), n_cnl = lob_num_cancel_msgs(c);
   const lob::WarpLayout L = lob::make_layout(S * 32, N * 8, n_act);
   if (((n_cnl + n_act) * 8) % 4 != 0) return fail(LOB_E_INVALID, "internal: data slice misaligned");
-  const size_t smem = (size_t)L.words * 4 * lob::kWarps;
-  int per_sm = 1;
-  int rc = prepare(lob::lob_step_kernel<S>, smem, d, &per_sm);
-  if (rc) return rc;
+  // one persistent CTA per SM; as many warps (= environments in flight) as shared memory and registers allow
+  const size_t per_warp = (size_t)L.words * 4;
+  cudaFuncAttributes fa;
+  cudaError_t e = cudaFuncGetAttributes(&fa, lob::lob_step_kernel<S>);
+  if (e != cudaSuccess) return fail(LOB_E_CUDA, "cudaFuncGetAttributes: %s", cudaGetErrorString(e));
+  int warps = (int)(((size_t)d.max_smem_optin - fa.sharedSizeBytes) / per_warp);
+  const int by_regs = fa.numRegs > 0 ? 65536 / (fa.numRegs * 32) : lob::kStepMaxWarps;
+  if (warps > by_regs) warps = by_regs;
+  if (warps > lob::kStepMaxWarps) warps = lob::kStepMaxWarps;
+  if (warps < 1)
+    return fail(LOB_E_INVALID, "configuration needs %zu B of shared memory per environment (device limit %d)", per_warp,
+                d.max_smem_optin);
+  const size_t smem = per_warp * warps;
+  e = cudaFuncSetAttribute(lob::lob_step_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return fail(LOB_E_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
   int need_extreme = 0;
   for (int t = 0; t < c->n_agent_types; ++t)
     if (c->agent[t].kind == LOB_AGENT_MM && c->agent[t].exclude_extreme_spreads) need_extreme = 1;
-  lob::lob_step_kernel<S><<<grid_for(batch, d.sms, per_sm), lob::kWarps * 32, smem, st>>>(*c, *b, batch, L, N, n_act, n_cnl,
-                                                                                      need_extreme);
+  long long ctas = (batch + warps - 1) / warps;
+  if (ctas > d.sms) ctas = d.sms;
+  lob::lob_step_kernel<S><<<(int)ctas, warps * 32, smem, st>>>(*c, *b, batch, L, N, n_act, n_cnl, need_extreme);
   return launched("lob_step_kernel");
 }
 

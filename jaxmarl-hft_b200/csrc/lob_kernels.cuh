@@ -265,12 +265,21 @@ __device__ __noinline__ void reset_env(const LobStepConfig& c, const LobStepBuff
   }
 }
 
+// Phase-synchronous persistent CTA: ONE CTA per SM with as many warps as shared memory / registers allow (one
+// environment per warp).  The step has three code phases -- (1) stage state + build the agent messages, (2) the
+// message scan, (3) rewards / observations / write-back -- and the warps of the CTA pass them together
+// (__syncthreads between phases), so that at any time the SM's instruction cache serves ONE phase's code to all of its
+// warps instead of three phases to desynchronised warps (the L1.5 instruction cache is 32 KB; ncu showed the
+// unsynchronised version stalled on instruction fetch: smsp stall_no_instruction 8.2 of ~16 per issue).
+constexpr int kStepMaxWarps = 20;
+
 template <int SLOTS>
-__global__ void __launch_bounds__(kWarps * 32, (SLOTS <= 4 ? 5 : SLOTS == 8 ? 3 : 1))
+__global__ void __launch_bounds__(kStepMaxWarps * 32, 1)
 lob_step_kernel(const __grid_constant__ LobStepConfig c, const __grid_constant__ LobStepBuffers b, long long batch,
                 WarpLayout L, int N, int n_act, int n_cnl, int need_extreme) {
   extern __shared__ __align__(128) int smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nwarps = blockDim.x >> 5;
   int* ws = smem + warp * L.words;
   uint64_t* bar = reinterpret_cast<uint64_t*>(ws + L.bar);
   int* msgs = ws + L.msgs;
@@ -285,60 +294,68 @@ lob_step_kernel(const __grid_constant__ LobStepConfig c, const __grid_constant__
   const int no = c.book.n_orders, nt = c.book.n_trades, Nd = c.n_data_msg_per_step, T = c.n_agent_types;
   const bool bulk_books = (no & 1) == 0;   // a side is no*24 bytes: 16-byte granular iff no is even
   const unsigned side_bytes = (unsigned)no * 24u;
-  const long long stride = (long long)gridDim.x * kWarps;
-  for (long long e = (long long)blockIdx.x * kWarps + warp; e < batch; e += stride) {
-    // ---- old world state (the reward sees it: marl:462) ----
+  const long long stride = (long long)gridDim.x * nwarps;
+  for (long long base = (long long)blockIdx.x * nwarps; base < batch; base += stride) {
+    const long long e = base + warp;
+    const bool active = e < batch;
     WorldIn w;
-    w.time0 = b.time[e * 2]; w.time1 = b.time[e * 2 + 1];
-    w.init_time0 = b.init_time[e * 2];
-    w.step_counter = b.step_counter[e];
-    w.max_steps = b.max_steps[e];
-    w.mid_price = b.mid_price[e];
-    w.old_ba_last = b.best_asks[(e * N + N - 1) * 2];
-    w.old_bb_last = b.best_bids[(e * N + N - 1) * 2];
-    const int start_index = b.start_index[e];
-    const int oid_counter = b.order_id_counter[e];
-    const int window_index = b.window_index[e];
+    int oid_counter = 0, window_index = 0;
+    float avg_sum = 0.f, sum_a = 0.f, sum_b = 0.f;
+    int prev_a = 0, prev_b = 0;
+    bool abort_episode = false;
 
-    // ---- stage both book sides and (B) the data-message slice (base:339-369; dynamic_slice clamps the start) with
-    //      the bulk-copy engine: one mbarrier phase ----
-    {
-      long long off = (long long)(int)(start_index + Nd * w.step_counter);
-      if (off > c.n_messages - Nd) off = c.n_messages - Nd;
-      if (off < 0) off = 0;
-      if (lane == 0) {
-        bulk_wait_read();        // the previous env's bulk stores have drained this warp's buffers
-        fence_async_smem();
-        mbar_expect_tx(&bar[0], (bulk_books ? 2u * side_bytes : 0u) + (unsigned)Nd * 32u);
-        if (bulk_books) {
-          bulk_g2s(bk.side_base(ASK), b.asks + e * no * 6, side_bytes, &bar[0]);
-          bulk_g2s(bk.side_base(BID), b.bids + e * no * 6, side_bytes, &bar[0]);
+    // =================================================== phase 1: stage state, build the agent messages ==========
+    if (active) {
+      // ---- old world state (the reward sees it: marl:462) ----
+      w.time0 = b.time[e * 2]; w.time1 = b.time[e * 2 + 1];
+      w.init_time0 = b.init_time[e * 2];
+      w.step_counter = b.step_counter[e];
+      w.max_steps = b.max_steps[e];
+      w.mid_price = b.mid_price[e];
+      w.old_ba_last = b.best_asks[(e * N + N - 1) * 2];
+      w.old_bb_last = b.best_bids[(e * N + N - 1) * 2];
+      const int start_index = b.start_index[e];
+      oid_counter = b.order_id_counter[e];
+      window_index = b.window_index[e];
+
+      // ---- stage both book sides and (B) the data-message slice (base:339-369; dynamic_slice clamps the start)
+      //      with the bulk-copy engine: one mbarrier phase ----
+      {
+        long long off = (long long)(int)(start_index + Nd * w.step_counter);
+        if (off > c.n_messages - Nd) off = c.n_messages - Nd;
+        if (off < 0) off = 0;
+        if (lane == 0) {
+          bulk_wait_read();        // the previous env's bulk stores have drained this warp's buffers
+          fence_async_smem();
+          mbar_expect_tx(&bar[0], (bulk_books ? 2u * side_bytes : 0u) + (unsigned)Nd * 32u);
+          if (bulk_books) {
+            bulk_g2s(bk.side_base(ASK), b.asks + e * no * 6, side_bytes, &bar[0]);
+            bulk_g2s(bk.side_base(BID), b.bids + e * no * 6, side_bytes, &bar[0]);
+          }
+          bulk_g2s(msgs + (n_cnl + n_act) * 8, b.message_data + off * 8, (unsigned)Nd * 32u, &bar[0]);
         }
-        bulk_g2s(msgs + (n_cnl + n_act) * 8, b.message_data + off * 8, (unsigned)Nd * 32u, &bar[0]);
+        __syncwarp();
       }
+      if (!bulk_books) { bk.load_side(ASK, b.asks + e * no * 6); bk.load_side(BID, b.bids + e * no * 6); }
+      bk.c.tr = b.trades + e * nt * 8;   // the trade log is worked on in place (HBM / L2): a row is one 32-byte sector
+      bk.fill_trades_empty();            // marl:348: the trade log is re-initialised every step
+      w.extreme_spread = false;
+      if (need_extreme) {   // mm:2545-2553 over the OLD per-message bests
+        bool any = false;
+        for (int i = lane; i < N; i += 32) {
+          const int a = b.best_asks[(e * N + i) * 2], bb = b.best_bids[(e * N + i) * 2];
+          const float mid = (float)(a + bb) / 2.0f;
+          any |= ((float)(a - bb) / mid > 0.1f);
+        }
+        w.extreme_spread = __any_sync(kFull, any);
+      }
+      mbar_wait(&bar[0], phase);
+      phase ^= 1u;
       __syncwarp();
-    }
-    if (!bulk_books) { bk.load_side(ASK, b.asks + e * no * 6); bk.load_side(BID, b.bids + e * no * 6); }
-    bk.c.tr = b.trades + e * nt * 8;   // the trade log is worked on in place (HBM / L2): a row is one 32-byte sector
-    bk.fill_trades_empty();            // marl:348: the trade log is re-initialised every step
-    w.extreme_spread = false;
-    if (need_extreme) {   // mm:2545-2553 over the OLD per-message bests
-      bool any = false;
-      for (int i = lane; i < N; i += 32) {
-        const int a = b.best_asks[(e * N + i) * 2], bb = b.best_bids[(e * N + i) * 2];
-        const float mid = (float)(a + bb) / 2.0f;
-        any |= ((float)(a - bb) / mid > 0.1f);
-      }
-      w.extreme_spread = __any_sync(kFull, any);
-    }
-    mbar_wait(&bar[0], phase);
-    phase ^= 1u;
-    __syncwarp();
-    bk.scan_side(ASK);
-    bk.scan_side(BID);
+      bk.scan_side(ASK);
+      bk.scan_side(BID);
 
-    // ---- (C) marl:254-315 agent messages: [cancels | permuted actions | data] ----
-    {
+      // ---- (C) marl:254-315 agent messages: [cancels | permuted actions | data] ----
       int ci = 0, ai = 0, flat = 0;
       for (int t = 0; t < T; ++t) {
         const LobAgentTypeConfig& ac = c.agent[t];
@@ -371,14 +388,14 @@ lob_step_kernel(const __grid_constant__ LobStepConfig c, const __grid_constant__
         if (c.shuffle_action_messages && b.perm) src = max(0, min(b.perm[e * n_act + i], n_act - 1));
         msgs[(n_cnl + i) * 8 + k] = act_all[src * 8 + k];
       }
+      __syncwarp();
     }
-    __syncwarp();
+    __syncthreads();
 
-    // ---- (D) marl:348-364 the scan, with the per-message best bid/ask (job:792-823) and the forward fill ----
-    float avg_sum = 0.f, sum_a = 0.f, sum_b = 0.f;
-    int prev_a = w.old_ba_last, prev_b = w.old_bb_last;
-    bool abort_episode = false;
-    {
+    // =================================================== phase 2: the message scan ===============================
+    if (active) {
+      // ---- (D) marl:348-364 the scan, with the per-message best bid/ask (job:792-823) and the forward fill ----
+      prev_a = w.old_ba_last; prev_b = w.old_bb_last;
       const int4* m4 = reinterpret_cast<const int4*>(msgs);
       int2* gq = reinterpret_cast<int2*>((lane == 0 ? b.best_asks : b.best_bids) + e * N * 2);
 #pragma unroll 1
@@ -395,23 +412,26 @@ lob_step_kernel(const __grid_constant__ LobStepConfig c, const __grid_constant__
         sum_a += (float)ap; sum_b += (float)bp;
         if (lane < 2) gq[i] = (lane == 0) ? make_int2(ap, aq) : make_int2(bp, bq);
       }
+      __syncwarp();
     }
-    __syncwarp();
-    const int ft0 = msgs[(N - 1) * 8 + 6], ft1 = msgs[(N - 1) * 8 + 7];   // marl:419
-    StepOut so;
-    so.ba_last = prev_a; so.bb_last = prev_b;
-    so.avg_mid = avg_sum / (float)N;
-    so.ep_done = (w.max_steps - w.step_counter - 1) <= 1;                   // marl:717-718
+    __syncthreads();
 
-    // ---- (F) new world state marl:489-515 ----
-    const int new_step = w.step_counter + 1;
-    const float new_mid = (float)(so.bb_last + so.ba_last) / 2.0f;
-    const float new_dt = (float)ft0 + (float)ft1 / 1e9f - (float)w.time0 - (float)w.time1 / 1e9f;
-    const int new_oid_counter = oid_counter - n_act;
-    const int vol_a = bk.volume(ASK), vol_b = bk.volume(BID);
+    // =================================================== phase 3: rewards, state, observations, write-back ========
+    if (active) {
+      const int ft0 = msgs[(N - 1) * 8 + 6], ft1 = msgs[(N - 1) * 8 + 7];   // marl:419
+      StepOut so;
+      so.ba_last = prev_a; so.bb_last = prev_b;
+      so.avg_mid = avg_sum / (float)N;
+      so.ep_done = (w.max_steps - w.step_counter - 1) <= 1;                   // marl:717-718
 
-    // ---- (E)+(G)+(I)+(J)+(K) per agent: reward, state, done, info, obs ----
-    {
+      // ---- (F) new world state marl:489-515 ----
+      const int new_step = w.step_counter + 1;
+      const float new_mid = (float)(so.bb_last + so.ba_last) / 2.0f;
+      const float new_dt = (float)ft0 + (float)ft1 / 1e9f - (float)w.time0 - (float)w.time1 / 1e9f;
+      const int new_oid_counter = oid_counter - n_act;
+      const int vol_a = bk.volume(ASK), vol_b = bk.volume(BID);
+
+      // ---- (E)+(G)+(I)+(J)+(K) per agent: reward, state, done, info, obs ----
       int flat = 0;
       for (int t = 0; t < T; ++t) {
         const LobAgentTypeConfig& ac = c.agent[t];
@@ -472,37 +492,37 @@ lob_step_kernel(const __grid_constant__ LobStepConfig c, const __grid_constant__
           }
         }
       }
-    }
-    // ---- world info marl:618-639 ----
-    if (lane == 0) {
-      b.done_all[e] = so.ep_done ? 1 : 0;
-      int* wi = b.info_world_i32 + e * LOB_WINFO_I32_COLS;
-      float* wf = b.info_world_f32 + e * LOB_WINFO_F32_COLS;
-      wi[0] = window_index; wi[1] = new_step; wi[2] = ft0; wi[3] = ft1; wi[4] = new_oid_counter;
-      wi[5] = so.ba_last; wi[6] = so.bb_last; wi[7] = new_step; wi[8] = so.ep_done ? 1 : 0;
-      wi[9] = abort_episode ? 1 : 0; wi[10] = so.ba_last - so.bb_last;
-      wf[0] = new_mid; wf[1] = sum_a / (float)N; wf[2] = sum_b / (float)N; wf[3] = new_dt;
-    }
-    if (so.ep_done) {   // marl:787-803 auto-reset, fused: the reset state is only touched when the episode ended
-      reset_env(c, b, e, bk, N);
-    } else if (lane == 0) {
-      b.step_counter[e] = new_step;
-      b.time[e * 2] = ft0; b.time[e * 2 + 1] = ft1;
-      b.order_id_counter[e] = new_oid_counter;
-      b.mid_price[e] = new_mid;
-      b.delta_time[e] = new_dt;
-    }
-    __syncwarp();
-    // ---- write back: same layout in HBM, so the bulk-copy engine does it ----
-    if (!bulk_books) { bk.store_side(ASK, b.asks + e * no * 6); bk.store_side(BID, b.bids + e * no * 6); }
-    fence_async_smem();
-    __syncwarp();
-    if (lane == 0) {
-      if (bulk_books) {
-        bulk_s2g(b.asks + e * no * 6, bk.side_base(ASK), side_bytes);
-        bulk_s2g(b.bids + e * no * 6, bk.side_base(BID), side_bytes);
+      // ---- world info marl:618-639 ----
+      if (lane == 0) {
+        b.done_all[e] = so.ep_done ? 1 : 0;
+        int* wi = b.info_world_i32 + e * LOB_WINFO_I32_COLS;
+        float* wf = b.info_world_f32 + e * LOB_WINFO_F32_COLS;
+        wi[0] = window_index; wi[1] = new_step; wi[2] = ft0; wi[3] = ft1; wi[4] = new_oid_counter;
+        wi[5] = so.ba_last; wi[6] = so.bb_last; wi[7] = new_step; wi[8] = so.ep_done ? 1 : 0;
+        wi[9] = abort_episode ? 1 : 0; wi[10] = so.ba_last - so.bb_last;
+        wf[0] = new_mid; wf[1] = sum_a / (float)N; wf[2] = sum_b / (float)N; wf[3] = new_dt;
       }
-      bulk_commit();
+      if (so.ep_done) {   // marl:787-803 auto-reset, fused: the reset state is only touched when the episode ended
+        reset_env(c, b, e, bk, N);
+      } else if (lane == 0) {
+        b.step_counter[e] = new_step;
+        b.time[e * 2] = ft0; b.time[e * 2 + 1] = ft1;
+        b.order_id_counter[e] = new_oid_counter;
+        b.mid_price[e] = new_mid;
+        b.delta_time[e] = new_dt;
+      }
+      __syncwarp();
+      // ---- write back: same layout in HBM, so the bulk-copy engine does it ----
+      if (!bulk_books) { bk.store_side(ASK, b.asks + e * no * 6); bk.store_side(BID, b.bids + e * no * 6); }
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        if (bulk_books) {
+          bulk_s2g(b.asks + e * no * 6, bk.side_base(ASK), side_bytes);
+          bulk_s2g(b.bids + e * no * 6, bk.side_base(BID), side_bytes);
+        }
+        bulk_commit();
+      }
     }
   }
   if (lane == 0) bulk_wait_all();

@@ -380,3 +380,12 @@ def iinfo(dt):
 
 def finfo(dt):
     return np.finfo(_dt(dt))
+
+int_ = int32
+float_ = float32
+uint = uint32
+integer = np.integer
+floating = np.floating
+number = np.number
+dtype = np.dtype
+bool = bool_  # noqa: A001

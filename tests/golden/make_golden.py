@@ -108,12 +108,6 @@ def run_env_case(name, json_name, seed, B, steps, n_events=30000, stress=False, 
         record = {"B": np.int64(B), "steps": np.int64(steps), "json": np.array(json_name),
                   "day_seed": np.int64(5 if not stress else 9), "n_events": np.int64(n_events), "stress": np.int64(stress),
                   "world_overrides": np.array(repr(sorted(world_overrides.items())))}
-        # reset draws: per env one window randint (base_env.reset_env) + one is_sell randint per EXE type
-        rw, rs = [], []
-        for fn, caller, k, args, res in reset_trace:
-            if fn != "randint":
-                continue
-            (rw if "reset_env" in caller and args[2] == env.n_windows and len(rw) * 1 <= len(rs) * 10 + len(rw) else rs)
         record["reset_trace"] = np.array([f"{fn}|{caller}|{args}|{np.asarray(res).tolist()}" for fn, caller, k, args, res in reset_trace])
         st0 = flatten_state(state, n_types, None)
         for k2, v in st0.items():
@@ -148,7 +142,7 @@ def run_env_case(name, json_name, seed, B, steps, n_events=30000, stress=False, 
                 record[f"step{s}/winfo/{k2}"] = _np(v)
             for k2, v in flatten_state(state, n_types, None).items():
                 record[f"step{s}/state/{k2}"] = v
-        record["n_windows"] = np.int64(env.n_windows)
+        record["n_windows"] = np.int64(env.base_env.n_windows)
         record["type_names"] = np.array(env.type_names)
         path = os.path.join(out_dir, f"{name}.npz")
         np.savez_compressed(path, **record)
