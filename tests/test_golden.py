@@ -1,0 +1,216 @@
+"""The CPU oracle (and, on a GPU box, the CUDA path) against golden vectors produced by executing the UNMODIFIED reference
+sources under the NumPy JAX emulation (tests/golden/make_golden.py, tests/golden/jaxshim).
+
+What is pinned: job.scan_through_entire_array_save_bidask + get_L2_state on adversarial streams (full books, eviction,
+the -1 wrap, trade-log overflow, IOC / LIM / MKT type-4 interpretation), and MARLEnv.reset / MARLEnv.step rollouts through
+the reference's own loader, reset-state precompute, agent message construction, rewards, observations, info dicts and
+auto-reset.  Integer leaves are compared bit for bit.  Float leaves: rel 1e-5, except the quantities the reference
+itself computes by cancelling two ~1e5-sized float32 sums (EXE advantage / drift / reward and their running means),
+whose value depends on XLA's unspecified reduction order at the 1e-3 level -- those are compared with an absolute
+tolerance derived from the float32 rounding of the operands (see DESIGN.md "Float parity").
+"""
+import ast
+import glob
+import os
+
+import numpy as np
+import pytest
+
+import helpers as H
+from jaxmarl_hft_b200 import abi, config as C, env as E, lobster, states
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+REPLAY_CASES = sorted(glob.glob(os.path.join(GOLDEN, "replay_*.npz")))
+ENV_CASES = sorted(glob.glob(os.path.join(GOLDEN, "env_*.npz")))
+
+# float leaves that are differences of large float32 sums in the reference (exec_env.py:1640-1665)
+ILL_CONDITIONED = ("advantage", "drift", "reward", "slippage", "price_adv", "price_drift", "revenue_direction",
+                   "advantage_return", "drift_return", "slippage_rm", "price_adv_rm", "price_drift_rm")
+
+
+def _book_cfg(z):
+    return C.book_config(C.World_EnvironmentConfig(nOrders=int(z["no"]), nTrades=int(z["nt"]),
+                                                   type_4_interpretation=int(z["t4"]), check_book_fill=bool(z["fill"])))
+
+
+@pytest.mark.parametrize("path", REPLAY_CASES, ids=[os.path.basename(p) for p in REPLAY_CASES])
+def test_oracle_replay_matches_reference(oracle, path):
+    z = np.load(path)
+    B, T, no, nt = int(z["B"]), int(z["T"]), int(z["no"]), int(z["nt"])
+    bc = _book_cfg(z)
+    for b in range(B):
+        a = np.full((no, 6), -1, np.int32); d = a.copy(); t = np.full((nt, 8), -1, np.int32)
+        ba, bb = oracle.scan_save_bidask(bc, a, d, t, z["msgs"][b * T:(b + 1) * T])
+        np.testing.assert_array_equal(a, z["asks"][b]); np.testing.assert_array_equal(d, z["bids"][b])
+        np.testing.assert_array_equal(t, z["trades"][b])
+        np.testing.assert_array_equal(ba, z["best_asks"][b]); np.testing.assert_array_equal(bb, z["best_bids"][b])
+    np.testing.assert_array_equal(oracle.l2(bc, z["asks"], z["bids"], 10), z["l2"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", REPLAY_CASES, ids=[os.path.basename(p) for p in REPLAY_CASES])
+def test_cuda_replay_matches_reference(path):
+    import torch
+    z = np.load(path)
+    B, T, no, nt = int(z["B"]), int(z["T"]), int(z["no"]), int(z["nt"])
+    bc = _book_cfg(z)
+    a = np.full((B, no, 6), -1, np.int32); d = a.copy(); t = np.full((B, nt, 8), -1, np.int32)
+    ga, gb, gt, best = H.cuda_replay(bc, a, d, t, z["msgs"], np.arange(B, dtype=np.int64) * T, T, want_best=True)
+    np.testing.assert_array_equal(ga, z["asks"]); np.testing.assert_array_equal(gb, z["bids"])
+    np.testing.assert_array_equal(gt, z["trades"])
+    # the reference's last per-message best pair is the unfilled get_best_bid_and_ask_inclQuants of the final book
+    np.testing.assert_array_equal(best[:, 0:2], z["best_asks"][:, -1]); np.testing.assert_array_equal(best[:, 2:4], z["best_bids"][:, -1])
+    l2 = E.l2_state(bc, torch.from_numpy(ga).cuda(), torch.from_numpy(gb).cuda(), 10).cpu().numpy()
+    np.testing.assert_array_equal(l2, z["l2"])
+
+
+# ---- env rollouts -------------------------------------------------------------------------------------------------
+def _parse_trace(lines):
+    out = []
+    for s in lines:
+        fn, caller, args, res = str(s).split("|")
+        out.append((fn, caller, ast.literal_eval(args), ast.literal_eval(res)))
+    return out
+
+
+def _set_draws(arrays, trace, B, n_act, T, kinds):
+    """One vmapped call under the shim runs env by env: split its trace into B groups."""
+    n_exe = sum(1 for k in kinds if k == abi.AGENT_EXE)
+    per = len(trace) // B
+    assert per * B == len(trace)
+    for e in range(B):
+        grp = trace[e * per:(e + 1) * per]
+        perms = [r for fn, c, a, r in grp if fn == "permutation"]
+        win = [r for fn, c, a, r in grp if fn == "randint" and c.startswith("reset_env:224")]
+        sell = [r for fn, c, a, r in grp if fn == "randint" and not c.startswith("reset_env:224")]
+        if perms:
+            arrays["perm"][e, :n_act] = perms[0]
+        assert len(win) == 1 and len(sell) == n_exe, (grp,)
+        arrays["reset_window"][e] = win[0]
+        it = iter(sell)
+        for t in range(T):
+            arrays["reset_is_sell"][e, t] = next(it) if kinds[t] == abi.AGENT_EXE else 0
+
+
+_STATE_ALIAS = {}
+
+
+def _compare(z, prefix, arrays, cfg, what, n_steps=1):
+    """Every golden leaf under ``prefix`` against our buffer table."""
+    T = cfg.n_agent_types
+    errs = []
+
+    def chk(name, got, ref):
+        ref = np.asarray(ref)
+        got = np.asarray(got).reshape(ref.shape) if np.asarray(got).size == ref.size else np.asarray(got)
+        if ref.dtype.kind in "iub":
+            if not np.array_equal(got.astype(np.int64), ref.astype(np.int64)):
+                errs.append(f"{what} {name}: int mismatch at {np.argwhere(got.astype(np.int64) != ref.astype(np.int64))[:4].tolist()} "
+                            f"got {got.ravel()[:6]} ref {ref.ravel()[:6]}")
+        else:
+            t = next((int(c) for c in name if c.isdigit()), -1)
+            ill = 0 <= t < T and cfg.agent[t].kind == abi.AGENT_EXE and any(k in name for k in ILL_CONDITIONED)
+            cum = n_steps if name.endswith("_return") else 1   # running sums accumulate the per-step rounding
+            ok = np.allclose(got, ref, rtol=1e-5, atol=(0.25 * cum if ill else 1e-6), equal_nan=True)
+            if not ok:
+                errs.append(f"{what} {name}: float mismatch got {got.ravel()[:6]} ref {ref.ravel()[:6]}")
+
+    for k in z.files:
+        if not k.startswith(prefix):
+            continue
+        leaf = k[len(prefix):]
+        if leaf.startswith("state/"):
+            name = leaf[6:]
+            if name in arrays:
+                chk(name, arrays[name], z[k])
+        elif leaf.startswith("obs"):
+            chk(leaf, arrays[leaf], z[k])
+        elif leaf.startswith("reward") or leaf.startswith("done_agents"):
+            chk(leaf, arrays[leaf], z[k])
+        elif leaf == "done_all":
+            chk(leaf, arrays["done_all"], z[k])
+    return errs
+
+
+def _compare_info(z, prefix, arrays, cfg):
+    errs = []
+    wi, wf = arrays["info_world_i32"], arrays["info_world_f32"]
+    world = {k: wi[:, j] for j, k in enumerate(abi.WINFO_I32)}
+    world.update({k: wf[:, j] for j, k in enumerate(abi.WINFO_F32)})
+    for key in z.files:
+        if key.startswith(prefix + "winfo/"):
+            name = key.split("/")[-1]
+            ref = z[key]
+            got = np.stack([world["time_s"], world["time_ns"]], 1) if name == "time" else world[name]
+            if ref.dtype.kind in "iub":
+                if not np.array_equal(got.astype(np.int64), ref.astype(np.int64)):
+                    errs.append(f"winfo {name}: got {got} ref {ref}")
+            elif not np.allclose(got, ref, rtol=1e-5, atol=1e-6):
+                errs.append(f"winfo {name}: got {got} ref {ref}")
+    for t in range(cfg.n_agent_types):
+        ki, kf = abi.info_cols(cfg.agent[t].kind)
+        d = {k: arrays[f"info_i32_{t}"][..., j] for j, k in enumerate(ki)}
+        d.update({k: arrays[f"info_f32_{t}"][..., j] for j, k in enumerate(kf)})
+        for key in z.files:
+            if key.startswith(f"{prefix}info{t}/"):
+                name = key.split("/")[-1]
+                ref = z[key]
+                got = d[name].reshape(ref.shape)
+                if ref.dtype.kind in "iub":
+                    if not np.array_equal(got.astype(np.int64), ref.astype(np.int64)):
+                        errs.append(f"info{t} {name}: got {got.ravel()} ref {ref.ravel()}")
+                else:
+                    ill = cfg.agent[t].kind == abi.AGENT_EXE and any(k in name for k in ILL_CONDITIONED + ("reward",))
+                    if not np.allclose(got, ref, rtol=1e-5, atol=(0.25 if ill else 1e-6), equal_nan=True):
+                        errs.append(f"info{t} {name}: got {got.ravel()} ref {ref.ravel()}")
+    return errs
+
+
+def _setup(z):
+    name = str(z["json"]).replace(".json", "")
+    mac = H.load_mac(name)
+    day = lobster.generate_day(seed=int(z["day_seed"]), n_events=int(z["n_events"]), stress=bool(int(z["stress"])))
+    ld = H.load_for(mac, day)
+    return mac, ld
+
+
+def _rollout(z, env, step_fn, reset_fn, get_arrays, set_inputs):
+    cfg = env.cfg
+    B, steps, T = int(z["B"]), int(z["steps"]), cfg.n_agent_types
+    kinds = [cfg.agent[t].kind for t in range(T)]
+    n_act = C.num_action_msgs(cfg)
+    inp = states.alloc_numpy(cfg, B)
+    _set_draws(inp, _parse_trace(z["reset_trace"]), B, n_act, T, kinds)
+    set_inputs(inp)
+    reset_fn()
+    errs = _compare(z, "reset/", get_arrays(), cfg, "reset")
+    assert not errs, "\n".join(errs[:10])
+    for s in range(steps):
+        _set_draws(inp, _parse_trace(z[f"step{s}/trace"]), B, n_act, T, kinds)
+        for t in range(T):
+            inp[f"actions{t}"][...] = z[f"step{s}/actions{t}"]
+        set_inputs(inp)
+        step_fn()
+        arr = get_arrays()
+        errs = _compare(z, f"step{s}/", arr, cfg, f"step {s}", s + 1) + _compare_info(z, f"step{s}/", arr, cfg)
+        assert not errs, f"step {s}:\n" + "\n".join(errs[:12])
+
+
+@pytest.mark.parametrize("path", ENV_CASES, ids=[os.path.basename(p) for p in ENV_CASES])
+def test_oracle_env_matches_reference(oracle, path):
+    z = np.load(path)
+    mac, ld = _setup(z)
+    env = H.OracleEnv(oracle, mac, ld, int(z["B"]))
+    assert env.cfg.n_windows == int(z["n_windows"])
+    _rollout(z, env, env.step, env.reset, lambda: env.arrays, lambda inp: H.copy_inputs(inp, env.arrays))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", ENV_CASES, ids=[os.path.basename(p) for p in ENV_CASES])
+def test_cuda_env_matches_reference(oracle, path):
+    z = np.load(path)
+    mac, ld = _setup(z)
+    bc = C.book_config(mac.world_config)
+    params = E.build_reset_params(ld, mac.world_config, E._cuda_replay_fn(bc, "cuda:0"))
+    gpu = H.CudaEnv(mac, ld, int(z["B"]), params)
+    _rollout(z, gpu, gpu.step, gpu.reset, gpu.numpy, gpu.set_inputs)
