@@ -265,6 +265,41 @@ __device__ __noinline__ void reset_env(const LobStepConfig& c, const LobStepBuff
   }
 }
 
+// marl:348-364 the scan of one step's message list, with the per-message best bid/ask (job:792-823) and the forward
+// fill (marl:723-749) done online.  A function of its own so that the hot loop gets its own register allocation:
+// nothing of the surrounding step (world scalars, agent bookkeeping) is live in it.
+struct ScanOut { float avg_sum, sum_a, sum_b; int prev_a, prev_b, abort_episode; };
+template <int SLOTS>
+__device__ __noinline__ ScanOut scan_messages(BookCtx ctx, const int4* m4, int N, int* best_asks, int* best_bids,
+                                              int prev_a, int prev_b) {
+  Book<SLOTS> bk;
+  bk.c = ctx;
+  bk.scan_side(ASK);
+  bk.scan_side(BID);
+  bk.ntr = 0; bk.tr_odd = false;   // the trade log was re-initialised for this step
+  ScanOut o;
+  o.avg_sum = 0.f; o.sum_a = 0.f; o.sum_b = 0.f; o.abort_episode = 0;
+  const int lane = lane_id();
+  int2* gq = reinterpret_cast<int2*>(lane == 0 ? best_asks : best_bids);
+#pragma unroll 1
+  for (int i = 0; i < N; ++i) {
+    bk.process(m4[2 * i], m4[2 * i + 1]);
+    bk.ensure(ASK);
+    bk.ensure(BID);
+    int ap = bk.bestp[ASK], aq = bk.bestq[ASK], bp = bk.bestp[BID], bq = bk.bestq[BID];
+    o.abort_episode |= (ap == -1) | (bp == -1);
+    if (ap == -1) { ap = prev_a; aq = 0; }      // marl:723-749 _ffill_best_prices, online
+    if (bp == -1) { bp = prev_b; bq = 0; }
+    prev_a = ap; prev_b = bp;
+    o.avg_sum += (float)(bp + ap) / 2.0f;
+    o.sum_a += (float)ap; o.sum_b += (float)bp;
+    if (lane < 2) gq[i] = (lane == 0) ? make_int2(ap, aq) : make_int2(bp, bq);
+  }
+  __syncwarp();
+  o.prev_a = prev_a; o.prev_b = prev_b;
+  return o;
+}
+
 // Phase-synchronous persistent CTA: ONE CTA per SM with as many warps as shared memory / registers allow (one
 // environment per warp).  The step has three code phases -- (1) stage state + build the agent messages, (2) the
 // message scan, (3) rewards / observations / write-back -- and the warps of the CTA pass them together
@@ -352,8 +387,6 @@ lob_step_kernel(const __grid_constant__ LobStepConfig c, const __grid_constant__
       mbar_wait(&bar[0], phase);
       phase ^= 1u;
       __syncwarp();
-      bk.scan_side(ASK);
-      bk.scan_side(BID);
 
       // ---- (C) marl:254-315 agent messages: [cancels | permuted actions | data] ----
       int ci = 0, ai = 0, flat = 0;
@@ -394,25 +427,10 @@ lob_step_kernel(const __grid_constant__ LobStepConfig c, const __grid_constant__
 
     // =================================================== phase 2: the message scan ===============================
     if (active) {
-      // ---- (D) marl:348-364 the scan, with the per-message best bid/ask (job:792-823) and the forward fill ----
-      prev_a = w.old_ba_last; prev_b = w.old_bb_last;
-      const int4* m4 = reinterpret_cast<const int4*>(msgs);
-      int2* gq = reinterpret_cast<int2*>((lane == 0 ? b.best_asks : b.best_bids) + e * N * 2);
-#pragma unroll 1
-      for (int i = 0; i < N; ++i) {
-        bk.process(m4[2 * i], m4[2 * i + 1]);
-        bk.ensure(ASK);
-        bk.ensure(BID);
-        int ap = bk.bestp[ASK], aq = bk.bestq[ASK], bp = bk.bestp[BID], bq = bk.bestq[BID];
-        abort_episode |= (ap == -1) | (bp == -1);
-        if (ap == -1) { ap = prev_a; aq = 0; }      // marl:723-749 _ffill_best_prices, online
-        if (bp == -1) { bp = prev_b; bq = 0; }
-        prev_a = ap; prev_b = bp;
-        avg_sum += (float)(bp + ap) / 2.0f;
-        sum_a += (float)ap; sum_b += (float)bp;
-        if (lane < 2) gq[i] = (lane == 0) ? make_int2(ap, aq) : make_int2(bp, bq);
-      }
-      __syncwarp();
+      const ScanOut so2 = scan_messages<SLOTS>(bk.c, reinterpret_cast<const int4*>(msgs), N, b.best_asks + e * N * 2,
+                                               b.best_bids + e * N * 2, w.old_ba_last, w.old_bb_last);
+      avg_sum = so2.avg_sum; sum_a = so2.sum_a; sum_b = so2.sum_b;
+      prev_a = so2.prev_a; prev_b = so2.prev_b; abort_episode = so2.abort_episode != 0;
     }
     __syncthreads();
 

@@ -1,0 +1,94 @@
+"""The C-ABI library (csrc/liblobstep.so) without a GPU: it loads, exports every symbol include/lobstep.h declares, its
+structs match the ctypes mirror, and its host-side validation rejects bad calls before touching the device."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+from jaxmarl_hft_b200 import _lib, abi, config as Cfg
+import helpers as H
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "lobstep.h")
+
+
+def _declared_functions():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    names = re.findall(r"^\s*(?:const\s+)?[A-Za-z_][A-Za-z0-9_\*\s]*?\b(lob_[a-z0-9_]+)\s*\(", src, flags=re.M)
+    return sorted(set(names))
+
+
+def test_header_declares_the_expected_entry_points():
+    names = _declared_functions()
+    for must in ("lob_step_launch", "lob_reset_launch", "lob_replay_launch", "lob_l2_launch", "lob_host_replay_run",
+                 "lob_last_error", "lob_abi_version", "lob_launch_count"):
+        assert must in names
+
+
+def test_library_exports_every_declared_symbol():
+    L = _lib.lib()
+    for name in _declared_functions():
+        assert hasattr(L, name), f"liblobstep.so does not export {name}"
+
+
+def test_struct_sizes_match_ctypes_mirror():
+    L = _lib.lib()
+    abi.check_sizes(L)
+    assert L.lob_abi_version() == abi.LOB_ABI_VERSION
+
+
+def test_derived_sizes_match_reference_formula():
+    """marl_env.py:85-94: N = Nd + sum_i n_i * num_messages_by_agent_i."""
+    L = _lib.lib()
+    for name, N, n_act in (("2_player_fq_fqc", 112, 6), ("exec_longrun_fixed_quants_complex", 108, 4),
+                           ("hetero_deep_book", 136, 18)):
+        mac = H.load_mac(name)
+        cfg = Cfg.to_step_config(mac, 4, 30000)
+        assert L.lob_num_msgs_per_step(C.byref(cfg)) == N == Cfg.num_msgs_per_step(cfg)
+        assert L.lob_num_action_msgs(C.byref(cfg)) == n_act == Cfg.num_action_msgs(cfg)
+        assert L.lob_num_cancel_msgs(C.byref(cfg)) == n_act
+
+
+def test_bad_calls_fail_loudly_before_the_device():
+    """Validation happens on the host: these return an error code with a message and never reach CUDA."""
+    L = _lib.lib()
+    mac = H.load_mac("2_player_fq_fqc")
+    cfg = Cfg.to_step_config(mac, 4, 30000)
+    bufs = abi.LobStepBuffers()     # all NULL
+    assert L.lob_step_launch(C.byref(cfg), C.byref(bufs), 8, None) == abi.LOB_E_INVALID
+    assert b"null" in L.lob_last_error()
+    bad = Cfg.to_step_config(mac, 4, 30000)
+    bad.book.n_orders = 100000
+    assert L.lob_step_launch(C.byref(bad), C.byref(bufs), 8, None) == abi.LOB_E_INVALID
+    bad = Cfg.to_step_config(mac, 4, 30000)
+    bad.book.cancel_mode = 2
+    assert L.lob_reset_launch(C.byref(bad), C.byref(bufs), 8, None) == abi.LOB_E_UNSUPPORTED
+    bad = Cfg.to_step_config(mac, 4, 30000)
+    bad.ep_type_fixed_time = 1
+    assert L.lob_step_launch(C.byref(bad), C.byref(bufs), 8, None) == abi.LOB_E_UNSUPPORTED
+    rb = abi.LobReplayBuffers()
+    bc = Cfg.book_config(mac.world_config)
+    assert L.lob_replay_launch(C.byref(bc), C.byref(rb), 8, None) == abi.LOB_E_INVALID
+
+
+def test_host_config_rejects_what_the_reference_rejects():
+    import dataclasses
+    mac = H.load_mac("2_player_fq_fqc")
+    agents = dict(mac.dict_of_agents_configs)
+    agents["MarketMaking"] = dataclasses.replace(agents["MarketMaking"], reward_function="nonsense")
+    with pytest.raises(ValueError):
+        Cfg.to_step_config(H.with_agents(mac, agents, [1, 1]), 4, 30000)
+    with pytest.raises(ValueError):
+        dataclasses.replace(agents["MarketMaking"], action_space="fixed_quants", tenth_action="bogus")
+
+
+def test_product_package_never_imports_the_oracle():
+    """The oracle is test infrastructure: nothing under jaxmarl-hft_b200/ may import or load it."""
+    pkg = os.path.join(ROOT, "jaxmarl-hft_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "lob_oracle" not in txt and "from oracle" not in txt and "import oracle" not in txt, f
