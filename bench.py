@@ -42,6 +42,17 @@ def _peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def _traffic(kernel):
+    """DRAM bytes per launch of ``kernel`` from the committed ncu capture (profiles/traffic.json), or None."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f).get(kernel)
+        if d:
+            return d["bytes"]
+    return None
+
+
 def _load_day(mac):
     from jaxmarl_hft_b200 import lobster
     cache = os.path.join(ROOT, ".cache")
@@ -343,7 +354,7 @@ def run_native(args):
                        "l2_policy": f"inputs larger than L2: {B * (2 * No * 24 + Nt * 32) / 1e6:.0f} MB of book state per GPU"},
             "base_env_steps_per_sec": value / ND,
             "roofline": {"bound": "hbm", "kernel": "lob_replay_kernel", "achieved": achieved, "peak": hbm_peak,
-                         "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                         "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": _traffic("lob_replay_kernel"), "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": bytes_per_launch, "kernel_ms": kern_ms},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * 8, "d2h_bytes_per_step": B * 16,
                     "api": "BaseLOBEnv.replay: start offsets from pinned host memory, best bid/ask per book read back; "
@@ -355,7 +366,7 @@ def run_native(args):
                          "config": {"workload": "MARLEnv.step 2_player_fq_fqc (MM fixed_quants + EXE fixed_quants_complex), "
                                                 "BASELINE configs[3] shapes", "envs_per_gpu": args.envs, "msgs_per_env_step": N},
                          "roofline": {"bound": "hbm", "kernel": "lob_step_kernel", "achieved": step_achieved,
-                                      "peak": hbm_peak, "unit": "GB/s", "frac": step_achieved / hbm_peak, "traffic": None,
+                                      "peak": hbm_peak, "unit": "GB/s", "frac": step_achieved / hbm_peak, "traffic": _traffic("lob_step_kernel"),
                                       "algorithmic_bytes_per_env_step": step_bytes, "kernel_ms": step_kern_ms},
                          "e2e": {"value": step_e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": step_h2d,
                                  "d2h_bytes_per_step": step_d2h},

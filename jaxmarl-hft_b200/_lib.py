@@ -7,7 +7,7 @@ import os
 from . import abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "csrc", "liblobstep.so")
+SO_PATH = os.environ.get("LOB_SO") or os.path.join(_HERE, "csrc", "liblobstep.so")   # LOB_SO: a variant build (development)
 _lib = None
 
 

@@ -17,7 +17,7 @@ OBJ = os.path.join(CSRC, "build")
 SLOTS = (1, 2, 4, 8, 16)
 # --fmad=false: a*b+c stays two roundings, as in the XLA lowering of the reference's float32 expressions
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--fmad=false",
-              "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
+              "-Xcompiler", "-fPIC", "-Xptxas", "-v"] + os.environ.get("LOB_NVCC_EXTRA", "").split()
 
 
 def _nvcc():

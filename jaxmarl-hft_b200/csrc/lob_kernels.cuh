@@ -17,7 +17,13 @@
 namespace lob {
 
 constexpr int kWarps = 4;            // warps (= environments in flight) per CTA
-constexpr int kReplayChunk = 32;     // messages per staged chunk of the replay kernel (1 KB, double buffered)
+#ifndef LOB_REPLAY_CHUNK
+#define LOB_REPLAY_CHUNK 32
+#endif
+#ifndef LOB_REPLAY_MINB
+#define LOB_REPLAY_MINB 6
+#endif
+constexpr int kReplayChunk = LOB_REPLAY_CHUNK;   // messages per staged chunk of the replay kernel (double buffered)
 constexpr int kMaxAgents = 16;       // agents per environment, all types
 
 // ---- bulk-copy engine + mbarrier (PTX) ----------------------------------------------------------------------
@@ -86,7 +92,7 @@ __host__ __device__ inline WarpLayout make_layout(int nrows, int msg_words, int 
 // ================================================================================================ replay ====
 // base_env.py:189-216 / job:736-756: book b scans msgs[start[b] .. start[b]+T); the trade log persists.
 template <int SLOTS>
-__global__ void __launch_bounds__(kWarps * 32, (SLOTS <= 4 ? 6 : SLOTS == 8 ? 3 : 1))
+__global__ void __launch_bounds__(kWarps * 32, (SLOTS <= 4 ? LOB_REPLAY_MINB : SLOTS == 8 ? 3 : 1))
 lob_replay_kernel(const __grid_constant__ LobBookConfig cfg, const __grid_constant__ LobReplayBuffers B,
                   long long n_books, WarpLayout L) {
   extern __shared__ __align__(128) int smem[];
