@@ -251,6 +251,14 @@ int lob_replay_launch(const LobBookConfig* cfg, const LobReplayBuffers* bufs, in
 int lob_l2_launch(const LobBookConfig* cfg, const int32_t* asks, const int32_t* bids, int32_t* l2,
                   int32_t n_levels, int64_t n_books, void* cuda_stream);
 
+/* The PRNG products of one step, drawn on the device by a counter-based generator: perm [B,n_action] (a uniform
+ * random permutation per environment, marl_env.py:293-295), reset_window [B] in [0, n_windows) or window_selector when it
+ * is >= 0 (base_env.py:222-225), reset_is_sell [B,n_agent_types] in {0,1} (exec_env.py:221).  The reference draws these
+ * with jax.random inside the step; here they are inputs of lob_step_launch, and this is the host layer's default source
+ * (any other source, e.g. jax.random through the FFI stub, is equally valid).  Deterministic in (seed, counter). */
+int lob_draw_launch(const LobStepConfig* cfg, const LobStepBuffers* bufs, int64_t batch, int32_t window_selector,
+                    uint64_t seed, uint64_t counter, void* cuda_stream);
+
 /* Host-buffer replay (the end-to-end leg): copies books/msgs/start host->device, replays,
  * copies books/trades back, synchronises the stream.  Device scratch is owned by the handle. */
 typedef struct LobHostReplay LobHostReplay;

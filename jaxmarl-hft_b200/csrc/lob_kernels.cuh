@@ -312,7 +312,10 @@ __device__ __noinline__ ScanOut scan_messages(BookCtx ctx, const int4* m4, int N
 // (__syncthreads between phases), so that at any time the SM's instruction cache serves ONE phase's code to all of its
 // warps instead of three phases to desynchronised warps (the L1.5 instruction cache is 32 KB; ncu showed the
 // unsynchronised version stalled on instruction fetch: smsp stall_no_instruction 8.2 of ~16 per issue).
-constexpr int kStepMaxWarps = 20;
+#ifndef LOB_STEP_MAXW
+#define LOB_STEP_MAXW 20
+#endif
+constexpr int kStepMaxWarps = LOB_STEP_MAXW;
 
 template <int SLOTS>
 __global__ void __launch_bounds__(kStepMaxWarps * 32, 1)
@@ -623,6 +626,35 @@ lob_l2_kernel(const __grid_constant__ LobBookConfig cfg, const int* __restrict__
         int4 o = make_int4(ask_p, max(va, 0), bid_p, max(vb, 0));
         *reinterpret_cast<int4*>(l2 + (b * n_levels + lv) * 4) = o;
       }
+    }
+  }
+}
+
+// ================================================================================================== draw ====
+// Counter-based PRNG products of one step (see lob_draw_launch in include/lobstep.h).  One thread per environment;
+// splitmix64 of (seed, counter, env, draw index); Fisher-Yates for the permutation.
+__device__ __forceinline__ unsigned long long mix64(unsigned long long z) {
+  z += 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+static __global__ void lob_draw_kernel(int* __restrict__ perm, int* __restrict__ reset_window, int* __restrict__ reset_is_sell,
+                                long long batch, int n_act, int n_windows, int n_types, int window_selector,
+                                unsigned long long seed, unsigned long long counter) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= batch) return;
+  unsigned long long st = mix64(seed ^ mix64(counter ^ mix64((unsigned long long)e)));
+  auto next = [&]() { st = mix64(st); return st; };
+  if (reset_window) reset_window[e] = window_selector >= 0 ? window_selector : (int)(((next() >> 32) * (unsigned long long)n_windows) >> 32);
+  if (reset_is_sell)
+    for (int t = 0; t < n_types; ++t) reset_is_sell[e * n_types + t] = (int)(next() >> 63);
+  if (perm && n_act > 0) {
+    int* p = perm + e * n_act;
+    for (int i = 0; i < n_act; ++i) p[i] = i;
+    for (int i = n_act - 1; i > 0; --i) {
+      const int j = (int)(((next() >> 32) * (unsigned long long)(i + 1)) >> 32);
+      const int a = p[i]; p[i] = p[j]; p[j] = a;
     }
   }
 }

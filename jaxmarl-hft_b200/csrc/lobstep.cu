@@ -243,6 +243,23 @@ int lob_l2_launch(const LobBookConfig* cfg, const int32_t* asks, const int32_t* 
   return rc;
 }
 
+int lob_draw_launch(const LobStepConfig* cfg, const LobStepBuffers* bufs, int64_t batch, int32_t window_selector,
+                    uint64_t seed, uint64_t counter, void* cuda_stream) {
+  if (!cfg || !bufs) return fail(LOB_E_INVALID, "null argument");
+  if (cfg->n_agent_types < 0 || cfg->n_agent_types > LOB_MAX_AGENT_TYPES || cfg->n_windows < 1)
+    return fail(LOB_E_INVALID, "bad configuration for lob_draw_launch");
+  if (window_selector >= cfg->n_windows) return fail(LOB_E_INVALID, "window_selector=%d outside [0,%d)", window_selector, cfg->n_windows);
+  if (batch < 0) return fail(LOB_E_INVALID, "batch=%lld", (long long)batch);
+  if (batch == 0) return LOB_OK;
+  const int n_act = lob_num_action_msgs(cfg);
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  const int threads = 128;
+  lob::lob_draw_kernel<<<(unsigned)((batch + threads - 1) / threads), threads, 0, st>>>(
+      const_cast<int*>(bufs->perm), const_cast<int*>(bufs->reset_window), const_cast<int*>(bufs->reset_is_sell), batch, n_act,
+      cfg->n_windows, cfg->n_agent_types, window_selector, seed, counter);
+  return launched("lob_draw_kernel");
+}
+
 /* ---- host-buffer replay: the end-to-end leg (H2D + replay + D2H inside one call) ---- */
 struct LobHostReplay {
   LobBookConfig cfg;

@@ -195,9 +195,9 @@ class MARLEnv:
                 1000 if isinstance(c, MarketMaking_EnvironmentConfig) else 10000,
                 (abi.obs_dim(self.cfg.agent[i].kind, self.cfg.agent[i].observation_space),), np.float32)
             for i, c in enumerate(self.list_of_agents_configs)]
-        self._gen = torch.Generator(device=self.device)
-        self._gen.manual_seed(int(seed))
-        self._arrays = None
+        self._seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+        self._counter = 0
+        self._cache = {}
 
     # -- API of the reference ------------------------------------------------------------------------------
     def action_space(self):
@@ -214,53 +214,57 @@ class MARLEnv:
             agent_params.append({"trader_id": np.arange(a.trader_id_start, a.trader_id_start - a.n_agents, -1)})
         return MultiAgentParams(loaded_params=self.base_env.default_params, agent_params=agent_params)
 
-    def _draw(self, arrays):
-        """The PRNG products of one step (see module docstring)."""
-        import torch
-        B, W = self.num_envs, self.cfg.n_windows
-        sel = self.multi_agent_config.world_config.window_selector
-        if sel == -1:
-            arrays["reset_window"].copy_(torch.randint(0, W, (B,), generator=self._gen, device=self.device,
-                                                       dtype=torch.int32))
-        else:
-            arrays["reset_window"].fill_(sel)
-        arrays["reset_is_sell"].copy_(torch.randint(0, 2, arrays["reset_is_sell"].shape, generator=self._gen,
-                                                    device=self.device, dtype=torch.int32))
-        n_act = self.num_action_msgs_per_step_by_all_agents
-        if n_act > 0:
-            r = torch.rand((B, n_act), generator=self._gen, device=self.device)
-            arrays["perm"].copy_(torch.argsort(r, dim=1).to(torch.int32))
+    # -- per-buffer-table caches: the state leaves are updated in place, so pointers and views never change ----------
+    def _bound(self, arrays):
+        key = id(arrays)
+        hit = self._cache.get(key)
+        if hit is None or hit[0] is not arrays:
+            bufs = states.pack_buffers(self.cfg, arrays, self.base_env.device_params())
+            T = self.cfg.n_agent_types
+            obs = [arrays[f"obs{t}"] for t in range(T)]
+            rewards = [arrays[f"reward{t}"] for t in range(T)]
+            import torch
+            dones = {"__all__": arrays["done_all"].view(torch.bool),
+                     "agents": [arrays[f"done_agents{t}"].view(torch.bool) for t in range(T)]}
+            hit = (arrays, bufs, obs, rewards, dones, self.unpack_info(arrays), _state_view(self.cfg, arrays))
+            self._cache = {key: hit}
+        return hit
 
-    def reset(self, key=None, params: MultiAgentParams = None, arrays=None):
+    def _draw(self, arrays, bufs):
+        """The PRNG products of one step (see module docstring): lob_draw_launch, counter-based, on the device."""
+        self._counter += 1
+        _lib.check(_lib.lib().lob_draw_launch(C.byref(self.cfg), C.byref(bufs), self.num_envs,
+                                              int(self.multi_agent_config.world_config.window_selector),
+                                              self._seed, self._counter, _lib.current_stream_ptr()), "lob_draw_launch")
+
+    def reset(self, key=None, params: MultiAgentParams = None, arrays=None, draw=True):
         """marl_env.py:764 -> (obs list [B,n_i,d_i], MultiAgentState)."""
         if params is None:
             raise ValueError("Params must be provided to reset the environment.")
         L = _lib.lib()
         if arrays is None:
             arrays = states.alloc_torch(self.cfg, self.num_envs, self.device)
-            self._draw(arrays)
-        bufs = states.pack_buffers(self.cfg, arrays, self.base_env.device_params())
+        _, bufs, obs, _, _, _, state = self._bound(arrays)
+        if draw:
+            self._draw(arrays, bufs)
         _lib.check(L.lob_reset_launch(C.byref(self.cfg), C.byref(bufs), self.num_envs, _lib.current_stream_ptr()),
                    "lob_reset_launch")
-        obs = [arrays[f"obs{t}"] for t in range(self.cfg.n_agent_types)]
-        return obs, _state_view(self.cfg, arrays)
+        return obs, state
 
     def step(self, key, state: MultiAgentState, actions, params: MultiAgentParams = None, draw=True):
-        """marl_env.py:776 -> (obs, state, rewards, dones, infos); ``state``'s buffers are donated."""
+        """marl_env.py:776 -> (obs, state, rewards, dones, infos); ``state``'s buffers are donated (updated in place)
+        and the returned tensors are views of them."""
         L = _lib.lib()
         arrays = state.arrays
+        _, bufs, obs, rewards, dones, info, view = self._bound(arrays)
         for t, a in enumerate(actions):
-            arrays[f"actions{t}"].copy_(a.reshape(arrays[f"actions{t}"].shape))
+            dst = arrays[f"actions{t}"]
+            dst.copy_(a.reshape(dst.shape), non_blocking=True)
         if draw:
-            self._draw(arrays)
-        bufs = states.pack_buffers(self.cfg, arrays, self.base_env.device_params())
+            self._draw(arrays, bufs)
         _lib.check(L.lob_step_launch(C.byref(self.cfg), C.byref(bufs), self.num_envs, _lib.current_stream_ptr()),
                    "lob_step_launch")
-        T = self.cfg.n_agent_types
-        obs = [arrays[f"obs{t}"] for t in range(T)]
-        rewards = [arrays[f"reward{t}"] for t in range(T)]
-        dones = {"__all__": arrays["done_all"].bool(), "agents": [arrays[f"done_agents{t}"].bool() for t in range(T)]}
-        return obs, _state_view(self.cfg, arrays), rewards, dones, self.unpack_info(arrays)
+        return obs, view, rewards, dones, info
 
     def unpack_info(self, arrays):
         """Packed info columns -> the reference's dict keys (marl:624-639, mm:2695-2730, exe:1809-1829)."""

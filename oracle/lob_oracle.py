@@ -75,7 +75,13 @@ class Oracle:
         return out
 
     def max_threads(self):
-        return int(self.lib.lob_oracle_max_threads())
+        """Host threads the OpenMP legs may use: the CPUs this process may run on (libgomp alone reports 1 when the
+        environment pins OMP_NUM_THREADS)."""
+        try:
+            n = len(os.sched_getaffinity(0))
+        except AttributeError:
+            n = os.cpu_count() or 1
+        return max(int(self.lib.lob_oracle_max_threads()), n)
 
 
 def load():

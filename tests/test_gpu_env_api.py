@@ -1,0 +1,82 @@
+"""The public Python API (env.MARLEnv / BaseLOBEnv, the reference's names) on a B200: shapes, dict keys, the device-side
+PRNG products, and agreement with the oracle when it is fed the same draws."""
+import numpy as np
+import pytest
+
+import helpers as H
+from jaxmarl_hft_b200 import abi, config as C, env as E
+
+pytestmark = pytest.mark.gpu
+
+
+def test_draw_kernel_products_are_valid_and_deterministic():
+    import torch
+    mac = H.load_mac("hetero_deep_book")
+    ld = H.load_for(mac, H.small_day(n_events=30000))
+    env = E.MARLEnv(None, mac, num_envs=4096, loaded=ld, device="cuda:0", seed=7)
+    obs, state = env.reset(None, env.default_params)
+    a = {k: state.arrays[k].clone() for k in ("perm", "reset_window", "reset_is_sell")}
+    n_act = env.num_action_msgs_per_step_by_all_agents
+    srt = torch.sort(a["perm"], dim=1).values.cpu().numpy()
+    np.testing.assert_array_equal(srt, np.tile(np.arange(n_act), (4096, 1)))       # every row is a permutation
+    assert int(a["reset_window"].min()) >= 0 and int(a["reset_window"].max()) < env.cfg.n_windows
+    assert set(np.unique(a["reset_is_sell"].cpu().numpy())) <= {0, 1}
+    assert len(np.unique(a["reset_window"].cpu().numpy())) == env.cfg.n_windows    # all windows get drawn
+    first = a["perm"][:, 0].float().mean().item()
+    assert abs(first - (n_act - 1) / 2) < 0.5                                       # roughly uniform
+    env2 = E.MARLEnv(None, mac, num_envs=4096, loaded=ld, device="cuda:0", seed=7)
+    _, st2 = env2.reset(None, env2.default_params)
+    for k in a:
+        assert torch.equal(a[k], st2.arrays[k])                                     # deterministic in (seed, counter)
+
+
+def test_marl_env_api_matches_reference_surface_and_oracle(oracle):
+    import torch
+    mac = H.load_mac("2_player_fq_fqc")
+    ld = H.load_for(mac, H.small_day(n_events=30000))
+    B = 64
+    env = E.MARLEnv(None, mac, num_envs=B, loaded=ld, device="cuda:0", seed=3)
+    assert env.type_names == ["MM", "EXE"] and env.num_agents == 2
+    assert [s.n for s in env.action_spaces] == [10, 13]
+    assert [s.shape for s in env.observation_spaces] == [(2,), (12,)]
+    params = env.default_params
+    assert params.loaded_params.message_data.shape == (ld.msgs.shape[0], 8)
+    obs, state = env.reset(None, params)
+    assert [tuple(o.shape) for o in obs] == [(B, 1, 2), (B, 1, 12)]
+    assert tuple(state.world_state.ask_raw_orders.shape) == (B, 100, 6)
+    ref = H.OracleEnv(oracle, mac, ld, B)
+    ref.arrays.update({k: v.copy() for k, v in H.to_numpy(state.arrays).items()})   # same reset state + draws
+    rng = np.random.default_rng(0)
+    for s in range(66):
+        acts = [torch.from_numpy(rng.integers(0, sp.n, size=(B, 1)).astype(np.int32)).cuda() for sp in env.action_spaces]
+        obs, state, rewards, dones, info = env.step(None, state, acts, params)
+        got = H.to_numpy(state.arrays)
+        H.copy_inputs(got, ref.arrays)              # the oracle gets the draws the device made
+        ref.step()
+        H.assert_arrays_match(ref.arrays, got, ref.cfg)
+        assert dones["__all__"].dtype == torch.bool and tuple(dones["agents"][1].shape) == (B, 1)
+    assert set(info["world"]) >= {"window_index", "end_mid_price", "time", "average_best_ask", "abort_episode", "spread"}
+    assert set(info["agents"][0]) == set(abi.MMINFO_I32 + abi.MMINFO_F32)
+    assert set(info["agents"][1]) == set(abi.EXEINFO_I32 + abi.EXEINFO_F32)
+    with pytest.raises(ValueError):
+        env.reset(None, None)
+
+
+def test_base_env_replay_api(oracle):
+    import torch
+    mac = H.load_mac("2_player_fq_fqc")
+    ld = H.load_for(mac, H.small_day(n_events=30000))
+    be = E.BaseLOBEnv(mac.world_config, loaded=ld, device="cuda:0")
+    p = be.default_params
+    W = be.n_windows
+    a = p.init_states_array["init_asks"].clone(); b = p.init_states_array["init_bids"].clone()
+    t = p.init_states_array["init_trades"].clone()
+    start = torch.from_numpy(ld.starts.astype(np.int64)).cuda()
+    best = torch.zeros((W, 4), dtype=torch.int32, device="cuda")
+    be.replay(a, b, t, start, 100, best_out=best)      # one base-env step (base_env.py:189) for every window
+    ra, rb, rt = (x.cpu().numpy().copy() for x in (p.init_states_array["init_asks"], p.init_states_array["init_bids"],
+                                                    p.init_states_array["init_trades"]))
+    rbest = np.zeros((W, 4), np.int32)
+    oracle.replay(be.book_cfg, ra, rb, rt, ld.msgs, ld.starts.astype(np.int64), 100, best_out=rbest)
+    np.testing.assert_array_equal(a.cpu().numpy(), ra); np.testing.assert_array_equal(b.cpu().numpy(), rb)
+    np.testing.assert_array_equal(t.cpu().numpy(), rt); np.testing.assert_array_equal(best.cpu().numpy(), rbest)
