@@ -158,6 +158,8 @@ def run_native(args):
 
     ws, rank, local = _dist()
     if ws > 1:
+        # NCCL's version banner goes to stdout and would precede the one JSON line the driver parses
+        os.environ["NCCL_DEBUG"] = os.environ.get("LOB_NCCL_DEBUG", "WARN")
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     torch.cuda.set_device(local)
     dev = torch.device(f"cuda:{local}")

@@ -88,12 +88,50 @@ def collect_prng(trace, B, n_act, n_types):
     return perms, windows, sells
 
 
-def run_env_case(name, json_name, seed, B, steps, n_events=30000, stress=False, out_dir=HERE, **world_overrides):
+def hetero_agents(mac):
+    """3 agent types for the reference: MM fixed_quants (engineered obs, spooner reward, far-touch reference),
+    EXE fixed_quants_complex (far_touch doom price, lambda 0.5), directional (MM class, directional_trading)."""
+    from gymnax_exchange.jaxob.jaxob_config import MultiAgentConfig
+    d = dict(mac.dict_of_agents_configs)
+    mm, ex = d["MarketMaking"], d["Execution"]
+    agents = {
+        "MarketMaking": dataclasses.replace(mm, observation_space="engineered", reward_function="spooner",
+                                            reference_price="far_touch", unwind_price="far_touch", inv_penalty="quadratic",
+                                            fixed_quant_value=5, clip_reward=True, exclude_extreme_spreads=True,
+                                            volume_traded_bonus="market_share", unwind_price_penalty=3),
+        "Execution": dataclasses.replace(ex, reference_price="far_touch", reward_lambda=0.5, task_size=300, task="random"),
+        "Directional": dataclasses.replace(mm, short_name="DIR", action_space="directional_trading", observation_space="basic",
+                                           reward_function="delta_portfolio_value", reference_price="mid_avg",
+                                           unwind_price="mid_avg", fixed_quant_value=7),
+    }
+    return MultiAgentConfig(world_config=mac.world_config, dict_of_agents_configs=agents, number_of_agents_per_type=[2, 2, 1])
+
+
+def mm_complex_agents(mac):
+    from gymnax_exchange.jaxob.jaxob_config import MultiAgentConfig
+    d = dict(mac.dict_of_agents_configs)
+    mm, ex = d["MarketMaking"], d["Execution"]
+    agents = {
+        "MarketMaking": dataclasses.replace(mm, reward_function="complex", reference_price="near_touch", unwind_price="mid",
+                                            inv_penalty="threshold", inv_penalty_threshold=2.0, auto_liquidate_threshold=3,
+                                            observation_space="engineered", normalize=False, fixed_quant_value=4),
+        "Execution": dataclasses.replace(ex, observation_space="basic", reward_function="finish_fast", task="sell",
+                                         normalize=False, task_size=80),
+    }
+    return MultiAgentConfig(world_config=mac.world_config, dict_of_agents_configs=agents, number_of_agents_per_type=[2, 1])
+
+
+MUTATORS = {"hetero": hetero_agents, "mm_complex": mm_complex_agents}
+
+
+def run_env_case(name, json_name, seed, B, steps, n_events=30000, stress=False, out_dir=HERE, mutate=None, **world_overrides):
     from gymnax_exchange.jaxen.marl_env import MARLEnv
     import jax.random as jr
     with tempfile.TemporaryDirectory() as tmp:
         write_day(tmp, seed=5 if not stress else 9, n_events=n_events, stress=stress)
         mac = reference_config(json_name, tmp, **world_overrides)
+        if mutate:
+            mac = MUTATORS[mutate](mac)
         env = MARLEnv(jr.PRNGKey(seed), mac)
         params = env.default_params
         n_types = len(env.instance_list)
@@ -107,7 +145,7 @@ def run_env_case(name, json_name, seed, B, steps, n_events=30000, stress=False, 
         reset_trace = list(jr.TRACE)
         record = {"B": np.int64(B), "steps": np.int64(steps), "json": np.array(json_name),
                   "day_seed": np.int64(5 if not stress else 9), "n_events": np.int64(n_events), "stress": np.int64(stress),
-                  "world_overrides": np.array(repr(sorted(world_overrides.items())))}
+                  "world_overrides": np.array(repr(sorted(world_overrides.items()))), "mutate": np.array(mutate or "")}
         record["reset_trace"] = np.array([f"{fn}|{caller}|{args}|{np.asarray(res).tolist()}" for fn, caller, k, args, res in reset_trace])
         st0 = flatten_state(state, n_types, None)
         for k2, v in st0.items():
@@ -188,3 +226,7 @@ if __name__ == "__main__":
     if "env" in which:
         run_env_case("env_2player", "2_player_fq_fqc.json", seed=3, B=3, steps=68)
         run_env_case("env_exec", "exec_longrun_fixed_quants_complex.json", seed=4, B=2, steps=20)
+    if "env2" in which:
+        run_env_case("env_hetero_smallbook", "2_player_fq_fqc.json", seed=6, B=2, steps=66, stress=True, mutate="hetero",
+                     nOrders=40, nTrades=24)
+        run_env_case("env_mm_complex", "2_player_fq_fqc.json", seed=7, B=2, steps=66, mutate="mm_complex")

@@ -73,9 +73,11 @@ def _parse_trace(lines):
     return out
 
 
-def _set_draws(arrays, trace, B, n_act, T, kinds):
+def _set_draws(arrays, trace, B, n_act, T, kinds, n_agents=None, random_task=None):
     """One vmapped call under the shim runs env by env: split its trace into B groups."""
-    n_exe = sum(1 for k in kinds if k == abi.AGENT_EXE)
+    n_agents = n_agents or [1] * T
+    random_task = random_task or [kinds[t] == abi.AGENT_EXE for t in range(T)]  # exec_env.py:220-223: only task="random" draws
+    n_exe = sum(n_agents[t] for t in range(T) if random_task[t])   # one draw per agent, same key per type (Q9)
     per = len(trace) // B
     assert per * B == len(trace)
     for e in range(B):
@@ -89,7 +91,12 @@ def _set_draws(arrays, trace, B, n_act, T, kinds):
         arrays["reset_window"][e] = win[0]
         it = iter(sell)
         for t in range(T):
-            arrays["reset_is_sell"][e, t] = next(it) if kinds[t] == abi.AGENT_EXE else 0
+            if random_task[t]:
+                draws = [next(it) for _ in range(n_agents[t])]
+                assert len(set(draws)) == 1    # marl_env.py:187: all agents of a type share the reset key
+                arrays["reset_is_sell"][e, t] = draws[0]
+            else:
+                arrays["reset_is_sell"][e, t] = 0
 
 
 _STATE_ALIAS = {}
@@ -166,9 +173,41 @@ def _compare_info(z, prefix, arrays, cfg):
     return errs
 
 
+def _mutate(mac, how):
+    """The same agent sets tests/golden/make_golden.py builds for the reference (MUTATORS there), in our config classes."""
+    import dataclasses
+    d = dict(mac.dict_of_agents_configs)
+    mm, ex = d["MarketMaking"], d["Execution"]
+    if how == "hetero":
+        agents = {
+            "MarketMaking": dataclasses.replace(mm, observation_space="engineered", reward_function="spooner",
+                                                reference_price="far_touch", unwind_price="far_touch", inv_penalty="quadratic",
+                                                fixed_quant_value=5, clip_reward=True, exclude_extreme_spreads=True,
+                                                volume_traded_bonus="market_share", unwind_price_penalty=3),
+            "Execution": dataclasses.replace(ex, reference_price="far_touch", reward_lambda=0.5, task_size=300, task="random"),
+            "Directional": dataclasses.replace(mm, short_name="DIR", action_space="directional_trading",
+                                               observation_space="basic", reward_function="delta_portfolio_value",
+                                               reference_price="mid_avg", unwind_price="mid_avg", fixed_quant_value=7),
+        }
+        return H.with_agents(mac, agents, [2, 2, 1])
+    if how == "mm_complex":
+        agents = {
+            "MarketMaking": dataclasses.replace(mm, reward_function="complex", reference_price="near_touch", unwind_price="mid",
+                                                inv_penalty="threshold", inv_penalty_threshold=2.0, auto_liquidate_threshold=3,
+                                                observation_space="engineered", normalize=False, fixed_quant_value=4),
+            "Execution": dataclasses.replace(ex, observation_space="basic", reward_function="finish_fast", task="sell",
+                                             normalize=False, task_size=80),
+        }
+        return H.with_agents(mac, agents, [2, 1])
+    raise KeyError(how)
+
+
 def _setup(z):
     name = str(z["json"]).replace(".json", "")
-    mac = H.load_mac(name)
+    overrides = dict(ast.literal_eval(str(z["world_overrides"]))) if "world_overrides" in z.files else {}
+    mac = H.load_mac(name, **overrides)
+    if "mutate" in z.files and str(z["mutate"]):
+        mac = _mutate(mac, str(z["mutate"]))
     day = lobster.generate_day(seed=int(z["day_seed"]), n_events=int(z["n_events"]), stress=bool(int(z["stress"])))
     ld = H.load_for(mac, day)
     return mac, ld
@@ -180,13 +219,15 @@ def _rollout(z, env, step_fn, reset_fn, get_arrays, set_inputs):
     kinds = [cfg.agent[t].kind for t in range(T)]
     n_act = C.num_action_msgs(cfg)
     inp = states.alloc_numpy(cfg, B)
-    _set_draws(inp, _parse_trace(z["reset_trace"]), B, n_act, T, kinds)
+    n_agents = [cfg.agent[t].n_agents for t in range(T)]
+    rnd = [cfg.agent[t].kind == abi.AGENT_EXE and cfg.agent[t].task == abi.EXE_TASKS["random"] for t in range(T)]
+    _set_draws(inp, _parse_trace(z["reset_trace"]), B, n_act, T, kinds, n_agents, rnd)
     set_inputs(inp)
     reset_fn()
     errs = _compare(z, "reset/", get_arrays(), cfg, "reset")
     assert not errs, "\n".join(errs[:10])
     for s in range(steps):
-        _set_draws(inp, _parse_trace(z[f"step{s}/trace"]), B, n_act, T, kinds)
+        _set_draws(inp, _parse_trace(z[f"step{s}/trace"]), B, n_act, T, kinds, n_agents, rnd)
         for t in range(T):
             inp[f"actions{t}"][...] = z[f"step{s}/actions{t}"]
         set_inputs(inp)
