@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define LOB_ABI_VERSION 1
+#define LOB_ABI_VERSION 2
 #define LOB_MAX_AGENT_TYPES 4
 #define LOB_MAX_AGENT_I32 4  /* int32 state leaves per agent type */
 #define LOB_MAX_AGENT_F32 10 /* float32 state leaves per agent type */
@@ -55,9 +55,12 @@ extern "C" {
 enum LobAgentKind { LOB_AGENT_MM = 0, LOB_AGENT_EXE = 1 };
 
 /* MarketMaking_EnvironmentConfig.action_space  jaxob_config.py:55 ; mm_env.py:161-178 */
-enum LobMMActionSpace { LOB_MM_ACT_FIXED_QUANTS = 0, LOB_MM_ACT_DIRECTIONAL = 1 };
+enum LobMMActionSpace { LOB_MM_ACT_FIXED_QUANTS = 0, LOB_MM_ACT_DIRECTIONAL = 1,
+                         LOB_MM_ACT_BOB_RL = 2 /* mm_env.py:1474 */, LOB_MM_ACT_BOB_STRATEGY = 3 /* mm_env.py:1400 */ };
 /* Execution_EnvironmentConfig.action_space     jaxob_config.py:157 ; exec_env.py:162-175 */
-enum LobEXEActionSpace { LOB_EXE_ACT_FIXED_QUANTS = 0, LOB_EXE_ACT_FIXED_QUANTS_COMPLEX = 1 };
+enum LobEXEActionSpace { LOB_EXE_ACT_FIXED_QUANTS = 0, LOB_EXE_ACT_FIXED_QUANTS_COMPLEX = 1,
+                          LOB_EXE_ACT_FIXED_QUANTS_1MSG = 2 /* exec_env.py:732 */, LOB_EXE_ACT_SIMPLEST_CASE = 3 /* :935 */,
+                          LOB_EXE_ACT_TWAP = 4 /* :1126 */ };
 /* observation_space  mm_env.py:2767-2788 ; exec_env.py:179-186 */
 enum LobObsSpace { LOB_OBS_ENGINEERED = 0, LOB_OBS_BASIC = 1 };
 /* MM reward_function  mm_env.py:2489-2513 */
@@ -123,6 +126,7 @@ typedef struct LobAgentTypeConfig {
   int32_t n_ticks_in_book;
   int32_t larger_far_touch_quant;
   int32_t doom_price_penalty;
+  int32_t bob_v0;                       /* market making: bobRL / bobStrategy base quantity (1, 2, 5 or 10) */
   /* python floats of the config: kept as double, narrowed to f32 where JAX's weak typing does */
   double auto_liquidate_alpha;
   double inv_penalty_lambda;

@@ -256,6 +256,9 @@ def agent_type_config(cfg, n_agents: int, trader_id_start: int) -> abi.LobAgentT
         a.action_space = _enum(abi.MM_ACTION_SPACES, cfg.action_space, "action_space")
         a.reward_function = _enum(abi.MM_REWARDS, cfg.reward_function, "reward_space")
         a.n_ticks_offset = cfg.n_ticks_offset
+        a.bob_v0 = cfg.bob_v0
+        if cfg.action_space in ("bobRL", "bobStrategy") and cfg.bob_v0 not in _BOB_RL_ACTIONS and cfg.action_space == "bobRL":
+            raise ValueError("cfg.bob_v0 must be one of [1,2,5,10]")  # mm:1522
         a.tenth_action_market_order = int(cfg.tenth_action == "MarketOrder")
         if cfg.sell_buy_all_option:
             raise NotImplementedError("sell_buy_all_option=True (mm:1018-1024) is not built")
@@ -287,6 +290,9 @@ def agent_type_config(cfg, n_agents: int, trader_id_start: int) -> abi.LobAgentT
         a.task_size = cfg.task_size
         a.n_ticks_in_book = cfg.n_ticks_in_book
         a.larger_far_touch_quant = int(cfg.larger_far_touch_quant)
+        if cfg.action_space == "fixed_quants_1msg" and cfg.larger_far_touch_quant:
+            # exec_env.py:790 branches in Python on a traced action: the reference cannot trace this combination
+            raise NotImplementedError("fixed_quants_1msg with larger_far_touch_quant=True does not trace in the reference")
         a.doom_price_penalty = cfg.doom_price_penalty
         if cfg.reference_price not in ("mid", "far_touch"):
             raise ValueError("Invalid reference price type.")  # exe:1576-1580

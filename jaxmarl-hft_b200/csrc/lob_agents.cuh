@@ -179,8 +179,8 @@ static __device__ __noinline__ MMOut mm_get_messages(BookCtx bk, const LobStepCo
   MMOut o;
   int best_ask = 0, best_bid = 0;
   bool empty_book = false;
-  if (ac.action_space == LOB_MM_ACT_FIXED_QUANTS) {
-    // mm:979-985 best prices excluding own orders
+  if (ac.action_space != LOB_MM_ACT_DIRECTIONAL) {
+    // mm:979-985 (== mm:1411-1430, 1482-1500) best prices excluding own orders
     int mn = bk.maxint, mx = INT32_MIN;
 #pragma unroll 1
     for (int r = lane; r < bk.no; r += 32) {
@@ -235,6 +235,27 @@ static __device__ __noinline__ MMOut mm_get_messages(BookCtx bk, const LobStepCo
     o.posted_bid_price = bid_price; o.posted_ask_price = ask_price;
     o.bid_dist = best_bid - bid_price; o.ask_dist = ask_price - best_ask;
     o.bid_quant = bid_quant; o.ask_quant = ask_quant;
+  } else if (ac.action_space == LOB_MM_ACT_BOB_RL || ac.action_space == LOB_MM_ACT_BOB_STRATEGY) {
+    // mm:1474-1560 / mm:1400-1471: quotes AT the best prices, sizes from a table / the inventory-skewed formula
+    if (ac.fixed_action_setting) action = ac.fixed_action;
+    int bid_quant, ask_quant;
+    if (ac.action_space == LOB_MM_ACT_BOB_RL) {
+      const int v0 = ac.bob_v0;
+      const int ai = clamp_index(action, 2 * v0 + 1);
+      const int k = (ai + 1) / 2;   // tables of mm:1502-1520: 0 -> (v0, v0), 2k-1 -> (v0+k, v0-k), 2k -> (v0-k, v0+k)
+      const int bq = (ai == 0) ? v0 : ((ai & 1) ? v0 + k : v0 - k);
+      const int aq = (ai == 0) ? v0 : ((ai & 1) ? v0 - k : v0 + k);
+      bid_quant = bq * ac.fixed_quant_value; ask_quant = aq * ac.fixed_quant_value;
+    } else {
+      const float kappa = (float)(action + 1) / (float)(ac.bob_v0 * 5);
+      const float v0 = (float)ac.bob_v0, pos = (float)inventory;
+      bid_quant = f2i(rintf(v0 * jmaxf(1.0f - kappa * pos, 0.0f)));
+      ask_quant = f2i(rintf(v0 * jmaxf(1.0f + kappa * pos, 0.0f)));
+    }
+    if (empty_book) { bid_quant = 0; ask_quant = 0; }
+    quants[0] = bid_quant; quants[1] = ask_quant; prices[0] = best_bid; prices[1] = best_ask;
+    o.posted_bid_price = 0; o.posted_ask_price = 0; o.bid_dist = 0; o.ask_dist = 0;
+    o.bid_quant = bid_quant; o.ask_quant = ask_quant;
   } else {  // directional_trading
     const int ba = ifloordiv(w.old_ba_last, tick) * tick, bb = ifloordiv(w.old_bb_last, tick) * tick;
     const int ai = clamp_index(action, 3);
@@ -275,29 +296,51 @@ static __device__ __noinline__ void exe_get_messages(BookCtx bk, const LobStepCo
     lv[2] = best_bid;
     lv[3] = best_bid - tick * ac.n_ticks_in_book;
   }
-  int q[4] = {0, 0, 0, 0};
-  int first0 = 1;  // quant_array[1][0]
-  if (ac.action_space == LOB_EXE_ACT_FIXED_QUANTS_COMPLEX) {
-    const int ai = clamp_index(action, 13);
-    const int mult = (ai >= 9) ? 5 : (ai >= 5) ? 2 : 1;
-    if (ai > 0) {
-      const int col = (ai - 1) & 3;
-#pragma unroll
-      for (int k = 0; k < 4; ++k) if (k == col) q[k] = mult;
+  const int quant_left = task_to_execute - quant_executed;
+  const int ka = ac.num_action_messages_by_agent;
+  int q[4] = {0, 0, 0, 0}, pr[4] = {lv[0], lv[1], lv[2], lv[3]};
+  if (ac.action_space == LOB_EXE_ACT_FIXED_QUANTS_1MSG) {        // exe:732-835
+    const int ai = clamp_index(action, 5);
+    pr[0] = (ai == 0) ? 0 : (ai == 1) ? lv[0] : (ai == 2) ? lv[1] : (ai == 3) ? lv[2] : lv[3];
+    const int sel = (ai == 0) ? 0 : ac.fixed_quant_value;
+    q[0] = (sel <= quant_left) ? sel : 0;
+  } else if (ac.action_space == LOB_EXE_ACT_TWAP) {              // exe:1126-1227
+    const int steps_left = w.max_steps - w.step_counter - 1;
+    const int qts = f2i(ceilf((float)max(quant_left, 0) / (float)steps_left));
+    const int ai = clamp_index(action, 2);
+    pr[0] = lv[0]; pr[1] = lv[2];
+    q[0] = (ai == 0) ? qts : 0; q[1] = (ai == 1) ? qts : 0;
+  } else if (ac.action_space == LOB_EXE_ACT_SIMPLEST_CASE) {     // exe:935-999
+    const int ai = clamp_index(action, 3);
+    pr[0] = lv[0]; pr[1] = lv[2];
+    q[0] = (ai == 1) ? ac.fixed_quant_value : 0; q[1] = (ai == 2) ? ac.fixed_quant_value : 0;
+    if (!(q[0] + q[1] <= quant_left)) {
+      q[0] = f2i(floorf((float)(ac.fixed_quant_value * quant_left)));
+      q[1] = f2i(floorf((float)(0 * quant_left)));
     }
   } else {
-    const int ai = clamp_index(action, 5);
-    if (ac.larger_far_touch_quant) first0 = 10;
+    int first0 = 1;  // quant_array[1][0]
+    if (ac.action_space == LOB_EXE_ACT_FIXED_QUANTS_COMPLEX) {
+      const int ai = clamp_index(action, 13);
+      const int mult = (ai >= 9) ? 5 : (ai >= 5) ? 2 : 1;
+      if (ai > 0) {
+        const int col = (ai - 1) & 3;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) if (ai == k + 1) q[k] = (k == 0 && ac.larger_far_touch_quant) ? 10 : 1;
-  }
-  int total = 0;
+        for (int k = 0; k < 4; ++k) if (k == col) q[k] = mult;
+      }
+    } else {
+      const int ai = clamp_index(action, 5);
+      if (ac.larger_far_touch_quant) first0 = 10;
 #pragma unroll
-  for (int k = 0; k < 4; ++k) { q[k] *= ac.fixed_quant_value; total += q[k]; }
-  const int quant_left = task_to_execute - quant_executed;
-  if (!(total <= quant_left)) {
-    q[0] = f2i(floorf((float)(first0 * quant_left)));
-    q[1] = f2i(floorf((float)(0 * quant_left))); q[2] = q[1]; q[3] = q[1];
+      for (int k = 0; k < 4; ++k) if (ai == k + 1) q[k] = (k == 0 && ac.larger_far_touch_quant) ? 10 : 1;
+    }
+    int total = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { q[k] *= ac.fixed_quant_value; total += q[k]; }
+    if (!(total <= quant_left)) {
+      q[0] = f2i(floorf((float)(first0 * quant_left)));
+      q[1] = f2i(floorf((float)(0 * quant_left))); q[2] = q[1]; q[3] = q[1];
+    }
   }
   const int side = 1 - is_sell * 2;
   const int sz = ac.num_messages_by_agent / 2;
@@ -305,11 +348,13 @@ static __device__ __noinline__ void exe_get_messages(BookCtx bk, const LobStepCo
   if (lane_id() == 0) {
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      int4* m = reinterpret_cast<int4*>(act + k * 8);
-      m[0] = make_int4(1, side, q[k], lv[k]);
-      m[1] = make_int4(c.placeholder_order_id, tid, w.time0 + ac.time_delay_obs_act, w.time1 + ac.time_delay_obs_act);
+      if (k < ka) {
+        int4* m = reinterpret_cast<int4*>(act + k * 8);
+        m[0] = make_int4(1, side, q[k], pr[k]);
+        m[1] = make_int4(c.placeholder_order_id, tid, w.time0 + ac.time_delay_obs_act, w.time1 + ac.time_delay_obs_act);
+      }
     }
-    filter_messages(act, ac.num_action_messages_by_agent, cnl, sz);
+    filter_messages(act, ka, cnl, sz);
   }
   __syncwarp();
 }

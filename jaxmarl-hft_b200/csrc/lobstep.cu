@@ -70,16 +70,21 @@ int check_step_cfg(const LobStepConfig* c) {
     if (kc != ka || ka < 1 || ka > 16)
       return fail(LOB_E_INVALID, "agent[%d]: cancel (%d) and action (%d) message counts must match and be in [1,16]", t, kc, ka);
     if (a->kind == LOB_AGENT_MM) {
-      if (a->action_space != LOB_MM_ACT_FIXED_QUANTS && a->action_space != LOB_MM_ACT_DIRECTIONAL)
+      if (a->action_space < LOB_MM_ACT_FIXED_QUANTS || a->action_space > LOB_MM_ACT_BOB_STRATEGY)
         return fail(LOB_E_UNSUPPORTED, "agent[%d]: MM action space %d is not built", t, a->action_space);
+      if ((a->action_space == LOB_MM_ACT_BOB_RL || a->action_space == LOB_MM_ACT_BOB_STRATEGY) &&
+          (a->bob_v0 < 1 || a->bob_v0 > 1000))
+        return fail(LOB_E_INVALID, "agent[%d].bob_v0=%d", t, a->bob_v0);
       if (ka != 2) return fail(LOB_E_INVALID, "agent[%d]: MM action spaces built here post 2 messages", t);
       if (a->sell_buy_all_option) return fail(LOB_E_UNSUPPORTED, "agent[%d]: sell_buy_all_option is not built", t);
       if (a->reward_function < 0 || a->reward_function > LOB_MM_REW_DELTA_PORTFOLIO_VALUE)
         return fail(LOB_E_INVALID, "agent[%d].reward_function=%d", t, a->reward_function);
     } else {
-      if (a->action_space != LOB_EXE_ACT_FIXED_QUANTS && a->action_space != LOB_EXE_ACT_FIXED_QUANTS_COMPLEX)
+      if (a->action_space < LOB_EXE_ACT_FIXED_QUANTS || a->action_space > LOB_EXE_ACT_TWAP)
         return fail(LOB_E_UNSUPPORTED, "agent[%d]: EXE action space %d is not built", t, a->action_space);
-      if (ka != 4) return fail(LOB_E_INVALID, "agent[%d]: EXE action spaces built here post 4 messages", t);
+      const int want = a->action_space == LOB_EXE_ACT_FIXED_QUANTS_1MSG ? 1
+                       : (a->action_space == LOB_EXE_ACT_SIMPLEST_CASE || a->action_space == LOB_EXE_ACT_TWAP) ? 2 : 4;
+      if (ka != want) return fail(LOB_E_INVALID, "agent[%d]: this EXE action space posts %d messages, config says %d", t, want, ka);
       if (a->reward_function < 0 || a->reward_function > LOB_EXE_REW_SIMPLEST_CASE)
         return fail(LOB_E_INVALID, "agent[%d].reward_function=%d", t, a->reward_function);
       if (a->reference_price != LOB_REF_MID && a->reference_price != LOB_REF_FAR_TOUCH)

@@ -515,11 +515,60 @@ static void mm_action_directional(const LobStepConfig* c, const LobAgentTypeConf
   ex->bid_quant = bid_quant; ex->ask_quant = ask_quant;
 }
 
+/* mm:1474-1560 _getActionMsgs_BobRL and mm:1400-1471 _getActionMsgs_BobStrategy: quotes AT the best prices (own orders
+ * excluded), sizes from a table (bobRL) or from the inventory-skewed formula round(v0 * max(1 -+ kappa * inventory, 0)) */
+static void mm_action_bob(const LobStepConfig* c, const LobAgentTypeConfig* ac, int32_t action, const World* w,
+                          const MMState* st, int32_t trader_id, int32_t* out /* [2][8] */, MMExtras* ex) {
+  const int no = c->book.n_orders;
+  const int32_t tick = c->tick_size;
+  const int N = lob_num_msgs_per_step(c);
+  if (ac->fixed_action_setting) action = ac->fixed_action;
+  int32_t mn = c->book.maxint, best_bid = -1;
+  for (int r = 0; r < no; ++r) {
+    int32_t pa = (w->asks[r * 6 + OF_TID] != trader_id) ? w->asks[r * 6 + OF_P] : -1;
+    int32_t pb = (w->bids[r * 6 + OF_TID] != trader_id) ? w->bids[r * 6 + OF_P] : -1;
+    mn = imin32(mn, pa == -1 ? c->book.maxint : pa);
+    best_bid = (r == 0) ? pb : imax32(best_bid, pb);
+  }
+  int32_t best_ask = (mn == c->book.maxint) ? -1 : mn;
+  int empty_book = (best_ask == -1) || (best_bid == -1);
+  best_ask = ifloordiv(best_ask, tick) * tick;
+  best_bid = ifloordiv(best_bid, tick) * tick;
+  if (empty_book) { best_bid = w->best_bids[(N - 1) * 2]; best_ask = w->best_asks[(N - 1) * 2]; }
+  int32_t bid_quant, ask_quant;
+  if (ac->action_space == LOB_MM_ACT_BOB_RL) {
+    const int v0 = ac->bob_v0, n = 2 * v0 + 1; /* tables of mm:1502-1520: index 0 -> (v0, v0), 2k-1 -> (v0+k, v0-k), 2k -> (v0-k, v0+k) */
+    int ai = clamp_index(action, n);
+    int k = (ai + 1) / 2;
+    int32_t bq = (ai == 0) ? v0 : ((ai & 1) ? v0 + k : v0 - k);
+    int32_t aq = (ai == 0) ? v0 : ((ai & 1) ? v0 - k : v0 + k);
+    bid_quant = bq * ac->fixed_quant_value;
+    ask_quant = aq * ac->fixed_quant_value;
+  } else { /* bobStrategy */
+    float kappa = (float)(action + 1) / (float)(ac->bob_v0 * 5);
+    float v0 = (float)ac->bob_v0, pos = (float)st->inventory;
+    bid_quant = f2i(rintf(v0 * jmaxf(1.0f - kappa * pos, 0.0f)));
+    ask_quant = f2i(rintf(v0 * jmaxf(1.0f + kappa * pos, 0.0f)));
+  }
+  if (empty_book) { bid_quant = 0; ask_quant = 0; }
+  int32_t sides[2] = {1, -1}, quants[2] = {bid_quant, ask_quant}, prices[2] = {best_bid, best_ask};
+  for (int k = 0; k < 2; ++k) {
+    int32_t* o = out + k * 8;
+    o[0] = 1; o[1] = sides[k]; o[2] = quants[k]; o[3] = prices[k];
+    o[4] = c->placeholder_order_id; o[5] = trader_id;
+    o[6] = w->time[0] + ac->time_delay_obs_act; o[7] = w->time[1] + ac->time_delay_obs_act;
+  }
+  ex->posted_bid_price = 0; ex->posted_ask_price = 0;
+  ex->bid_distance_from_best = 0; ex->ask_distance_from_best = 0;
+  ex->bid_quant = bid_quant; ex->ask_quant = ask_quant;
+}
+
 /* mm:1869-1913 get_messages */
 static void mm_get_messages(const LobStepConfig* c, const LobAgentTypeConfig* ac, int32_t action, const World* w,
                             const MMState* st, int32_t trader_id, int32_t* act, int32_t* cnl, MMExtras* ex) {
   if (ac->action_space == LOB_MM_ACT_FIXED_QUANTS) mm_action_fixed_quant(c, ac, action, w, st, trader_id, act, ex);
-  else mm_action_directional(c, ac, action, w, trader_id, act, ex);
+  else if (ac->action_space == LOB_MM_ACT_DIRECTIONAL) mm_action_directional(c, ac, action, w, trader_id, act, ex);
+  else mm_action_bob(c, ac, action, w, st, trader_id, act, ex);
   int sz = ac->num_messages_by_agent / 4;
   get_cancel_msgs(w->bids, c->book.n_orders, trader_id, sz, 1, w->time[0], w->time[1], cnl);
   get_cancel_msgs(w->asks, c->book.n_orders, trader_id, sz, -1, w->time[0], w->time[1], cnl + sz * 8);
@@ -769,15 +818,16 @@ static void mm_get_obs(const LobStepConfig* c, const LobAgentTypeConfig* ac, con
 
 /* -------------------------------------------------------------- EXE agent */
 
-/* exe:623-724 (fixed_quants; the reference forgets the extras tuple -> "the obvious fix") and
- * exe:838-932 (fixed_quants_complex) */
+/* exe:623-724 (fixed_quants; the reference forgets the extras tuple -> "the obvious fix"), exe:838-932
+ * (fixed_quants_complex), exe:732-835 (fixed_quants_1msg), exe:935-999 (simplest_case), exe:1126-1227 (twap) */
 static void exe_action(const LobStepConfig* c, const LobAgentTypeConfig* ac, int32_t action, const World* w,
-                       const EXEState* st, int32_t trader_id, int32_t* out /* [4][8] */) {
+                       const EXEState* st, int32_t trader_id, int32_t* out /* [ka][8] */) {
   const int32_t tick = c->tick_size;
   const int N = lob_num_msgs_per_step(c);
+  const int ka = ac->num_action_messages_by_agent;
   int32_t best_ask = ifloordiv(w->best_asks[(N - 1) * 2], tick) * tick;
   int32_t best_bid = ifloordiv(w->best_bids[(N - 1) * 2], tick) * tick;
-  int32_t lv[4];
+  int32_t lv[4]; /* FT, M, NT, PP */
   if (st->is_sell_task) { /* exe:871-878 */
     lv[0] = best_bid;
     float mid = ffloordiv((float)(best_bid + best_ask) / 2.0f, (float)tick);
@@ -790,26 +840,50 @@ static void exe_action(const LobStepConfig* c, const LobAgentTypeConfig* ac, int
     lv[2] = best_bid;
     lv[3] = best_bid - tick * ac->n_ticks_in_book;
   }
-  int32_t q[4] = {0, 0, 0, 0};
-  int32_t first_row[4] = {1, 0, 0, 0}; /* quant_array[1] */
-  if (ac->action_space == LOB_EXE_ACT_FIXED_QUANTS_COMPLEX) {
-    static const int32_t mult[13] = {0, 1, 1, 1, 1, 2, 2, 2, 2, 5, 5, 5, 5};
-    int ai = clamp_index(action, 13);
-    if (ai > 0) q[(ai - 1) % 4] = mult[ai];
-  } else {
-    int ai = clamp_index(action, 5);
-    if (ai > 0) q[ai - 1] = (ai == 1 && ac->larger_far_touch_quant) ? 10 : 1;
-    if (ac->larger_far_touch_quant) first_row[0] = 10;
-  }
-  int32_t total = 0;
-  for (int k = 0; k < 4; ++k) { q[k] *= ac->fixed_quant_value; total += q[k]; }
   int32_t quant_left = st->task_to_execute - st->quant_executed;
-  if (!(total <= quant_left)) /* exe:920-924: where(.., quants, floor(quant_array[1]*quant_left)).astype(int32) */
-    for (int k = 0; k < 4; ++k) q[k] = f2i(floorf((float)(first_row[k] * quant_left)));
+  int32_t q[4] = {0, 0, 0, 0}, pr[4] = {lv[0], lv[1], lv[2], lv[3]};
+  if (ac->action_space == LOB_EXE_ACT_FIXED_QUANTS_1MSG) { /* exe:732-835: one message, price and size picked by the action */
+    int ai = clamp_index(action, 5);
+    pr[0] = (ai == 0) ? 0 : lv[ai - 1];
+    int32_t sel = (ai == 0) ? 0 : ac->fixed_quant_value;
+    q[0] = (sel <= quant_left) ? sel : 0;
+  } else if (ac->action_space == LOB_EXE_ACT_TWAP) { /* exe:1126-1227: ceil(quant_left / steps_left) at FT (action 0) or NT */
+    int32_t steps_left = w->max_steps - w->step_counter - 1;
+    int32_t ql = imax32(quant_left, 0);
+    int32_t quant_this_step = f2i(ceilf((float)ql / (float)steps_left));
+    int ai = clamp_index(action, 2);
+    pr[0] = lv[0]; pr[1] = lv[2];
+    q[0] = (ai == 0) ? quant_this_step : 0;
+    q[1] = (ai == 1) ? quant_this_step : 0;
+  } else if (ac->action_space == LOB_EXE_ACT_SIMPLEST_CASE) { /* exe:935-999 */
+    int ai = clamp_index(action, 3);
+    pr[0] = lv[0]; pr[1] = lv[2];
+    q[0] = (ai == 1) ? ac->fixed_quant_value : 0;
+    q[1] = (ai == 2) ? ac->fixed_quant_value : 0;
+    if (!(q[0] + q[1] <= quant_left)) {
+      q[0] = f2i(floorf((float)(ac->fixed_quant_value * quant_left)));
+      q[1] = f2i(floorf((float)(0 * quant_left)));
+    }
+  } else {
+    int32_t first_row[4] = {1, 0, 0, 0}; /* quant_array[1] */
+    if (ac->action_space == LOB_EXE_ACT_FIXED_QUANTS_COMPLEX) {
+      static const int32_t mult[13] = {0, 1, 1, 1, 1, 2, 2, 2, 2, 5, 5, 5, 5};
+      int ai = clamp_index(action, 13);
+      if (ai > 0) q[(ai - 1) % 4] = mult[ai];
+    } else {
+      int ai = clamp_index(action, 5);
+      if (ai > 0) q[ai - 1] = (ai == 1 && ac->larger_far_touch_quant) ? 10 : 1;
+      if (ac->larger_far_touch_quant) first_row[0] = 10;
+    }
+    int32_t total = 0;
+    for (int k = 0; k < 4; ++k) { q[k] *= ac->fixed_quant_value; total += q[k]; }
+    if (!(total <= quant_left)) /* exe:920-924: where(.., quants, floor(quant_array[1]*quant_left)).astype(int32) */
+      for (int k = 0; k < 4; ++k) q[k] = f2i(floorf((float)(first_row[k] * quant_left)));
+  }
   int32_t side = 1 - st->is_sell_task * 2;
-  for (int k = 0; k < 4; ++k) {
+  for (int k = 0; k < ka; ++k) {
     int32_t* o = out + k * 8;
-    o[0] = 1; o[1] = side; o[2] = q[k]; o[3] = lv[k];
+    o[0] = 1; o[1] = side; o[2] = q[k]; o[3] = pr[k];
     o[4] = c->placeholder_order_id; o[5] = trader_id;
     o[6] = w->time[0] + ac->time_delay_obs_act; o[7] = w->time[1] + ac->time_delay_obs_act;
   }

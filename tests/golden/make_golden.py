@@ -121,7 +121,32 @@ def mm_complex_agents(mac):
     return MultiAgentConfig(world_config=mac.world_config, dict_of_agents_configs=agents, number_of_agents_per_type=[2, 1])
 
 
-MUTATORS = {"hetero": hetero_agents, "mm_complex": mm_complex_agents}
+def bob_twap_agents(mac):
+    from gymnax_exchange.jaxob.jaxob_config import MultiAgentConfig
+    d = dict(mac.dict_of_agents_configs)
+    mm, ex = d["MarketMaking"], d["Execution"]
+    agents = {
+        "MarketMaking": dataclasses.replace(mm, action_space="bobRL", bob_v0=2, fixed_quant_value=3),
+        "Execution": dataclasses.replace(ex, action_space="twap", task_size=200),
+    }
+    return MultiAgentConfig(world_config=mac.world_config, dict_of_agents_configs=agents, number_of_agents_per_type=[2, 1])
+
+
+def bobstrat_1msg_agents(mac):
+    from gymnax_exchange.jaxob.jaxob_config import MultiAgentConfig
+    d = dict(mac.dict_of_agents_configs)
+    mm, ex = d["MarketMaking"], d["Execution"]
+    agents = {
+        "MarketMaking": dataclasses.replace(mm, action_space="bobStrategy", bob_v0=5, observation_space="engineered"),
+        "Execution": dataclasses.replace(ex, action_space="fixed_quants_1msg", task_size=60, fixed_quant_value=7),
+        "Exec2": dataclasses.replace(ex, short_name="EXE2", action_space="simplest_case", reward_function="simplest_case",
+                                     task="buy", task_size=40, fixed_quant_value=9),
+    }
+    return MultiAgentConfig(world_config=mac.world_config, dict_of_agents_configs=agents, number_of_agents_per_type=[1, 2, 1])
+
+
+MUTATORS = {"hetero": hetero_agents, "mm_complex": mm_complex_agents, "bob_twap": bob_twap_agents,
+            "bobstrat_1msg": bobstrat_1msg_agents}
 
 
 def run_env_case(name, json_name, seed, B, steps, n_events=30000, stress=False, out_dir=HERE, mutate=None, **world_overrides):
@@ -230,3 +255,6 @@ if __name__ == "__main__":
         run_env_case("env_hetero_smallbook", "2_player_fq_fqc.json", seed=6, B=2, steps=66, stress=True, mutate="hetero",
                      nOrders=40, nTrades=24)
         run_env_case("env_mm_complex", "2_player_fq_fqc.json", seed=7, B=2, steps=66, mutate="mm_complex")
+    if "env3" in which:
+        run_env_case("env_bob_twap", "2_player_fq_fqc.json", seed=8, B=2, steps=66, mutate="bob_twap")
+        run_env_case("env_bobstrat_1msg", "2_player_fq_fqc.json", seed=9, B=2, steps=66, mutate="bobstrat_1msg")

@@ -199,6 +199,18 @@ def _mutate(mac, how):
                                              normalize=False, task_size=80),
         }
         return H.with_agents(mac, agents, [2, 1])
+    if how == "bob_twap":
+        agents = {"MarketMaking": dataclasses.replace(mm, action_space="bobRL", bob_v0=2, fixed_quant_value=3),
+                  "Execution": dataclasses.replace(ex, action_space="twap", task_size=200)}
+        return H.with_agents(mac, agents, [2, 1])
+    if how == "bobstrat_1msg":
+        agents = {
+            "MarketMaking": dataclasses.replace(mm, action_space="bobStrategy", bob_v0=5, observation_space="engineered"),
+            "Execution": dataclasses.replace(ex, action_space="fixed_quants_1msg", task_size=60, fixed_quant_value=7),
+            "Exec2": dataclasses.replace(ex, short_name="EXE2", action_space="simplest_case", reward_function="simplest_case",
+                                         task="buy", task_size=40, fixed_quant_value=9),
+        }
+        return H.with_agents(mac, agents, [1, 2, 1])
     raise KeyError(how)
 
 
