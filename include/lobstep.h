@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define LOB_ABI_VERSION 2
+#define LOB_ABI_VERSION 3
 #define LOB_MAX_AGENT_TYPES 4
 #define LOB_MAX_AGENT_I32 4  /* int32 state leaves per agent type */
 #define LOB_MAX_AGENT_F32 10 /* float32 state leaves per agent type */
@@ -56,7 +56,8 @@ enum LobAgentKind { LOB_AGENT_MM = 0, LOB_AGENT_EXE = 1 };
 
 /* MarketMaking_EnvironmentConfig.action_space  jaxob_config.py:55 ; mm_env.py:161-178 */
 enum LobMMActionSpace { LOB_MM_ACT_FIXED_QUANTS = 0, LOB_MM_ACT_DIRECTIONAL = 1,
-                         LOB_MM_ACT_BOB_RL = 2 /* mm_env.py:1474 */, LOB_MM_ACT_BOB_STRATEGY = 3 /* mm_env.py:1400 */ };
+                         LOB_MM_ACT_BOB_RL = 2 /* mm_env.py:1474 */, LOB_MM_ACT_BOB_STRATEGY = 3 /* mm_env.py:1400 */,
+                         LOB_MM_ACT_SIMPLE = 4 /* :1123 */, LOB_MM_ACT_SPREAD_SKEW = 5 /* :1667 */, LOB_MM_ACT_AVST = 6 /* :1248 */ };
 /* Execution_EnvironmentConfig.action_space     jaxob_config.py:157 ; exec_env.py:162-175 */
 enum LobEXEActionSpace { LOB_EXE_ACT_FIXED_QUANTS = 0, LOB_EXE_ACT_FIXED_QUANTS_COMPLEX = 1,
                           LOB_EXE_ACT_FIXED_QUANTS_1MSG = 2 /* exec_env.py:732 */, LOB_EXE_ACT_SIMPLEST_CASE = 3 /* :935 */,
@@ -127,6 +128,8 @@ typedef struct LobAgentTypeConfig {
   int32_t larger_far_touch_quant;
   int32_t doom_price_penalty;
   int32_t bob_v0;                       /* market making: bobRL / bobStrategy base quantity (1, 2, 5 or 10) */
+  int32_t simple_nothing_action;        /* MM 'simple': 4-entry tables (mm_env.py:1133) */
+  int32_t multiplier_type_spread;       /* MM 'spread_skew': multiplier_type == "spread" (else "tick")  mm_env.py:1725 */
   /* python floats of the config: kept as double, narrowed to f32 where JAX's weak typing does */
   double auto_liquidate_alpha;
   double inv_penalty_lambda;
@@ -138,6 +141,10 @@ typedef struct LobAgentTypeConfig {
   double rebate_bps;
   double unrealizedPnL_lambda;
   double reward_lambda;
+  double spread_multiplier;             /* MM 'spread_skew' */
+  double skew_multiplier;
+  double avst_k_parameter;              /* MM 'AvSt' */
+  double avst_var_parameter;
 } LobAgentTypeConfig;
 
 /* ---- the whole step: MultiAgentConfig  jaxob_config.py:205-250 */

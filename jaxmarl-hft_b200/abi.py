@@ -5,7 +5,7 @@ Field order and types follow the header exactly; ``check_sizes`` compares ``ctyp
 """
 import ctypes as C
 
-LOB_ABI_VERSION = 2
+LOB_ABI_VERSION = 3
 LOB_MAX_AGENT_TYPES = 4
 LOB_MAX_AGENT_I32 = 4
 LOB_MAX_AGENT_F32 = 10
@@ -14,7 +14,8 @@ LOB_OK, LOB_E_INVALID, LOB_E_UNSUPPORTED, LOB_E_CUDA = 0, -1, -2, -3
 
 # enums (values are part of the ABI)
 AGENT_MM, AGENT_EXE = 0, 1
-MM_ACTION_SPACES = {"fixed_quants": 0, "directional_trading": 1, "bobRL": 2, "bobStrategy": 3}
+MM_ACTION_SPACES = {"fixed_quants": 0, "directional_trading": 1, "bobRL": 2, "bobStrategy": 3, "simple": 4, "spread_skew": 5,
+                    "AvSt": 6}
 EXE_ACTION_SPACES = {"fixed_quants": 0, "fixed_quants_complex": 1, "fixed_quants_1msg": 2, "simplest_case": 3, "twap": 4}
 OBS_SPACES = {"engineered": 0, "basic": 1}
 MM_REWARDS = {"portfolio_value": 0, "buy_sell_pnl": 1, "complex": 2, "zero_inv": 3, "spooner": 4,
@@ -59,10 +60,10 @@ class LobAgentTypeConfig(C.Structure):
         "fixed_action_setting", "fixed_action", "auto_liquidate_threshold", "unwind_price_penalty", "inv_penalty",
         "volume_traded_bonus_market_share", "reference_price", "unwind_price", "clip_reward",
         "exclude_extreme_spreads", "task", "task_size", "n_ticks_in_book", "larger_far_touch_quant",
-        "doom_price_penalty", "bob_v0")] + [(n, f64) for n in (
+        "doom_price_penalty", "bob_v0", "simple_nothing_action", "multiplier_type_spread")] + [(n, f64) for n in (
             "auto_liquidate_alpha", "inv_penalty_lambda", "inv_penalty_quadratic_factor", "inv_penalty_threshold",
             "reward_scaling_quo", "inventoryPnL_eta", "inventoryPnL_gamma", "rebate_bps", "unrealizedPnL_lambda",
-            "reward_lambda")]
+            "reward_lambda", "spread_multiplier", "skew_multiplier", "avst_k_parameter", "avst_var_parameter")]
 
 
 class LobStepConfig(C.Structure):

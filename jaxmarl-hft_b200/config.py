@@ -257,6 +257,14 @@ def agent_type_config(cfg, n_agents: int, trader_id_start: int) -> abi.LobAgentT
         a.reward_function = _enum(abi.MM_REWARDS, cfg.reward_function, "reward_space")
         a.n_ticks_offset = cfg.n_ticks_offset
         a.bob_v0 = cfg.bob_v0
+        a.simple_nothing_action = int(cfg.simple_nothing_action)
+        if cfg.multiplier_type not in ("tick", "spread"):
+            raise ValueError(f"Invalid multiplier_type {cfg.multiplier_type!r}")
+        a.multiplier_type_spread = int(cfg.multiplier_type == "spread")
+        a.spread_multiplier = cfg.spread_multiplier
+        a.skew_multiplier = cfg.skew_multiplier
+        a.avst_k_parameter = cfg.avst_k_parameter
+        a.avst_var_parameter = cfg.avst_var_parameter
         if cfg.action_space in ("bobRL", "bobStrategy") and cfg.bob_v0 not in _BOB_RL_ACTIONS and cfg.action_space == "bobRL":
             raise ValueError("cfg.bob_v0 must be one of [1,2,5,10]")  # mm:1522
         a.tenth_action_market_order = int(cfg.tenth_action == "MarketOrder")

@@ -36,6 +36,7 @@ __device__ __forceinline__ float jminf(float a, float b) { return (a != a || b !
 __device__ __forceinline__ int f2i(float x) { return (int)x; }
 __device__ __forceinline__ int clamp_index(int a, int n) { if (a < 0) a += n; return max(0, min(a, n - 1)); }
 __device__ __forceinline__ int isign(int a) { return (a > 0) - (a < 0); }
+__device__ __forceinline__ int imod(int a, int b) { int r = a % b; if (r != 0 && ((r < 0) != (b < 0))) r += b; return r; }  // jnp.remainder
 
 // butterfly combine of the 32 per-lane partial sums (see the header note)
 __device__ __forceinline__ float wsumf(float v) {
@@ -179,7 +180,9 @@ static __device__ __noinline__ MMOut mm_get_messages(BookCtx bk, const LobStepCo
   MMOut o;
   int best_ask = 0, best_bid = 0;
   bool empty_book = false;
-  if (ac.action_space != LOB_MM_ACT_DIRECTIONAL) {
+  const bool excl_own = ac.action_space == LOB_MM_ACT_FIXED_QUANTS || ac.action_space == LOB_MM_ACT_BOB_RL ||
+                        ac.action_space == LOB_MM_ACT_BOB_STRATEGY || ac.action_space == LOB_MM_ACT_AVST;
+  if (excl_own) {
     // mm:979-985 (== mm:1411-1430, 1482-1500) best prices excluding own orders
     int mn = bk.maxint, mx = INT32_MIN;
 #pragma unroll 1
@@ -256,6 +259,56 @@ static __device__ __noinline__ MMOut mm_get_messages(BookCtx bk, const LobStepCo
     quants[0] = bid_quant; quants[1] = ask_quant; prices[0] = best_bid; prices[1] = best_ask;
     o.posted_bid_price = 0; o.posted_ask_price = 0; o.bid_dist = 0; o.ask_dist = 0;
     o.bid_quant = bid_quant; o.ask_quant = ask_quant;
+  } else if (ac.action_space == LOB_MM_ACT_SIMPLE || ac.action_space == LOB_MM_ACT_SPREAD_SKEW) {
+    // mm:1123-1246 (sell_buy_all_option == False) / mm:1667-1808: quotes around the last forward-filled best prices
+    const float tickf = (float)tick;
+    const int ba = ifloordiv(w.old_ba_last, tick) * tick, bb = ifloordiv(w.old_bb_last, tick) * tick;
+    int bid_price, ask_price, bid_quant, ask_quant;
+    if (ac.action_space == LOB_MM_ACT_SIMPLE) {
+      if (ac.fixed_action_setting) action = ac.fixed_action;
+      const int ai = clamp_index(action, ac.simple_nothing_action ? 4 : 3);
+      const float bid_offset = (ai == 1) ? -2000.f : 0.f, ask_offset = (ai == 2) ? -2000.f : 0.f;
+      bid_quant = ((ai == 0 || ai == 1) ? 1 : 0) * ac.fixed_quant_value;
+      ask_quant = ((ai == 0 || ai == 2) ? 1 : 0) * ac.fixed_quant_value;
+      const float tick_offset = (float)(ac.n_ticks_offset * tick);
+      const float bp = (float)bb - bid_offset * tick_offset, ap = (float)ba + ask_offset * tick_offset;
+      bid_price = f2i(ffloordiv(jmaxf(bp, 0.f), tickf) * tickf);
+      ask_price = f2i(ffloordiv(ap, tickf) * tickf);
+    } else {
+      const float mid_price = (float)(ba + bb) / 2.0f;
+      const int spread_type = ifloordiv(action, 3), skew_type = imod(action, 3);
+      const float new_spread = (float)(ba - bb) * ((spread_type == 0) ? 1.0f : (float)ac.spread_multiplier);
+      const float skew_ticks = (skew_type == 0) ? (float)(-ac.skew_multiplier) : ((skew_type == 1) ? 0.f : (float)ac.skew_multiplier);
+      const float skewed_mid = ac.multiplier_type_spread ? mid_price + skew_ticks * new_spread : mid_price + skew_ticks * tickf;
+      const float half_spread = ffloordiv(new_spread, 2.0f);
+      bid_price = f2i(ffloordiv(skewed_mid - half_spread, tickf) * tickf);
+      ask_price = f2i(ffloordiv(skewed_mid + half_spread, tickf) * tickf);
+      bid_quant = ac.fixed_quant_value; ask_quant = ac.fixed_quant_value;
+    }
+    quants[0] = bid_quant; quants[1] = ask_quant; prices[0] = bid_price; prices[1] = ask_price;
+    o.posted_bid_price = 0; o.posted_ask_price = 0; o.bid_dist = 0; o.ask_dist = 0;
+    o.bid_quant = bid_quant; o.ask_quant = ask_quant;
+  } else if (ac.action_space == LOB_MM_ACT_AVST) {   // mm:1248-1398 Avellaneda-Stoikov quotes (fixed_steps time)
+    const float tickf = (float)tick;
+    const int mid_price = ifloordiv(best_ask + best_bid, 2);
+    const int ai = clamp_index(action, 8);
+    const float gamma = (ai == 0) ? 0.1f : (ai == 1) ? 0.2f : (ai == 2) ? 0.5f : (ai == 3) ? 1.f : (ai == 4) ? 2.f
+                        : (ai == 5) ? 5.f : (ai == 6) ? 10.f : 20.f;
+    const float k = (float)ac.avst_k_parameter, variance = (float)ac.avst_var_parameter;
+    const float normalized_time = (float)(c.episode_time - w.step_counter) / (float)c.episode_time;
+    const float res_price = (float)mid_price - (((float)inventory * gamma) * variance) * normalized_time;
+    float spread = (gamma * variance) * normalized_time + (2.0f / gamma) * logf(1.0f + gamma / k);
+    spread = jminf(jmaxf(spread, tickf), (float)c.book.maxint);
+    float bp = res_price - spread / 2.0f, ap = res_price + spread / 2.0f;
+    bp = jminf(jmaxf(bp, 0.f), (float)c.book.maxint);
+    ap = jminf(jmaxf(ap, 0.f), (float)c.book.maxint);
+    int bid_price = f2i(ffloordiv(bp, tickf) * tickf), ask_price = f2i(ffloordiv(ap, tickf) * tickf);
+    bid_price = min(bid_price, (ifloordiv(mid_price, tick) - (imod(mid_price, tick) == 0 ? 1 : 0)) * tick);
+    ask_price = max(ask_price, (ifloordiv(mid_price, tick) + 1) * tick);
+    quants[0] = ac.fixed_quant_value; quants[1] = ac.fixed_quant_value; prices[0] = bid_price; prices[1] = ask_price;
+    o.posted_bid_price = bid_price; o.posted_ask_price = ask_price;
+    o.bid_dist = best_bid - bid_price; o.ask_dist = ask_price - best_ask;
+    o.bid_quant = ac.fixed_quant_value; o.ask_quant = ac.fixed_quant_value;
   } else {  // directional_trading
     const int ba = ifloordiv(w.old_ba_last, tick) * tick, bb = ifloordiv(w.old_bb_last, tick) * tick;
     const int ai = clamp_index(action, 3);

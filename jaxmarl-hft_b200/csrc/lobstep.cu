@@ -70,7 +70,7 @@ int check_step_cfg(const LobStepConfig* c) {
     if (kc != ka || ka < 1 || ka > 16)
       return fail(LOB_E_INVALID, "agent[%d]: cancel (%d) and action (%d) message counts must match and be in [1,16]", t, kc, ka);
     if (a->kind == LOB_AGENT_MM) {
-      if (a->action_space < LOB_MM_ACT_FIXED_QUANTS || a->action_space > LOB_MM_ACT_BOB_STRATEGY)
+      if (a->action_space < LOB_MM_ACT_FIXED_QUANTS || a->action_space > LOB_MM_ACT_AVST)
         return fail(LOB_E_UNSUPPORTED, "agent[%d]: MM action space %d is not built", t, a->action_space);
       if ((a->action_space == LOB_MM_ACT_BOB_RL || a->action_space == LOB_MM_ACT_BOB_STRATEGY) &&
           (a->bob_v0 < 1 || a->bob_v0 > 1000))

@@ -563,11 +563,114 @@ static void mm_action_bob(const LobStepConfig* c, const LobAgentTypeConfig* ac, 
   ex->bid_quant = bid_quant; ex->ask_quant = ask_quant;
 }
 
+/* jnp.remainder on int32: sign follows the divisor */
+static inline int32_t imod(int32_t a, int32_t b) { int32_t r = a % b; if (r != 0 && ((r < 0) != (b < 0))) r += b; return r; }
+
+/* mm:1123-1246 _getActionMsgs_simple (sell_buy_all_option == False) and mm:1667-1808 _getActionMsgs_spread_skew: both
+ * quote around the last forward-filled best prices of the world state */
+static void mm_action_simple_or_skew(const LobStepConfig* c, const LobAgentTypeConfig* ac, int32_t action, const World* w,
+                                     int32_t trader_id, int32_t* out, MMExtras* ex) {
+  const int32_t tick = c->tick_size;
+  const float tickf = (float)tick;
+  const int N = lob_num_msgs_per_step(c);
+  int32_t best_ask = ifloordiv(w->best_asks[(N - 1) * 2], tick) * tick;
+  int32_t best_bid = ifloordiv(w->best_bids[(N - 1) * 2], tick) * tick;
+  int32_t bid_price, ask_price, bid_quant, ask_quant;
+  if (ac->action_space == LOB_MM_ACT_SIMPLE) {
+    const int n = ac->simple_nothing_action ? 4 : 3;
+    if (ac->fixed_action_setting) action = ac->fixed_action;
+    int ai = clamp_index(action, n);
+    const float bid_offset = (ai == 1) ? -2000.f : 0.f, ask_offset = (ai == 2) ? -2000.f : 0.f;
+    bid_quant = ((ai == 0 || ai == 1) ? 1 : 0) * ac->fixed_quant_value;
+    ask_quant = ((ai == 0 || ai == 2) ? 1 : 0) * ac->fixed_quant_value;
+    const float tick_offset = (float)(ac->n_ticks_offset * tick);
+    float bp = (float)best_bid - bid_offset * tick_offset;
+    float ap = (float)best_ask + ask_offset * tick_offset;
+    bid_price = f2i(ffloordiv(jmaxf(bp, 0.f), tickf) * tickf);
+    ask_price = f2i(ffloordiv(ap, tickf) * tickf);
+  } else {
+    float mid_price = (float)(best_ask + best_bid) / 2.0f;
+    int32_t current_spread = best_ask - best_bid;
+    int32_t spread_type = ifloordiv(action, 3), skew_type = imod(action, 3);
+    float spread_multiplier = (spread_type == 0) ? 1.0f : (float)ac->spread_multiplier;
+    float new_spread = (float)current_spread * spread_multiplier;
+    float skew_ticks = (skew_type == 0) ? (float)(-ac->skew_multiplier) : ((skew_type == 1) ? 0.f : (float)ac->skew_multiplier);
+    float skewed_mid = ac->multiplier_type_spread ? mid_price + skew_ticks * new_spread : mid_price + skew_ticks * tickf;
+    float half_spread = ffloordiv(new_spread, 2.0f);
+    float bp = skewed_mid - half_spread, ap = skewed_mid + half_spread;
+    bid_price = f2i(ffloordiv(bp, tickf) * tickf);
+    ask_price = f2i(ffloordiv(ap, tickf) * tickf);
+    bid_quant = ac->fixed_quant_value; ask_quant = ac->fixed_quant_value;
+  }
+  int32_t sides[2] = {1, -1}, quants[2] = {bid_quant, ask_quant}, prices[2] = {bid_price, ask_price};
+  for (int k = 0; k < 2; ++k) {
+    int32_t* o = out + k * 8;
+    o[0] = 1; o[1] = sides[k]; o[2] = quants[k]; o[3] = prices[k];
+    o[4] = c->placeholder_order_id; o[5] = trader_id;
+    o[6] = w->time[0] + ac->time_delay_obs_act; o[7] = w->time[1] + ac->time_delay_obs_act;
+  }
+  ex->posted_bid_price = 0; ex->posted_ask_price = 0;
+  ex->bid_distance_from_best = 0; ex->ask_distance_from_best = 0;
+  ex->bid_quant = bid_quant; ex->ask_quant = ask_quant;
+}
+
+/* mm:1248-1398 _getActionMsgs_AvSt (Avellaneda-Stoikov quotes; fixed_steps time) */
+static void mm_action_avst(const LobStepConfig* c, const LobAgentTypeConfig* ac, int32_t action, const World* w,
+                           const MMState* st, int32_t trader_id, int32_t* out, MMExtras* ex) {
+  const int no = c->book.n_orders;
+  const int32_t tick = c->tick_size;
+  const float tickf = (float)tick;
+  const int N = lob_num_msgs_per_step(c);
+  int32_t mn = c->book.maxint, best_bid = -1;
+  for (int r = 0; r < no; ++r) {
+    int32_t pa = (w->asks[r * 6 + OF_TID] != trader_id) ? w->asks[r * 6 + OF_P] : -1;
+    int32_t pb = (w->bids[r * 6 + OF_TID] != trader_id) ? w->bids[r * 6 + OF_P] : -1;
+    mn = imin32(mn, pa == -1 ? c->book.maxint : pa);
+    best_bid = (r == 0) ? pb : imax32(best_bid, pb);
+  }
+  int32_t best_ask = (mn == c->book.maxint) ? -1 : mn;
+  int empty_book = (best_ask == -1) || (best_bid == -1);
+  best_ask = ifloordiv(best_ask, tick) * tick;
+  best_bid = ifloordiv(best_bid, tick) * tick;
+  if (empty_book) { best_bid = w->best_bids[(N - 1) * 2]; best_ask = w->best_asks[(N - 1) * 2]; }
+  int32_t mid_price = ifloordiv(best_ask + best_bid, 2);
+  static const float gamma_values[8] = {0.1f, 0.2f, 0.5f, 1.f, 2.f, 5.f, 10.f, 20.f};
+  float gamma = gamma_values[clamp_index(action, 8)];
+  const float k = (float)ac->avst_k_parameter, variance = (float)ac->avst_var_parameter;
+  int32_t time_left = c->episode_time - w->step_counter;
+  float normalized_time = (float)time_left / (float)c->episode_time;
+  float res_price = (float)mid_price - (((float)st->inventory * gamma) * variance) * normalized_time;
+  float spread = (gamma * variance) * normalized_time + (2.0f / gamma) * logf(1.0f + gamma / k);
+  spread = jminf(jmaxf(spread, tickf), (float)c->book.maxint);
+  float bp = res_price - spread / 2.0f, ap = res_price + spread / 2.0f;
+  bp = jminf(jmaxf(bp, 0.f), (float)c->book.maxint);
+  ap = jminf(jmaxf(ap, 0.f), (float)c->book.maxint);
+  int32_t bid_price = f2i(ffloordiv(bp, tickf) * tickf);
+  int32_t ask_price = f2i(ffloordiv(ap, tickf) * tickf);
+  int32_t round_down = (ifloordiv(mid_price, tick) - (imod(mid_price, tick) == 0 ? 1 : 0)) * tick;
+  int32_t round_up = (ifloordiv(mid_price, tick) + 1) * tick;
+  bid_price = imin32(bid_price, round_down);
+  ask_price = imax32(ask_price, round_up);
+  int32_t sides[2] = {1, -1}, prices[2] = {bid_price, ask_price};
+  for (int j = 0; j < 2; ++j) {
+    int32_t* o = out + j * 8;
+    o[0] = 1; o[1] = sides[j]; o[2] = ac->fixed_quant_value; o[3] = prices[j];
+    o[4] = c->placeholder_order_id; o[5] = trader_id;
+    o[6] = w->time[0] + ac->time_delay_obs_act; o[7] = w->time[1] + ac->time_delay_obs_act;
+  }
+  ex->posted_bid_price = bid_price; ex->posted_ask_price = ask_price;
+  ex->bid_distance_from_best = best_bid - bid_price; ex->ask_distance_from_best = ask_price - best_ask;
+  ex->bid_quant = ac->fixed_quant_value; ex->ask_quant = ac->fixed_quant_value;
+}
+
 /* mm:1869-1913 get_messages */
 static void mm_get_messages(const LobStepConfig* c, const LobAgentTypeConfig* ac, int32_t action, const World* w,
                             const MMState* st, int32_t trader_id, int32_t* act, int32_t* cnl, MMExtras* ex) {
   if (ac->action_space == LOB_MM_ACT_FIXED_QUANTS) mm_action_fixed_quant(c, ac, action, w, st, trader_id, act, ex);
   else if (ac->action_space == LOB_MM_ACT_DIRECTIONAL) mm_action_directional(c, ac, action, w, trader_id, act, ex);
+  else if (ac->action_space == LOB_MM_ACT_SIMPLE || ac->action_space == LOB_MM_ACT_SPREAD_SKEW)
+    mm_action_simple_or_skew(c, ac, action, w, trader_id, act, ex);
+  else if (ac->action_space == LOB_MM_ACT_AVST) mm_action_avst(c, ac, action, w, st, trader_id, act, ex);
   else mm_action_bob(c, ac, action, w, st, trader_id, act, ex);
   int sz = ac->num_messages_by_agent / 4;
   get_cancel_msgs(w->bids, c->book.n_orders, trader_id, sz, 1, w->time[0], w->time[1], cnl);

@@ -145,7 +145,21 @@ def bobstrat_1msg_agents(mac):
     return MultiAgentConfig(world_config=mac.world_config, dict_of_agents_configs=agents, number_of_agents_per_type=[1, 2, 1])
 
 
-MUTATORS = {"hetero": hetero_agents, "mm_complex": mm_complex_agents, "bob_twap": bob_twap_agents,
+def simple_skew_avst_agents(mac):
+    from gymnax_exchange.jaxob.jaxob_config import MultiAgentConfig
+    d = dict(mac.dict_of_agents_configs)
+    mm, ex = d["MarketMaking"], d["Execution"]
+    agents = {
+        "MarketMaking": dataclasses.replace(mm, action_space="simple", n_actions=4, fixed_quant_value=2),
+        "Skew": dataclasses.replace(mm, short_name="SK", action_space="spread_skew", multiplier_type="spread", fixed_quant_value=3,
+                                    reward_function="spooner"),
+        "AvSt": dataclasses.replace(mm, short_name="AV", action_space="AvSt", observation_space="engineered", fixed_quant_value=4),
+        "Execution": ex,
+    }
+    return MultiAgentConfig(world_config=mac.world_config, dict_of_agents_configs=agents, number_of_agents_per_type=[1, 1, 2, 1])
+
+
+MUTATORS = {"simple_skew_avst": simple_skew_avst_agents, "hetero": hetero_agents, "mm_complex": mm_complex_agents, "bob_twap": bob_twap_agents,
             "bobstrat_1msg": bobstrat_1msg_agents}
 
 
@@ -257,4 +271,5 @@ if __name__ == "__main__":
         run_env_case("env_mm_complex", "2_player_fq_fqc.json", seed=7, B=2, steps=66, mutate="mm_complex")
     if "env3" in which:
         run_env_case("env_bob_twap", "2_player_fq_fqc.json", seed=8, B=2, steps=66, mutate="bob_twap")
+        run_env_case("env_simple_skew_avst", "2_player_fq_fqc.json", seed=10, B=2, steps=66, mutate="simple_skew_avst")
         run_env_case("env_bobstrat_1msg", "2_player_fq_fqc.json", seed=9, B=2, steps=66, mutate="bobstrat_1msg")

@@ -199,6 +199,16 @@ def _mutate(mac, how):
                                              normalize=False, task_size=80),
         }
         return H.with_agents(mac, agents, [2, 1])
+    if how == "simple_skew_avst":
+        agents = {
+            "MarketMaking": dataclasses.replace(mm, action_space="simple", n_actions=4, fixed_quant_value=2),
+            "Skew": dataclasses.replace(mm, short_name="SK", action_space="spread_skew", multiplier_type="spread",
+                                        fixed_quant_value=3, reward_function="spooner"),
+            "AvSt": dataclasses.replace(mm, short_name="AV", action_space="AvSt", observation_space="engineered",
+                                        fixed_quant_value=4),
+            "Execution": ex,
+        }
+        return H.with_agents(mac, agents, [1, 1, 2, 1])
     if how == "bob_twap":
         agents = {"MarketMaking": dataclasses.replace(mm, action_space="bobRL", bob_v0=2, fixed_quant_value=3),
                   "Execution": dataclasses.replace(ex, action_space="twap", task_size=200)}

@@ -211,7 +211,8 @@ def test_full_size_properties():
 
 
 @pytest.mark.parametrize("mm_space,exe_space", [("bobRL", "twap"), ("bobStrategy", "fixed_quants_1msg"),
-                                                ("bobRL", "simplest_case")])
+                                                ("bobRL", "simplest_case"), ("simple", "twap"),
+                                                ("spread_skew", "fixed_quants_complex"), ("AvSt", "fixed_quants_complex")])
 def test_step_more_action_spaces(oracle, mm_space, exe_space):
     """First "next" row of SURVEY 8(f): MM bobRL / bobStrategy (mm_env.py:1474 / :1400) and EXE twap /
     fixed_quants_1msg / simplest_case (exec_env.py:1126 / :732 / :935)."""
@@ -219,7 +220,8 @@ def test_step_more_action_spaces(oracle, mm_space, exe_space):
     mac = H.load_mac("2_player_fq_fqc")
     agents = dict(mac.dict_of_agents_configs)
     agents["MarketMaking"] = dataclasses.replace(agents["MarketMaking"], action_space=mm_space, bob_v0=5,
-                                                 observation_space="engineered", fixed_quant_value=2)
+                                                 observation_space="engineered", fixed_quant_value=2,
+                                                 **({"n_actions": 4} if mm_space == "simple" else {}))
     agents["Execution"] = dataclasses.replace(agents["Execution"], action_space=exe_space, task_size=150,
                                               reward_function="simplest_case" if exe_space == "simplest_case" else "normal")
     _rollout_parity(oracle, H.with_agents(mac, agents, [2, 2]), H.small_day(n_events=30000), B=32, steps=66, seed=11,
