@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define LOB_ABI_VERSION 3
+#define LOB_ABI_VERSION 4
 #define LOB_MAX_AGENT_TYPES 4
 #define LOB_MAX_AGENT_I32 4  /* int32 state leaves per agent type */
 #define LOB_MAX_AGENT_F32 10 /* float32 state leaves per agent type */
@@ -61,9 +61,10 @@ enum LobMMActionSpace { LOB_MM_ACT_FIXED_QUANTS = 0, LOB_MM_ACT_DIRECTIONAL = 1,
 /* Execution_EnvironmentConfig.action_space     jaxob_config.py:157 ; exec_env.py:162-175 */
 enum LobEXEActionSpace { LOB_EXE_ACT_FIXED_QUANTS = 0, LOB_EXE_ACT_FIXED_QUANTS_COMPLEX = 1,
                           LOB_EXE_ACT_FIXED_QUANTS_1MSG = 2 /* exec_env.py:732 */, LOB_EXE_ACT_SIMPLEST_CASE = 3 /* :935 */,
-                          LOB_EXE_ACT_TWAP = 4 /* :1126 */ };
+                          LOB_EXE_ACT_TWAP = 4 /* :1126 */,
+                          LOB_EXE_ACT_FIXED_PRICES = 5 /* :1001; the action is a VECTOR of n_actions quantities */ };
 /* observation_space  mm_env.py:2767-2788 ; exec_env.py:179-186 */
-enum LobObsSpace { LOB_OBS_ENGINEERED = 0, LOB_OBS_BASIC = 1 };
+enum LobObsSpace { LOB_OBS_ENGINEERED = 0, LOB_OBS_BASIC = 1, LOB_OBS_SIMPLEST_CASE = 2 /* EXE only, exec_env.py:1841 */ };
 /* MM reward_function  mm_env.py:2489-2513 */
 enum LobMMReward {
   LOB_MM_REW_PORTFOLIO_VALUE = 0, LOB_MM_REW_BUY_SELL_PNL = 1, LOB_MM_REW_COMPLEX = 2,
@@ -216,7 +217,7 @@ typedef struct LobStepBuffers {
   int32_t* agent_i32[LOB_MAX_AGENT_TYPES][LOB_MAX_AGENT_I32];
   float*   agent_f32[LOB_MAX_AGENT_TYPES][LOB_MAX_AGENT_F32];
   /* inputs */
-  const int32_t* actions[LOB_MAX_AGENT_TYPES]; /* [B,n_i] */
+  const int32_t* actions[LOB_MAX_AGENT_TYPES]; /* [B,n_i]; [B,n_i,n_actions] for the EXE fixed_prices action space */
   const int32_t* perm;             /* [B,n_action]  jax.random.permutation(shuffle_key, n_action)  marl_env.py:294-295 ; may be NULL when !shuffle */
   const int32_t* reset_window;     /* [B] randint(world_key, 0, W) of the auto-reset  base_env.py:222-225 */
   const int32_t* reset_is_sell;    /* [B,n_agent_types] randint(agent_key,0,2) per type (shared by its agents, marl_env.py:187) */

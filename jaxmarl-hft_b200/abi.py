@@ -5,7 +5,7 @@ Field order and types follow the header exactly; ``check_sizes`` compares ``ctyp
 """
 import ctypes as C
 
-LOB_ABI_VERSION = 3
+LOB_ABI_VERSION = 4
 LOB_MAX_AGENT_TYPES = 4
 LOB_MAX_AGENT_I32 = 4
 LOB_MAX_AGENT_F32 = 10
@@ -16,8 +16,9 @@ LOB_OK, LOB_E_INVALID, LOB_E_UNSUPPORTED, LOB_E_CUDA = 0, -1, -2, -3
 AGENT_MM, AGENT_EXE = 0, 1
 MM_ACTION_SPACES = {"fixed_quants": 0, "directional_trading": 1, "bobRL": 2, "bobStrategy": 3, "simple": 4, "spread_skew": 5,
                     "AvSt": 6}
-EXE_ACTION_SPACES = {"fixed_quants": 0, "fixed_quants_complex": 1, "fixed_quants_1msg": 2, "simplest_case": 3, "twap": 4}
-OBS_SPACES = {"engineered": 0, "basic": 1}
+EXE_ACTION_SPACES = {"fixed_quants": 0, "fixed_quants_complex": 1, "fixed_quants_1msg": 2, "simplest_case": 3, "twap": 4,
+                     "fixed_prices": 5}
+OBS_SPACES = {"engineered": 0, "basic": 1, "simplest_case": 2}
 MM_REWARDS = {"portfolio_value": 0, "buy_sell_pnl": 1, "complex": 2, "zero_inv": 3, "spooner": 4,
               "spooner_damped": 5, "spooner_asym_damped": 6, "spooner_asym_damped2": 7, "spooner_scaled": 8,
               "delta_portfolio_value": 9}
@@ -111,11 +112,16 @@ def check_sizes(lib):
             raise RuntimeError(f"ABI mismatch: {fn}() = {got}, ctypes mirror = {C.sizeof(cls)}")
 
 
+def action_width(a) -> int:
+    """Ints per agent in the actions buffer: n_actions for the EXE fixed_prices space (a vector of quantities), else 1."""
+    return int(a.n_actions) if (a.kind == AGENT_EXE and a.action_space == EXE_ACTION_SPACES["fixed_prices"]) else 1
+
+
 def obs_dim(kind, observation_space):
     """mm_env.py:3195-3223 ; exec_env.py:2188-2202 (fixed_steps)."""
     if kind == AGENT_MM:
         return 2 if observation_space == OBS_SPACES["basic"] else 8
-    return 3 if observation_space == OBS_SPACES["basic"] else 12
+    return 12 if observation_space == OBS_SPACES["engineered"] else 3
 
 
 def info_cols(kind):

@@ -252,6 +252,8 @@ def agent_type_config(cfg, n_agents: int, trader_id_start: int) -> abi.LobAgentT
     a.reward_scaling_quo = cfg.reward_scaling_quo
     a.observation_space = _enum(abi.OBS_SPACES, cfg.observation_space, "observation_space")
     if isinstance(cfg, MarketMaking_EnvironmentConfig):
+        if cfg.observation_space == "simplest_case":
+            raise ValueError("Invalid observation_space specified.")  # mm_env.py:2787
         a.kind = abi.AGENT_MM
         a.action_space = _enum(abi.MM_ACTION_SPACES, cfg.action_space, "action_space")
         a.reward_function = _enum(abi.MM_REWARDS, cfg.reward_function, "reward_space")
@@ -306,6 +308,8 @@ def agent_type_config(cfg, n_agents: int, trader_id_start: int) -> abi.LobAgentT
             raise ValueError("Invalid reference price type.")  # exe:1576-1580
         a.reference_price = abi.REF_PRICES[cfg.reference_price]
         a.reward_lambda = cfg.reward_lambda
+        if cfg.action_space == "fixed_prices" and not (1 <= cfg.n_actions <= 4):
+            raise ValueError("fixed_prices supports 1 to 4 price levels (exec_env.py:1047-1054)")
     else:
         raise ValueError(f"Invalid agent type: {type(cfg).__name__}")  # marl:79
     return a

@@ -161,7 +161,7 @@ static __device__ __noinline__ void filter_messages(int* act, int ka, int* cnl, 
 
 // Old-world scalars every agent function needs (warp-uniform)
 struct WorldIn {
-  int time0, time1, init_time0, step_counter, max_steps;
+  int time0, time1, init_time0, init_time1, step_counter, max_steps;
   int old_ba_last, old_bb_last;   // world_state.best_asks[-1,0] / best_bids[-1,0]
   float mid_price;
   bool extreme_spread;            // any((ba-bb)/((ba+bb)/2) > 0.1) over the OLD per-message bests (mm:2545-2553)
@@ -333,9 +333,12 @@ static __device__ __noinline__ MMOut mm_get_messages(BookCtx bk, const LobStepCo
 
 // exe:1229-1273 get_messages (fixed_quants exe:623-724 / fixed_quants_complex exe:838-932)
 static __device__ __noinline__ void exe_get_messages(BookCtx bk, const LobStepConfig& c, const LobAgentTypeConfig& ac,
-                                                     int action, const WorldIn& w, int task_to_execute,
-                                                     int quant_executed, int is_sell, int tid, int* act, int* cnl) {
+                                                     const int* __restrict__ av /* action (vector for fixed_prices) */,
+                                                     const int* __restrict__ old_best_asks, const int* __restrict__ old_best_bids,
+                                                     int N, const WorldIn& w, int task_to_execute, int quant_executed,
+                                                     int is_sell, int tid, int* act, int* cnl) {
   const int tick = c.tick_size;
+  const int action = av[0];
   const int best_ask = ifloordiv(w.old_ba_last, tick) * tick, best_bid = ifloordiv(w.old_bb_last, tick) * tick;
   int lv[4];
   if (is_sell) {
@@ -352,7 +355,33 @@ static __device__ __noinline__ void exe_get_messages(BookCtx bk, const LobStepCo
   const int quant_left = task_to_execute - quant_executed;
   const int ka = ac.num_action_messages_by_agent;
   int q[4] = {0, 0, 0, 0}, pr[4] = {lv[0], lv[1], lv[2], lv[3]};
-  if (ac.action_space == LOB_EXE_ACT_FIXED_QUANTS_1MSG) {        // exe:732-835
+  if (ac.action_space == LOB_EXE_ACT_FIXED_PRICES) {             // exe:1001-1124: quantity at each price level
+    const int A = ac.n_actions;
+    float sa = 0.f, sb = 0.f;   // float32 mean of the last 10 per-message bests (exe:1102-1103), summed left to right
+#pragma unroll 1
+    for (int i = N - 10; i < N; ++i) { sa += (float)old_best_asks[i * 2]; sb += (float)old_best_bids[i * 2]; }
+    const float tickf = (float)tick;
+    const int ba = f2i(ffloordiv(sa / 10.0f, tickf) * tickf), bb = f2i(ffloordiv(sb / 10.0f, tickf) * tickf);
+    int FT, M, NT, PP;
+    if (is_sell) {
+      FT = ifloordiv(bb, tick) * tick;
+      M = f2i(ceilf(ffloordiv((float)(bb + ba) / 2.0f, tickf)) * tickf);
+      NT = ba; PP = ba + tick * ac.n_ticks_in_book;
+    } else {
+      FT = ifloordiv(ba, tick) * tick;
+      M = ifloordiv(ifloordiv(bb + ba, 2), tick) * tick;
+      NT = bb; PP = bb - tick * ac.n_ticks_in_book;
+    }
+    pr[0] = FT;
+    if (A == 4) { pr[1] = M; pr[2] = NT; pr[3] = PP; } else if (A == 3) { pr[1] = NT; pr[2] = PP; } else if (A == 2) { pr[1] = NT; }
+    int S = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) if (k < A) S += av[k];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (k < A) q[k] = (S > quant_left) ? f2i((float)av[k] / (float)S * (float)quant_left) : av[k];
+    if (A == 4 && pr[1] == pr[2]) { q[2] = q[2] + q[1]; q[1] = 0; pr[1] = -1; }   // combine_mid_nt exe:1018-1023
+  } else if (ac.action_space == LOB_EXE_ACT_FIXED_QUANTS_1MSG) { // exe:732-835
     const int ai = clamp_index(action, 5);
     pr[0] = (ai == 0) ? 0 : (ai == 1) ? lv[0] : (ai == 2) ? lv[1] : (ai == 3) ? lv[2] : lv[3];
     const int sel = (ai == 0) ? 0 : ac.fixed_quant_value;
@@ -719,11 +748,21 @@ static __device__ __noinline__ EXEReward exe_get_reward(int* tr, int nt, const L
 
 // exe:1879-1906 / exe:1913-2079 (fixed_steps), alphabetical key order
 static __device__ __noinline__ void exe_write_obs(const LobAgentTypeConfig& ac, float* obs, const EXEState& st, int ba, int bb,
-                                                  int ask_vol, int bid_vol, int step_counter, int max_steps, bool zero) {
+                                                  int ask_vol, int bid_vol, int step_counter, int max_steps, bool zero,
+                                                  float mid_price, float time_used, int episode_time) {
   if (lane_id() != 0) return;
   const bool nz = ac.normalize;
   const float ts = (float)ac.task_size;
   const int rem = st.task_to_execute - st.quant_executed;
+  if (ac.observation_space == LOB_OBS_SIMPLEST_CASE) {   // exe:1841-1875, keys in alphabetical order
+    const float ep = (float)episode_time;
+    const float ptime = (ep - time_used) / ep;
+    const float pquant = (float)rem / (float)st.task_to_execute;
+    obs[0] = zero ? 0.f : (nz ? (mid_price - 7560000.0f) / 1e3f : mid_price);
+    obs[1] = zero ? 0.f : (nz ? (pquant - 0.5f) / 1.0f : pquant);
+    obs[2] = zero ? 0.f : (nz ? (ptime - 0.5f) / 1.0f : ptime);
+    return;
+  }
   if (ac.observation_space == LOB_OBS_BASIC) {
     obs[0] = zero ? 0.f : (nz ? (float)(ba - 1550000) / 1e3f : (float)ba);
     obs[1] = zero ? 0.f : (nz ? (float)(bb - 1550000) / 1e3f : (float)bb);

@@ -213,7 +213,7 @@ __device__ __forceinline__ void store_exe_state(const LobStepBuffers& b, int t, 
 
 __device__ __forceinline__ int obs_dim_of(const LobAgentTypeConfig& a) {
   if (a.kind == LOB_AGENT_MM) return a.observation_space == LOB_OBS_BASIC ? 2 : 8;
-  return a.observation_space == LOB_OBS_BASIC ? 3 : 12;
+  return a.observation_space == LOB_OBS_ENGINEERED ? 12 : 3;
 }
 
 // marl_env.py:130-207 reset_env for env e: the precomputed state of window reset_window[e] replaces every leaf.
@@ -265,7 +265,7 @@ __device__ __noinline__ void reset_env(const LobStepConfig& c, const LobStepBuff
         s.task_to_execute = ac.task_size;
         s.p_vwap = mid / (float)c.tick_size;
         if (lane == 0) store_exe_state(b, t, idx, s);
-        exe_write_obs(ac, b.obs[t] + idx * d, s, ap, bp, qa, qb, 0, max_steps, false);
+        exe_write_obs(ac, b.obs[t] + idx * d, s, ap, bp, qa, qb, 0, max_steps, false, mid, 0.0f, c.episode_time);
       }
     }
   }
@@ -352,7 +352,7 @@ lob_step_kernel(const __grid_constant__ LobStepConfig c, const __grid_constant__
     if (active) {
       // ---- old world state (the reward sees it: marl:462) ----
       w.time0 = b.time[e * 2]; w.time1 = b.time[e * 2 + 1];
-      w.init_time0 = b.init_time[e * 2];
+      w.init_time0 = b.init_time[e * 2]; w.init_time1 = b.init_time[e * 2 + 1];
       w.step_counter = b.step_counter[e];
       w.max_steps = b.max_steps[e];
       w.mid_price = b.mid_price[e];
@@ -405,8 +405,10 @@ lob_step_kernel(const __grid_constant__ LobStepConfig c, const __grid_constant__
         for (int a = 0; a < ac.n_agents; ++a, ++flat) {
           const long long idx = e * ac.n_agents + a;
           const int tid = ac.trader_id_start - a;
-          const int action = b.actions[t][idx];
+          const int aw = (ac.kind == LOB_AGENT_EXE && ac.action_space == LOB_EXE_ACT_FIXED_PRICES) ? ac.n_actions : 1;
+          const int* av = b.actions[t] + idx * aw;
           if (ac.kind == LOB_AGENT_MM) {
+            const int action = av[0];
             const int inventory = b.agent_i32[t][2][idx];
             MMOut o = mm_get_messages(bk.c, c, ac, action, w, inventory, tid, act_all + ai * 8, msgs + ci * 8);
             if (lane == 0) {
@@ -415,8 +417,9 @@ lob_step_kernel(const __grid_constant__ LobStepConfig c, const __grid_constant__
               s[4] = o.bid_quant; s[5] = o.ask_quant;
             }
           } else {
-            exe_get_messages(bk.c, c, ac, action, w, b.agent_i32[t][0][idx], b.agent_i32[t][1][idx],
-                             b.agent_i32[t][2][idx], tid, act_all + ai * 8, msgs + ci * 8);
+            exe_get_messages(bk.c, c, ac, av, b.best_asks + e * N * 2, b.best_bids + e * N * 2, N, w,
+                             b.agent_i32[t][0][idx], b.agent_i32[t][1][idx], b.agent_i32[t][2][idx], tid,
+                             act_all + ai * 8, msgs + ci * 8);
           }
           ci += kc; ai += ka;
         }
@@ -515,7 +518,8 @@ lob_step_kernel(const __grid_constant__ LobStepConfig c, const __grid_constant__
               fi[0] = R.slippage; fi[1] = ns.vwap_rm; fi[2] = R.drift; fi[3] = R.advantage; fi[4] = R.reward;
             }
             if (!so.ep_done)   // marl:690-698: a finished agent observes zeros until the episode ends
-              exe_write_obs(ac, obs, ns, so.ba_last, so.bb_last, vol_a, vol_b, new_step, w.max_steps, done);
+              exe_write_obs(ac, obs, ns, so.ba_last, so.bb_last, vol_a, vol_b, new_step, w.max_steps, done, new_mid,
+                            (float)(ft0 - w.init_time0) + (float)(ft1 - w.init_time1) / 1e9f, c.episode_time);
           }
         }
       }

@@ -80,9 +80,14 @@ int check_step_cfg(const LobStepConfig* c) {
       if (a->reward_function < 0 || a->reward_function > LOB_MM_REW_DELTA_PORTFOLIO_VALUE)
         return fail(LOB_E_INVALID, "agent[%d].reward_function=%d", t, a->reward_function);
     } else {
-      if (a->action_space < LOB_EXE_ACT_FIXED_QUANTS || a->action_space > LOB_EXE_ACT_TWAP)
+      if (a->action_space < LOB_EXE_ACT_FIXED_QUANTS || a->action_space > LOB_EXE_ACT_FIXED_PRICES)
         return fail(LOB_E_UNSUPPORTED, "agent[%d]: EXE action space %d is not built", t, a->action_space);
-      const int want = a->action_space == LOB_EXE_ACT_FIXED_QUANTS_1MSG ? 1
+      if (a->action_space == LOB_EXE_ACT_FIXED_PRICES && (a->n_actions < 1 || a->n_actions > 4))
+        return fail(LOB_E_INVALID, "agent[%d]: fixed_prices supports 1..4 price levels, got %d", t, a->n_actions);
+      if (a->action_space == LOB_EXE_ACT_FIXED_PRICES && lob_num_msgs_per_step(c) < 10)
+        return fail(LOB_E_UNSUPPORTED, "agent[%d]: fixed_prices averages the last 10 per-message best prices", t);
+      const int want = a->action_space == LOB_EXE_ACT_FIXED_PRICES ? a->n_actions
+                       : a->action_space == LOB_EXE_ACT_FIXED_QUANTS_1MSG ? 1
                        : (a->action_space == LOB_EXE_ACT_SIMPLEST_CASE || a->action_space == LOB_EXE_ACT_TWAP) ? 2 : 4;
       if (ka != want) return fail(LOB_E_INVALID, "agent[%d]: this EXE action space posts %d messages, config says %d", t, want, ka);
       if (a->reward_function < 0 || a->reward_function > LOB_EXE_REW_SIMPLEST_CASE)
@@ -90,7 +95,8 @@ int check_step_cfg(const LobStepConfig* c) {
       if (a->reference_price != LOB_REF_MID && a->reference_price != LOB_REF_FAR_TOUCH)
         return fail(LOB_E_INVALID, "agent[%d]: EXE reference_price must be mid or far_touch", t);
     }
-    if (a->observation_space != LOB_OBS_ENGINEERED && a->observation_space != LOB_OBS_BASIC)
+    if (a->observation_space != LOB_OBS_ENGINEERED && a->observation_space != LOB_OBS_BASIC &&
+        !(a->observation_space == LOB_OBS_SIMPLEST_CASE && a->kind == LOB_AGENT_EXE))
       return fail(LOB_E_UNSUPPORTED, "agent[%d]: observation space %d is not built", t, a->observation_space);
   }
   if (total > lob::kMaxAgents) return fail(LOB_E_INVALID, "%d agents per environment (max %d)", total, lob::kMaxAgents);
@@ -177,7 +183,7 @@ int32_t lob_num_msgs_per_step(const LobStepConfig* c) {
 int32_t lob_obs_dim(const LobStepConfig* c, int32_t t) {
   const LobAgentTypeConfig* a = &c->agent[t];
   if (a->kind == LOB_AGENT_MM) return a->observation_space == LOB_OBS_BASIC ? 2 : 8;
-  return a->observation_space == LOB_OBS_BASIC ? 3 : 12;
+  return a->observation_space == LOB_OBS_ENGINEERED ? 12 : 3;
 }
 int32_t lob_info_i32_cols(const LobStepConfig* c, int32_t t) {
   return c->agent[t].kind == LOB_AGENT_MM ? LOB_MMINFO_I32_COLS : LOB_EXEINFO_I32_COLS;

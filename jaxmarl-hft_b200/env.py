@@ -24,7 +24,7 @@ import numpy as np
 from . import _lib, abi, lobster, states
 from .config import (Execution_EnvironmentConfig, MarketMaking_EnvironmentConfig, MultiAgentConfig,
                      World_EnvironmentConfig, book_config, num_action_msgs, num_msgs_per_step, to_step_config)
-from .spaces import Box, Discrete
+from .spaces import Box, Discrete, MultiDiscrete
 
 
 # ---- state / params containers (field names of StatesandParams.py:14-122) ---------------------------------
@@ -189,7 +189,9 @@ class MARLEnv:
         self.cfg = to_step_config(multi_agent_config, self.base_env.n_windows, self.base_env.loaded.msgs.shape[0])
         self.num_msgs_per_step = num_msgs_per_step(self.cfg)
         self.num_action_msgs_per_step_by_all_agents = num_action_msgs(self.cfg)
-        self.action_spaces = [Discrete(c.n_actions) for c in self.list_of_agents_configs]
+        self.action_spaces = [MultiDiscrete([c.fixed_quant_value] * c.n_actions)   # exec_env.py:2167-2171
+                              if getattr(c, "action_space", "") == "fixed_prices" and isinstance(c, Execution_EnvironmentConfig)
+                              else Discrete(c.n_actions) for c in self.list_of_agents_configs]
         self.observation_spaces = [
             Box(-1000 if isinstance(c, MarketMaking_EnvironmentConfig) else -10000,
                 1000 if isinstance(c, MarketMaking_EnvironmentConfig) else 10000,

@@ -27,3 +27,20 @@ class Box:
     def contains(self, x) -> bool:
         x = np.asarray(x)
         return bool(x.shape == self.shape and np.all(x >= self.low) and np.all(x <= self.high))
+
+
+class MultiDiscrete:
+    """from_JAXMARL/spaces.py:45: a vector of categorical variables (the EXE fixed_prices action space)."""
+
+    def __init__(self, num_categories, dtype=np.int32):
+        self.n = list(num_categories)
+        self.num_categories = np.asarray(num_categories, dtype=np.int64)
+        self.shape = (len(self.num_categories),)
+        self.dtype = dtype
+
+    def sample(self, rng: np.random.Generator):
+        return (rng.random(self.shape) * self.num_categories).astype(self.dtype)
+
+    def contains(self, x) -> bool:
+        x = np.asarray(x)
+        return bool(x.shape == self.shape and np.all(x >= 0) and np.all(x < self.num_categories))

@@ -45,7 +45,8 @@ def leaf_specs(cfg: abi.LobStepConfig, batch: int):
         for name in lf:
             sp[f"a{t}_{name}"] = ((B, n), np.float32, "s")
         ki, kf = abi.info_cols(a.kind)
-        sp[f"actions{t}"] = ((B, n), np.int32, "i")
+        aw = abi.action_width(a)
+        sp[f"actions{t}"] = ((B, n) if aw == 1 else (B, n, aw), np.int32, "i")
         sp[f"obs{t}"] = ((B, n, abi.obs_dim(a.kind, a.observation_space)), np.float32, "o")
         sp[f"reward{t}"] = ((B, n), np.float32, "o")
         sp[f"done_agents{t}"] = ((B, n), np.uint8, "o")

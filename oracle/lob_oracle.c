@@ -923,8 +923,9 @@ static void mm_get_obs(const LobStepConfig* c, const LobAgentTypeConfig* ac, con
 
 /* exe:623-724 (fixed_quants; the reference forgets the extras tuple -> "the obvious fix"), exe:838-932
  * (fixed_quants_complex), exe:732-835 (fixed_quants_1msg), exe:935-999 (simplest_case), exe:1126-1227 (twap) */
-static void exe_action(const LobStepConfig* c, const LobAgentTypeConfig* ac, int32_t action, const World* w,
-                       const EXEState* st, int32_t trader_id, int32_t* out /* [ka][8] */) {
+static void exe_action(const LobStepConfig* c, const LobAgentTypeConfig* ac, const int32_t* av /* action (vector) */,
+                       const World* w, const EXEState* st, int32_t trader_id, int32_t* out /* [ka][8] */) {
+  const int32_t action = av[0];
   const int32_t tick = c->tick_size;
   const int N = lob_num_msgs_per_step(c);
   const int ka = ac->num_action_messages_by_agent;
@@ -945,7 +946,32 @@ static void exe_action(const LobStepConfig* c, const LobAgentTypeConfig* ac, int
   }
   int32_t quant_left = st->task_to_execute - st->quant_executed;
   int32_t q[4] = {0, 0, 0, 0}, pr[4] = {lv[0], lv[1], lv[2], lv[3]};
-  if (ac->action_space == LOB_EXE_ACT_FIXED_QUANTS_1MSG) { /* exe:732-835: one message, price and size picked by the action */
+  if (ac->action_space == LOB_EXE_ACT_FIXED_PRICES) { /* exe:1001-1124: the action is the quantity at each price level */
+    const int A = ac->n_actions;
+    /* best prices = float32 mean of the last 10 per-message bests, floored to the tick (exe:1102-1103) */
+    float sa = 0.f, sb = 0.f;
+    for (int i = N - 10; i < N; ++i) { sa += (float)w->best_asks[clamp_index(i, N) * 2]; sb += (float)w->best_bids[clamp_index(i, N) * 2]; }
+    int32_t ba = f2i(ffloordiv(sa / 10.0f, (float)tick) * (float)tick), bb = f2i(ffloordiv(sb / 10.0f, (float)tick) * (float)tick);
+    int32_t FT, M, NT, PP;
+    if (st->is_sell_task) {
+      FT = ifloordiv(bb, tick) * tick;
+      M = f2i(ceilf(ffloordiv((float)(bb + ba) / 2.0f, (float)tick)) * (float)tick);
+      NT = ba; PP = ba + tick * ac->n_ticks_in_book;
+    } else {
+      FT = ifloordiv(ba, tick) * tick;
+      M = ifloordiv(ifloordiv(bb + ba, 2), tick) * tick;
+      NT = bb; PP = bb - tick * ac->n_ticks_in_book;
+    }
+    if (A == 4) { pr[0] = FT; pr[1] = M; pr[2] = NT; pr[3] = PP; }
+    else if (A == 3) { pr[0] = FT; pr[1] = NT; pr[2] = PP; }
+    else if (A == 2) { pr[0] = FT; pr[1] = NT; }
+    else { pr[0] = FT; }
+    int32_t S = 0;
+    for (int k = 0; k < A; ++k) S += av[k];
+    for (int k = 0; k < A; ++k)
+      q[k] = (S > quant_left) ? f2i((float)av[k] / (float)S * (float)quant_left) : av[k];
+    if (A == 4 && pr[1] == pr[2]) { q[2] = q[2] + q[1]; q[1] = 0; pr[1] = -1; } /* combine_mid_nt exe:1018-1023 */
+  } else if (ac->action_space == LOB_EXE_ACT_FIXED_QUANTS_1MSG) { /* exe:732-835: one message, price and size picked by the action */
     int ai = clamp_index(action, 5);
     pr[0] = (ai == 0) ? 0 : lv[ai - 1];
     int32_t sel = (ai == 0) ? 0 : ac->fixed_quant_value;
@@ -993,9 +1019,9 @@ static void exe_action(const LobStepConfig* c, const LobAgentTypeConfig* ac, int
 }
 
 /* exe:1229-1273 get_messages */
-static void exe_get_messages(const LobStepConfig* c, const LobAgentTypeConfig* ac, int32_t action, const World* w,
+static void exe_get_messages(const LobStepConfig* c, const LobAgentTypeConfig* ac, const int32_t* av, const World* w,
                              const EXEState* st, int32_t trader_id, int32_t* act, int32_t* cnl) {
-  exe_action(c, ac, action, w, st, trader_id, act);
+  exe_action(c, ac, av, w, st, trader_id, act);
   int sz = ac->num_messages_by_agent / 2;
   get_cancel_msgs(st->is_sell_task ? w->asks : w->bids, c->book.n_orders, trader_id, sz, 1 - st->is_sell_task * 2,
                   w->time[0], w->time[1], cnl);
@@ -1107,6 +1133,16 @@ static void exe_get_obs(const LobStepConfig* c, const LobAgentTypeConfig* ac, co
   const int32_t ba = w->best_asks[(N - 1) * 2], bb = w->best_bids[(N - 1) * 2];
   const int nz = ac->normalize;
   const float ts = (float)ac->task_size;
+  if (ac->observation_space == LOB_OBS_SIMPLEST_CASE) { /* exe:1841-1875: mid_price, percent_remaining_quant, percent_time_remaining */
+    const float ep = (float)c->episode_time;
+    float used = (float)(w->time[0] - w->init_time[0]) + (float)(w->time[1] - w->init_time[1]) / 1e9f;
+    float ptime = (ep - used) / ep;
+    float pquant = (float)(st->task_to_execute - st->quant_executed) / (float)st->task_to_execute;
+    obs[0] = nz ? (w->mid_price - 7560000.0f) / 1e3f : w->mid_price;
+    obs[1] = nz ? (pquant - 0.5f) / 1.0f : pquant;
+    obs[2] = nz ? (ptime - 0.5f) / 1.0f : ptime;
+    return;
+  }
   if (ac->observation_space == LOB_OBS_BASIC) { /* best_ask_price, best_bid_price, remaining_quant */
     int32_t rem = st->task_to_execute - st->quant_executed;
     obs[0] = nz ? (float)(ba - 1550000) / 1e3f : (float)ba;
@@ -1154,7 +1190,7 @@ int32_t lob_num_msgs_per_step(const LobStepConfig* c) { /* marl:85-94 */
 int32_t lob_obs_dim(const LobStepConfig* c, int32_t t) {
   const LobAgentTypeConfig* a = &c->agent[t];
   if (a->kind == LOB_AGENT_MM) return a->observation_space == LOB_OBS_BASIC ? 2 : 8;
-  return a->observation_space == LOB_OBS_BASIC ? 3 : 12;
+  return a->observation_space == LOB_OBS_ENGINEERED ? 12 : 3;
 }
 int32_t lob_info_i32_cols(const LobStepConfig* c, int32_t t) {
   return c->agent[t].kind == LOB_AGENT_MM ? LOB_MMINFO_I32_COLS : LOB_EXEINFO_I32_COLS;
@@ -1308,13 +1344,15 @@ static void step_one(const LobStepConfig* c, const LobStepBuffers* b, int64_t e,
     for (int a = 0; a < ac->n_agents; ++a, ++flat) {
       int64_t idx = e * ac->n_agents + a;
       int32_t tid = ac->trader_id_start - a;
-      int32_t action = b->actions[t][idx];
+      const int aw = (ac->kind == LOB_AGENT_EXE && ac->action_space == LOB_EXE_ACT_FIXED_PRICES) ? ac->n_actions : 1;
+      const int32_t* av = b->actions[t] + idx * aw;
+      int32_t action = av[0];
       if (ac->kind == LOB_AGENT_MM) {
         MMState s; load_mm(b, t, idx, &s);
         mm_get_messages(c, ac, action, &w, &s, tid, act_all + ai * 8, msgs + ci * 8, &mmx[flat]);
       } else {
         EXEState s; load_exe(b, t, idx, &s);
-        exe_get_messages(c, ac, action, &w, &s, tid, act_all + ai * 8, msgs + ci * 8);
+        exe_get_messages(c, ac, av, &w, &s, tid, act_all + ai * 8, msgs + ci * 8);
       }
       ci += kc; ai += ka;
     }

@@ -140,7 +140,7 @@ def bobstrat_1msg_agents(mac):
         "MarketMaking": dataclasses.replace(mm, action_space="bobStrategy", bob_v0=5, observation_space="engineered"),
         "Execution": dataclasses.replace(ex, action_space="fixed_quants_1msg", task_size=60, fixed_quant_value=7),
         "Exec2": dataclasses.replace(ex, short_name="EXE2", action_space="simplest_case", reward_function="simplest_case",
-                                     task="buy", task_size=40, fixed_quant_value=9),
+                                     observation_space="simplest_case", task="buy", task_size=40, fixed_quant_value=9),
     }
     return MultiAgentConfig(world_config=mac.world_config, dict_of_agents_configs=agents, number_of_agents_per_type=[1, 2, 1])
 
@@ -159,7 +159,20 @@ def simple_skew_avst_agents(mac):
     return MultiAgentConfig(world_config=mac.world_config, dict_of_agents_configs=agents, number_of_agents_per_type=[1, 1, 2, 1])
 
 
-MUTATORS = {"simple_skew_avst": simple_skew_avst_agents, "hetero": hetero_agents, "mm_complex": mm_complex_agents, "bob_twap": bob_twap_agents,
+def fixed_prices_agents(mac):
+    from gymnax_exchange.jaxob.jaxob_config import MultiAgentConfig
+    d = dict(mac.dict_of_agents_configs)
+    mm, ex = d["MarketMaking"], d["Execution"]
+    agents = {
+        "MarketMaking": mm,
+        "Execution": dataclasses.replace(ex, action_space="fixed_prices", n_actions=4, fixed_quant_value=11, task_size=120),
+        "Exec2": dataclasses.replace(ex, short_name="EXE2", action_space="fixed_prices", n_actions=2, fixed_quant_value=6,
+                                     task="sell", task_size=90),
+    }
+    return MultiAgentConfig(world_config=mac.world_config, dict_of_agents_configs=agents, number_of_agents_per_type=[1, 2, 1])
+
+
+MUTATORS = {"fixed_prices": fixed_prices_agents, "simple_skew_avst": simple_skew_avst_agents, "hetero": hetero_agents, "mm_complex": mm_complex_agents, "bob_twap": bob_twap_agents,
             "bobstrat_1msg": bobstrat_1msg_agents}
 
 
@@ -196,10 +209,15 @@ def run_env_case(name, json_name, seed, B, steps, n_events=30000, stress=False, 
             step_keys = jr.split(k_step, B)
             actions = []
             for t in range(n_types):
-                n_a = env.action_spaces[t].n
-                a = rng.integers(0, n_a, size=(B, n_per[t])).astype(np.int32)
-                if s % 9 == 4:
-                    a[::3] = rng.integers(-2, n_a + 3, size=a[::3].shape)   # out-of-range actions (gather wrap + clamp)
+                sp = env.action_spaces[t]
+                if np.ndim(sp.n) == 0:
+                    n_a = int(sp.n)
+                    a = rng.integers(0, n_a, size=(B, n_per[t])).astype(np.int32)
+                    if s % 9 == 4:
+                        a[::3] = rng.integers(-2, n_a + 3, size=a[::3].shape)   # out-of-range actions (gather wrap + clamp)
+                else:   # MultiDiscrete (EXE fixed_prices): a vector of quantities per agent
+                    cats = np.asarray(sp.num_categories)
+                    a = rng.integers(0, cats, size=(B, n_per[t], len(cats))).astype(np.int32)
                 actions.append(a)
             # the trainer squeezes single-agent types (marl_env.py:265-266 handles both)
             jax_actions = [jnp.asarray(a[:, 0] if a.shape[1] == 1 else a) for a in actions]

@@ -75,7 +75,9 @@ def draw_prng(rng, cfg, arrays):
 
 def draw_actions(rng, cfg, arrays):
     for t in range(cfg.n_agent_types):
-        arrays[f"actions{t}"][:] = rng.integers(0, cfg.agent[t].n_actions, size=arrays[f"actions{t}"].shape)
+        a = cfg.agent[t]
+        hi = a.fixed_quant_value if abi.action_width(a) > 1 else a.n_actions   # fixed_prices: a vector of quantities
+        arrays[f"actions{t}"][:] = rng.integers(0, hi, size=arrays[f"actions{t}"].shape)
 
 
 def copy_inputs(src, dst):

@@ -209,6 +209,14 @@ def _mutate(mac, how):
             "Execution": ex,
         }
         return H.with_agents(mac, agents, [1, 1, 2, 1])
+    if how == "fixed_prices":
+        agents = {
+            "MarketMaking": mm,
+            "Execution": dataclasses.replace(ex, action_space="fixed_prices", n_actions=4, fixed_quant_value=11, task_size=120),
+            "Exec2": dataclasses.replace(ex, short_name="EXE2", action_space="fixed_prices", n_actions=2, fixed_quant_value=6,
+                                         task="sell", task_size=90),
+        }
+        return H.with_agents(mac, agents, [1, 2, 1])
     if how == "bob_twap":
         agents = {"MarketMaking": dataclasses.replace(mm, action_space="bobRL", bob_v0=2, fixed_quant_value=3),
                   "Execution": dataclasses.replace(ex, action_space="twap", task_size=200)}
@@ -218,7 +226,7 @@ def _mutate(mac, how):
             "MarketMaking": dataclasses.replace(mm, action_space="bobStrategy", bob_v0=5, observation_space="engineered"),
             "Execution": dataclasses.replace(ex, action_space="fixed_quants_1msg", task_size=60, fixed_quant_value=7),
             "Exec2": dataclasses.replace(ex, short_name="EXE2", action_space="simplest_case", reward_function="simplest_case",
-                                         task="buy", task_size=40, fixed_quant_value=9),
+                                         observation_space="simplest_case", task="buy", task_size=40, fixed_quant_value=9),
         }
         return H.with_agents(mac, agents, [1, 2, 1])
     raise KeyError(how)

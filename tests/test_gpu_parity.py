@@ -226,3 +226,15 @@ def test_step_more_action_spaces(oracle, mm_space, exe_space):
                                               reward_function="simplest_case" if exe_space == "simplest_case" else "normal")
     _rollout_parity(oracle, H.with_agents(mac, agents, [2, 2]), H.small_day(n_events=30000), B=32, steps=66, seed=11,
                     stress_actions=True)
+
+
+def test_step_fixed_prices_vector_actions(oracle):
+    """EXE fixed_prices (exec_env.py:1001): the action is a vector of quantities per price level ([B,n_i,n_actions])."""
+    import dataclasses
+    mac = H.load_mac("2_player_fq_fqc")
+    agents = dict(mac.dict_of_agents_configs)
+    ex = agents["Execution"]
+    agents["Execution"] = dataclasses.replace(ex, action_space="fixed_prices", n_actions=4, fixed_quant_value=11, task_size=120)
+    agents["Exec2"] = dataclasses.replace(ex, short_name="EXE2", action_space="fixed_prices", n_actions=1, fixed_quant_value=6,
+                                          observation_space="simplest_case", task="sell", task_size=90)
+    _rollout_parity(oracle, H.with_agents(mac, agents, [1, 2, 2]), H.small_day(n_events=30000), B=32, steps=66, seed=13)
