@@ -303,6 +303,8 @@ def agent_type_config(cfg, n_agents: int, trader_id_start: int) -> abi.LobAgentT
         if cfg.action_space == "fixed_quants_1msg" and cfg.larger_far_touch_quant:
             # exec_env.py:790 branches in Python on a traced action: the reference cannot trace this combination
             raise NotImplementedError("fixed_quants_1msg with larger_far_touch_quant=True does not trace in the reference")
+        if not isinstance(cfg.doom_price_penalty, int):
+            raise NotImplementedError("a non-integer doom_price_penalty turns exec_env.py:1564-1575 into float32 arithmetic: not built")
         a.doom_price_penalty = cfg.doom_price_penalty
         if cfg.reference_price not in ("mid", "far_touch"):
             raise ValueError("Invalid reference price type.")  # exe:1576-1580

@@ -92,3 +92,17 @@ def test_product_package_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "lob_oracle" not in txt and "from oracle" not in txt and "import oracle" not in txt, f
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/config/env_configs"), reason="reference not mounted")
+def test_shipped_reference_env_configs_lower():
+    """11 of the reference's 12 env JSONs lower to the POD config; the stale twelfth is rejected loudly."""
+    import glob
+    ok, bad = [], []
+    for f in sorted(glob.glob("/root/reference/config/env_configs/*.json")):
+        try:
+            Cfg.to_step_config(Cfg.load_config_from_file(f), 4, 30000)
+            ok.append(os.path.basename(f))
+        except NotImplementedError:
+            bad.append(os.path.basename(f))
+    assert bad == ["exec_discrete_steps.json"] and len(ok) == 11
