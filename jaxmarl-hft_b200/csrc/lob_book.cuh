@@ -43,13 +43,16 @@ struct Msg {
 
 // What the generic functions need, passed BY VALUE (all warp-uniform) so that no book state has its address taken.
 struct BookCtx {
-  int* rows;   // shared memory: row r of side s at rows + (s * nrows + r) * 6
+  int rows_off; // word offset of the book inside the kernel's dynamic shared memory: row r of side s at
+               // dyn_smem() + rows_off + (s * nrows + r) * 6.  An OFFSET, not a pointer, so that the functions that receive a
+               // BookCtx by value still address it as shared memory (LDS / STS, not generic loads)
   int* tr;     // trade log of the current environment (worked on in place in global memory), row r at tr + r * 8
   int nrows;   // rows allocated per side (SLOTS * 32 >= no)
   int no, nt;
   int maxint, init_id, init_lo, t4, check_fill;
 };
-__device__ __forceinline__ int* rowp(const BookCtx& c, int s, int r) { return c.rows + (s * c.nrows + r) * 6; }
+__device__ __forceinline__ int* dyn_smem() { extern __shared__ __align__(128) int lob_dyn_smem[]; return lob_dyn_smem; }
+__device__ __forceinline__ int* rowp(const BookCtx& c, int s, int r) { return dyn_smem() + c.rows_off + (s * c.nrows + r) * 6; }
 
 struct Best { int p, q, n; };
 
@@ -306,7 +309,7 @@ struct Book {
   bool tr_odd;        // the rows after ntr are not all free -> the trade slot must be searched (generic path)
 
   __device__ __forceinline__ void init(const LobBookConfig& cfg, int* smem_book) {
-    c.rows = smem_book; c.tr = nullptr; c.nrows = kRows;
+    c.rows_off = (int)(smem_book - dyn_smem()); c.tr = nullptr; c.nrows = kRows;
     c.no = cfg.n_orders; c.nt = cfg.n_trades;
     c.maxint = cfg.maxint; c.init_id = cfg.init_id; c.init_lo = cfg.init_id - 2 * cfg.book_depth;
     c.t4 = cfg.type_4_interpretation; c.check_fill = cfg.check_book_fill;
@@ -314,8 +317,8 @@ struct Book {
     for (int i = lane_id(); i < 2 * kRows * 6; i += 32) smem_book[i] = -1;
     __syncwarp();
   }
-  __device__ __forceinline__ int* row(int s, int r) const { return c.rows + (s * kRows + r) * 6; }
-  __device__ __forceinline__ int* side_base(int s) const { return c.rows + s * kRows * 6; }
+  __device__ __forceinline__ int* row(int s, int r) const { return dyn_smem() + c.rows_off + (s * kRows + r) * 6; }
+  __device__ __forceinline__ int* side_base(int s) const { return dyn_smem() + c.rows_off + s * kRows * 6; }
 
   // ---- plain (non-bulk) global <-> shared copies: same layout on both sides ----
   __device__ __forceinline__ void load_side(int s, const int* __restrict__ g) {
@@ -356,8 +359,9 @@ struct Book {
   __device__ __forceinline__ void rescan() { scan_side(ASK); scan_side(BID); scan_trades(); }
 
   // job:933-984 on a side without odd rows: live prices are >= 0, every other row (blank or padding) has price -1
-  static __device__ __noinline__ Best best_scan(const int* side_rows, int is_bid, int maxint, int n_blank) {
+  static __device__ __noinline__ Best best_scan(int side_off, int is_bid, int maxint, int n_blank) {
     const int lane = lane_id();
+    const int* side_rows = dyn_smem() + side_off;
     int2 pq[SLOTS];
     int ext = is_bid ? -1 : maxint;
 #pragma unroll
@@ -378,7 +382,7 @@ struct Book {
     return b;
   }
   __device__ __forceinline__ void recompute(int s) {
-    const Best b = odd[s] ? g_best(c, s) : best_scan(side_base(s), s == BID, c.maxint, nneg[s]);
+    const Best b = odd[s] ? g_best(c, s) : best_scan(c.rows_off + s * kRows * 6, s == BID, c.maxint, nneg[s]);
     bestp[s] = b.p; bestq[s] = b.q; bestn[s] = b.n; valid[s] = true;
   }
   __device__ __forceinline__ void ensure(int s) { if (!valid[s]) recompute(s); }

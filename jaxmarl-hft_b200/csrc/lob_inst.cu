@@ -28,8 +28,9 @@ int launch_step(const LobStepConfig* c, const LobStepBuffers* b, int64_t batch, 
   cudaFuncAttributes fa;
   cudaError_t e = cudaFuncGetAttributes(&fa, lob::lob_step_kernel<S>);
   if (e != cudaSuccess) return fail(LOB_E_CUDA, "cudaFuncGetAttributes: %s", cudaGetErrorString(e));
-  int warps = (int)(((size_t)d.max_smem_optin - fa.sharedSizeBytes) / per_warp);
-  const int by_regs = fa.numRegs > 0 ? 65536 / (fa.numRegs * 32) : lob::kStepMaxWarps;
+  const int G = lob::kStepCtasPerSm;   // CTAs (phase-synchronous groups) per SM
+  int warps = (int)((((size_t)d.max_smem_optin + 1024) / G - 1024 - fa.sharedSizeBytes) / per_warp);
+  const int by_regs = fa.numRegs > 0 ? 65536 / (fa.numRegs * 32) / G : lob::kStepMaxWarps;
   if (warps > by_regs) warps = by_regs;
   if (warps > lob::kStepMaxWarps) warps = lob::kStepMaxWarps;
   if (warps < 1)
@@ -42,7 +43,7 @@ int launch_step(const LobStepConfig* c, const LobStepBuffers* b, int64_t batch, 
   for (int t = 0; t < c->n_agent_types; ++t)
     if (c->agent[t].kind == LOB_AGENT_MM && c->agent[t].exclude_extreme_spreads) need_extreme = 1;
   long long ctas = (batch + warps - 1) / warps;
-  if (ctas > d.sms) ctas = d.sms;
+  if (ctas > (long long)d.sms * G) ctas = (long long)d.sms * G;
   lob::lob_step_kernel<S><<<(int)ctas, warps * 32, smem, st>>>(*c, *b, batch, L, N, n_act, n_cnl, need_extreme);
   return launched("lob_step_kernel");
 }

@@ -95,7 +95,7 @@ template <int SLOTS>
 __global__ void __launch_bounds__(kWarps * 32, (SLOTS <= 4 ? LOB_REPLAY_MINB : SLOTS == 8 ? 3 : 1))
 lob_replay_kernel(const __grid_constant__ LobBookConfig cfg, const __grid_constant__ LobReplayBuffers B,
                   long long n_books, WarpLayout L) {
-  extern __shared__ __align__(128) int smem[];
+  int* const smem = dyn_smem();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int* ws = smem + warp * L.words;
   uint64_t* bar = reinterpret_cast<uint64_t*>(ws + L.bar);
@@ -315,13 +315,17 @@ __device__ __noinline__ ScanOut scan_messages(BookCtx ctx, const int4* m4, int N
 #ifndef LOB_STEP_MAXW
 #define LOB_STEP_MAXW 20
 #endif
-constexpr int kStepMaxWarps = LOB_STEP_MAXW;
+#ifndef LOB_STEP_CTAS
+#define LOB_STEP_CTAS 1
+#endif
+constexpr int kStepCtasPerSm = LOB_STEP_CTAS;                 // phase-synchronous groups per SM
+constexpr int kStepMaxWarps = LOB_STEP_MAXW / LOB_STEP_CTAS;  // warps per CTA
 
 template <int SLOTS>
-__global__ void __launch_bounds__(kStepMaxWarps * 32, 1)
+__global__ void __launch_bounds__(kStepMaxWarps * 32, kStepCtasPerSm)
 lob_step_kernel(const __grid_constant__ LobStepConfig c, const __grid_constant__ LobStepBuffers b, long long batch,
                 WarpLayout L, int N, int n_act, int n_cnl, int need_extreme) {
-  extern __shared__ __align__(128) int smem[];
+  int* const smem = dyn_smem();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nwarps = blockDim.x >> 5;
   int* ws = smem + warp * L.words;
@@ -564,7 +568,7 @@ template <int SLOTS>
 __global__ void __launch_bounds__(kWarps * 32)
 lob_reset_kernel(const __grid_constant__ LobStepConfig c, const __grid_constant__ LobStepBuffers b, long long batch,
                  WarpLayout L, int N) {
-  extern __shared__ __align__(128) int smem[];
+  int* const smem = dyn_smem();
   const int warp = threadIdx.x >> 5;
   int* ws = smem + warp * L.words;
   Book<SLOTS> bk;
