@@ -9,7 +9,7 @@ namespace lobhost {
 
 template <int S>
 int launch_replay(const LobBookConfig* cfg, const LobReplayBuffers* bufs, int64_t n_books, cudaStream_t st, const DevInfo& d) {
-  const lob::WarpLayout L = lob::make_layout(S * 32, 2 * lob::kReplayChunk * 8, 0);
+  const lob::WarpLayout L = lob::make_layout(S * 32, 2 * lob::kReplayChunk * 8, 0, 0);
   const size_t smem = (size_t)L.words * 4 * lob::kWarps;
   int per_sm = 1;
   int rc = prepare(lob::lob_replay_kernel<S>, smem, d, &per_sm);
@@ -21,7 +21,9 @@ int launch_replay(const LobBookConfig* cfg, const LobReplayBuffers* bufs, int64_
 template <int S>
 int launch_step(const LobStepConfig* c, const LobStepBuffers* b, int64_t batch, cudaStream_t st, const DevInfo& d) {
   const int N = lob_num_msgs_per_step(c), n_act = lob_num_action_msgs(c), n_cnl = lob_num_cancel_msgs(c);
-  const lob::WarpLayout L = lob::make_layout(S * 32, N * 8, n_act);
+  int n_agents = 0;
+  for (int t = 0; t < c->n_agent_types; ++t) n_agents += c->agent[t].n_agents;
+  const lob::WarpLayout L = lob::make_layout(S * 32, N * 8, n_act, n_agents);
   if (((n_cnl + n_act) * 8) % 4 != 0) return fail(LOB_E_INVALID, "internal: data slice misaligned");
   // one persistent CTA per SM; as many warps (= environments in flight) as shared memory and registers allow
   const size_t per_warp = (size_t)L.words * 4;
@@ -30,9 +32,9 @@ int launch_step(const LobStepConfig* c, const LobStepBuffers* b, int64_t batch, 
   if (e != cudaSuccess) return fail(LOB_E_CUDA, "cudaFuncGetAttributes: %s", cudaGetErrorString(e));
   const int G = lob::kStepCtasPerSm;   // CTAs (phase-synchronous groups) per SM
   int warps = (int)((((size_t)d.max_smem_optin + 1024) / G - 1024 - fa.sharedSizeBytes) / per_warp);
-  const int by_regs = fa.numRegs > 0 ? 65536 / (fa.numRegs * 32) / G : lob::kStepMaxWarps;
+  const int by_regs = fa.numRegs > 0 ? 65536 / (fa.numRegs * 32) / G : lob::step_max_warps(S);
   if (warps > by_regs) warps = by_regs;
-  if (warps > lob::kStepMaxWarps) warps = lob::kStepMaxWarps;
+  if (warps > lob::step_max_warps(S)) warps = lob::step_max_warps(S);
   if (warps < 1)
     return fail(LOB_E_INVALID, "configuration needs %zu B of shared memory per environment (device limit %d)", per_warp,
                 d.max_smem_optin);
@@ -51,7 +53,7 @@ int launch_step(const LobStepConfig* c, const LobStepBuffers* b, int64_t batch, 
 template <int S>
 int launch_reset(const LobStepConfig* c, const LobStepBuffers* b, int64_t batch, cudaStream_t st, const DevInfo& d) {
   const int N = lob_num_msgs_per_step(c);
-  const lob::WarpLayout L = lob::make_layout(S * 32, 0, 0);
+  const lob::WarpLayout L = lob::make_layout(S * 32, 0, 0, 0);
   const size_t smem = (size_t)L.words * 4 * lob::kWarps;
   int per_sm = 1;
   int rc = prepare(lob::lob_reset_kernel<S>, smem, d, &per_sm);

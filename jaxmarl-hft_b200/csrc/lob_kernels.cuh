@@ -70,11 +70,11 @@ struct WarpLayout {
   int book;      // 2 sides * nrows * 6 (nrows = SLOTS * 32, padded with blank rows)
   int msgs;      // step: N * 8 ; replay: 2 * kReplayChunk * 8      (16-byte aligned)
   int act;       // step: n_act * 8
-  int scratch;   // step: kMaxAgents * 8
+  int scratch;   // step: n_agents * 8 (what the action phase leaves for the info / state update)
   int bar;       // 2 mbarriers (4 words, 8-byte aligned)
   int words;     // per-warp total, multiple of 4
 };
-__host__ __device__ inline WarpLayout make_layout(int nrows, int msg_words, int n_act) {
+__host__ __device__ inline WarpLayout make_layout(int nrows, int msg_words, int n_act, int n_agents) {
   WarpLayout L;
   int o = 0;
   L.book = o; o += 12 * nrows;
@@ -82,7 +82,7 @@ __host__ __device__ inline WarpLayout make_layout(int nrows, int msg_words, int 
   L.msgs = o; o += msg_words;
   o = (o + 3) & ~3;
   L.act = o; o += n_act * 8;
-  L.scratch = o; o += kMaxAgents * 8;
+  L.scratch = o; o += n_agents * 8;
   o = (o + 3) & ~3;
   L.bar = o; o += 4;
   L.words = (o + 3) & ~3;
@@ -319,10 +319,12 @@ __device__ __noinline__ ScanOut scan_messages(BookCtx ctx, const int4* m4, int N
 #define LOB_STEP_CTAS 1
 #endif
 constexpr int kStepCtasPerSm = LOB_STEP_CTAS;                 // phase-synchronous groups per SM
-constexpr int kStepMaxWarps = LOB_STEP_MAXW / LOB_STEP_CTAS;  // warps per CTA
+constexpr int kStepMaxWarps = LOB_STEP_MAXW / LOB_STEP_CTAS;  // warps per CTA (book capacity classes up to 128 rows)
+// deeper books are shared-memory limited to fewer warps anyway: give them the registers
+__host__ __device__ constexpr int step_max_warps(int slots) { return slots <= 4 ? kStepMaxWarps : slots == 8 ? 12 : 7; }
 
 template <int SLOTS>
-__global__ void __launch_bounds__(kStepMaxWarps * 32, kStepCtasPerSm)
+__global__ void __launch_bounds__(step_max_warps(SLOTS) * 32, kStepCtasPerSm)
 lob_step_kernel(const __grid_constant__ LobStepConfig c, const __grid_constant__ LobStepBuffers b, long long batch,
                 WarpLayout L, int N, int n_act, int n_cnl, int need_extreme) {
   int* const smem = dyn_smem();

@@ -244,7 +244,7 @@ def run_env_case(name, json_name, seed, B, steps, n_events=30000, stress=False, 
         print("wrote", path, os.path.getsize(path) // 1024, "KiB")
 
 
-def run_replay_case(name, seed, B, T, no, nt, t4, fill, out_dir=HERE):
+def run_replay_case(name, seed, B, T, no, nt, t4, fill, out_dir=HERE, adversarial=False):
     """job.scan_through_entire_array_save_bidask on adversarial random streams + job.get_L2_state of the result."""
     import helpers as H
     from gymnax_exchange.jaxob import JaxOrderBookArrays as job
@@ -254,7 +254,8 @@ def run_replay_case(name, seed, B, T, no, nt, t4, fill, out_dir=HERE):
     cfg = JAXLOB_Configuration(nOrders=no, nTrades=nt, type_4_interpretation=t4, check_book_fill=fill)
     bc = C.book_config(C.World_EnvironmentConfig(nOrders=no, nTrades=nt, type_4_interpretation=t4, check_book_fill=fill))
     rng = np.random.default_rng(seed)
-    msgs = H.random_messages(rng, B * T, bc, price_lo=99_000, price_hi=100_600 if no < 64 else 101_500)
+    msgs = (H.adversarial_messages(rng, B * T, bc) if adversarial else
+            H.random_messages(rng, B * T, bc, price_lo=99_000, price_hi=100_600 if no < 64 else 101_500))
     rec = {"msgs": msgs, "B": np.int64(B), "T": np.int64(T), "no": np.int64(no), "nt": np.int64(nt), "t4": np.int64(t4),
            "fill": np.int64(fill)}
     A, Bd, Tr, BA, BB, L2 = [], [], [], [], [], []
@@ -280,6 +281,9 @@ if __name__ == "__main__":
         run_replay_case("replay_small_full", seed=12, B=6, T=400, no=20, nt=8, t4=0, fill=True)
         run_replay_case("replay_t4lim_nofill", seed=13, B=4, T=300, no=24, nt=16, t4=1, fill=False)
         run_replay_case("replay_mkt", seed=14, B=4, T=300, no=32, nt=16, t4=2, fill=True)
+    if "replay_adv" in which:
+        run_replay_case("replay_adversarial", seed=15, B=6, T=400, no=24, nt=12, t4=0, fill=True, adversarial=True)
+        run_replay_case("replay_adversarial_100", seed=16, B=4, T=500, no=100, nt=100, t4=1, fill=True, adversarial=True)
     if "env" in which:
         run_env_case("env_2player", "2_player_fq_fqc.json", seed=3, B=3, steps=68)
         run_env_case("env_exec", "exec_longrun_fixed_quants_complex.json", seed=4, B=2, steps=20)

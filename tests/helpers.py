@@ -190,3 +190,18 @@ def random_messages(rng, n, book_cfg, price_lo=99_000, price_hi=101_000, tick=10
     m[bad, 1] = rng.choice([0, -1, 1, 2], size=bad.sum())
     m[t == 0, 2:] = 0
     return m
+
+
+def adversarial_messages(rng, n, book_cfg, tick=100):
+    """Streams no market would produce: -1 in every field position, zero / negative quantities and prices, order id -1,
+    time -1, INT32 extremes, ids colliding with the INITID range.  They drive the fast paths' bail-out conditions and
+    the literal generic path (rows holding stray -1 fields, non-positive quantities, negative prices)."""
+    m = random_messages(rng, n, book_cfg, price_lo=99_500, price_hi=100_500, tick=tick, id_pool=60, weird=0.05)
+    def hit(p):
+        return rng.random(n) < p
+    for col, vals, p in ((2, [0, -1, -7, 1, 2**31 - 1], 0.06), (3, [-1, 0, -300, 2**31 - 1, 100_000], 0.05),
+                         (4, [-1, 0, book_cfg.init_id, book_cfg.init_id - 3], 0.05), (5, [-1, 0], 0.03),
+                         (6, [-1, 0, 2**31 - 1], 0.03), (7, [-1, 2**31 - 1, 0], 0.03)):
+        sel = hit(p)
+        m[sel, col] = rng.choice(vals, size=int(sel.sum()))
+    return m

@@ -238,3 +238,28 @@ def test_step_fixed_prices_vector_actions(oracle):
     agents["Exec2"] = dataclasses.replace(ex, short_name="EXE2", action_space="fixed_prices", n_actions=1, fixed_quant_value=6,
                                           observation_space="simplest_case", task="sell", task_size=90)
     _rollout_parity(oracle, H.with_agents(mac, agents, [1, 2, 2]), H.small_day(n_events=30000), B=32, steps=66, seed=13)
+
+
+@pytest.mark.parametrize("no,nt,t4,fill", [(100, 100, 0, True), (24, 12, 0, True), (33, 7, 1, False), (64, 32, 2, True),
+                                           (200, 64, 0, True)])
+def test_replay_adversarial_streams_bit_exact(oracle, no, nt, t4, fill):
+    """Inputs no market produces (-1 in any field, non-positive quantities / prices, INT32 extremes): the fast paths must
+    bail out to the literal generic path exactly where the reference's array semantics differ."""
+    rng = np.random.default_rng(no * 7 + nt)
+    bc = _book_cfg(no, nt, type_4_interpretation=t4, check_book_fill=fill)
+    B, T = 96, 600
+    msgs = H.adversarial_messages(rng, B * T, bc)
+    start = np.arange(B, dtype=np.int64) * T
+    a0 = np.full((B, no, 6), -1, np.int32); b0 = a0.copy(); t0 = np.full((B, nt, 8), -1, np.int32)
+    ra, rb, rt = a0.copy(), b0.copy(), t0.copy()
+    rbest = np.zeros((B, 4), np.int32)
+    oracle.replay(bc, ra, rb, rt, msgs, start, T, best_out=rbest)
+    ga, gb, gt, gbest = H.cuda_replay(bc, a0, b0, t0, msgs, start, T, want_best=True)
+    np.testing.assert_array_equal(ga, ra); np.testing.assert_array_equal(gb, rb)
+    np.testing.assert_array_equal(gt, rt); np.testing.assert_array_equal(gbest, rbest)
+    # and continuing from those (odd) states, in two more legs, with an ordinary stream
+    msgs2 = H.random_messages(rng, B * 300, bc, price_lo=99_500, price_hi=100_500)
+    start2 = np.arange(B, dtype=np.int64) * 300
+    oracle.replay(bc, ra, rb, rt, msgs2, start2, 300)
+    ga, gb, gt = H.cuda_replay(bc, ga, gb, gt, msgs2, start2, 300)
+    np.testing.assert_array_equal(ga, ra); np.testing.assert_array_equal(gb, rb); np.testing.assert_array_equal(gt, rt)
