@@ -34,6 +34,10 @@ __device__ __forceinline__ int wmin(int v) { return __reduce_min_sync(kFull, v);
 __device__ __forceinline__ int wmax(int v) { return __reduce_max_sync(kFull, v); }
 __device__ __forceinline__ int wsum(int v) { return __reduce_add_sync(kFull, v); }
 
+// int32 arithmetic wraps in the reference (XLA); signed overflow is undefined in C++, so wrap explicitly
+__device__ __forceinline__ int wsub(int a, int b) { return (int)((unsigned)a - (unsigned)b); }
+__device__ __forceinline__ int wadd(int a, int b) { return (int)((unsigned)a + (unsigned)b); }
+
 enum { F_P = 0, F_Q = 1, F_OID = 2, F_TID = 3, F_TS = 4, F_TNS = 5 };
 enum { ASK = 0, BID = 1 };
 
@@ -109,7 +113,7 @@ static __device__ __noinline__ void g_cancel(BookCtx c, int s, Msg m) {
     if (idx == kBig) idx = c.no - 1;   // JAX normalises index -1: the LAST row loses quantity (quirk Q2)
   }
   __syncwarp();
-  if (lane_id() == 0) rowp(c, s, idx)[F_Q] -= m.qty;
+  if (lane_id() == 0) { int* q = rowp(c, s, idx) + F_Q; *q = wsub(*q, m.qty); }
   __syncwarp();
   g_remove_zero_neg(c, s);
 }
@@ -159,8 +163,8 @@ static __device__ __noinline__ int g_match(BookCtx c, int opp, Msg m, int qtm) {
     const bool cross = (opp == BID) ? (tp >= m.price) : (tp <= m.price);
     if (!(cross && qtm > 0 && tp != -1)) break;
     const int oq = o[F_Q], ooid = o[F_OID], otid = o[F_TID];
-    const int newq = max(0, oq - qtm);
-    qtm = qtm - oq;
+    const int newq = max(0, wsub(oq, qtm));
+    qtm = wsub(qtm, oq);
     int e = kBig;   // job:205: first trade row whose column 4 (time_s) is -1, else the last row (quirk Q3)
     _Pragma("unroll 1")
     for (int r = lane; r < c.nt; r += 32)
@@ -170,7 +174,7 @@ static __device__ __noinline__ int g_match(BookCtx c, int opp, Msg m, int qtm) {
     __syncwarp();
     if (lane == 0) {
       int* t = c.tr + e * 8;
-      t[0] = tp; t[1] = -m.side * (oq - newq); t[2] = ooid; t[3] = m.oid; t[4] = m.ts; t[5] = m.tns; t[6] = otid; t[7] = m.tid;
+      t[0] = tp; t[1] = (int)(0u - (unsigned)m.side * (unsigned)wsub(oq, newq)); t[2] = ooid; t[3] = m.oid; t[4] = m.ts; t[5] = m.tns; t[6] = otid; t[7] = m.tid;
       o[F_Q] = newq;
     }
     __syncwarp();
@@ -274,7 +278,8 @@ static __device__ __noinline__ SideScan g_scan_side(BookCtx c, int s) {
     const bool all = (a.x == -1) & (a.y == -1) & (b.x == -1) & (b.y == -1) & (d.x == -1) & (d.y == -1);
     if (any) m |= 1u << k;
     neg += (a.x < 0);
-    od |= (!all) & (any | (a.y <= 0) | (a.x < 0));
+    // (an ask AT maxint is matchable, job:256-268, yet reads as "no ask" in get_best_*, job:940: not modelled by the caches)
+    od |= (!all) & (any | (a.y <= 0) | (a.x < 0) | ((s == ASK) & (a.x == c.maxint)));
   }
   SideScan r;
   r.flag = m; r.nneg = wsum(neg); r.odd = __any_sync(kFull, od) ? 1 : 0;
@@ -404,7 +409,7 @@ struct Book {
     }
     nneg[S] += (rp >= 0);
     if (valid[S] && rp == bestp[S]) {
-      bestq[S] -= rq; bestn[S] -= 1;
+      bestq[S] = wsub(bestq[S], rq); bestn[S] -= 1;
       if (bestn[S] <= 0) valid[S] = false;
     }
   }
@@ -419,10 +424,15 @@ struct Book {
       const bool cross = (OPP == BID) ? (tp >= m.price) : (tp <= m.price);
       if (!(cross && qtm > 0 && tp != -1)) break;
       int top = kBig;
+      bool degenerate = false;   // a best-level order stamped time_s == maxint: job:242-268 then ranks EVERY row
       if (bestn[OPP] == 1) {
 #pragma unroll
         for (int k = SLOTS - 1; k >= 0; --k) { const int r = k * 32 + lane; if (row(OPP, r)[F_P] == tp) top = r; }
         top = wmin(top);
+        if (top < c.no) {
+          const int2 tt = *reinterpret_cast<const int2*>(row(OPP, top) + F_TS);
+          degenerate = (tt.x == c.maxint) | (tt.y == c.maxint);
+        } else degenerate = true;
       } else {   // job:242-268: min time_s, then min time_ns, then lowest row
         int t[SLOTS], n[SLOTS];
         int mt = c.maxint;
@@ -435,7 +445,7 @@ struct Book {
           mt = min(mt, t[k]);
         }
         mt = wmin(mt);
-        if (mt == c.maxint) { top = g_top(c, OPP); }   // degenerate timestamps: literal search
+        if (mt == c.maxint) degenerate = true;
         else {
           int mn = c.maxint;
 #pragma unroll
@@ -444,25 +454,32 @@ struct Book {
 #pragma unroll
           for (int k = SLOTS - 1; k >= 0; --k) if (n[k] == mn) top = k * 32 + lane;
           top = wmin(top);
-          if (top >= c.no) top = g_top(c, OPP);
+          degenerate = (top >= c.no) | (mn == c.maxint);
         }
+      }
+      if (degenerate) {          // the literal loop from here on (it may stop at a blank row), then rebuild the summaries
+        __syncwarp();
+        qtm = g_match(c, OPP, m, qtm);
+        scan_side(OPP);
+        scan_trades();
+        return qtm;
       }
       const int* o = row(OPP, top);
       const int2 pq = *reinterpret_cast<const int2*>(o);
       const int2 ot = *reinterpret_cast<const int2*>(o + F_OID);
       const int oq = pq.y;
-      const int newq = max(0, oq - qtm);
-      qtm = qtm - oq;
+      const int newq = max(0, wsub(oq, qtm));
+      qtm = wsub(qtm, oq);
       const int e = (ntr < c.nt) ? ntr : c.nt - 1;        // job:205 (quirk Q3)
       if (lane == 0) {
         int4* t4p = reinterpret_cast<int4*>(c.tr + e * 8);
-        t4p[0] = make_int4(tp, -m.side * (oq - newq), ot.x, m.oid);
+        t4p[0] = make_int4(tp, (int)(0u - (unsigned)m.side * (unsigned)wsub(oq, newq)), ot.x, m.oid);
         t4p[1] = make_int4(m.ts, m.tns, ot.y, m.tid);
       }
       if (ntr < c.nt && m.ts != -1) ntr += 1;
       if (newq > 0) {
         if (lane == (top & 31)) row(OPP, top)[F_Q] = newq;
-        bestq[OPP] += newq - oq;
+        bestq[OPP] = wadd(bestq[OPP], wsub(newq, oq));
       } else {
         blank_live<OPP>(top, tp, oq);
       }
@@ -491,7 +508,7 @@ struct Book {
     const int r = first_flagged(OWN);
     if (q == 0 && r != kBig && !odd[OWN]) return;   // written into a blank row and blanked again (job:83): no-op
     const bool neg1 = (m.price == -1) | (m.oid == -1) | (m.tid == -1) | (m.ts == -1) | (m.tns == -1);
-    if (q == 0 || r == kBig || odd[OWN] || neg1 || m.price <= 0) {
+    if (q == 0 || r == kBig || odd[OWN] || neg1 || m.price <= 0 || m.price == c.maxint) {   // (an ask AT maxint reads as "empty", job:940)
       Msg a = m;
       a.qty = qtm;
       __syncwarp();
@@ -509,7 +526,7 @@ struct Book {
       const int bp = bestp[OWN];
       const bool better = (bp == -1) | ((OWN == ASK) ? (m.price < bp) : (m.price > bp));
       if (better) { bestp[OWN] = m.price; bestq[OWN] = q; bestn[OWN] = 1; }
-      else if (m.price == bp) { bestq[OWN] += q; bestn[OWN] += 1; }
+      else if (m.price == bp) { bestq[OWN] = wadd(bestq[OWN], q); bestn[OWN] += 1; }
     }
   }
 
@@ -542,10 +559,10 @@ struct Book {
       scan_side(S);
       return;
     }
-    const int nq = pq.y - m.qty;
+    const int nq = wsub(pq.y, m.qty);
     if (nq > 0) {
       if (lane == (idx & 31)) row(S, idx)[F_Q] = nq;
-      if (valid[S] && pq.x == bestp[S]) bestq[S] -= m.qty;
+      if (valid[S] && pq.x == bestp[S]) bestq[S] = wsub(bestq[S], m.qty);
     } else {
       blank_live<S>(idx, pq.x, pq.y);
     }

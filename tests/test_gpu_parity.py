@@ -263,3 +263,31 @@ def test_replay_adversarial_streams_bit_exact(oracle, no, nt, t4, fill):
     oracle.replay(bc, ra, rb, rt, msgs2, start2, 300)
     ga, gb, gt = H.cuda_replay(bc, ga, gb, gt, msgs2, start2, 300)
     np.testing.assert_array_equal(ga, ra); np.testing.assert_array_equal(gb, rb); np.testing.assert_array_equal(gt, rt)
+
+
+def test_step_on_adversarial_day(oracle):
+    """env.step with a day tensor made of adversarial messages: the per-message best bid/ask rows, rewards and
+    observations go through the same bail-out logic as the replay."""
+    import dataclasses
+    mac = H.load_mac("2_player_fq_fqc", nOrders=48, nTrades=20)
+    ld = H.load_for(mac, H.small_day(n_events=30000))
+    rng = np.random.default_rng(21)
+    bc = C.book_config(mac.world_config)
+    adv = H.adversarial_messages(rng, ld.msgs.shape[0], bc, tick=100)
+    adv[:, 3] = np.where(adv[:, 3] > 90_000, adv[:, 3] + 1_400_000, adv[:, 3])      # around the day's price level
+    keep = rng.random(ld.msgs.shape[0]) < 0.5                                         # half real flow, half adversarial
+    msgs = np.where(keep[:, None], ld.msgs, adv).astype(np.int32)
+    ld2 = dataclasses.replace(ld, msgs=np.ascontiguousarray(msgs))
+    B = 64
+    ref = H.OracleEnv(oracle, mac, ld2, B)
+    gpu = H.CudaEnv(mac, ld2, B, ref.params)
+    H.draw_prng(rng, ref.cfg, ref.arrays); gpu.set_inputs(ref.arrays)
+    ref.reset(); gpu.reset()
+    for s in range(66):
+        H.draw_prng(rng, ref.cfg, ref.arrays); H.draw_actions(rng, ref.cfg, ref.arrays)
+        gpu.set_inputs(ref.arrays)
+        ref.step(n_threads=8); gpu.step()
+        try:
+            H.assert_arrays_match(ref.arrays, gpu.numpy(), ref.cfg)
+        except AssertionError as e:
+            raise AssertionError(f"step {s}: {e}") from None
