@@ -79,8 +79,14 @@ static inline float ffloordiv(float x1, float x2) {
 /* jnp.maximum / jnp.minimum propagate NaN */
 static inline float jmaxf(float a, float b) { return (a != a || b != b) ? NAN : (a > b ? a : b); }
 static inline float jminf(float a, float b) { return (a != a || b != b) ? NAN : (a < b ? a : b); }
-/* convert_element_type f32 -> s32 truncates toward zero */
-static inline int32_t f2i(float x) { return (int32_t)x; }
+/* convert_element_type f32 -> s32 truncates toward zero.  Out-of-range values are implementation-defined in XLA; the
+ * reference runs on CUDA GPUs, where the conversion (cvt.rzi.s32.f32) saturates and maps NaN to 0: restated here. */
+static inline int32_t f2i(float x) {
+  if (x != x) return 0;
+  if (x >= 2147483648.0f) return 2147483647;
+  if (x <= -2147483648.0f) return (int32_t)(-2147483647 - 1);
+  return (int32_t)x;
+}
 
 /* The fixed reduction order of float sums over the trade log (see the header): 32 interleaved partial sums, then a
  * butterfly.  term[r] is the r-th addend. */
