@@ -270,6 +270,10 @@ int lob_l2_launch(const LobBookConfig* cfg, const int32_t* asks, const int32_t* 
  * (any other source, e.g. jax.random through the FFI stub, is equally valid).  Deterministic in (seed, counter). */
 int lob_draw_launch(const LobStepConfig* cfg, const LobStepBuffers* bufs, int64_t batch, int32_t window_selector,
                     uint64_t seed, uint64_t counter, void* cuda_stream);
+/* The same with the counter kept in DEVICE memory: the draw uses *counter_dev and a second one-thread kernel increments it,
+ * so the call can be captured in a CUDA graph and replayed (every replay draws fresh values). */
+int lob_draw_launch_dev(const LobStepConfig* cfg, const LobStepBuffers* bufs, int64_t batch, int32_t window_selector,
+                        uint64_t seed, uint64_t* counter_dev, void* cuda_stream);
 
 /* Host-buffer replay (the end-to-end leg): copies books/msgs/start host->device, replays,
  * copies books/trades back, synchronises the stream.  Device scratch is owned by the handle. */

@@ -32,6 +32,8 @@ def lib():
         L.lob_reset_launch.argtypes = [C.POINTER(abi.LobStepConfig), C.POINTER(abi.LobStepBuffers), C.c_int64, vp]
         L.lob_draw_launch.argtypes = [C.POINTER(abi.LobStepConfig), C.POINTER(abi.LobStepBuffers), C.c_int64, C.c_int32,
                                       C.c_uint64, C.c_uint64, vp]
+        L.lob_draw_launch_dev.argtypes = [C.POINTER(abi.LobStepConfig), C.POINTER(abi.LobStepBuffers), C.c_int64, C.c_int32,
+                                          C.c_uint64, vp, vp]
         L.lob_replay_launch.argtypes = [C.POINTER(abi.LobBookConfig), C.POINTER(abi.LobReplayBuffers), C.c_int64, vp]
         L.lob_l2_launch.argtypes = [C.POINTER(abi.LobBookConfig), abi.p_i32, abi.p_i32, abi.p_i32, C.c_int32,
                                     C.c_int64, vp]

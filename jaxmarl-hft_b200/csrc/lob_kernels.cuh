@@ -651,9 +651,11 @@ __device__ __forceinline__ unsigned long long mix64(unsigned long long z) {
 }
 static __global__ void lob_draw_kernel(int* __restrict__ perm, int* __restrict__ reset_window, int* __restrict__ reset_is_sell,
                                 long long batch, int n_act, int n_windows, int n_types, int window_selector,
-                                unsigned long long seed, unsigned long long counter) {
+                                unsigned long long seed, unsigned long long counter,
+                                const unsigned long long* __restrict__ counter_dev) {
   const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= batch) return;
+  if (counter_dev) counter = *counter_dev;
   unsigned long long st = mix64(seed ^ mix64(counter ^ mix64((unsigned long long)e)));
   auto next = [&]() { st = mix64(st); return st; };
   if (reset_window) reset_window[e] = window_selector >= 0 ? window_selector : (int)(((next() >> 32) * (unsigned long long)n_windows) >> 32);
@@ -668,5 +670,7 @@ static __global__ void lob_draw_kernel(int* __restrict__ perm, int* __restrict__
     }
   }
 }
+
+static __global__ void lob_bump_kernel(unsigned long long* counter_dev) { *counter_dev += 1ull; }
 
 }  // namespace lob

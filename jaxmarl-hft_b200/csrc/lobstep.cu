@@ -254,8 +254,8 @@ int lob_l2_launch(const LobBookConfig* cfg, const int32_t* asks, const int32_t* 
   return rc;
 }
 
-int lob_draw_launch(const LobStepConfig* cfg, const LobStepBuffers* bufs, int64_t batch, int32_t window_selector,
-                    uint64_t seed, uint64_t counter, void* cuda_stream) {
+static int draw_impl(const LobStepConfig* cfg, const LobStepBuffers* bufs, int64_t batch, int32_t window_selector,
+                     uint64_t seed, uint64_t counter, uint64_t* counter_dev, void* cuda_stream) {
   if (!cfg || !bufs) return fail(LOB_E_INVALID, "null argument");
   if (cfg->n_agent_types < 0 || cfg->n_agent_types > LOB_MAX_AGENT_TYPES || cfg->n_windows < 1)
     return fail(LOB_E_INVALID, "bad configuration for lob_draw_launch");
@@ -267,8 +267,22 @@ int lob_draw_launch(const LobStepConfig* cfg, const LobStepBuffers* bufs, int64_
   const int threads = 128;
   lob::lob_draw_kernel<<<(unsigned)((batch + threads - 1) / threads), threads, 0, st>>>(
       const_cast<int*>(bufs->perm), const_cast<int*>(bufs->reset_window), const_cast<int*>(bufs->reset_is_sell), batch, n_act,
-      cfg->n_windows, cfg->n_agent_types, window_selector, seed, counter);
-  return launched("lob_draw_kernel");
+      cfg->n_windows, cfg->n_agent_types, window_selector, seed, counter,
+      reinterpret_cast<const unsigned long long*>(counter_dev));
+  int rc = launched("lob_draw_kernel");
+  if (rc || !counter_dev) return rc;
+  lob::lob_bump_kernel<<<1, 1, 0, st>>>(reinterpret_cast<unsigned long long*>(counter_dev));
+  return launched("lob_bump_kernel");
+}
+
+int lob_draw_launch(const LobStepConfig* cfg, const LobStepBuffers* bufs, int64_t batch, int32_t window_selector,
+                    uint64_t seed, uint64_t counter, void* cuda_stream) {
+  return draw_impl(cfg, bufs, batch, window_selector, seed, counter, nullptr, cuda_stream);
+}
+int lob_draw_launch_dev(const LobStepConfig* cfg, const LobStepBuffers* bufs, int64_t batch, int32_t window_selector,
+                        uint64_t seed, uint64_t* counter_dev, void* cuda_stream) {
+  if (!counter_dev) return fail(LOB_E_INVALID, "counter_dev is null");
+  return draw_impl(cfg, bufs, batch, window_selector, seed, 0, counter_dev, cuda_stream);
 }
 
 /* ---- host-buffer replay: the end-to-end leg (H2D + replay + D2H inside one call) ---- */

@@ -198,7 +198,7 @@ class MARLEnv:
                 (abi.obs_dim(self.cfg.agent[i].kind, self.cfg.agent[i].observation_space),), np.float32)
             for i, c in enumerate(self.list_of_agents_configs)]
         self._seed = int(seed) & 0xFFFFFFFFFFFFFFFF
-        self._counter = 0
+        self._counter_dev = None
         self._cache = {}
 
     # -- API of the reference ------------------------------------------------------------------------------
@@ -234,10 +234,13 @@ class MARLEnv:
 
     def _draw(self, arrays, bufs):
         """The PRNG products of one step (see module docstring): lob_draw_launch, counter-based, on the device."""
-        self._counter += 1
-        _lib.check(_lib.lib().lob_draw_launch(C.byref(self.cfg), C.byref(bufs), self.num_envs,
-                                              int(self.multi_agent_config.world_config.window_selector),
-                                              self._seed, self._counter, _lib.current_stream_ptr()), "lob_draw_launch")
+        if self._counter_dev is None:
+            import torch
+            self._counter_dev = torch.ones(1, dtype=torch.int64, device=self.device)   # device-resident: graph-capturable
+        _lib.check(_lib.lib().lob_draw_launch_dev(C.byref(self.cfg), C.byref(bufs), self.num_envs,
+                                                  int(self.multi_agent_config.world_config.window_selector), self._seed,
+                                                  C.c_void_p(self._counter_dev.data_ptr()), _lib.current_stream_ptr()),
+                   "lob_draw_launch_dev")
 
     def reset(self, key=None, params: MultiAgentParams = None, arrays=None, draw=True):
         """marl_env.py:764 -> (obs list [B,n_i,d_i], MultiAgentState)."""
@@ -267,6 +270,32 @@ class MARLEnv:
         _lib.check(L.lob_step_launch(C.byref(self.cfg), C.byref(bufs), self.num_envs, _lib.current_stream_ptr()),
                    "lob_step_launch")
         return obs, view, rewards, dones, info
+
+    def capture_step(self, state: MultiAgentState, actions, params: MultiAgentParams = None, pre=None, post=None):
+        """One step as a CUDA graph: [pre()] + actions copy + PRNG draw + step kernel [+ post()] captured on the current
+        stream (the rollout-fusion row of SURVEY 8f-4: one graph launch per step instead of 4+ launches and their Python).
+        ``actions`` are the device tensors the graph reads every replay; ``pre`` / ``post`` are optional callables that
+        enqueue copies (e.g. pinned host -> ``actions``, results -> pinned host).  Returns (graph, outputs) where outputs
+        is what ``step`` returns (views of the in-place buffers)."""
+        import torch
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):                      # warm-up outside capture (allocations, attribute queries)
+            if pre:
+                pre()
+            out = self.step(None, state, actions, params)
+            if post:
+                post(out)
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            if pre:
+                pre()
+            out = self.step(None, state, actions, params)
+            if post:
+                post(out)
+        return g, out
 
     def unpack_info(self, arrays):
         """Packed info columns -> the reference's dict keys (marl:624-639, mm:2695-2730, exe:1809-1829)."""

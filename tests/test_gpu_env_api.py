@@ -80,3 +80,31 @@ def test_base_env_replay_api(oracle):
     oracle.replay(be.book_cfg, ra, rb, rt, ld.msgs, ld.starts.astype(np.int64), 100, best_out=rbest)
     np.testing.assert_array_equal(a.cpu().numpy(), ra); np.testing.assert_array_equal(b.cpu().numpy(), rb)
     np.testing.assert_array_equal(t.cpu().numpy(), rt); np.testing.assert_array_equal(best.cpu().numpy(), rbest)
+
+
+def test_capture_step_graph_replays_like_eager_steps(oracle):
+    """MARLEnv.capture_step: the graph (actions copy + device draw + step) replayed k times == k eager steps of a twin
+    env with the same seed (the draw counter lives in device memory, so every replay draws fresh values)."""
+    import torch
+    mac = H.load_mac("2_player_fq_fqc")
+    ld = H.load_for(mac, H.small_day(n_events=30000))
+    B = 128
+    envs = [E.MARLEnv(None, mac, num_envs=B, loaded=ld, device="cuda:0", seed=11) for _ in range(2)]
+    params = [e.default_params for e in envs]
+    states_ = [e.reset(None, p)[1] for e, p in zip(envs, params)]
+    rng = np.random.default_rng(1)
+    acts = [torch.zeros((B, 1), dtype=torch.int32, device="cuda") for _ in range(2)]
+    graph, out = envs[0].capture_step(states_[0], acts, params[0])     # warm-up + capture run 2 steps with zero actions
+    for _ in range(2):
+        envs[1].step(None, states_[1], acts, params[1])
+    for k in range(5):
+        a_np = [rng.integers(0, sp.n, size=(B, 1)).astype(np.int32) for sp in envs[0].action_spaces]
+        for t in range(2):
+            acts[t].copy_(torch.from_numpy(a_np[t]))
+        graph.replay()
+        envs[1].step(None, states_[1], acts, params[1])
+    torch.cuda.synchronize()
+    a, b = H.to_numpy(states_[0].arrays), H.to_numpy(states_[1].arrays)
+    for k in a:
+        np.testing.assert_array_equal(a[k], b[k], err_msg=k)
+    assert int(a["step_counter"].max()) == 7
