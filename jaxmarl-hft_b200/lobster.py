@@ -271,9 +271,10 @@ def merge_market_orders(typ, qty, price, direction, time_s, time_ns):
     return keep, qty, price
 
 
-def preprocess_day(day: RawDay, day_start=34200, day_end=57600):
+def preprocess_day(day: RawDay, day_start=34200, day_end=57600, return_time=False):
     """ldr:891-945 ``_pre_process_msg_ob``.  Returns (msgs int64 [M,8] in the OUTPUT column order of ldr:1068-1070,
-    orderbook int64 [M,4*levels]) with ``book[i]`` = state before ``msgs[i]``."""
+    orderbook int64 [M,4*levels]) with ``book[i]`` = state before ``msgs[i]``; with ``return_time`` also the float64
+    ``time`` column (the one the fixed_time window filter of ldr:1040-1049 compares against)."""
     m = day.messages
     t = m[:, 0]
     time_s = t.astype(np.int64)
@@ -291,6 +292,8 @@ def preprocess_day(day: RawDay, day_start=34200, day_end=57600):
     typ = np.where(typ == 3, 2, typ)                                    # ldr:932
     book = day.orderbook[rows]                                          # ldr:938
     out = np.stack([typ, direction, qty, price, oid, oid, time_s, time_ns], axis=1)   # trader_id := order_id ldr:935
+    if return_time:
+        return out[1:], book[:-1], t[rows][1:]
     return out[1:], book[:-1]                                           # ldr:941-942
 
 
@@ -307,14 +310,36 @@ def window_indices(n_msgs, window_length, n_data_msg_per_step, window_resolution
     return starts, ends
 
 
-def load_days(days, window_length, n_data_msg_per_step, window_resolution, day_start=34200, day_end=57600) -> LoadedDay:
-    """ldr:626-695 ``run_loading`` over one or more days (fixed_steps windows), concatenated with cumulative
-    message offsets (ldr:664-679)."""
+def window_indices_fixed_time(time, window_length, window_resolution, day_start, day_end):
+    """fixed_time branch of ldr:996 / :1040-1053: one window per ``range(day_start, day_end+1, resolution)[:-1]``
+    start holding the messages with ``start <= time < start + window_length``; ``ends`` is the index of the LAST
+    message in the window (inclusive, ldr:1049) and windows without data are dropped (ldr:1052-1053)."""
+    grid = np.arange(day_start, day_end + 1, window_resolution, dtype=np.int64)
+    if grid.shape[0] < 2:
+        raise ValueError("Not enough range to get a slice")
+    lo = np.searchsorted(time, grid[:-1].astype(np.float64), side="left")                  # first time >= start
+    hi = np.searchsorted(time, (grid[:-1] + window_length).astype(np.float64), side="left")  # first time >= end
+    ok = hi > lo
+    return lo[ok].astype(np.int64), (hi[ok] - 1).astype(np.int64)
+
+
+def load_days(days, window_length, n_data_msg_per_step, window_resolution, day_start=34200, day_end=57600,
+              window_type="fixed_steps") -> LoadedDay:
+    """ldr:626-695 ``run_loading`` over one or more days, concatenated with cumulative message offsets
+    (ldr:664-679).  ``window_type`` is the reference's ``type_`` ("fixed_steps" | "fixed_time")."""
+    if window_type not in ("fixed_steps", "fixed_time"):
+        raise NotImplementedError('Use either "fixed_time" or "fixed_steps"')      # ldr:998
     all_m, all_s, all_e, all_b, all_x = [], [], [], [], []
     offset = 0
     for d in days:
-        m, ob = preprocess_day(d, day_start, day_end)
-        s, e = window_indices(m.shape[0], window_length, n_data_msg_per_step, window_resolution)
+        if window_type == "fixed_time":
+            m, ob, tm = preprocess_day(d, day_start, day_end, return_time=True)
+            if np.any(np.diff(tm) < 0):
+                raise ValueError("fixed_time windows need a time-sorted message file")
+            s, e = window_indices_fixed_time(tm, window_length, window_resolution, day_start, day_end)
+        else:
+            m, ob = preprocess_day(d, day_start, day_end)
+            s, e = window_indices(m.shape[0], window_length, n_data_msg_per_step, window_resolution)
         all_b.append(ob[s])
         all_x.append(e - s)
         all_s.append(s + offset)
@@ -348,7 +373,7 @@ def load_or_generate(world, seed=20220103, n_events=400_000, stress=False, cache
     day = generate_day(seed=seed, n_events=n_events, levels=world.book_depth, tick=world.tick_size,
                        day_start=world.day_start, day_end=world.day_end, stress=stress)
     ld = load_days([day], world.episode_time, world.n_data_msg_per_step, world.start_resolution,
-                   world.day_start, world.day_end)
+                   world.day_start, world.day_end, window_type=world.ep_type)
     if path is not None:
         np.savez_compressed(path, msgs=ld.msgs, starts=ld.starts, ends=ld.ends, obs=ld.books,
                             max_msgs_in_windows_arr=ld.max_msgs)
