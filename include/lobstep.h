@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define LOB_ABI_VERSION 4
+#define LOB_ABI_VERSION 5
 #define LOB_MAX_AGENT_TYPES 4
 #define LOB_MAX_AGENT_I32 4  /* int32 state leaves per agent type */
 #define LOB_MAX_AGENT_F32 10 /* float32 state leaves per agent type */
@@ -153,7 +153,8 @@ typedef struct LobStepConfig {
   LobBookConfig book;
   int32_t n_data_msg_per_step;   /* Nd */
   int32_t tick_size;
-  int32_t ep_type_fixed_time;    /* 0 = "fixed_steps" (supported), 1 = "fixed_time" (LOB_E_UNSUPPORTED) */
+  int32_t ep_type_fixed_time;    /* 0 = "fixed_steps", 1 = "fixed_time" (base_env.py:358-368 message masking, the 10- /
+                                    15-dim engineered observations mm_env.py:3032, exec_env.py:1943) */
   int32_t episode_time;
   int32_t order_id_counter_start;/* order_id_counter_start_when_resetting (-200) */
   int32_t placeholder_order_id;  /* -198 */

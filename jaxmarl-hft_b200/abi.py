@@ -5,7 +5,7 @@ Field order and types follow the header exactly; ``check_sizes`` compares ``ctyp
 """
 import ctypes as C
 
-LOB_ABI_VERSION = 4
+LOB_ABI_VERSION = 5
 LOB_MAX_AGENT_TYPES = 4
 LOB_MAX_AGENT_I32 = 4
 LOB_MAX_AGENT_F32 = 10
@@ -117,11 +117,11 @@ def action_width(a) -> int:
     return int(a.n_actions) if (a.kind == AGENT_EXE and a.action_space == EXE_ACTION_SPACES["fixed_prices"]) else 1
 
 
-def obs_dim(kind, observation_space):
-    """mm_env.py:3195-3223 ; exec_env.py:2188-2202 (fixed_steps)."""
+def obs_dim(kind, observation_space, fixed_time=False):
+    """mm_env.py:3195-3223 ; exec_env.py:2188-2202 (the engineered spaces grow time fields under fixed_time)."""
     if kind == AGENT_MM:
-        return 2 if observation_space == OBS_SPACES["basic"] else 8
-    return 12 if observation_space == OBS_SPACES["engineered"] else 3
+        return 2 if observation_space == OBS_SPACES["basic"] else (10 if fixed_time else 8)
+    return (15 if fixed_time else 12) if observation_space == OBS_SPACES["engineered"] else 3
 
 
 def info_cols(kind):

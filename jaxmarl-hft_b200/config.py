@@ -319,8 +319,8 @@ def agent_type_config(cfg, n_agents: int, trader_id_start: int) -> abi.LobAgentT
 
 def to_step_config(mac: MultiAgentConfig, n_windows: int, n_messages: int) -> abi.LobStepConfig:
     w = mac.world_config
-    if w.ep_type != "fixed_steps":
-        raise NotImplementedError(f"ep_type={w.ep_type!r}: only 'fixed_steps' is built (base:358-368 is 'next')")
+    if w.ep_type not in ("fixed_steps", "fixed_time"):
+        raise NotImplementedError('Use either "fixed_time" or "fixed_steps"')      # ldr:998
     if w.any_message_obs_space or w.debug_mode:
         raise NotImplementedError("message-based observation spaces / debug_mode logging are not built")
     types = list(mac.dict_of_agents_configs.values())
@@ -332,7 +332,7 @@ def to_step_config(mac: MultiAgentConfig, n_windows: int, n_messages: int) -> ab
     c.book = book_config(w)
     c.n_data_msg_per_step = w.n_data_msg_per_step
     c.tick_size = w.tick_size
-    c.ep_type_fixed_time = 0
+    c.ep_type_fixed_time = int(w.ep_type == "fixed_time")
     c.episode_time = w.episode_time
     c.order_id_counter_start = w.order_id_counter_start_when_resetting
     c.placeholder_order_id = w.placeholder_order_id
@@ -345,6 +345,9 @@ def to_step_config(mac: MultiAgentConfig, n_windows: int, n_messages: int) -> ab
     tid = w.trader_id_range_start  # marl:103-115: ids count down across types
     for i, (cfg, n) in enumerate(zip(types, mac.number_of_agents_per_type)):
         c.agent[i] = agent_type_config(cfg, n, tid)
+        if (c.ep_type_fixed_time and c.agent[i].kind == abi.AGENT_EXE
+                and c.agent[i].action_space == abi.EXE_ACTION_SPACES["twap"]):
+            raise NotImplementedError("TWAP not implemented for fixed time episodes")   # exe:1141-1142
         tid -= n
     return c
 

@@ -295,7 +295,9 @@ static __device__ __noinline__ MMOut mm_get_messages(BookCtx bk, const LobStepCo
     const float gamma = (ai == 0) ? 0.1f : (ai == 1) ? 0.2f : (ai == 2) ? 0.5f : (ai == 3) ? 1.f : (ai == 4) ? 2.f
                         : (ai == 5) ? 5.f : (ai == 6) ? 10.f : 20.f;
     const float k = (float)ac.avst_k_parameter, variance = (float)ac.avst_var_parameter;
-    const float normalized_time = (float)(c.episode_time - w.step_counter) / (float)c.episode_time;
+    const int time_left = c.ep_type_fixed_time ? c.episode_time - wsub(w.time0, w.init_time0)   // mm:1291-1292
+                                               : c.episode_time - w.step_counter;
+    const float normalized_time = (float)time_left / (float)c.episode_time;
     const float res_price = (float)mid_price - (((float)inventory * gamma) * variance) * normalized_time;
     float spread = (gamma * variance) * normalized_time + (2.0f / gamma) * logf(1.0f + gamma / k);
     spread = jminf(jmaxf(spread, tickf), (float)c.book.maxint);
@@ -617,9 +619,21 @@ static __device__ __noinline__ MMReward mm_get_reward(int* tr, int nt, const Lob
   return R;
 }
 
-// mm:2963-3154 observation (fixed_steps), alphabetical key order
+// The clock fields of the fixed_time observation variants (mm:3014-3015, exe:1936-1937): world time after the step,
+// the episode's init_time, the step's delta_time.
+struct ObsTime {
+  int fixed_time, episode_time, t0, t1, i0, i1;
+  float delta_time;
+  __device__ __forceinline__ float now() const { return (float)t0 + (float)t1 / 1e9f; }
+  __device__ __forceinline__ float remaining() const {
+    return (float)episode_time - (now() - ((float)i0 + (float)i1 / 1e9f));
+  }
+};
+
+// mm:2963-3154 observation, alphabetical key order
 static __device__ __noinline__ void mm_write_obs(const LobAgentTypeConfig& ac, float* obs, int inventory, float mid_price,
-                                                 int ba, int bb, int qa, int qb, int step_counter, bool zero) {
+                                                 int ba, int bb, int qa, int qb, int step_counter, bool zero,
+                                                 const ObsTime& ot) {
   if (lane_id() != 0) return;
   const bool nz = ac.normalize;
   const int spread = abs(ba - bb);
@@ -627,6 +641,12 @@ static __device__ __noinline__ void mm_write_obs(const LobAgentTypeConfig& ac, f
     obs[0] = zero ? 0.f : (nz ? (float)inventory / 10.0f : (float)inventory);
     obs[1] = zero ? 0.f : (nz ? (float)spread / 1e4f : (float)spread);
     return;
+  }
+  if (ot.fixed_time) {   // mm:3032-3069: + delta_time (first) and time_remaining (last)
+    const float rem = ot.remaining();
+    obs[0] = zero ? 0.f : (nz ? ot.delta_time / 10.0f : ot.delta_time);
+    obs[9] = zero ? 0.f : (nz ? rem / (float)ot.episode_time : rem);
+    obs += 1;
   }
   float v[8];
   v[0] = nz ? (float)inventory / 10.0f : (float)inventory;
@@ -746,16 +766,17 @@ static __device__ __noinline__ EXEReward exe_get_reward(int* tr, int nt, const L
   return R;
 }
 
-// exe:1879-1906 / exe:1913-2079 (fixed_steps), alphabetical key order
+// exe:1879-1906 / exe:1913-2079, alphabetical key order
 static __device__ __noinline__ void exe_write_obs(const LobAgentTypeConfig& ac, float* obs, const EXEState& st, int ba, int bb,
                                                   int ask_vol, int bid_vol, int step_counter, int max_steps, bool zero,
-                                                  float mid_price, float time_used, int episode_time) {
+                                                  float mid_price, const ObsTime& ot) {
   if (lane_id() != 0) return;
   const bool nz = ac.normalize;
   const float ts = (float)ac.task_size;
   const int rem = st.task_to_execute - st.quant_executed;
   if (ac.observation_space == LOB_OBS_SIMPLEST_CASE) {   // exe:1841-1875, keys in alphabetical order
-    const float ep = (float)episode_time;
+    const float ep = (float)ot.episode_time;
+    const float time_used = (float)(ot.t0 - ot.i0) + (float)(ot.t1 - ot.i1) / 1e9f;
     const float ptime = (ep - time_used) / ep;
     const float pquant = (float)rem / (float)st.task_to_execute;
     obs[0] = zero ? 0.f : (nz ? (mid_price - 7560000.0f) / 1e3f : mid_price);
@@ -773,6 +794,13 @@ static __device__ __noinline__ void exe_write_obs(const LobAgentTypeConfig& ac, 
   const int q_aggr = st.is_sell_task ? bid_vol : ask_vol, q_pass = st.is_sell_task ? ask_vol : bid_vol;
   const float ratio = (max_steps == 0) ? 0.f : 1.0f - (float)step_counter / (float)max_steps;
   const int spread = abs(p_aggr - p_pass);
+  if (ot.fixed_time) {   // exe:1943-2010: + delta_time (first), time and time_remaining (last two)
+    const float now = ot.now(), left = ot.remaining();
+    obs[0] = zero ? 0.f : (nz ? ot.delta_time / 10.0f : ot.delta_time);
+    obs[13] = zero ? 0.f : (nz ? now / 1e5f : now);
+    obs[14] = zero ? 0.f : (nz ? left / (float)ot.episode_time : left);
+    obs += 1;
+  }
   float v[12];
   v[0] = nz ? (float)st.quant_executed / ts : (float)st.quant_executed;
   v[1] = nz ? st.init_price / 1e7f : st.init_price;

@@ -211,9 +211,9 @@ __device__ __forceinline__ void store_exe_state(const LobStepBuffers& b, int t, 
   f[7][idx] = s.price_drift_rm; f[8][idx] = s.vwap_rm; f[9][idx] = s.trade_duration;
 }
 
-__device__ __forceinline__ int obs_dim_of(const LobAgentTypeConfig& a) {
-  if (a.kind == LOB_AGENT_MM) return a.observation_space == LOB_OBS_BASIC ? 2 : 8;
-  return a.observation_space == LOB_OBS_ENGINEERED ? 12 : 3;
+__device__ __forceinline__ int obs_dim_of(const LobAgentTypeConfig& a, int fixed_time) {   // == lob_obs_dim
+  if (a.kind == LOB_AGENT_MM) return a.observation_space == LOB_OBS_BASIC ? 2 : (fixed_time ? 10 : 8);
+  return a.observation_space == LOB_OBS_ENGINEERED ? (fixed_time ? 15 : 12) : 3;
 }
 
 // marl_env.py:130-207 reset_env for env e: the precomputed state of window reset_window[e] replaces every leaf.
@@ -249,15 +249,16 @@ __device__ __noinline__ void reset_env(const LobStepConfig& c, const LobStepBuff
     b.mid_price[e] = mid; b.delta_time[e] = 0.0f;
   }
   const int qa = bk.volume(ASK), qb = bk.volume(BID);
+  const ObsTime ot = {c.ep_type_fixed_time, c.episode_time, it0, it1, it0, it1, 0.0f};   // marl:169 time = init_time
   for (int t = 0; t < T; ++t) {
     const LobAgentTypeConfig& ac = c.agent[t];
-    const int d = obs_dim_of(ac);
+    const int d = obs_dim_of(ac, c.ep_type_fixed_time);
     for (int a = 0; a < ac.n_agents; ++a) {
       const long long idx = e * ac.n_agents + a;
       if (ac.kind == LOB_AGENT_MM) {   // mm:417-459
         MMState s = {0, 0, 0, 0.f, 0.f};
         if (lane == 0) store_mm_state(b, t, idx, s);
-        mm_write_obs(ac, b.obs[t] + idx * d, 0, mid, ap, bp, qa, qb, 0, false);
+        mm_write_obs(ac, b.obs[t] + idx * d, 0, mid, ap, bp, qa, qb, 0, false, ot);
       } else {                          // exe:210-266
         EXEState s = {};
         s.is_sell_task = (ac.task == LOB_TASK_RANDOM) ? b.reset_is_sell[e * T + t] : (ac.task == LOB_TASK_BUY ? 0 : 1);
@@ -265,7 +266,7 @@ __device__ __noinline__ void reset_env(const LobStepConfig& c, const LobStepBuff
         s.task_to_execute = ac.task_size;
         s.p_vwap = mid / (float)c.tick_size;
         if (lane == 0) store_exe_state(b, t, idx, s);
-        exe_write_obs(ac, b.obs[t] + idx * d, s, ap, bp, qa, qb, 0, max_steps, false, mid, 0.0f, c.episode_time);
+        exe_write_obs(ac, b.obs[t] + idx * d, s, ap, bp, qa, qb, 0, max_steps, false, mid, ot);
       }
     }
   }
@@ -402,6 +403,16 @@ lob_step_kernel(const __grid_constant__ LobStepConfig c, const __grid_constant__
       mbar_wait(&bar[0], phase);
       phase ^= 1u;
       __syncwarp();
+      if (c.ep_type_fixed_time) {   // base:358-368: messages at or past the episode end keep only their time stamp
+        const int end_time_s = wadd(w.init_time0, c.episode_time);   // marl:246
+        int* dm = msgs + (n_cnl + n_act) * 8;
+        for (int i = lane; i < Nd; i += 32)
+          if (dm[i * 8 + 6] >= end_time_s) {
+            *reinterpret_cast<int4*>(dm + i * 8) = make_int4(0, 0, 0, 0);
+            *reinterpret_cast<int2*>(dm + i * 8 + 4) = make_int2(0, 0);
+          }
+        __syncwarp();
+      }
 
       // ---- (C) marl:254-315 agent messages: [cancels | permuted actions | data] ----
       int ci = 0, ai = 0, flat = 0;
@@ -468,10 +479,11 @@ lob_step_kernel(const __grid_constant__ LobStepConfig c, const __grid_constant__
       const int vol_a = bk.volume(ASK), vol_b = bk.volume(BID);
 
       // ---- (E)+(G)+(I)+(J)+(K) per agent: reward, state, done, info, obs ----
+      const ObsTime ot = {c.ep_type_fixed_time, c.episode_time, ft0, ft1, w.init_time0, w.init_time1, new_dt};
       int flat = 0;
       for (int t = 0; t < T; ++t) {
         const LobAgentTypeConfig& ac = c.agent[t];
-        const int d = obs_dim_of(ac);
+        const int d = obs_dim_of(ac, c.ep_type_fixed_time);
         for (int a = 0; a < ac.n_agents; ++a, ++flat) {
           const long long idx = e * ac.n_agents + a;
           const int tid = ac.trader_id_start - a;
@@ -500,7 +512,7 @@ lob_step_kernel(const __grid_constant__ LobStepConfig c, const __grid_constant__
               fi[13] = R.sellPnL; fi[14] = R.inventoryValue;
             }
             if (!so.ep_done)
-              mm_write_obs(ac, obs, ns.inventory, new_mid, so.ba_last, so.bb_last, vol_a, vol_b, new_step, false);
+              mm_write_obs(ac, obs, ns.inventory, new_mid, so.ba_last, so.bb_last, vol_a, vol_b, new_step, false, ot);
           } else {
             EXEState s; load_exe_state(b, t, idx, s);
             const EXEReward R = exe_get_reward(bk.c.tr, nt, c, ac, w, so, s, tid);
@@ -524,8 +536,7 @@ lob_step_kernel(const __grid_constant__ LobStepConfig c, const __grid_constant__
               fi[0] = R.slippage; fi[1] = ns.vwap_rm; fi[2] = R.drift; fi[3] = R.advantage; fi[4] = R.reward;
             }
             if (!so.ep_done)   // marl:690-698: a finished agent observes zeros until the episode ends
-              exe_write_obs(ac, obs, ns, so.ba_last, so.bb_last, vol_a, vol_b, new_step, w.max_steps, done, new_mid,
-                            (float)(ft0 - w.init_time0) + (float)(ft1 - w.init_time1) / 1e9f, c.episode_time);
+              exe_write_obs(ac, obs, ns, so.ba_last, so.bb_last, vol_a, vol_b, new_step, w.max_steps, done, new_mid, ot);
           }
         }
       }

@@ -55,7 +55,6 @@ int check_step_cfg(const LobStepConfig* c) {
   if (rc) return rc;
   if (c->n_agent_types < 0 || c->n_agent_types > LOB_MAX_AGENT_TYPES)
     return fail(LOB_E_INVALID, "n_agent_types=%d", c->n_agent_types);
-  if (c->ep_type_fixed_time) return fail(LOB_E_UNSUPPORTED, "ep_type 'fixed_time' is not built (base:358-368)");
   if (c->n_data_msg_per_step < 1) return fail(LOB_E_INVALID, "n_data_msg_per_step=%d", c->n_data_msg_per_step);
   if (c->tick_size < 1) return fail(LOB_E_INVALID, "tick_size=%d", c->tick_size);
   if (c->n_windows < 1) return fail(LOB_E_INVALID, "n_windows=%d", c->n_windows);
@@ -179,11 +178,12 @@ int32_t lob_num_cancel_msgs(const LobStepConfig* c) {
 int32_t lob_num_msgs_per_step(const LobStepConfig* c) {
   return c->n_data_msg_per_step + lob_num_action_msgs(c) + lob_num_cancel_msgs(c);
 }
-/* mm_env.py:3195-3223 ; exec_env.py:2188-2202 (fixed_steps) */
+/* mm_env.py:3195-3223 ; exec_env.py:2188-2202 */
 int32_t lob_obs_dim(const LobStepConfig* c, int32_t t) {
   const LobAgentTypeConfig* a = &c->agent[t];
-  if (a->kind == LOB_AGENT_MM) return a->observation_space == LOB_OBS_BASIC ? 2 : 8;
-  return a->observation_space == LOB_OBS_ENGINEERED ? 12 : 3;
+  const int ft = c->ep_type_fixed_time != 0;
+  if (a->kind == LOB_AGENT_MM) return a->observation_space == LOB_OBS_BASIC ? 2 : (ft ? 10 : 8);
+  return a->observation_space == LOB_OBS_ENGINEERED ? (ft ? 15 : 12) : 3;
 }
 int32_t lob_info_i32_cols(const LobStepConfig* c, int32_t t) {
   return c->agent[t].kind == LOB_AGENT_MM ? LOB_MMINFO_I32_COLS : LOB_EXEINFO_I32_COLS;

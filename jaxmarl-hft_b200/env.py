@@ -96,10 +96,16 @@ def build_reset_params(loaded: lobster.LoadedDay, world, replay_fn):
     trades = np.full((W, Nt, 8), -1, np.int32)
     start = (np.arange(W, dtype=np.int64) * 2 * depth)
     asks, bids, trades = replay_fn(asks, bids, trades, np.ascontiguousarray(init_msgs), start, 2 * depth)
+    if world.ep_type == "fixed_time":   # base:288-291: the window's nominal start on the time grid, not a message time
+        span = world.day_end - world.day_start - world.episode_time + world.start_resolution
+        t0 = (np.arange(W, dtype=np.int64) * world.start_resolution) % span + world.day_start
+        init_time = np.stack([t0, np.zeros_like(t0)], axis=1).astype(np.int32)
+    else:
+        init_time = np.ascontiguousarray(first[:, 6:8], np.int32)
     return {
         "message_data": np.ascontiguousarray(loaded.msgs, np.int32),
         "init_asks": asks, "init_bids": bids, "init_trades": trades,
-        "init_init_time": np.ascontiguousarray(first[:, 6:8], np.int32),                 # fixed_steps: base:288-291
+        "init_init_time": init_time,                                                     # base:288-291
         "init_max_steps": (loaded.max_msgs // world.n_data_msg_per_step + 1).astype(np.int32),  # base:323-324
         "init_start_index": loaded.starts.astype(np.int32),
     }
@@ -145,8 +151,8 @@ class BaseLOBEnv:
         self.device = device
         self.book_cfg = book_config(cfg)
         self.n_data_msg_per_step = cfg.n_data_msg_per_step
-        if cfg.ep_type != "fixed_steps":
-            raise NotImplementedError("only ep_type='fixed_steps' is built")
+        if cfg.ep_type not in ("fixed_steps", "fixed_time"):
+            raise NotImplementedError('Use either "fixed_time" or "fixed_steps"')   # ldr:998
         self.loaded = loaded if loaded is not None else lobster.load_or_generate(cfg, **(synth or {}))
         self.n_windows = int(self.loaded.starts.shape[0])
         self.start_indeces, self.end_indeces = self.loaded.starts, self.loaded.ends
@@ -195,7 +201,8 @@ class MARLEnv:
         self.observation_spaces = [
             Box(-1000 if isinstance(c, MarketMaking_EnvironmentConfig) else -10000,
                 1000 if isinstance(c, MarketMaking_EnvironmentConfig) else 10000,
-                (abi.obs_dim(self.cfg.agent[i].kind, self.cfg.agent[i].observation_space),), np.float32)
+                (abi.obs_dim(self.cfg.agent[i].kind, self.cfg.agent[i].observation_space,
+                             bool(self.cfg.ep_type_fixed_time)),), np.float32)
             for i, c in enumerate(self.list_of_agents_configs)]
         self._seed = int(seed) & 0xFFFFFFFFFFFFFFFF
         self._counter_dev = None

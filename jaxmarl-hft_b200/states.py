@@ -47,7 +47,7 @@ def leaf_specs(cfg: abi.LobStepConfig, batch: int):
         ki, kf = abi.info_cols(a.kind)
         aw = abi.action_width(a)
         sp[f"actions{t}"] = ((B, n) if aw == 1 else (B, n, aw), np.int32, "i")
-        sp[f"obs{t}"] = ((B, n, abi.obs_dim(a.kind, a.observation_space)), np.float32, "o")
+        sp[f"obs{t}"] = ((B, n, abi.obs_dim(a.kind, a.observation_space, bool(cfg.ep_type_fixed_time))), np.float32, "o")
         sp[f"reward{t}"] = ((B, n), np.float32, "o")
         sp[f"done_agents{t}"] = ((B, n), np.uint8, "o")
         sp[f"info_i32_{t}"] = ((B, n, len(ki)), np.int32, "o")

@@ -643,7 +643,8 @@ static void mm_action_avst(const LobStepConfig* c, const LobAgentTypeConfig* ac,
   static const float gamma_values[8] = {0.1f, 0.2f, 0.5f, 1.f, 2.f, 5.f, 10.f, 20.f};
   float gamma = gamma_values[clamp_index(action, 8)];
   const float k = (float)ac->avst_k_parameter, variance = (float)ac->avst_var_parameter;
-  int32_t time_left = c->episode_time - w->step_counter;
+  int32_t time_left = c->ep_type_fixed_time ? c->episode_time - (w->time[0] - w->init_time[0]) /* mm:1291-1292 */
+                                             : c->episode_time - w->step_counter;
   float normalized_time = (float)time_left / (float)c->episode_time;
   float res_price = (float)mid_price - (((float)st->inventory * gamma) * variance) * normalized_time;
   float spread = (gamma * variance) * normalized_time + (2.0f / gamma) * logf(1.0f + gamma / k);
@@ -913,8 +914,25 @@ static void mm_get_obs(const LobStepConfig* c, const LobAgentTypeConfig* ac, con
     obs[1] = nz ? (float)spread / 1e4f : (float)spread;
     return;
   }
-  /* engineered, fixed_steps: inventory, mid_price, p_ask, p_bid, q_ask, q_bid, spread, step_counter */
   const int32_t qa = get_volume(w->asks, no), qb = get_volume(w->bids, no);
+  if (c->ep_type_fixed_time) { /* mm:3032-3069: delta_time, inventory, mid_price, p_ask, p_bid, q_ask, q_bid, spread,
+                                  step_counter, time_remaining */
+    const float time = (float)w->time[0] + (float)w->time[1] / 1e9f;                    /* mm:3014 */
+    const float elapsed = time - ((float)w->init_time[0] + (float)w->init_time[1] / 1e9f);
+    const float remaining = (float)c->episode_time - elapsed;
+    obs[0] = nz ? w->delta_time / 10.0f : w->delta_time;
+    obs[1] = nz ? (float)st->inventory / 10.0f : (float)st->inventory;
+    obs[2] = nz ? w->mid_price / 1e6f : w->mid_price;
+    obs[3] = nz ? (float)ba / 1e6f : (float)ba;
+    obs[4] = nz ? (float)bb / 1e6f : (float)bb;
+    obs[5] = nz ? (float)qa / 1000.0f : (float)qa;
+    obs[6] = nz ? (float)qb / 1000.0f : (float)qb;
+    obs[7] = nz ? (float)spread / 1e4f : (float)spread;
+    obs[8] = nz ? (float)w->step_counter / 10.0f : (float)w->step_counter;
+    obs[9] = nz ? remaining / (float)c->episode_time : remaining;
+    return;
+  }
+  /* engineered, fixed_steps: inventory, mid_price, p_ask, p_bid, q_ask, q_bid, spread, step_counter */
   obs[0] = nz ? (float)st->inventory / 10.0f : (float)st->inventory;
   obs[1] = nz ? w->mid_price / 1e6f : w->mid_price;
   obs[2] = nz ? (float)ba / 1e6f : (float)ba;
@@ -1162,6 +1180,29 @@ static void exe_get_obs(const LobStepConfig* c, const LobAgentTypeConfig* ac, co
   float remaining_ratio = (w->max_steps == 0) ? 0.f : 1.0f - (float)w->step_counter / (float)w->max_steps;
   int32_t spread = iabs32(p_aggr - p_pass);
   int32_t rem = st->task_to_execute - st->quant_executed;
+  if (c->ep_type_fixed_time) { /* exe:1943-2010: delta_time, executed_quant, init_price, is_sell_task, p_aggr, p_pass,
+                                  q_aggr, q_pass, remaining_quant, remaining_ratio, spread, step_counter, task_size,
+                                  time, time_remaining */
+    const float time = (float)w->time[0] + (float)w->time[1] / 1e9f;                    /* exe:1936 */
+    const float elapsed = time - ((float)w->init_time[0] + (float)w->init_time[1] / 1e9f);
+    const float remaining = (float)c->episode_time - elapsed;
+    obs[0] = nz ? w->delta_time / 10.0f : w->delta_time;
+    obs[1] = nz ? (float)st->quant_executed / ts : (float)st->quant_executed;
+    obs[2] = nz ? st->init_price / 1e7f : st->init_price;
+    obs[3] = nz ? (float)st->is_sell_task / 1.0f : (float)st->is_sell_task;
+    obs[4] = nz ? ((float)p_aggr - st->init_price) / 1e5f : (float)p_aggr;
+    obs[5] = nz ? ((float)p_pass - st->init_price) / 1e5f : (float)p_pass;
+    obs[6] = nz ? (float)q_aggr / 1000.0f : (float)q_aggr;
+    obs[7] = nz ? (float)q_pass / 1000.0f : (float)q_pass;
+    obs[8] = nz ? (float)rem / ts : (float)rem;
+    obs[9] = nz ? remaining_ratio / 1.0f : remaining_ratio;
+    obs[10] = nz ? (float)spread / 1e4f : (float)spread;
+    obs[11] = nz ? (float)w->step_counter / 30.0f : (float)w->step_counter;
+    obs[12] = nz ? (float)st->task_to_execute / ts : (float)st->task_to_execute;
+    obs[13] = nz ? time / 1e5f : time;
+    obs[14] = nz ? remaining / (float)c->episode_time : remaining;
+    return;
+  }
   /* executed_quant, init_price, is_sell_task, p_aggr, p_pass, q_aggr, q_pass, remaining_quant, remaining_ratio,
      spread, step_counter, task_size */
   obs[0] = nz ? (float)st->quant_executed / ts : (float)st->quant_executed;
@@ -1195,8 +1236,9 @@ int32_t lob_num_msgs_per_step(const LobStepConfig* c) { /* marl:85-94 */
 }
 int32_t lob_obs_dim(const LobStepConfig* c, int32_t t) {
   const LobAgentTypeConfig* a = &c->agent[t];
-  if (a->kind == LOB_AGENT_MM) return a->observation_space == LOB_OBS_BASIC ? 2 : 8;
-  return a->observation_space == LOB_OBS_ENGINEERED ? 12 : 3;
+  const int ft = c->ep_type_fixed_time != 0; /* mm:3198-3201, exe:2193-2196 */
+  if (a->kind == LOB_AGENT_MM) return a->observation_space == LOB_OBS_BASIC ? 2 : (ft ? 10 : 8);
+  return a->observation_space == LOB_OBS_ENGINEERED ? (ft ? 15 : 12) : 3;
 }
 int32_t lob_info_i32_cols(const LobStepConfig* c, int32_t t) {
   return c->agent[t].kind == LOB_AGENT_MM ? LOB_MMINFO_I32_COLS : LOB_EXEINFO_I32_COLS;
@@ -1339,6 +1381,11 @@ static void step_one(const LobStepConfig* c, const LobStepBuffers* b, int64_t e,
   if (off < 0) off = 0;
   int32_t* data = msgs + (n_cnl + n_act) * 8;
   memcpy(data, b->message_data + off * 8, sizeof(int32_t) * Nd * 8);
+  if (c->ep_type_fixed_time) { /* base:358-368: messages at or past the episode end keep only their time stamp */
+    const int32_t end_time_s = (int32_t)((uint32_t)w.init_time[0] + (uint32_t)c->episode_time); /* marl:246 */
+    for (int i = 0; i < Nd; ++i)
+      if (data[i * 8 + 6] >= end_time_s) memset(data + i * 8, 0, sizeof(int32_t) * 6);
+  }
 
   /* (C) marl:254-315 */
   MMExtras mmx[64];  /* per agent extras, all types flattened */
@@ -1514,7 +1561,6 @@ static size_t step_ws_words(const LobStepConfig* c) {
 
 static int check_cfg(const LobStepConfig* c) {
   if (c->n_agent_types < 0 || c->n_agent_types > LOB_MAX_AGENT_TYPES) return LOB_E_INVALID;
-  if (c->ep_type_fixed_time) return LOB_E_UNSUPPORTED;
   if (c->book.cancel_mode > 1) return LOB_E_UNSUPPORTED;
   int total = 0;
   for (int t = 0; t < c->n_agent_types; ++t) {

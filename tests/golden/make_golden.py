@@ -172,7 +172,25 @@ def fixed_prices_agents(mac):
     return MultiAgentConfig(world_config=mac.world_config, dict_of_agents_configs=agents, number_of_agents_per_type=[1, 2, 1])
 
 
-MUTATORS = {"fixed_prices": fixed_prices_agents, "simple_skew_avst": simple_skew_avst_agents, "hetero": hetero_agents, "mm_complex": mm_complex_agents, "bob_twap": bob_twap_agents,
+def fixed_time_agents(mac):
+    """fixed_time episodes: both engineered observation variants (10 / 15 fields), AvSt (time-based horizon) and the
+    simplest_case EXE observation."""
+    from gymnax_exchange.jaxob.jaxob_config import MultiAgentConfig
+    d = dict(mac.dict_of_agents_configs)
+    mm, ex = d["MarketMaking"], d["Execution"]
+    agents = {
+        "MarketMaking": dataclasses.replace(mm, observation_space="engineered"),
+        "AvSt": dataclasses.replace(mm, short_name="AV", action_space="AvSt", observation_space="engineered", normalize=False,
+                                    fixed_quant_value=4),
+        "Execution": ex,
+        "Exec2": dataclasses.replace(ex, short_name="EXE2", observation_space="simplest_case", normalize=False, task="buy",
+                                     task_size=70),
+    }
+    return MultiAgentConfig(world_config=mac.world_config, dict_of_agents_configs=agents,
+                            number_of_agents_per_type=[1, 1, 2, 1])
+
+
+MUTATORS = {"fixed_time": fixed_time_agents, "fixed_prices": fixed_prices_agents, "simple_skew_avst": simple_skew_avst_agents, "hetero": hetero_agents, "mm_complex": mm_complex_agents, "bob_twap": bob_twap_agents,
             "bobstrat_1msg": bobstrat_1msg_agents}
 
 
@@ -291,6 +309,12 @@ if __name__ == "__main__":
         run_env_case("env_hetero_smallbook", "2_player_fq_fqc.json", seed=6, B=2, steps=66, stress=True, mutate="hetero",
                      nOrders=40, nTrades=24)
         run_env_case("env_mm_complex", "2_player_fq_fqc.json", seed=7, B=2, steps=66, mutate="mm_complex")
+    if "env_ft" in which:
+        run_env_case("env_fixed_time", "2_player_fq_fqc.json", seed=21, B=4, steps=60, mutate="fixed_time",
+                     ep_type="fixed_time", episode_time=1800, start_resolution=900)
+        # the last window's nominal start wraps to day_start (base:288-290), so every data message is past the end
+        run_env_case("env_fixed_time_masked", "2_player_fq_fqc.json", seed=22, B=2, steps=24, mutate="fixed_time",
+                     ep_type="fixed_time", episode_time=1800, start_resolution=900, window_selector=25)
     if "env3" in which:
         run_env_case("env_bob_twap", "2_player_fq_fqc.json", seed=8, B=2, steps=66, mutate="bob_twap")
         run_env_case("env_simple_skew_avst", "2_player_fq_fqc.json", seed=10, B=2, steps=66, mutate="simple_skew_avst")

@@ -35,7 +35,8 @@ def small_day(seed=5, n_events=30000, stress=False, levels=10):
 
 def load_for(mac, day):
     w = mac.world_config
-    return lobster.load_days([day], w.episode_time, w.n_data_msg_per_step, w.start_resolution, w.day_start, w.day_end)
+    return lobster.load_days([day], w.episode_time, w.n_data_msg_per_step, w.start_resolution, w.day_start, w.day_end,
+                             window_type=w.ep_type)
 
 
 def oracle_replay_fn(oracle, book_cfg):

@@ -66,8 +66,9 @@ def test_bad_calls_fail_loudly_before_the_device():
     bad.book.cancel_mode = 2
     assert L.lob_reset_launch(C.byref(bad), C.byref(bufs), 8, None) == abi.LOB_E_UNSUPPORTED
     bad = Cfg.to_step_config(mac, 4, 30000)
-    bad.ep_type_fixed_time = 1
-    assert L.lob_step_launch(C.byref(bad), C.byref(bufs), 8, None) == abi.LOB_E_UNSUPPORTED
+    bad.ep_type_fixed_time = 1       # supported since ABI 5: validation proceeds to the (null) buffer table
+    assert L.lob_step_launch(C.byref(bad), C.byref(bufs), 8, None) == abi.LOB_E_INVALID
+    assert L.lob_obs_dim(C.byref(bad), 0) == 2 and L.lob_obs_dim(C.byref(bad), 1) == 15   # MM basic, EXE engineered
     rb = abi.LobReplayBuffers()
     bc = Cfg.book_config(mac.world_config)
     assert L.lob_replay_launch(C.byref(bc), C.byref(rb), 8, None) == abi.LOB_E_INVALID

@@ -107,3 +107,27 @@ def test_capture_step_graph_replays_like_eager_steps(oracle):
     for k in a:
         np.testing.assert_array_equal(a[k], b[k], err_msg=k)
     assert int(a["step_counter"].max()) == 6
+
+
+def test_marl_env_fixed_time_episodes():
+    """ep_type="fixed_time" through the public API: time-grid windows from the loader, 2- / 15-field observations, episodes
+    of different lengths all ending and auto-resetting (marl_env.py:717-718 counts steps in either mode)."""
+    import torch
+    mac = H.load_mac("2_player_fq_fqc", ep_type="fixed_time", episode_time=1800, start_resolution=900)
+    ld = H.load_for(mac, H.small_day(n_events=30000))
+    B = 256
+    env = E.MARLEnv(None, mac, num_envs=B, loaded=ld, device="cuda:0", seed=3)
+    assert [sp.shape for sp in env.observation_spaces] == [(2,), (15,)]
+    params = env.default_params
+    obs, state = env.reset(None, params)
+    assert obs[1].shape == (B, 1, 15)
+    g = torch.Generator(device="cuda"); g.manual_seed(0)
+    n_done = torch.zeros(B, dtype=torch.int64, device="cuda")
+    for _ in range(40):
+        acts = [torch.randint(0, sp.n, (B, 1), generator=g, device="cuda", dtype=torch.int32) for sp in env.action_spaces]
+        obs, state, rewards, dones, info = env.step(None, state, acts, params)
+        n_done += dones["__all__"].to(torch.int64)
+        assert torch.isfinite(obs[1]).all()
+    assert int(n_done.min()) >= 1                                  # every env finished at least one episode
+    it = state.world_state.init_time.cpu().numpy()
+    assert (it[:, 1] == 0).all() and ((it[:, 0] - 34200) % 900 == 0).all()   # base_env.py:288-290: on the time grid

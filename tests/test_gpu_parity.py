@@ -228,6 +228,26 @@ def test_step_more_action_spaces(oracle, mm_space, exe_space):
                     stress_actions=True)
 
 
+@pytest.mark.parametrize("episode_time,resolution", [(1800, 900), (900, 300)])
+def test_step_fixed_time_episodes(oracle, episode_time, resolution):
+    """ep_type="fixed_time" (base_env.py:288-291, :358-368; mm_env.py:3032, :1291; exec_env.py:1943): time-grid windows
+    of unequal length, init_time on the grid (the last windows wrap to day_start so their data is masked), the
+    10- / 15-field engineered observations and the AvSt horizon in seconds."""
+    import dataclasses
+    mac = H.load_mac("2_player_fq_fqc", ep_type="fixed_time", episode_time=episode_time, start_resolution=resolution)
+    agents = dict(mac.dict_of_agents_configs)
+    mm, ex = agents["MarketMaking"], agents["Execution"]
+    agents = {"MarketMaking": dataclasses.replace(mm, observation_space="engineered"),
+              "AvSt": dataclasses.replace(mm, short_name="AV", action_space="AvSt", observation_space="engineered",
+                                          normalize=False, fixed_quant_value=4),
+              "Execution": ex,
+              "Exec2": dataclasses.replace(ex, short_name="EXE2", observation_space="simplest_case", task="buy", task_size=70)}
+    ref, n_done = _rollout_parity(oracle, H.with_agents(mac, agents, [1, 2, 2, 1]), H.small_day(n_events=30000), B=64,
+                                  steps=40, seed=17, stress_actions=True)
+    assert n_done >= 64
+    assert len(set(ref.params["init_max_steps"].tolist())) > 1   # windows really differ in length
+
+
 def test_step_fixed_prices_vector_actions(oracle):
     """EXE fixed_prices (exec_env.py:1001): the action is a vector of quantities per price level ([B,n_i,n_actions])."""
     import dataclasses

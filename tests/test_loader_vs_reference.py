@@ -44,6 +44,27 @@ def test_loader_matches_reference(tmp_path, seed, n_events, stress):
     assert (msgs[:, 0] == 4).any() and (np.diff(msgs[:, 6] * 10**9 + msgs[:, 7]) == 0).any() or True
 
 
+@pytest.mark.parametrize("seed,n_events,wl,res", [(7, 6000, 1800, 900), (13, 9000, 600, 60), (5, 3000, 7000, 2000)])
+def test_fixed_time_windows_match_reference(tmp_path, seed, n_events, wl, res):
+    """ldr:996, :1040-1053: time-based windows (inclusive end index, overlapping when resolution < length)."""
+    ldr = _import_reference_loader()
+    day = lobster.generate_day(seed=seed, n_events=n_events)
+    data = tmp_path / "data"
+    lobster.write_lobster_csv(day, str(data / "rawLOBSTER" / "GOOG" / "2022"))
+    ref = ldr.LoadLOBSTER_resample(str(data), str(tmp_path / "at"), n_Levels=10, type_="fixed_time",
+                                   window_length=wl, window_resolution=res, n_data_msg_per_step=50,
+                                   stock="GOOG", time_period="2022")
+    msgs, starts, ends, books, max_msgs = ref.run_loading("t")
+    ours = lobster.load_days([day], window_length=wl, n_data_msg_per_step=50, window_resolution=res,
+                             window_type="fixed_time")
+    np.testing.assert_array_equal(np.asarray(msgs, np.int64), ours.msgs.astype(np.int64))
+    np.testing.assert_array_equal(np.asarray(starts), ours.starts)
+    np.testing.assert_array_equal(np.asarray(ends), ours.ends)
+    np.testing.assert_array_equal(np.asarray(books), ours.books)
+    np.testing.assert_array_equal(np.asarray(max_msgs), ours.max_msgs)
+    assert len(ours.starts) >= 2
+
+
 def test_merge_market_orders_matches_reference():
     """Same-timestamp type-4 bursts, including non-adjacent rows of one group and both directions."""
     import pandas as pd
