@@ -138,7 +138,7 @@ def run_reference(args):
     total = sum(times)
     value = B * WINDOW * len(times) / total
     sample = f"{B} books x {WINDOW} msgs per step, {len(times)} steps, OpenMP over books"
-    print(json.dumps({
+    return json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "int32", "data": "synthetic",
@@ -146,7 +146,7 @@ def run_reference(args):
                                "bounded sample", "books": B, "msgs_per_book_per_step": WINDOW},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }))
+    })
 
 
 # --------------------------------------------------------------------------------------------------- native arm
@@ -409,7 +409,8 @@ def run_native(args):
         }
         if cpu is not None:
             out["cpu_baseline"] = cpu
-        print(json.dumps(out))
+        return json.dumps(out)
+    return None
     if ws > 1:
         dist.destroy_process_group()
 
@@ -427,10 +428,19 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "native" else args.warmup
-    if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_native(args)
+    # stdout carries exactly ONE line (the JSON): anything a library prints on fd 1 meanwhile (NCCL's version banner)
+    # is sent to stderr, and the line is written to the saved descriptor at the end
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        line = run_reference(args) if args.impl == "reference" else run_native(args)
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved, 1)
+        os.close(saved)
+    if line is not None:
+        print(line, flush=True)
 
 
 if __name__ == "__main__":

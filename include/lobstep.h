@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define LOB_ABI_VERSION 5
+#define LOB_ABI_VERSION 6
 #define LOB_MAX_AGENT_TYPES 4
 #define LOB_MAX_AGENT_I32 4  /* int32 state leaves per agent type */
 #define LOB_MAX_AGENT_F32 10 /* float32 state leaves per agent type */
@@ -89,7 +89,9 @@ typedef struct LobBookConfig {
   int32_t maxint;                /* cfg.maxint (2147483647) */
   int32_t init_id;               /* cfg.init_id (-2) */
   int32_t book_depth;            /* cfg.book_depth */
-  int32_t cancel_mode;           /* 0/1 supported (identical in the reference: job:94-139); 2/3 need JAX PRNG -> LOB_E_UNSUPPORTED */
+  int32_t cancel_mode;           /* cst CancelMode: 0/1 by id then initial-liquidity match (identical in the reference:
+                                    job:94-139); 2/3 add the random same-price fallbacks of job:142-164, whose uniform
+                                    draws arrive in the cancel_u buffers (a PRNG product, like perm) */
   int32_t type_4_interpretation; /* 0 IOC, 1 LIM, 2 MKT  jaxob_constants.py:70-74 */
   int32_t check_book_fill;       /* job:395-401 / :484-490 */
 } LobBookConfig;
@@ -222,6 +224,9 @@ typedef struct LobStepBuffers {
   const int32_t* perm;             /* [B,n_action]  jax.random.permutation(shuffle_key, n_action)  marl_env.py:294-295 ; may be NULL when !shuffle */
   const int32_t* reset_window;     /* [B] randint(world_key, 0, W) of the auto-reset  base_env.py:222-225 */
   const int32_t* reset_is_sell;    /* [B,n_agent_types] randint(agent_key,0,2) per type (shared by its agents, marl_env.py:187) */
+  const float*   cancel_u;         /* [B,N,2] cancel_mode 2/3 only (else may be NULL): per message the uniform [0,1) draw of
+                                      jax.random.choice in get_random_id_match (job:146) and get_random_large_id_match
+                                      (job:161); choice = searchsorted(cumsum(p), sum(p) * (1 - u)) */
   /* params (shared by the batch; expand_dims => no leading B) */
   const int32_t* message_data;     /* [M,8] */
   const int32_t* init_asks;        /* [W,No,6] init_states_array leaves (base_env.py:285-296) */
@@ -252,6 +257,7 @@ typedef struct LobReplayBuffers {
   int32_t n_msgs;              /* T messages per book */
   int32_t _pad0;
   int32_t* best_out;           /* optional [B,4] = [best_ask, ask_vol, best_bid, bid_vol] after the scan (job:968), or NULL */
+  const float* cancel_u;       /* [B,T,2] uniform draws for cancel_mode 2/3 (see LobStepBuffers.cancel_u), else may be NULL */
 } LobReplayBuffers;
 
 int  lob_abi_version(void);
@@ -266,7 +272,8 @@ int lob_l2_launch(const LobBookConfig* cfg, const int32_t* asks, const int32_t* 
 
 /* The PRNG products of one step, drawn on the device by a counter-based generator: perm [B,n_action] (a uniform
  * random permutation per environment, marl_env.py:293-295), reset_window [B] in [0, n_windows) or window_selector when it
- * is >= 0 (base_env.py:222-225), reset_is_sell [B,n_agent_types] in {0,1} (exec_env.py:221).  The reference draws these
+ * is >= 0 (base_env.py:222-225), reset_is_sell [B,n_agent_types] in {0,1} (exec_env.py:221) and, under cancel_mode 2/3,
+ * cancel_u [B,N,2] (multiples of 2^-23 in [0,1), as jax.random.uniform yields for float32).  The reference draws these
  * with jax.random inside the step; here they are inputs of lob_step_launch, and this is the host layer's default source
  * (any other source, e.g. jax.random through the FFI stub, is equally valid).  Deterministic in (seed, counter). */
 int lob_draw_launch(const LobStepConfig* cfg, const LobStepBuffers* bufs, int64_t batch, int32_t window_selector,

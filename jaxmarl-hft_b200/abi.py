@@ -5,7 +5,7 @@ Field order and types follow the header exactly; ``check_sizes`` compares ``ctyp
 """
 import ctypes as C
 
-LOB_ABI_VERSION = 5
+LOB_ABI_VERSION = 6
 LOB_MAX_AGENT_TYPES = 4
 LOB_MAX_AGENT_I32 = 4
 LOB_MAX_AGENT_F32 = 10
@@ -83,7 +83,7 @@ class LobStepBuffers(C.Structure):
         ("agent_i32", (p_i32 * LOB_MAX_AGENT_I32) * LOB_MAX_AGENT_TYPES),
         ("agent_f32", (p_f32 * LOB_MAX_AGENT_F32) * LOB_MAX_AGENT_TYPES),
         ("actions", p_i32 * LOB_MAX_AGENT_TYPES),
-        ("perm", p_i32), ("reset_window", p_i32), ("reset_is_sell", p_i32),
+        ("perm", p_i32), ("reset_window", p_i32), ("reset_is_sell", p_i32), ("cancel_u", p_f32),
         ("message_data", p_i32), ("init_asks", p_i32), ("init_bids", p_i32), ("init_trades", p_i32),
         ("init_init_time", p_i32), ("init_max_steps", p_i32), ("init_start_index", p_i32),
         ("obs", p_f32 * LOB_MAX_AGENT_TYPES), ("reward", p_f32 * LOB_MAX_AGENT_TYPES),
@@ -94,7 +94,8 @@ class LobStepBuffers(C.Structure):
 
 class LobReplayBuffers(C.Structure):
     _fields_ = [("asks", p_i32), ("bids", p_i32), ("trades", p_i32), ("msgs", p_i32), ("start", p_i64),
-                ("n_msgs_total", i64), ("n_msgs", i32), ("_pad0", i32), ("best_out", p_i32)]
+                ("n_msgs_total", i64), ("n_msgs", i32), ("_pad0", i32), ("best_out", p_i32),
+                ("cancel_u", p_f32)]
 
 
 _SIZEOF = {"lob_sizeof_book_config": LobBookConfig, "lob_sizeof_agent_type_config": LobAgentTypeConfig,

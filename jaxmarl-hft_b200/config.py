@@ -231,8 +231,8 @@ def _enum(table, value, what):
 def book_config(world: JAXLOB_Configuration) -> abi.LobBookConfig:
     if world.simulator_mode != 0:
         raise ValueError("The simulator mode does not match an expected value.")  # job:620-622
-    if world.cancel_mode not in (0, 1):
-        raise NotImplementedError("cancel_mode 2/3 draw jax.random.choice per message (job:142-164): not built")
+    if world.cancel_mode not in (0, 1, 2, 3):
+        raise ValueError(f"cancel_mode={world.cancel_mode}: not a cst.CancelMode value")
     return abi.LobBookConfig(n_orders=world.nOrders, n_trades=world.nTrades, maxint=world.maxint,
                              init_id=world.init_id, book_depth=world.book_depth, cancel_mode=world.cancel_mode,
                              type_4_interpretation=world.type_4_interpretation,

@@ -54,6 +54,9 @@ struct BookCtx {
   int nrows;   // rows allocated per side (SLOTS * 32 >= no)
   int no, nt;
   int maxint, init_id, init_lo, t4, check_fill;
+  int cmode;   // cst CancelMode; 2 / 3 add the random same-price fallbacks of job:142-164
+  int mi;      // index of the current message in the scan (selects its pair of uniform draws)
+  const float* cu;   // [n_msgs][2] uniform draws of this book's scan (cancel_mode 2/3), else unused
 };
 __device__ __forceinline__ int* dyn_smem() { extern __shared__ __align__(128) int lob_dyn_smem[]; return lob_dyn_smem; }
 __device__ __forceinline__ int* rowp(const BookCtx& c, int s, int r) { return dyn_smem() + c.rows_off + (s * c.nrows + r) * 6; }
@@ -96,7 +99,42 @@ static __device__ __noinline__ void g_add(BookCtx c, int s, Msg m) {
   __syncwarp();
   g_remove_zero_neg(c, s);
 }
-// job:94-139 cancel_order + get_init_id_match (cancel_mode 0/1)
+// job:142-164 get_random_id_match (need_qty) / get_random_large_id_match: jax.random.choice(key, ids, p=|sign(ids)|) is
+//   p_cuml = cumsum(p); r = p_cuml[-1] * (1 - uniform(key)); ind = searchsorted(p_cuml, r)   (float32, side="left")
+// with ids = order id of the rows at the message's price (and, need_qty, holding at least its quantity), 0 elsewhere;
+// then the FIRST row carrying the chosen id.  u is that uniform draw (an input).  Returns kBig when no row carries it.
+static __device__ __noinline__ int g_random_match(BookCtx c, int s, Msg m, bool need_qty, float u) {
+  const int lane = lane_id();
+  int total = 0;
+  _Pragma("unroll 1")
+  for (int base = 0; base < c.no; base += 32) {
+    const int r = base + lane;
+    bool w = false;
+    if (r < c.no) { const int* p = rowp(c, s, r); w = (p[F_P] == m.price) && (!need_qty || p[F_Q] >= m.qty) && (p[F_OID] != 0); }
+    total += __popc(__ballot_sync(kFull, w));
+  }
+  const float rr = (float)total * (1.0f - u);
+  int ind = 0, prior = 0;
+  _Pragma("unroll 1")
+  for (int base = 0; base < c.no; base += 32) {
+    const int r = base + lane;
+    bool w = false;
+    if (r < c.no) { const int* p = rowp(c, s, r); w = (p[F_P] == m.price) && (!need_qty || p[F_Q] >= m.qty) && (p[F_OID] != 0); }
+    const unsigned bal = __ballot_sync(kFull, w);
+    const int incl = prior + __popc(bal & (0xffffffffu >> (31 - lane)));   // candidates among rows <= r
+    ind += __popc(__ballot_sync(kFull, (r < c.no) && ((float)incl < rr)));
+    prior += __popc(bal);
+  }
+  ind = min(ind, c.no - 1);
+  const int* q = rowp(c, s, ind);
+  const int chosen = ((q[F_P] == m.price) && (!need_qty || q[F_Q] >= m.qty)) ? q[F_OID] : 0;
+  int idx = kBig;
+  _Pragma("unroll 1")
+  for (int r = lane; r < c.no; r += 32)
+    if (rowp(c, s, r)[F_OID] == chosen) idx = min(idx, r);
+  return wmin(idx);
+}
+// job:94-139 cancel_order + get_init_id_match
 static __device__ __noinline__ void g_cancel(BookCtx c, int s, Msg m) {
   int idx = kBig;
   _Pragma("unroll 1")
@@ -110,6 +148,11 @@ static __device__ __noinline__ void g_cancel(BookCtx c, int s, Msg m) {
       if (p[F_P] == m.price && p[F_OID] <= c.init_id && p[F_OID] >= c.init_lo && p[F_Q] >= m.qty) idx = min(idx, r);
     }
     idx = wmin(idx);
+    if (idx == kBig && c.cmode >= 2) {   // job:131-136, :149-154
+      const float u0 = c.cu[2 * c.mi], u1 = c.cu[2 * c.mi + 1];
+      idx = g_random_match(c, s, m, true, u0);
+      if (idx == kBig && c.cmode == 3) idx = g_random_match(c, s, m, false, u1);
+    }
     if (idx == kBig) idx = c.no - 1;   // JAX normalises index -1: the LAST row loses quantity (quirk Q2)
   }
   __syncwarp();
@@ -318,6 +361,7 @@ struct Book {
     c.no = cfg.n_orders; c.nt = cfg.n_trades;
     c.maxint = cfg.maxint; c.init_id = cfg.init_id; c.init_lo = cfg.init_id - 2 * cfg.book_depth;
     c.t4 = cfg.type_4_interpretation; c.check_fill = cfg.check_book_fill;
+    c.cmode = cfg.cancel_mode; c.mi = 0; c.cu = nullptr;
     // padding rows [no, kRows) of both sides are blank for the whole kernel
     for (int i = lane_id(); i < 2 * kRows * 6; i += 32) smem_book[i] = -1;
     __syncwarp();
@@ -549,6 +593,12 @@ struct Book {
         if (pq.x == m.price && o <= c.init_id && o >= c.init_lo && pq.y >= m.qty) j = k * 32 + lane;
       }
       j = wmin(j);
+      if (j >= c.no && c.cmode >= 2) {   // the random same-price fallbacks (job:142-164) live in the generic path
+        __syncwarp();
+        g_cancel(c, S, m);
+        scan_side(S);
+        return;
+      }
       idx = (j < c.no) ? j : c.no - 1;
     }
     const int2 pq = *reinterpret_cast<const int2*>(row(S, idx));

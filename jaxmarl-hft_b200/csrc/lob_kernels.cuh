@@ -131,6 +131,7 @@ lob_replay_kernel(const __grid_constant__ LobBookConfig cfg, const __grid_consta
     }
     __syncwarp();
     bk.c.tr = B.trades + b * nt * 8;   // the trade log is worked on in place (HBM / L2): a row is one 32-byte sector
+    bk.c.cu = B.cancel_u + b * (long long)B.n_msgs * 2;   // only dereferenced under cancel_mode 2/3
     if (!bulk_books) { bk.load_side(ASK, B.asks + b * no * 6); bk.load_side(BID, B.bids + b * no * 6); }
     mbar_wait(&bar[0], ph0);
     ph0 ^= 1u;
@@ -153,7 +154,7 @@ lob_replay_kernel(const __grid_constant__ LobBookConfig cfg, const __grid_consta
       const int n = min(T - c * kReplayChunk, kReplayChunk);
       const int4* m4 = reinterpret_cast<const int4*>(mbuf + cur * kReplayChunk * 8);
 #pragma unroll 1
-      for (int i = 0; i < n; ++i) bk.process(m4[2 * i], m4[2 * i + 1]);
+      for (int i = 0; i < n; ++i) { bk.c.mi = c * kReplayChunk + i; bk.process(m4[2 * i], m4[2 * i + 1]); }
     }
     __syncwarp();
     if (B.best_out) {
@@ -290,6 +291,7 @@ __device__ __noinline__ ScanOut scan_messages(BookCtx ctx, const int4* m4, int N
   int2* gq = reinterpret_cast<int2*>(lane == 0 ? best_asks : best_bids);
 #pragma unroll 1
   for (int i = 0; i < N; ++i) {
+    bk.c.mi = i;
     bk.process(m4[2 * i], m4[2 * i + 1]);
     bk.ensure(ASK);
     bk.ensure(BID);
@@ -389,6 +391,7 @@ lob_step_kernel(const __grid_constant__ LobStepConfig c, const __grid_constant__
       }
       if (!bulk_books) { bk.load_side(ASK, b.asks + e * no * 6); bk.load_side(BID, b.bids + e * no * 6); }
       bk.c.tr = b.trades + e * nt * 8;   // the trade log is worked on in place (HBM / L2): a row is one 32-byte sector
+      bk.c.cu = b.cancel_u + e * N * 2;  // only dereferenced under cancel_mode 2/3
       bk.fill_trades_empty();            // marl:348: the trade log is re-initialised every step
       w.extreme_spread = false;
       if (need_extreme) {   // mm:2545-2553 over the OLD per-message bests
@@ -680,6 +683,18 @@ static __global__ void lob_draw_kernel(int* __restrict__ perm, int* __restrict__
       const int a = p[i]; p[i] = p[j]; p[j] = a;
     }
   }
+}
+
+// The uniform draws of the random cancel fallbacks (cancel_mode 2/3): multiples of 2^-23 in [0, 1), as
+// jax.random.uniform produces for float32.  One thread per draw.
+static __global__ void lob_draw_uniform_kernel(float* __restrict__ u, long long n, unsigned long long seed,
+                                               unsigned long long counter,
+                                               const unsigned long long* __restrict__ counter_dev) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (counter_dev) counter = *counter_dev;
+  const unsigned long long z = mix64(seed ^ mix64(counter ^ mix64(0xC0FFEEull + (unsigned long long)i)));
+  u[i] = (float)(unsigned)(z >> 41) * (1.0f / 8388608.0f);
 }
 
 static __global__ void lob_bump_kernel(unsigned long long* counter_dev) { *counter_dev += 1ull; }

@@ -41,9 +41,6 @@ int check_book(const LobBookConfig* c) {
   if (c->n_orders < 1 || c->n_orders > 512) return fail(LOB_E_INVALID, "n_orders=%d outside [1,512]", c->n_orders);
   if (c->n_trades < 1 || c->n_trades > 4096) return fail(LOB_E_INVALID, "n_trades=%d outside [1,4096]", c->n_trades);
   if (c->cancel_mode < 0 || c->cancel_mode > 3) return fail(LOB_E_INVALID, "cancel_mode=%d", c->cancel_mode);
-  if (c->cancel_mode > 1)
-    return fail(LOB_E_UNSUPPORTED, "cancel_mode %d draws jax.random.choice per message (job:142-164): not built",
-                c->cancel_mode);
   if (c->type_4_interpretation < 0 || c->type_4_interpretation > 2)
     return fail(LOB_E_INVALID, "type_4_interpretation=%d", c->type_4_interpretation);
   return LOB_OK;
@@ -112,6 +109,7 @@ int check_step_bufs(const LobStepConfig* c, const LobStepBuffers* b, bool step) 
   REQ(reset_window); REQ(init_asks); REQ(init_bids); REQ(init_trades); REQ(init_init_time); REQ(init_max_steps);
   REQ(init_start_index);
   if (step) { REQ(message_data); REQ(done_all); REQ(info_world_i32); REQ(info_world_f32); }
+  if (step && c->book.cancel_mode >= 2) REQ(cancel_u);   // job:142-164: the uniform draws are an input
 #undef REQ
   if (step && !aligned16(b->message_data)) return fail(LOB_E_INVALID, "message_data must be 16-byte aligned");
   if (!aligned16(b->asks) || !aligned16(b->bids) || !aligned16(b->trades) || !aligned16(b->best_asks) ||
@@ -199,6 +197,9 @@ int lob_replay_launch(const LobBookConfig* cfg, const LobReplayBuffers* bufs, in
     return fail(LOB_E_INVALID, "replay buffers are incomplete");
   if (bufs->n_msgs < 0 || bufs->n_msgs_total < 0) return fail(LOB_E_INVALID, "negative message count");
   if (bufs->n_msgs > 0 && !bufs->msgs) return fail(LOB_E_INVALID, "replay buffer 'msgs' is null");
+  if (cfg->cancel_mode >= 2 && bufs->n_msgs > 0 && !bufs->cancel_u)
+    return fail(LOB_E_INVALID, "replay buffer 'cancel_u' is null (cancel_mode %d draws per message, job:142-164)",
+                cfg->cancel_mode);
   if (!aligned16(bufs->msgs) || !aligned16(bufs->asks) || !aligned16(bufs->bids) || !aligned16(bufs->trades) ||
       (bufs->best_out && !aligned16(bufs->best_out)))
     return fail(LOB_E_INVALID, "replay buffers must be 16-byte aligned");
@@ -270,6 +271,12 @@ static int draw_impl(const LobStepConfig* cfg, const LobStepBuffers* bufs, int64
       cfg->n_windows, cfg->n_agent_types, window_selector, seed, counter,
       reinterpret_cast<const unsigned long long*>(counter_dev));
   int rc = launched("lob_draw_kernel");
+  if (!rc && bufs->cancel_u && cfg->book.cancel_mode >= 2) {   // job:146, :161: two uniform draws per message
+    const long long n = (long long)batch * lob_num_msgs_per_step(cfg) * 2;
+    lob::lob_draw_uniform_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(
+        const_cast<float*>(bufs->cancel_u), n, seed, counter, reinterpret_cast<const unsigned long long*>(counter_dev));
+    rc = launched("lob_draw_uniform_kernel");
+  }
   if (rc || !counter_dev) return rc;
   lob::lob_bump_kernel<<<1, 1, 0, st>>>(reinterpret_cast<unsigned long long*>(counter_dev));
   return launched("lob_bump_kernel");
@@ -298,6 +305,10 @@ struct LobHostReplay {
 
 LobHostReplay* lob_host_replay_create(const LobBookConfig* cfg, int64_t max_books, int64_t max_msgs_total, int device) {
   if (check_book(cfg)) return nullptr;
+  if (cfg->cancel_mode >= 2) {
+    fail(LOB_E_UNSUPPORTED, "host replay handle: cancel_mode %d needs per-message draws; use lob_replay_launch", cfg->cancel_mode);
+    return nullptr;
+  }
   if (max_books < 1 || max_msgs_total < 1) { fail(LOB_E_INVALID, "host replay: empty capacity"); return nullptr; }
   if (cudaSetDevice(device) != cudaSuccess) { fail(LOB_E_CUDA, "cudaSetDevice(%d) failed", device); return nullptr; }
   LobHostReplay* h = new LobHostReplay();

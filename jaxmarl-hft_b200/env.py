@@ -112,10 +112,11 @@ def build_reset_params(loaded: lobster.LoadedDay, world, replay_fn):
 
 
 # ---- device-side replay -------------------------------------------------------------------------------------
-def replay_books(book_cfg: abi.LobBookConfig, asks, bids, trades, msgs, start, n_msgs, best_out=None):
-    """``job.scan_through_entire_array`` for every book (torch CUDA tensors, in place)."""
+def replay_books(book_cfg: abi.LobBookConfig, asks, bids, trades, msgs, start, n_msgs, best_out=None, cancel_u=None):
+    """``job.scan_through_entire_array`` for every book (torch CUDA tensors, in place).  ``cancel_u`` float32
+    [B, n_msgs, 2]: the uniform draws of the random cancel fallbacks (cancel_mode 2/3, job:142-164)."""
     L = _lib.lib()
-    r = states.pack_replay(asks, bids, trades, msgs, start, n_msgs, best_out)
+    r = states.pack_replay(asks, bids, trades, msgs, start, n_msgs, best_out, cancel_u)
     _lib.check(L.lob_replay_launch(C.byref(book_cfg), C.byref(r), asks.shape[0], _lib.current_stream_ptr()),
                "lob_replay_launch")
 
@@ -131,8 +132,17 @@ def l2_state(book_cfg: abi.LobBookConfig, asks, bids, n_levels):
     return out
 
 
+def limit_only_book_config(book_cfg: abi.LobBookConfig) -> abi.LobBookConfig:
+    """The book config for replaying streams that hold only limit orders (the reset-state precompute, base:245-281):
+    no cancel is processed, so no random-cancel draws (cancel_mode 2/3) have to be supplied."""
+    c = abi.LobBookConfig.from_buffer_copy(book_cfg)
+    c.cancel_mode = min(int(c.cancel_mode), 1)
+    return c
+
+
 def _cuda_replay_fn(book_cfg, device):
     import torch
+    book_cfg = limit_only_book_config(book_cfg)
 
     def fn(asks, bids, trades, msgs, start, n_msgs):
         ta, tb, tt = (torch.from_numpy(x).to(device) for x in (asks, bids, trades))

@@ -36,6 +36,8 @@ def leaf_specs(cfg: abi.LobStepConfig, batch: int):
         "info_world_i32": ((B, len(abi.WINFO_I32)), np.int32, "o"),
         "info_world_f32": ((B, len(abi.WINFO_F32)), np.float32, "o"),
     }
+    if cfg.book.cancel_mode >= 2:   # job:142-164: the uniform draws of the two random-cancel fallbacks, per message
+        sp["cancel_u"] = ((B, N, 2), np.float32, "i")
     for t in range(T):
         a = cfg.agent[t]
         n = a.n_agents
@@ -108,6 +110,7 @@ def pack_buffers(cfg: abi.LobStepConfig, arrays: dict, params: dict) -> abi.LobS
     b.perm = _ptr(arrays["perm"], C.c_int32)
     b.reset_window = _ptr(arrays["reset_window"], C.c_int32)
     b.reset_is_sell = _ptr(arrays["reset_is_sell"], C.c_int32)
+    b.cancel_u = _ptr(arrays.get("cancel_u"), C.c_float)
     for name in PARAMS:
         setattr(b, name, _ptr(params[name], C.c_int32))
     b.done_all = _ptr(arrays["done_all"], C.c_uint8)
@@ -116,7 +119,7 @@ def pack_buffers(cfg: abi.LobStepConfig, arrays: dict, params: dict) -> abi.LobS
     return b
 
 
-def pack_replay(asks, bids, trades, msgs, start, n_msgs, best_out=None) -> abi.LobReplayBuffers:
+def pack_replay(asks, bids, trades, msgs, start, n_msgs, best_out=None, cancel_u=None) -> abi.LobReplayBuffers:
     r = abi.LobReplayBuffers()
     r.asks, r.bids, r.trades = _ptr(asks, C.c_int32), _ptr(bids, C.c_int32), _ptr(trades, C.c_int32)
     r.msgs = _ptr(msgs, C.c_int32)
@@ -124,4 +127,5 @@ def pack_replay(asks, bids, trades, msgs, start, n_msgs, best_out=None) -> abi.L
     r.n_msgs_total = int(msgs.shape[0])
     r.n_msgs = int(n_msgs)
     r.best_out = _ptr(best_out, C.c_int32)
+    r.cancel_u = _ptr(cancel_u, C.c_float)
     return r

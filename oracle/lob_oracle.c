@@ -143,12 +143,44 @@ static int get_init_id_match(const LobBookConfig* c, const int32_t* side, int no
   return -1;
 }
 
-/* job:94-117 cancel_order */
-static void cancel_order(const LobBookConfig* c, int32_t* side, int no, const Msg* m) {
+/* job:142-164 get_random_id_match (need_qty) / get_random_large_id_match (!need_qty).
+ * jax.random.choice(key, order_ids, p=|sign(order_ids)|) as published (jax/_src/random.py, replace=True, p given):
+ *   p_cuml = cumsum(p) ; r = p_cuml[-1] * (1 - uniform(key)) ; ind = searchsorted(p_cuml, r, side="left")
+ * with p promoted to float32.  u = that uniform draw (an input: PRNG products are never recomputed here). */
+static int get_random_match(const int32_t* side, int no, const Msg* m, int need_qty, float u) {
+  float total = 0.f;
+  for (int r = 0; r < no; ++r) {
+    const int32_t* row = side + r * 6;
+    int32_t id = (row[OF_P] == m->price && (!need_qty || row[OF_Q] >= m->qty)) ? row[OF_OID] : 0;
+    total += (id != 0) ? 1.0f : 0.0f;
+  }
+  const float rr = total * (1.0f - u);
+  int ind = 0;
+  float cum = 0.f;
+  for (int r = 0; r < no; ++r) {
+    const int32_t* row = side + r * 6;
+    int32_t id = (row[OF_P] == m->price && (!need_qty || row[OF_Q] >= m->qty)) ? row[OF_OID] : 0;
+    cum += (id != 0) ? 1.0f : 0.0f;
+    ind += (cum < rr);
+  }
+  if (ind > no - 1) ind = no - 1; /* jnp.take clamps (cannot happen for u in [0,1)) */
+  const int32_t* row = side + ind * 6;
+  const int32_t chosen = (row[OF_P] == m->price && (!need_qty || row[OF_Q] >= m->qty)) ? row[OF_OID] : 0;
+  for (int r = 0; r < no; ++r)
+    if (side[r * 6 + OF_OID] == chosen) return r;
+  return -1;
+}
+
+/* job:94-117 cancel_order; cu = the message's two uniform draws (cancel_mode 2/3) or NULL */
+static void cancel_order(const LobBookConfig* c, int32_t* side, int no, const Msg* m, const float* cu) {
   int idx = -1;
   for (int r = 0; r < no; ++r)
     if (side[r * 6 + OF_OID] == m->oid) { idx = r; break; }
   if (idx == -1) idx = get_init_id_match(c, side, no, m);
+  if (idx == -1 && (c->cancel_mode == 2 || c->cancel_mode == 3)) { /* job:131-136 */
+    idx = get_random_match(side, no, m, 1, cu[0]);
+    if (idx == -1 && c->cancel_mode == 3) idx = get_random_match(side, no, m, 0, cu[1]); /* job:149-154 */
+  }
   if (idx < 0) idx += no; /* JAX normalises the -1 index: last row (quirk Q2) */
   side[idx * 6 + OF_Q] = side[idx * 6 + OF_Q] - m->qty;
   remove_zero_neg(side, no);
@@ -290,7 +322,7 @@ static void ask_lim(const LobBookConfig* c, Msg m, int32_t* asks, int32_t* bids,
 
 /* job:556-637 cond_type_side (GENERAL_EXCHANGE) */
 static void process_msg(const LobBookConfig* c, const int32_t* d, int32_t* asks, int32_t* bids, int32_t* trades,
-                        int32_t* scratch) {
+                        int32_t* scratch, const float* cu) {
   Msg m;
   m.type = d[0];
   m.side = (d[0] == 4) ? -d[1] : d[1]; /* job:575 */
@@ -306,8 +338,8 @@ static void process_msg(const LobBookConfig* c, const int32_t* d, int32_t* asks,
   switch (index) { /* lax.switch, job:596 */
     case 0: ask_lim(c, m, asks, bids, trades, scratch); break;
     case 1: bid_lim(c, m, asks, bids, trades, scratch); break;
-    case 2: cancel_order(c, asks, c->n_orders, &m); break;
-    case 3: cancel_order(c, bids, c->n_orders, &m); break;
+    case 2: cancel_order(c, asks, c->n_orders, &m, cu); break;
+    case 3: cancel_order(c, bids, c->n_orders, &m, cu); break;
     default: break; /* doNothing */
   }
 }
@@ -1423,7 +1455,7 @@ static void step_one(const LobStepConfig* c, const LobStepBuffers* b, int64_t e,
   int32_t* trades = b->trades + e * nt * 8;
   for (int i = 0; i < nt * 8; ++i) trades[i] = -1;
   for (int i = 0; i < N; ++i) { /* job:792-823 + job:688-732 */
-    process_msg(&c->book, msgs + i * 8, asks, bids, trades, scratch);
+    process_msg(&c->book, msgs + i * 8, asks, bids, trades, scratch, b->cancel_u ? b->cancel_u + (e * N + i) * 2 : NULL);
     int32_t best[4];
     best_incl_quants(&c->book, asks, bids, best);
     new_bestasks[i * 2] = best[0]; new_bestasks[i * 2 + 1] = best[1];
@@ -1561,7 +1593,7 @@ static size_t step_ws_words(const LobStepConfig* c) {
 
 static int check_cfg(const LobStepConfig* c) {
   if (c->n_agent_types < 0 || c->n_agent_types > LOB_MAX_AGENT_TYPES) return LOB_E_INVALID;
-  if (c->book.cancel_mode > 1) return LOB_E_UNSUPPORTED;
+  if (c->book.cancel_mode < 0 || c->book.cancel_mode > 3) return LOB_E_INVALID;
   int total = 0;
   for (int t = 0; t < c->n_agent_types; ++t) {
     const LobAgentTypeConfig* a = &c->agent[t];
@@ -1578,6 +1610,7 @@ static int check_cfg(const LobStepConfig* c) {
 int lob_oracle_step(const LobStepConfig* c, const LobStepBuffers* b, int64_t batch, int n_threads) {
   int rc = check_cfg(c);
   if (rc) return rc;
+  if (c->book.cancel_mode >= 2 && !b->cancel_u) return LOB_E_INVALID;
   const size_t words = step_ws_words(c);
 #ifdef _OPENMP
   if (n_threads > 0) omp_set_num_threads(n_threads);
@@ -1604,7 +1637,8 @@ int lob_oracle_reset(const LobStepConfig* c, const LobStepBuffers* b, int64_t ba
 
 /* base:189-216 / job:736-756: every book scans its own message window; trades persist */
 int lob_oracle_replay(const LobBookConfig* c, const LobReplayBuffers* b, int64_t n_books, int n_threads) {
-  if (c->cancel_mode > 1) return LOB_E_UNSUPPORTED;
+  if (c->cancel_mode < 0 || c->cancel_mode > 3) return LOB_E_INVALID;
+  if (c->cancel_mode >= 2 && !b->cancel_u) return LOB_E_INVALID;
   const int no = c->n_orders, nt = c->n_trades;
 #ifdef _OPENMP
   if (n_threads > 0) omp_set_num_threads(n_threads);
@@ -1620,7 +1654,9 @@ int lob_oracle_replay(const LobBookConfig* c, const LobReplayBuffers* b, int64_t
       int32_t* bids = b->bids + e * no * 6;
       int32_t* trades = b->trades + e * nt * 8;
       const int32_t* m = b->msgs + b->start[e] * 8;
-      for (int i = 0; i < b->n_msgs; ++i) process_msg(c, m + (int64_t)i * 8, asks, bids, trades, scratch);
+      for (int i = 0; i < b->n_msgs; ++i)
+        process_msg(c, m + (int64_t)i * 8, asks, bids, trades, scratch,
+                    b->cancel_u ? b->cancel_u + (e * b->n_msgs + i) * 2 : NULL);
       if (b->best_out) best_incl_quants(c, asks, bids, b->best_out + e * 4);
     }
     free(scratch);
@@ -1631,10 +1667,12 @@ int lob_oracle_replay(const LobBookConfig* c, const LobReplayBuffers* b, int64_t
 
 /* job:792-823 on ONE book, with the per-message best ask/bid rows (for known-answer tests) */
 int lob_oracle_scan_save_bidask(const LobBookConfig* c, int32_t* asks, int32_t* bids, int32_t* trades,
-                                const int32_t* msgs, int32_t n, int32_t* bestasks /* [n][2] */, int32_t* bestbids) {
+                                const int32_t* msgs, int32_t n, int32_t* bestasks /* [n][2] */, int32_t* bestbids,
+                                const float* cancel_u /* [n][2] or NULL */) {
+  if (c->cancel_mode >= 2 && !cancel_u) return LOB_E_INVALID;
   int32_t* scratch = (int32_t*)malloc(sizeof(int32_t) * 6 * c->n_orders);
   for (int i = 0; i < n; ++i) {
-    process_msg(c, msgs + (int64_t)i * 8, asks, bids, trades, scratch);
+    process_msg(c, msgs + (int64_t)i * 8, asks, bids, trades, scratch, cancel_u ? cancel_u + (int64_t)i * 2 : NULL);
     int32_t best[4];
     best_incl_quants(c, asks, bids, best);
     if (bestasks) { bestasks[i * 2] = best[0]; bestasks[i * 2 + 1] = best[1]; }

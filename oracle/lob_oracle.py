@@ -33,7 +33,7 @@ class Oracle:
         lib.lob_oracle_step.argtypes = [C.POINTER(abi.LobStepConfig), C.POINTER(abi.LobStepBuffers), C.c_int64, C.c_int]
         lib.lob_oracle_reset.argtypes = [C.POINTER(abi.LobStepConfig), C.POINTER(abi.LobStepBuffers), C.c_int64]
         lib.lob_oracle_replay.argtypes = [C.POINTER(abi.LobBookConfig), C.POINTER(abi.LobReplayBuffers), C.c_int64, C.c_int]
-        lib.lob_oracle_scan_save_bidask.argtypes = [C.POINTER(abi.LobBookConfig)] + [abi.p_i32] * 4 + [C.c_int32] + [abi.p_i32] * 2
+        lib.lob_oracle_scan_save_bidask.argtypes = [C.POINTER(abi.LobBookConfig)] + [abi.p_i32] * 4 + [C.c_int32] + [abi.p_i32] * 2 + [abi.p_f32]
         lib.lob_oracle_l2.argtypes = [C.POINTER(abi.LobBookConfig), abi.p_i32, abi.p_i32, abi.p_i32, C.c_int32, C.c_int64]
         lib.lob_oracle_max_threads.restype = C.c_int
 
@@ -53,18 +53,20 @@ class Oracle:
         bufs = states.pack_buffers(cfg, arrays, params)
         self._check(self.lib.lob_oracle_reset(C.byref(cfg), C.byref(bufs), batch), "lob_oracle_reset")
 
-    def replay(self, book_cfg, asks, bids, trades, msgs, start, n_msgs, best_out=None, n_threads=1):
-        r = states.pack_replay(asks, bids, trades, msgs, start, n_msgs, best_out)
+    def replay(self, book_cfg, asks, bids, trades, msgs, start, n_msgs, best_out=None, n_threads=1, cancel_u=None):
+        r = states.pack_replay(asks, bids, trades, msgs, start, n_msgs, best_out, cancel_u)
         self._check(self.lib.lob_oracle_replay(C.byref(book_cfg), C.byref(r), asks.shape[0], n_threads), "lob_oracle_replay")
 
-    def scan_save_bidask(self, book_cfg, asks, bids, trades, msgs):
+    def scan_save_bidask(self, book_cfg, asks, bids, trades, msgs, cancel_u=None):
         """job.scan_through_entire_array_save_bidask on ONE book; returns (bestasks[n,2], bestbids[n,2])."""
         msgs = np.ascontiguousarray(msgs, np.int32)
         n = msgs.shape[0]
         ba, bb = np.zeros((n, 2), np.int32), np.zeros((n, 2), np.int32)
         p = lambda a: a.ctypes.data_as(abi.p_i32)
         self._check(self.lib.lob_oracle_scan_save_bidask(C.byref(book_cfg), p(asks), p(bids), p(trades), p(msgs), n,
-                                                         p(ba), p(bb)), "lob_oracle_scan_save_bidask")
+                                                         p(ba), p(bb),
+                                                         None if cancel_u is None else cancel_u.ctypes.data_as(abi.p_f32)),
+                    "lob_oracle_scan_save_bidask")
         return ba, bb
 
     def l2(self, book_cfg, asks, bids, n_levels):

@@ -59,7 +59,11 @@ def vmap(fun, in_axes=0, out_axes=0, axis_name=None, **kw):
         for i in range(n):
             sl = [a if ax is None else tree_map(lambda l: _wrap(_np.take(_core._raw(l), i, axis=ax)), a)
                   for a, ax in zip(args, axes)]
-            outs.append(fun(*sl))
+            _core.VMAP_STACK.append(i)
+            try:
+                outs.append(fun(*sl))
+            finally:
+                _core.VMAP_STACK.pop()
         leaves0, td = tree_flatten(outs[0])
         cols = [[] for _ in leaves0]
         for o in outs:

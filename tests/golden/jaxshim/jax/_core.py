@@ -440,3 +440,6 @@ def mean_(a, axis=None, keepdims=False):
     n = a.size if axis is None else (np.prod([a.shape[x] for x in axis]) if isinstance(axis, tuple) else a.shape[axis])
     with np.errstate(all="ignore"):
         return wrap((s / np.float32(n)).astype(np.float32))
+
+
+VMAP_STACK = []   # index of the running element of every active vmap (outermost first)

@@ -33,6 +33,9 @@ def fori_loop(lower, upper, body_fun, init_val):
     return val
 
 
+SCAN_STACK = []   # index of the running iteration of every active scan (innermost last)
+
+
 def scan(f, init, xs=None, length=None, reverse=False, unroll=1):
     if xs is None:
         n = int(length)
@@ -43,7 +46,11 @@ def scan(f, init, xs=None, length=None, reverse=False, unroll=1):
     carry, ys = init, [None] * n
     for i in order:
         x = None if xs is None else tree_map(lambda a: wrap(a)[i], xs)
-        carry, y = f(carry, x)
+        SCAN_STACK.append(i)
+        try:
+            carry, y = f(carry, x)
+        finally:
+            SCAN_STACK.pop()
         ys[i] = y
     if n == 0 or ys[0] is None:
         return carry, None

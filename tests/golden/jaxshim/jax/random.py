@@ -70,10 +70,23 @@ def permutation(key, x, axis=0, independent=False):
 
 
 def choice(key, a, shape=(), replace=True, p=None, axis=0):
+    """jax.random.choice.  With ``p`` (scalar draw, replace=True) it follows jax/_src/random.py literally:
+    ``p_cuml = cumsum(p); r = p_cuml[-1] * (1 - uniform(key)); ind = searchsorted(p_cuml, r)`` in float32, and the
+    uniform draw is recorded (args = (outermost vmap index, innermost scan index)) so that a replay can feed it back."""
+    from . import lax as _lax
+    from . import _core
     r = _rng(key, 7)
     arr = _raw(a)
     if arr.ndim == 0:
         arr = np.arange(int(arr))
+    if p is not None and tuple(shape) == () and replace:
+        u = np.float32(int(r.integers(0, 2 ** 23)) / 2.0 ** 23)          # [0, 1), 23 mantissa bits as jax.random.uniform
+        p_cuml = np.cumsum(_raw(p).astype(np.float32), dtype=np.float32)
+        rr = np.float32(p_cuml[-1] * np.float32(np.float32(1.0) - u))
+        idx = min(int(np.searchsorted(p_cuml, rr, side="left")), arr.shape[0] - 1)
+        pos = (_core.VMAP_STACK[0] if _core.VMAP_STACK else -1, _lax.SCAN_STACK[-1] if _lax.SCAN_STACK else -1)
+        TRACE.append(("choice", _caller(), _raw(key).copy(), pos, float(u)))
+        return wrap(arr[idx])
     pp = None
     if p is not None:
         pp = _raw(p).astype(np.float64)

@@ -242,7 +242,10 @@ def run_env_case(name, json_name, seed, B, steps, n_events=30000, stress=False, 
             jr.TRACE.clear()
             obs, state, rewards, dones, info = jax.vmap(env.step, in_axes=(0, 0, 0, None))(step_keys, state, jax_actions, params)
             trace = list(jr.TRACE)
-            record[f"step{s}/trace"] = np.array([f"{fn}|{caller}|{args}|{np.asarray(res).tolist()}" for fn, caller, k, args, res in trace])
+            record[f"step{s}/trace"] = np.array([f"{fn}|{caller}|{args}|{np.asarray(res).tolist()}" for fn, caller, k, args, res in trace
+                                                 if fn != "choice"])
+            if int(getattr(mac.world_config, "cancel_mode", 1)) >= 2:
+                record[f"step{s}/cancel_u"] = choice_draws(trace, (B, env.num_msgs_per_step))
             for t in range(n_types):
                 record[f"step{s}/actions{t}"] = actions[t]
                 record[f"step{s}/obs{t}"] = _np(obs[t])
@@ -262,22 +265,38 @@ def run_env_case(name, json_name, seed, B, steps, n_events=30000, stress=False, 
         print("wrote", path, os.path.getsize(path) // 1024, "KiB")
 
 
-def run_replay_case(name, seed, B, T, no, nt, t4, fill, out_dir=HERE, adversarial=False):
+def choice_draws(trace, shape):
+    """The uniform draws of the random-cancel fallbacks (job:146, :161) recorded by the shim's jax.random.choice ->
+    float32 ``shape + (2,)`` indexed by (outermost vmap index if shape has two dims, message index)."""
+    cu = np.zeros(tuple(shape) + (2,), np.float32)
+    for fn, caller, key, pos, u in trace:
+        if fn != "choice":
+            continue
+        stage = 1 if caller.startswith("get_random_large_id_match") else 0
+        assert caller.startswith("get_random"), caller
+        idx = (pos[1],) if len(shape) == 1 else (pos[0], pos[1])
+        cu[idx + (stage,)] = u
+    return cu
+
+
+def run_replay_case(name, seed, B, T, no, nt, t4, fill, out_dir=HERE, adversarial=False, cancel_mode=1):
     """job.scan_through_entire_array_save_bidask on adversarial random streams + job.get_L2_state of the result."""
     import helpers as H
     from gymnax_exchange.jaxob import JaxOrderBookArrays as job
     from gymnax_exchange.jaxob.jaxob_config import JAXLOB_Configuration
     from jaxmarl_hft_b200 import config as C
     import jax.random as jr
-    cfg = JAXLOB_Configuration(nOrders=no, nTrades=nt, type_4_interpretation=t4, check_book_fill=fill)
-    bc = C.book_config(C.World_EnvironmentConfig(nOrders=no, nTrades=nt, type_4_interpretation=t4, check_book_fill=fill))
+    cfg = JAXLOB_Configuration(nOrders=no, nTrades=nt, type_4_interpretation=t4, check_book_fill=fill, cancel_mode=cancel_mode)
+    bc = C.book_config(C.World_EnvironmentConfig(nOrders=no, nTrades=nt, type_4_interpretation=t4, check_book_fill=fill,
+                                                 cancel_mode=cancel_mode))
     rng = np.random.default_rng(seed)
     msgs = (H.adversarial_messages(rng, B * T, bc) if adversarial else
             H.random_messages(rng, B * T, bc, price_lo=99_000, price_hi=100_600 if no < 64 else 101_500))
     rec = {"msgs": msgs, "B": np.int64(B), "T": np.int64(T), "no": np.int64(no), "nt": np.int64(nt), "t4": np.int64(t4),
-           "fill": np.int64(fill)}
-    A, Bd, Tr, BA, BB, L2 = [], [], [], [], [], []
+           "fill": np.int64(fill), "cancel_mode": np.int64(cancel_mode)}
+    A, Bd, Tr, BA, BB, L2, CU = [], [], [], [], [], [], []
     for b in range(B):
+        jr.TRACE.clear()
         asks = job.init_orderside(no)
         bids = job.init_orderside(no)
         trades = (jnp.ones((nt, 8)) * -1).astype(jnp.int32)
@@ -285,8 +304,12 @@ def run_replay_case(name, seed, B, T, no, nt, t4, fill, out_dir=HERE, adversaria
             cfg, jr.PRNGKey(0), jnp.asarray(msgs[b * T:(b + 1) * T]), (asks, bids, trades), T)
         A.append(_np(asks)); Bd.append(_np(bids)); Tr.append(_np(trades)); BA.append(_np(ba)); BB.append(_np(bb))
         L2.append(_np(job.get_L2_state(asks, bids, 10, cfg)))
+        CU.append(choice_draws(list(jr.TRACE), (T,)))
     rec.update(asks=np.stack(A), bids=np.stack(Bd), trades=np.stack(Tr), best_asks=np.stack(BA), best_bids=np.stack(BB),
                l2=np.stack(L2))
+    if cancel_mode >= 2:
+        rec["cancel_u"] = np.stack(CU)
+        print("  random-cancel draws used:", int((rec["cancel_u"] != 0).sum()))
     path = os.path.join(out_dir, f"{name}.npz")
     np.savez_compressed(path, **rec)
     print("wrote", path, os.path.getsize(path) // 1024, "KiB")
@@ -302,6 +325,11 @@ if __name__ == "__main__":
     if "replay_adv" in which:
         run_replay_case("replay_adversarial", seed=15, B=6, T=400, no=24, nt=12, t4=0, fill=True, adversarial=True)
         run_replay_case("replay_adversarial_100", seed=16, B=4, T=500, no=100, nt=100, t4=1, fill=True, adversarial=True)
+    if "replay_cnl" in which:
+        run_replay_case("replay_cancel_uniform", seed=17, B=6, T=400, no=24, nt=12, t4=0, fill=True, cancel_mode=2)
+        run_replay_case("replay_cancel_uniform_large", seed=18, B=6, T=500, no=100, nt=100, t4=0, fill=True, cancel_mode=3)
+        run_replay_case("replay_cancel_large_adversarial", seed=19, B=4, T=400, no=33, nt=16, t4=1, fill=True,
+                        adversarial=True, cancel_mode=3)
     if "env" in which:
         run_env_case("env_2player", "2_player_fq_fqc.json", seed=3, B=3, steps=68)
         run_env_case("env_exec", "exec_longrun_fixed_quants_complex.json", seed=4, B=2, steps=20)
@@ -315,6 +343,9 @@ if __name__ == "__main__":
         # the last window's nominal start wraps to day_start (base:288-290), so every data message is past the end
         run_env_case("env_fixed_time_masked", "2_player_fq_fqc.json", seed=22, B=2, steps=24, mutate="fixed_time",
                      ep_type="fixed_time", episode_time=1800, start_resolution=900, window_selector=25)
+    if "env_cnl" in which:
+        run_env_case("env_cancel_uniform_large", "2_player_fq_fqc.json", seed=23, B=3, steps=40, stress=True, mutate="hetero",
+                     nOrders=40, nTrades=24, cancel_mode=3)
     if "env3" in which:
         run_env_case("env_bob_twap", "2_player_fq_fqc.json", seed=8, B=2, steps=66, mutate="bob_twap")
         run_env_case("env_simple_skew_avst", "2_player_fq_fqc.json", seed=10, B=2, steps=66, mutate="simple_skew_avst")

@@ -40,6 +40,8 @@ def load_for(mac, day):
 
 
 def oracle_replay_fn(oracle, book_cfg):
+    book_cfg = E.limit_only_book_config(book_cfg)
+
     def fn(asks, bids, trades, msgs, start, n_msgs):
         oracle.replay(book_cfg, asks, bids, trades, msgs, start, n_msgs)
         return asks, bids, trades
@@ -72,6 +74,8 @@ def draw_prng(rng, cfg, arrays):
     n_act = C.num_action_msgs(cfg)
     if n_act:
         arrays["perm"][:] = np.argsort(rng.random((B, n_act)), axis=1)
+    if "cancel_u" in arrays:   # jax.random.uniform: multiples of 2^-23 in [0, 1)
+        arrays["cancel_u"][:] = rng.integers(0, 2 ** 23, size=arrays["cancel_u"].shape).astype(np.float32) / np.float32(2 ** 23)
 
 
 def draw_actions(rng, cfg, arrays):
@@ -83,7 +87,7 @@ def draw_actions(rng, cfg, arrays):
 
 def copy_inputs(src, dst):
     for k in src:
-        if k.startswith("actions") or k in ("perm", "reset_window", "reset_is_sell"):
+        if k.startswith("actions") or k in ("perm", "reset_window", "reset_is_sell", "cancel_u"):
             dst[k][...] = src[k]
 
 
@@ -130,7 +134,7 @@ class CudaEnv:
 
     def set_inputs(self, arrays_np):
         for k, v in arrays_np.items():
-            if k.startswith("actions") or k in ("perm", "reset_window", "reset_is_sell"):
+            if k.startswith("actions") or k in ("perm", "reset_window", "reset_is_sell", "cancel_u"):
                 self.arrays[k].copy_(self.torch.from_numpy(v))
 
     def _bufs(self):
@@ -153,7 +157,7 @@ class CudaEnv:
         return to_numpy(self.arrays)
 
 
-def cuda_replay(book_cfg, asks, bids, trades, msgs, start, n_msgs, want_best=False, device="cuda:0"):
+def cuda_replay(book_cfg, asks, bids, trades, msgs, start, n_msgs, want_best=False, device="cuda:0", cancel_u=None):
     """numpy in -> numpy out through lob_replay_launch."""
     import torch
     from jaxmarl_hft_b200 import env as E2
@@ -162,7 +166,8 @@ def cuda_replay(book_cfg, asks, bids, trades, msgs, start, n_msgs, want_best=Fal
     tm = torch.from_numpy(np.ascontiguousarray(msgs, np.int32)).to(dev)
     ts = torch.from_numpy(np.ascontiguousarray(start, np.int64)).to(dev)
     best = torch.zeros((asks.shape[0], 4), dtype=torch.int32, device=dev) if want_best else None
-    E2.replay_books(book_cfg, ta, tb, tt, tm, ts, n_msgs, best)
+    tu = None if cancel_u is None else torch.from_numpy(np.ascontiguousarray(cancel_u, np.float32)).to(dev)
+    E2.replay_books(book_cfg, ta, tb, tt, tm, ts, n_msgs, best, cancel_u=tu)
     torch.cuda.synchronize()
     out = (ta.cpu().numpy(), tb.cpu().numpy(), tt.cpu().numpy())
     return out + ((best.cpu().numpy(),) if want_best else ())

@@ -63,8 +63,9 @@ def test_bad_calls_fail_loudly_before_the_device():
     bad.book.n_orders = 100000
     assert L.lob_step_launch(C.byref(bad), C.byref(bufs), 8, None) == abi.LOB_E_INVALID
     bad = Cfg.to_step_config(mac, 4, 30000)
-    bad.book.cancel_mode = 2
-    assert L.lob_reset_launch(C.byref(bad), C.byref(bufs), 8, None) == abi.LOB_E_UNSUPPORTED
+    bad.book.cancel_mode = 7
+    assert L.lob_reset_launch(C.byref(bad), C.byref(bufs), 8, None) == abi.LOB_E_INVALID
+    assert b"cancel_mode" in L.lob_last_error()
     bad = Cfg.to_step_config(mac, 4, 30000)
     bad.ep_type_fixed_time = 1       # supported since ABI 5: validation proceeds to the (null) buffer table
     assert L.lob_step_launch(C.byref(bad), C.byref(bufs), 8, None) == abi.LOB_E_INVALID
@@ -72,6 +73,9 @@ def test_bad_calls_fail_loudly_before_the_device():
     rb = abi.LobReplayBuffers()
     bc = Cfg.book_config(mac.world_config)
     assert L.lob_replay_launch(C.byref(bc), C.byref(rb), 8, None) == abi.LOB_E_INVALID
+    bc.cancel_mode = 3               # random cancel fallbacks: the host-buffer handle has no draws to offer
+    assert not L.lob_host_replay_create(C.byref(bc), 4, 100, 0)
+    assert b"cancel_mode" in L.lob_last_error()
 
 
 def test_host_config_rejects_what_the_reference_rejects():

@@ -30,7 +30,8 @@ ILL_CONDITIONED = ("advantage", "drift", "reward", "slippage", "price_adv", "pri
 
 def _book_cfg(z):
     return C.book_config(C.World_EnvironmentConfig(nOrders=int(z["no"]), nTrades=int(z["nt"]),
-                                                   type_4_interpretation=int(z["t4"]), check_book_fill=bool(z["fill"])))
+                                                   type_4_interpretation=int(z["t4"]), check_book_fill=bool(z["fill"]),
+                                                   cancel_mode=int(z["cancel_mode"]) if "cancel_mode" in z.files else 1))
 
 
 @pytest.mark.parametrize("path", REPLAY_CASES, ids=[os.path.basename(p) for p in REPLAY_CASES])
@@ -40,7 +41,8 @@ def test_oracle_replay_matches_reference(oracle, path):
     bc = _book_cfg(z)
     for b in range(B):
         a = np.full((no, 6), -1, np.int32); d = a.copy(); t = np.full((nt, 8), -1, np.int32)
-        ba, bb = oracle.scan_save_bidask(bc, a, d, t, z["msgs"][b * T:(b + 1) * T])
+        cu = np.ascontiguousarray(z["cancel_u"][b]) if "cancel_u" in z.files else None
+        ba, bb = oracle.scan_save_bidask(bc, a, d, t, z["msgs"][b * T:(b + 1) * T], cancel_u=cu)
         np.testing.assert_array_equal(a, z["asks"][b]); np.testing.assert_array_equal(d, z["bids"][b])
         np.testing.assert_array_equal(t, z["trades"][b])
         np.testing.assert_array_equal(ba, z["best_asks"][b]); np.testing.assert_array_equal(bb, z["best_bids"][b])
@@ -55,7 +57,8 @@ def test_cuda_replay_matches_reference(path):
     B, T, no, nt = int(z["B"]), int(z["T"]), int(z["no"]), int(z["nt"])
     bc = _book_cfg(z)
     a = np.full((B, no, 6), -1, np.int32); d = a.copy(); t = np.full((B, nt, 8), -1, np.int32)
-    ga, gb, gt, best = H.cuda_replay(bc, a, d, t, z["msgs"], np.arange(B, dtype=np.int64) * T, T, want_best=True)
+    ga, gb, gt, best = H.cuda_replay(bc, a, d, t, z["msgs"], np.arange(B, dtype=np.int64) * T, T, want_best=True,
+                                     cancel_u=z["cancel_u"] if "cancel_u" in z.files else None)
     np.testing.assert_array_equal(ga, z["asks"]); np.testing.assert_array_equal(gb, z["bids"])
     np.testing.assert_array_equal(gt, z["trades"])
     # the reference's last per-message best pair is the unfilled get_best_bid_and_ask_inclQuants of the final book
@@ -281,6 +284,8 @@ def _rollout(z, env, step_fn, reset_fn, get_arrays, set_inputs):
         _set_draws(inp, _parse_trace(z[f"step{s}/trace"]), B, n_act, T, kinds, n_agents, rnd, wsel)
         for t in range(T):
             inp[f"actions{t}"][...] = z[f"step{s}/actions{t}"]
+        if "cancel_u" in inp:
+            inp["cancel_u"][...] = z[f"step{s}/cancel_u"]
         set_inputs(inp)
         step_fn()
         arr = get_arrays()

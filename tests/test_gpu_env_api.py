@@ -131,3 +131,26 @@ def test_marl_env_fixed_time_episodes():
     assert int(n_done.min()) >= 1                                  # every env finished at least one episode
     it = state.world_state.init_time.cpu().numpy()
     assert (it[:, 1] == 0).all() and ((it[:, 0] - 34200) % 900 == 0).all()   # base_env.py:288-290: on the time grid
+
+
+def test_marl_env_random_cancel_mode_draws():
+    """cancel_mode 3 through the public API: the device generator fills cancel_u (multiples of 2^-23 in [0,1), fresh every
+    step) and the step consumes it."""
+    import torch
+    mac = H.load_mac("2_player_fq_fqc", nOrders=40, nTrades=24, cancel_mode=3)
+    ld = H.load_for(mac, H.small_day(seed=9, n_events=30000, stress=True))
+    B = 64
+    env = E.MARLEnv(None, mac, num_envs=B, loaded=ld, device="cuda:0", seed=5)
+    params = env.default_params
+    obs, state = env.reset(None, params)
+    acts = [torch.zeros((B, 1), dtype=torch.int32, device="cuda") for _ in env.action_spaces]
+    seen = []
+    for _ in range(3):
+        obs, state, rewards, dones, info = env.step(None, state, acts, params)
+        u = state.arrays["cancel_u"].clone()
+        assert u.shape == (B, env.num_msgs_per_step, 2)
+        assert float(u.min()) >= 0.0 and float(u.max()) < 1.0
+        assert torch.equal(u * 2 ** 23, torch.round(u * 2 ** 23))
+        seen.append(u)
+    assert not torch.equal(seen[0], seen[1]) and not torch.equal(seen[1], seen[2])
+    assert 0.45 < float(seen[0].mean()) < 0.55

@@ -285,6 +285,41 @@ def test_replay_adversarial_streams_bit_exact(oracle, no, nt, t4, fill):
     np.testing.assert_array_equal(ga, ra); np.testing.assert_array_equal(gb, rb); np.testing.assert_array_equal(gt, rt)
 
 
+@pytest.mark.parametrize("mode,no,nt,adversarial", [(2, 100, 100, False), (3, 100, 100, False), (3, 24, 12, False),
+                                                    (2, 40, 16, True), (3, 200, 64, True)])
+def test_replay_random_cancel_modes_bit_exact(oracle, mode, no, nt, adversarial):
+    """cancel_mode 2 / 3 (job:142-164): a cancel that matches neither an order id nor initial liquidity falls on a uniformly
+    chosen order at its price (holding at least its quantity; mode 3: then any at its price).  The uniform draws are inputs,
+    so the choice -- cumsum / searchsorted as jax.random.choice -- is bit-exact."""
+    rng = np.random.default_rng(mode * 100 + no)
+    bc = _book_cfg(no, nt, cancel_mode=mode)
+    B, T = 96, 600
+    msgs = (H.adversarial_messages(rng, B * T, bc) if adversarial else
+            H.random_messages(rng, B * T, bc, price_lo=99_500, price_hi=100_300, id_pool=4000))   # most cancels miss their id
+    cu = (rng.integers(0, 2 ** 23, size=(B, T, 2)).astype(np.float32) / np.float32(2 ** 23))
+    cu[::7, ::5] = 0.0                                      # the smallest draw picks the LAST candidate (r = total)
+    start = np.arange(B, dtype=np.int64) * T
+    a0 = np.full((B, no, 6), -1, np.int32); b0 = a0.copy(); t0 = np.full((B, nt, 8), -1, np.int32)
+    ra, rb, rt = a0.copy(), b0.copy(), t0.copy()
+    rbest = np.zeros((B, 4), np.int32)
+    oracle.replay(bc, ra, rb, rt, msgs, start, T, best_out=rbest, cancel_u=cu, n_threads=8)
+    ga, gb, gt, gbest = H.cuda_replay(bc, a0, b0, t0, msgs, start, T, want_best=True, cancel_u=cu)
+    np.testing.assert_array_equal(ga, ra); np.testing.assert_array_equal(gb, rb)
+    np.testing.assert_array_equal(gt, rt); np.testing.assert_array_equal(gbest, rbest)
+    # the draws matter: the same stream under cancel_mode 1 ends in a different book
+    bc1 = _book_cfg(no, nt, cancel_mode=1)
+    xa, xb, xt = a0.copy(), b0.copy(), t0.copy()
+    oracle.replay(bc1, xa, xb, xt, msgs, start, T, n_threads=8)
+    assert not (np.array_equal(xa, ra) and np.array_equal(xb, rb))
+
+
+@pytest.mark.parametrize("mode", [2, 3])
+def test_step_random_cancel_modes(oracle, mode):
+    """env.step under cancel_mode 2 / 3 on the capacity-stress day (many data cancels miss their order id)."""
+    mac = H.load_mac("2_player_fq_fqc", nOrders=40, nTrades=24, cancel_mode=mode)
+    _rollout_parity(oracle, mac, H.small_day(seed=9, n_events=30000, stress=True), B=48, steps=66, seed=30 + mode)
+
+
 def test_step_on_adversarial_day(oracle):
     """env.step with a day tensor made of adversarial messages: the per-message best bid/ask rows, rewards and
     observations go through the same bail-out logic as the replay."""
