@@ -315,6 +315,67 @@ def run_replay_case(name, seed, B, T, no, nt, t4, fill, out_dir=HERE, adversaria
     print("wrote", path, os.path.getsize(path) // 1024, "KiB")
 
 
+def run_orderbook_case(name="orderbook_api", out_dir=HERE):
+    """The reference's OrderBook object (jaxob/jorderbook.py): its own __main__ scenario (jorderbook.py:288-318) and the
+    query methods on a book driven by a random stream."""
+    import helpers as H
+    from gymnax_exchange.jaxob.jorderbook import OrderBook
+    from gymnax_exchange.jaxob.jaxob_config import JAXLOB_Configuration
+    from jaxmarl_hft_b200 import config as C
+    ob = OrderBook(JAXLOB_Configuration(maxint=2147483647, nOrders=64, nTrades=32))
+    l2init = np.array([354200, 452, 350100, 89, 361200, 100, 344000, 400, 362900, 100, 343100, 100, 364000, 400, 338700, 100,
+                       371900, 1100, 337100, 1000, 372200, 100, 336400, 1000, 372300, 200, 336000, 300, 372800, 1000, 333600,
+                       1000, 374600, 1000, 332500, 100, 376700, 100, 331600, 100], np.int32)
+    rec = {"l2init": l2init, "no": np.int64(64), "nt": np.int64(32)}
+
+    def put(prefix, st):
+        rec[prefix + "asks"], rec[prefix + "bids"], rec[prefix + "trades"] = _np(st.asks), _np(st.bids), _np(st.trades)
+
+    state = ob.reset(jnp.asarray(l2init))
+    put("reset/", state)
+    quote = {"type": "limit", "side": "bid", "quantity": 99, "price": 346000, "trade_id": 8888, "order_id": 8888,
+             "timestamp": "3400.005000000"}
+    put("dict/", ob.process_order(state, quote))
+    put("market/", ob.process_order(state, dict(quote, type="market", price=355000, quantity=500)))
+    put("cancel/", ob.process_order(state, dict(quote, type="cancel", price=344000, quantity=150, order_id=-5)))
+    msgs2 = np.array([[1, 1, 99, 346000, 8888, 8888, 3400, 5000000], [1, -1, 2, 346000, 8777, 8777, 3401, 5060000]], np.int32)
+    put("one/", ob.process_order_array(state, jnp.asarray(msgs2[0])))
+    st2, l2s = ob.process_orders_array_l2(state, jnp.asarray(msgs2), 10)
+    put("two/", st2)
+    rec["two/l2"] = _np(l2s)
+    rec["q/vol_init"] = _np(ob.get_volume_at_price(state, 1, 344000, True))
+    rec["q/vol"] = _np(ob.get_volume_at_price(st2, 1, 346000, False))
+    rec["q/next_bid"], rec["q/next_ask"] = _np(ob.get_next_executable_order(state, 1)), _np(ob.get_next_executable_order(state, 0))
+    rec["q/best_bid"], rec["q/best_ask"] = _np(ob.get_best_price(state, 1)), _np(ob.get_best_price(state, 0))
+    ba, bb = ob.get_best_bid_and_ask_inclQuants(state)
+    rec["q/best_ask_q"], rec["q/best_bid_q"] = _np(ba), _np(bb)
+    # a livelier book: a random stream on top
+    bc = C.book_config(C.World_EnvironmentConfig(nOrders=64, nTrades=32))
+    stream = H.random_messages(np.random.default_rng(31), 500, bc, price_lo=340_000, price_hi=365_000, tick=100)
+    rec["stream"] = stream
+    st3 = ob.process_orders_array(state, jnp.asarray(stream))
+    put("stream/", st3)
+    rec["stream/l2"] = _np(ob.get_L2_state(st3, 7))
+    for side in (0, 1):
+        arr = _np(st3.bids if side == 1 else st3.asks)
+        rec[f"stream/ids{side}"] = _np(ob.get_side_ids(st3, side))
+        live = arr[arr[:, 0] != -1]
+        probe = [int(live[0, 2]), int(live[-1, 2]), 123456789]                 # two present ids, one absent
+        rec[f"stream/probe_ids{side}"] = np.array(probe, np.int64)
+        rec[f"stream/order{side}"] = np.stack([_np(ob.get_order(st3, side, i)) for i in probe])
+        rec[f"stream/order_p{side}"] = np.stack([_np(ob.get_order(st3, side, i, int(live[0, 0]))) for i in probe])
+        times = [(int(live[0, 4]), int(live[0, 5])), (int(live[-1, 4]), int(live[-1, 5])), (1, 2)]
+        rec[f"stream/probe_times{side}"] = np.array(times, np.int64)
+        rec[f"stream/at_time{side}"] = np.stack([_np(ob.get_order_at_time(st3, side, a, b)) for a, b in times])
+        rec[f"stream/at_time_p{side}"] = np.stack([_np(ob.get_order_at_time(st3, side, a, b, int(live[-1, 0]))) for a, b in times])
+        rec[f"stream/next{side}"] = _np(ob.get_next_executable_order(st3, side))
+        rec[f"stream/vol{side}"] = np.array([int(_np(ob.get_volume_at_price(st3, side, int(p), False))) for p in live[:5, 0]], np.int64)
+        rec[f"stream/vol_prices{side}"] = live[:5, 0].astype(np.int64)
+    path = os.path.join(out_dir, f"{name}.npz")
+    np.savez_compressed(path, **rec)
+    print("wrote", path, os.path.getsize(path) // 1024, "KiB")
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["replay", "env"]
     if "replay" in which:
@@ -325,6 +386,8 @@ if __name__ == "__main__":
     if "replay_adv" in which:
         run_replay_case("replay_adversarial", seed=15, B=6, T=400, no=24, nt=12, t4=0, fill=True, adversarial=True)
         run_replay_case("replay_adversarial_100", seed=16, B=4, T=500, no=100, nt=100, t4=1, fill=True, adversarial=True)
+    if "orderbook" in which:
+        run_orderbook_case()
     if "replay_cnl" in which:
         run_replay_case("replay_cancel_uniform", seed=17, B=6, T=400, no=24, nt=12, t4=0, fill=True, cancel_mode=2)
         run_replay_case("replay_cancel_uniform_large", seed=18, B=6, T=500, no=100, nt=100, t4=0, fill=True, cancel_mode=3)
