@@ -314,6 +314,47 @@ class MARLEnv:
                 post(out)
         return g, out
 
+    def capture_rollout(self, state: MultiAgentState, policy, n_steps: int, params: MultiAgentParams = None):
+        """``n_steps`` env steps with the policy in between as ONE CUDA graph -- the ``jit(lax.scan(vmap(env.step)))`` of
+        the trainer / Speed_test.py (ippo_rnn_JAXMARL.py:616-661, Speed_test.py:185-224) with the state resident in HBM
+        for the whole rollout.  ``policy(t, obs) -> list of int32 action tensors`` is called while capturing, so it must
+        consist of capturable device work (torch ops, e.g. a network forward + sampling with a CUDA generator).
+        Returns (graph, traj) with ``traj = {"obs": [list per type of [T,B,n_i,d_i]], "reward": [...[T,B,n_i]],
+        "done": [T,B] uint8, "done_agents": [...[T,B,n_i]]}``: step t's outputs land in row t on every replay."""
+        import torch
+        T = self.cfg.n_agent_types
+        arrays = state.arrays
+        B = self.num_envs
+        traj = {"obs": [torch.empty((n_steps,) + tuple(arrays[f"obs{t}"].shape), dtype=torch.float32, device=self.device)
+                        for t in range(T)],
+                "reward": [torch.empty((n_steps,) + tuple(arrays[f"reward{t}"].shape), dtype=torch.float32,
+                                       device=self.device) for t in range(T)],
+                "done_agents": [torch.empty((n_steps,) + tuple(arrays[f"done_agents{t}"].shape), dtype=torch.uint8,
+                                            device=self.device) for t in range(T)],
+                "done": torch.empty((n_steps, B), dtype=torch.uint8, device=self.device)}
+
+        def body(steps):
+            obs = [arrays[f"obs{t}"] for t in range(T)]
+            for k in range(steps):
+                acts = policy(k, obs)
+                obs, _, rewards, dones, _ = self.step(None, state, acts, params)
+                for t in range(T):
+                    traj["obs"][t][k].copy_(obs[t])
+                    traj["reward"][t][k].copy_(rewards[t])
+                    traj["done_agents"][t][k].copy_(arrays[f"done_agents{t}"])
+                traj["done"][k].copy_(arrays["done_all"])
+
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            body(1)                                       # warm-up outside capture: runs ONE step
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            body(n_steps)
+        return g, traj
+
     def unpack_info(self, arrays):
         """Packed info columns -> the reference's dict keys (marl:624-639, mm:2695-2730, exe:1809-1829)."""
         wi, wf = arrays["info_world_i32"], arrays["info_world_f32"]

@@ -154,3 +154,38 @@ def test_marl_env_random_cancel_mode_draws():
         seen.append(u)
     assert not torch.equal(seen[0], seen[1]) and not torch.equal(seen[1], seen[2])
     assert 0.45 < float(seen[0].mean()) < 0.55
+
+
+def test_capture_rollout_graph_equals_eager_steps():
+    """MARLEnv.capture_rollout: T steps + policy as one graph == T eager steps of a twin env (same seed, same policy)."""
+    import torch
+    mac = H.load_mac("2_player_fq_fqc")
+    ld = H.load_for(mac, H.small_day(n_events=30000))
+    B, T = 96, 8
+    envs = [E.MARLEnv(None, mac, num_envs=B, loaded=ld, device="cuda:0", seed=4) for _ in range(2)]
+    params = [e.default_params for e in envs]
+    states_ = [e.reset(None, p)[1] for e, p in zip(envs, params)]
+    n = [sp.n for sp in envs[0].action_spaces]
+
+    def policy(k, obs):    # a deterministic function of the observation: capturable device work only
+        return [((obs[t].abs().sum(-1) * 1000.0).to(torch.int64) % n[t]).to(torch.int32) for t in range(2)]
+
+    graph, traj = envs[0].capture_rollout(states_[0], policy, T, params[0])          # warm-up ran ONE step
+    obs1 = [states_[1].arrays[f"obs{t}"] for t in range(2)]
+    envs[1].step(None, states_[1], policy(0, obs1), params[1])
+    graph.replay()
+    ref = {"obs": [[], []], "reward": [[], []], "done": []}
+    for k in range(T):
+        o, _, r, d, _ = envs[1].step(None, states_[1], policy(k, obs1), params[1])
+        for t in range(2):
+            ref["obs"][t].append(o[t].clone()); ref["reward"][t].append(r[t].clone())
+        ref["done"].append(d["__all__"].clone())
+    torch.cuda.synchronize()
+    for t in range(2):
+        assert torch.equal(traj["obs"][t], torch.stack(ref["obs"][t]))
+        assert torch.equal(traj["reward"][t], torch.stack(ref["reward"][t]))
+    assert torch.equal(traj["done"].bool(), torch.stack(ref["done"]))
+    a, b = H.to_numpy(states_[0].arrays), H.to_numpy(states_[1].arrays)
+    for k in a:
+        np.testing.assert_array_equal(a[k], b[k], err_msg=k)
+    assert int(a["step_counter"].max()) == T + 1
