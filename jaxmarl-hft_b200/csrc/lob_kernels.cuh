@@ -277,34 +277,70 @@ __device__ __noinline__ void reset_env(const LobStepConfig& c, const LobStepBuff
 // fill (marl:723-749) done online.  A function of its own so that the hot loop gets its own register allocation:
 // nothing of the surrounding step (world scalars, agent bookkeeping) is live in it.
 struct ScanOut { float avg_sum, sum_a, sum_b; int prev_a, prev_b, abort_episode; };
+
+// marl:723-749 _ffill_best_prices for the 32 messages held one per lane: a price of -1 takes the last valid price before
+// it (carry = the last valid price of the previous messages / of the previous step) and its quantity becomes 0.
+__device__ __forceinline__ void ffill32(int& price, int& qty, int& carry, bool in_range, int last_lane) {
+  const int lane = lane_id();
+  const bool ok = in_range && price != -1;
+  int src = ok ? lane : -1;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int t = __shfl_up_sync(kFull, src, d);
+    if (lane >= d) src = max(src, t);
+  }
+  const int filled = __shfl_sync(kFull, price, max(src, 0));
+  qty = ok ? qty : 0;
+  price = (src >= 0) ? filled : carry;
+  carry = __shfl_sync(kFull, price, last_lane);
+}
+
 template <int SLOTS>
-__device__ __noinline__ ScanOut scan_messages(BookCtx ctx, const int4* m4, int N, int* best_asks, int* best_bids,
+__device__ __noinline__ ScanOut scan_messages(BookCtx ctx, int* msgs, int N, int* best_asks, int* best_bids,
                                               int prev_a, int prev_b) {
   Book<SLOTS> bk;
   bk.c = ctx;
   bk.scan_side(ASK);
   bk.scan_side(BID);
   bk.ntr = 0; bk.tr_odd = false;   // the trade log was re-initialised for this step
-  ScanOut o;
-  o.avg_sum = 0.f; o.sum_a = 0.f; o.sum_b = 0.f; o.abort_episode = 0;
   const int lane = lane_id();
-  int2* gq = reinterpret_cast<int2*>(lane == 0 ? best_asks : best_bids);
+  int4* m4 = reinterpret_cast<int4*>(msgs);
+  // ---- the sequential part: one message after the other.  The raw best pair after message i (job:792-823) is parked
+  //      in the first 16 bytes of the message's own shared-memory slot, which is dead once the message is processed ----
 #pragma unroll 1
   for (int i = 0; i < N; ++i) {
     bk.c.mi = i;
     bk.process(m4[2 * i], m4[2 * i + 1]);
-    bk.ensure(ASK);
-    bk.ensure(BID);
-    int ap = bk.bestp[ASK], aq = bk.bestq[ASK], bp = bk.bestp[BID], bq = bk.bestq[BID];
-    o.abort_episode |= (ap == -1) | (bp == -1);
-    if (ap == -1) { ap = prev_a; aq = 0; }      // marl:723-749 _ffill_best_prices, online
-    if (bp == -1) { bp = prev_b; bq = 0; }
-    prev_a = ap; prev_b = bp;
-    o.avg_sum += (float)(bp + ap) / 2.0f;
-    o.sum_a += (float)ap; o.sum_b += (float)bp;
-    if (lane < 2) gq[i] = (lane == 0) ? make_int2(ap, aq) : make_int2(bp, bq);
+    if (!(bk.valid[ASK] & bk.valid[BID])) { bk.ensure(ASK); bk.ensure(BID); }
+    if (lane == 0) m4[2 * i] = make_int4(bk.bestp[ASK], bk.bestq[ASK], bk.bestp[BID], bk.bestq[BID]);
   }
   __syncwarp();
+  // ---- the data-parallel part, 32 messages at a time: abort flag, forward fill, means, the [N,2] state rows ----
+  ScanOut o;
+  o.avg_sum = 0.f; o.abort_episode = 0;
+  float pa = 0.f, pb = 0.f;
+  int2* ga = reinterpret_cast<int2*>(best_asks);
+  int2* gb = reinterpret_cast<int2*>(best_bids);
+#pragma unroll 1
+  for (int base = 0; base < N; base += 32) {
+    const int i = base + lane;
+    const bool in = i < N;
+    int4 v = make_int4(-1, 0, -1, 0);
+    if (in) v = m4[2 * i];
+    o.abort_episode |= in & ((v.x == -1) | (v.z == -1));
+    const int last_lane = min(31, N - 1 - base);
+    ffill32(v.x, v.y, prev_a, in, last_lane);
+    ffill32(v.z, v.w, prev_b, in, last_lane);
+    if (in) {
+      ga[i] = make_int2(v.x, v.y); gb[i] = make_int2(v.z, v.w);   // marl:363-364
+      pa += (float)v.x; pb += (float)v.z;                           // lane-interleaved partial sums (wsumf order)
+    }
+    const float mid = in ? (float)(v.z + v.x) / 2.0f : 0.0f;
+#pragma unroll 8
+    for (int l = 0; l < 32; ++l) o.avg_sum += __shfl_sync(kFull, mid, l);   // left to right in message order
+  }
+  o.abort_episode = __any_sync(kFull, o.abort_episode != 0);
+  o.sum_a = wsumf(pa); o.sum_b = wsumf(pb);
   o.prev_a = prev_a; o.prev_b = prev_b;
   return o;
 }
@@ -459,7 +495,7 @@ lob_step_kernel(const __grid_constant__ LobStepConfig c, const __grid_constant__
 
     // =================================================== phase 2: the message scan ===============================
     if (active) {
-      const ScanOut so2 = scan_messages<SLOTS>(bk.c, reinterpret_cast<const int4*>(msgs), N, b.best_asks + e * N * 2,
+      const ScanOut so2 = scan_messages<SLOTS>(bk.c, msgs, N, b.best_asks + e * N * 2,
                                                b.best_bids + e * N * 2, w.old_ba_last, w.old_bb_last);
       avg_sum = so2.avg_sum; sum_a = so2.sum_a; sum_b = so2.sum_b;
       prev_a = so2.prev_a; prev_b = so2.prev_b; abort_episode = so2.abort_episode != 0;

@@ -31,8 +31,9 @@
  *     trade log use ONE fixed order, shared bit for bit with the CUDA path:
  *     row r is accumulated into partial sum r % 32 in increasing r, then the
  *     32 partial sums are combined by a butterfly (xor 16, 8, 4, 2, 1) --
- *     wsumf() below.  The per-message mid-price / best-price means are summed
- *     left-to-right in message order.
+ *     wsumf() below (trade log rows; the per-message best-price means of the
+ *     world info with "row" = message index).  The per-message mid-price mean is
+ *     summed left-to-right in message order.
  * Compile: gcc -O2 -fwrapv -ffp-contract=off -fno-fast-math (see Makefile).
  */
 #include <math.h>
@@ -99,6 +100,22 @@ static float wsumf(const float* term, int n) {
     for (int l = 0; l < 32; ++l) acc[l] = nxt[l];
   }
   return acc[0];
+}
+
+/* The per-message best ask / bid means of the world info (marl:629-630) in the wsumf order ("row" = message index).
+ * N <= LOB_ORACLE_MAX_N is checked by check_cfg. */
+#define LOB_ORACLE_MAX_N 4096
+static float mean_col0(const int32_t* pq /* [N][2] */, int N) {
+  float t[LOB_ORACLE_MAX_N];
+  for (int i = 0; i < N; ++i) t[i] = (float)pq[i * 2];
+  return wsumf(t, N) / (float)N;
+}
+/* The mid-price mean feeds rewards that multiply its error by quantity / tick, so its order is kept the one the golden
+ * vectors were produced with: left to right in message order. */
+static float mean_mid(const int32_t* bestasks, const int32_t* bestbids, int N) {
+  float avg_sum = 0.f;
+  for (int i = 0; i < N; ++i) avg_sum += (float)(bestbids[i * 2] + bestasks[i * 2]) / 2.0f;
+  return avg_sum / (float)N;
 }
 
 /* --------------------------------------------------------- order book core */
@@ -781,9 +798,7 @@ static float mm_get_reward(const LobStepConfig* c, const LobAgentTypeConfig* ac,
   extract_agent_trade_stats(trades, nt, tid, &s);
   int32_t buyQuant = sum_abs_q(s.agent_buys, nt), sellQuant = sum_abs_q(s.agent_sells, nt);
   int32_t inv_before = st->inventory + buyQuant - sellQuant;
-  float avg_sum = 0.f;
-  for (int i = 0; i < N; ++i) avg_sum += (float)(bestbids[i * 2] + bestasks[i * 2]) / 2.0f;
-  float averageMidprice = avg_sum / (float)N;
+  float averageMidprice = mean_mid(bestasks, bestbids, N);
   const int32_t bb_last = bestbids[(N - 1) * 2], ba_last = bestasks[(N - 1) * 2];
   float last_mid_price = (float)(bb_last + ba_last) / 2.0f;
 
@@ -1116,9 +1131,7 @@ static float exe_get_reward(const LobStepConfig* c, const LobAgentTypeConfig* ac
   int32_t quant_executed_this_step = iabs32(qsum);
   int32_t quant_left = st->task_to_execute - (st->quant_executed + quant_executed_this_step);
   int32_t penalty = ac->doom_price_penalty * tick;
-  float avg_sum = 0.f;
-  for (int i = 0; i < N; ++i) avg_sum += (float)(bestbids[i * 2] + bestasks[i * 2]) / 2.0f;
-  float averageMidprice = avg_sum / (float)N;
+  float averageMidprice = mean_mid(bestasks, bestbids, N);
   int32_t side_sign = st->is_sell_task * 2 - 1;
   int32_t reference_price;
   if (ac->reference_price == LOB_REF_MID) { /* exe:1564-1569 */
@@ -1562,15 +1575,13 @@ static void step_one(const LobStepConfig* c, const LobStepBuffers* b, int64_t e,
   b->done_all[e] = (uint8_t)ep_done;
 
   /* world info marl:618-639 */
-  float sa = 0.f, sb = 0.f;
-  for (int i = 0; i < N; ++i) { sa += (float)new_bestasks[i * 2]; sb += (float)new_bestbids[i * 2]; }
   int32_t* wi = b->info_world_i32 + e * LOB_WINFO_I32_COLS;
   float* wf = b->info_world_f32 + e * LOB_WINFO_F32_COLS;
   wi[0] = nw.window_index; wi[1] = nw.step_counter; wi[2] = nw.time[0]; wi[3] = nw.time[1];
   wi[4] = nw.order_id_counter; wi[5] = new_bestasks[(N - 1) * 2]; wi[6] = new_bestbids[(N - 1) * 2];
   wi[7] = nw.step_counter; wi[8] = ep_done; wi[9] = abort_episode;
   wi[10] = new_bestasks[(N - 1) * 2] - new_bestbids[(N - 1) * 2];
-  wf[0] = nw.mid_price; wf[1] = sa / (float)N; wf[2] = sb / (float)N; wf[3] = nw.delta_time;
+  wf[0] = nw.mid_price; wf[1] = mean_col0(new_bestasks, N); wf[2] = mean_col0(new_bestbids, N); wf[3] = nw.delta_time;
 
   if (ep_done) { /* marl:787-803 auto-reset: every state leaf and the obs are replaced */
     reset_one(c, b, e);
@@ -1603,6 +1614,7 @@ static int check_cfg(const LobStepConfig* c) {
     if (a->kind == LOB_AGENT_MM && a->sell_buy_all_option) return LOB_E_UNSUPPORTED;
   }
   if (total > 64) return LOB_E_INVALID;
+  if (lob_num_msgs_per_step(c) > LOB_ORACLE_MAX_N) return LOB_E_INVALID;
   return LOB_OK;
 }
 
