@@ -352,9 +352,15 @@ struct Book {
   int nneg[2];        // rows with price < 0
   int bestp[2], bestq[2], bestn[2];
   bool valid[2];      // best* caches valid
-  bool odd[2];        // side holds rows the fast paths do not model: a non-blank row with qty <= 0, a -1 field or price < 0
+  // Reasons to take the literal generic path, one bit each (0 = every fast path applies):
+  //   bit ASK / BID: the side holds rows the fast paths do not model (a non-blank row with qty <= 0, a -1 field, price < 0)
+  //   bit 2: the trade rows after ntr are not all free -> the trade slot must be searched
+  //   bit 3: type-4 messages are MKT orders (Type4Interpretation.MKT): prices are rewritten, always generic
+  unsigned oddm;
+  static constexpr unsigned kOddTrades = 4u, kOddMkt = 8u;
   int ntr;            // next trade row: first row whose time_s column is -1
-  bool tr_odd;        // the rows after ntr are not all free -> the trade slot must be searched (generic path)
+  __device__ __forceinline__ bool odd(int s) const { return (oddm >> s) & 1u; }
+  __device__ __forceinline__ void set_bit(unsigned bit, bool on) { oddm = on ? (oddm | bit) : (oddm & ~bit); }
 
   __device__ __forceinline__ void init(const LobBookConfig& cfg, int* smem_book) {
     c.rows_off = (int)(smem_book - dyn_smem()); c.tr = nullptr; c.nrows = kRows;
@@ -362,6 +368,7 @@ struct Book {
     c.maxint = cfg.maxint; c.init_id = cfg.init_id; c.init_lo = cfg.init_id - 2 * cfg.book_depth;
     c.t4 = cfg.type_4_interpretation; c.check_fill = cfg.check_book_fill;
     c.cmode = cfg.cancel_mode; c.mi = 0; c.cu = nullptr;
+    oddm = (cfg.type_4_interpretation == 2) ? kOddMkt : 0u;
     // padding rows [no, kRows) of both sides are blank for the whole kernel
     for (int i = lane_id(); i < 2 * kRows * 6; i += 32) smem_book[i] = -1;
     __syncwarp();
@@ -393,17 +400,17 @@ struct Book {
   __device__ __forceinline__ void fill_trades_empty() {
     int4* d = reinterpret_cast<int4*>(c.tr);
     for (int i = lane_id(); i < c.nt * 2; i += 32) d[i] = make_int4(-1, -1, -1, -1);
-    ntr = 0; tr_odd = false;
+    ntr = 0; set_bit(kOddTrades, false);
   }
 
   // ---- derive the register-resident summaries from shared memory ----
   __device__ __forceinline__ void scan_side(int s) {
     const SideScan r = g_scan_side(c, s);
-    flag[s] = r.flag; nneg[s] = r.nneg; odd[s] = r.odd != 0; valid[s] = false;
+    flag[s] = r.flag; nneg[s] = r.nneg; set_bit(1u << s, r.odd != 0); valid[s] = false;
   }
   __device__ __forceinline__ void scan_trades() {
     const TradeScan t = g_scan_trades(c);
-    ntr = t.ntr; tr_odd = t.odd != 0;
+    ntr = t.ntr; set_bit(kOddTrades, t.odd != 0);
   }
   __device__ __forceinline__ void rescan() { scan_side(ASK); scan_side(BID); scan_trades(); }
 
@@ -431,7 +438,7 @@ struct Book {
     return b;
   }
   __device__ __forceinline__ void recompute(int s) {
-    const Best b = odd[s] ? g_best(c, s) : best_scan(c.rows_off + s * kRows * 6, s == BID, c.maxint, nneg[s]);
+    const Best b = odd(s) ? g_best(c, s) : best_scan(c.rows_off + s * kRows * 6, s == BID, c.maxint, nneg[s]);
     bestp[s] = b.p; bestq[s] = b.q; bestn[s] = b.n; valid[s] = true;
   }
   __device__ __forceinline__ void ensure(int s) { if (!valid[s]) recompute(s); }
@@ -550,9 +557,9 @@ struct Book {
     if (m.type == 4 && c.t4 != 1) return;   // IOC remainder dropped, eviction kept
     const int q = max(0, qtm);
     const int r = first_flagged(OWN);
-    if (q == 0 && r != kBig && !odd[OWN]) return;   // written into a blank row and blanked again (job:83): no-op
+    if (q == 0 && r != kBig && !odd(OWN)) return;   // written into a blank row and blanked again (job:83): no-op
     const bool neg1 = (m.price == -1) | (m.oid == -1) | (m.tid == -1) | (m.ts == -1) | (m.tns == -1);
-    if (q == 0 || r == kBig || odd[OWN] || neg1 || m.price <= 0 || m.price == c.maxint) {   // (an ask AT maxint reads as "empty", job:940)
+    if (q == 0 || r == kBig || odd(OWN) || neg1 || m.price <= 0 || m.price == c.maxint) {   // (an ask AT maxint reads as "empty", job:940)
       Msg a = m;
       a.qty = qtm;
       __syncwarp();
@@ -624,13 +631,23 @@ struct Book {
     m.type = lo.x; m.side = (lo.x == 4) ? -lo.y : lo.y; m.qty = lo.z; m.price = lo.w;
     m.oid = hi.x; m.tid = hi.y; m.ts = hi.z; m.tns = hi.w;
     const int s = m.side, t = m.type;
-    if (s == 0 && t == 0) return;                          // doNothing
-    if (odd[ASK] | odd[BID] | tr_odd | (c.t4 == 2)) { generic(m); return; }
-    const bool lim = (t == 1) | (t == 4), cnl = (t == 2) | (t == 3);
-    if (cnl & (s == -1)) cancel<ASK>(m);
-    else if (cnl & (s == 1)) cancel<BID>(m);
-    else if (lim & (s == 1)) limit<BID>(m);
-    else limit<ASK>(m);                                    // index 0 is also the lax.switch target of every other (type, side)
+    if (oddm) {                                            // (the generic path has its own doNothing)
+      if (s == 0 && t == 0) return;
+      generic(m);
+      return;
+    }
+    // index = 0 ask_lim | 1 bid_lim | 2 ask_cancel | 3 bid_cancel | 4 doNothing (job:588-596); every other (type, side)
+    // is index 0.  Tested in the order of the frequent cases.
+    const bool cnl = (unsigned)(t - 2) <= 1u;
+    bool ask_lim = true;
+    if (s == 1) {
+      if (cnl) { cancel<BID>(m); ask_lim = false; }
+      else if ((t == 1) | (t == 4)) { limit<BID>(m); ask_lim = false; }
+    } else if (cnl & (s == -1)) { cancel<ASK>(m); ask_lim = false; }
+    if (ask_lim) {
+      if (s == 0 && t == 0) return;                        // doNothing
+      limit<ASK>(m);
+    }
     __syncwarp();
   }
 };

@@ -300,9 +300,10 @@ __device__ __noinline__ ScanOut scan_messages(BookCtx ctx, int* msgs, int N, int
                                               int prev_a, int prev_b) {
   Book<SLOTS> bk;
   bk.c = ctx;
+  bk.oddm = (ctx.t4 == 2) ? Book<SLOTS>::kOddMkt : 0u;
   bk.scan_side(ASK);
   bk.scan_side(BID);
-  bk.ntr = 0; bk.tr_odd = false;   // the trade log was re-initialised for this step
+  bk.ntr = 0;                      // the trade log was re-initialised for this step (bit kOddTrades stays clear)
   const int lane = lane_id();
   int4* m4 = reinterpret_cast<int4*>(msgs);
   // ---- the sequential part: one message after the other.  The raw best pair after message i (job:792-823) is parked
