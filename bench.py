@@ -353,6 +353,46 @@ def run_native(args):
     step_h2d = sum(a.numel() * 4 for a in acts_in)
     step_d2h = sum(h.numel() * h.element_size() for h in outs_h)
 
+    # ---- (3b) the other env.step configurations of BASELINE.json, kernel-only (same timing rules) ----
+    del env, state, obs, graph
+    others = []
+    for cfg_name, n_envs, label in (("exec_longrun_fixed_quants_complex", 8192, "BASELINE configs[2]: single execution agent"),
+                                    ("hetero_deep_book", 16384, "BASELINE configs[4] shapes: 3 MM + 2 EXE + 2 directional, "
+                                                                "512-row sides, 256-row trade log (131072 envs / 8 GPUs)")):
+        mac2 = H.load_mac(cfg_name)
+        ld2 = ld if mac2.world_config.n_data_msg_per_step == ND and mac2.world_config.episode_time == mac.world_config.episode_time else _load_day(mac2)
+        env2 = E.MARLEnv(None, mac2, num_envs=n_envs, loaded=ld2, device=dev, seed=77 + rank)
+        p2 = env2.default_params
+        _, st2 = env2.reset(None, p2)
+        T2 = env2.cfg.n_agent_types
+        g2 = torch.Generator(device=dev); g2.manual_seed(5 + rank)
+        a2 = [torch.randint(0, env2.action_spaces[t].n, (n_envs, env2.cfg.agent[t].n_agents), generator=g2, device=dev,
+                            dtype=torch.int32) for t in range(T2)]
+        for k in range(Wm):
+            env2.step(None, st2, a2, p2)
+        bufs2 = states.pack_buffers(env2.cfg, st2.arrays, env2.base_env.device_params())
+        barrier()
+        x0, x1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        x0.record()
+        for k in range(K):
+            _lib.check(L.lob_step_launch(ctypes.byref(env2.cfg), ctypes.byref(bufs2), n_envs, stream), "lob_step_launch")
+        x1.record()
+        barrier()
+        ms2 = max_over_ranks(x0.elapsed_time(x1))
+        No2, Nt2, N2 = env2.cfg.book.n_orders, env2.cfg.book.n_trades, env2.num_msgs_per_step
+        nmm = sum(env2.cfg.agent[t].n_agents for t in range(T2) if env2.cfg.agent[t].kind == 0)
+        nex = sum(env2.cfg.agent[t].n_agents for t in range(T2) if env2.cfg.agent[t].kind == 1)
+        dob = sum(env2.cfg.agent[t].n_agents * env2.observation_spaces[t].shape[0] for t in range(T2))
+        sr = 64 + 20 * nmm + 52 * nex + 4 * (nmm + nex) + 4 * env2.num_action_msgs_per_step_by_all_agents
+        sw = 64 + 20 * nmm + 52 * nex + 4 * dob + 5 * (nmm + nex) + 1 + 4 * (15 + 24 * nmm + 9 * nex)
+        by2 = (2 * No2 * 24 + env2.cfg.n_data_msg_per_step * 32 + sr) + (2 * No2 * 24 + Nt2 * 32 + 2 * N2 * 8 + sw)
+        v2 = ws * n_envs * K / (ms2 * 1e-3)
+        others.append({"workload": f"MARLEnv.step {cfg_name} ({label})", "envs_per_gpu": n_envs, "msgs_per_env_step": N2,
+                       "value": v2, "unit": "env-steps/s", "msgs_per_sec": v2 * N2, "ms_per_step": ms2 / K,
+                       "algorithmic_bytes_per_env_step": by2,
+                       "roofline_frac": by2 * n_envs * K / (ms2 * 1e-3) / 1e9 / hbm_peak / 1.0})
+        del env2, st2, bufs2
+
     # ---- (4) CPU baseline beside it (rank 0, N=1): the oracle on a bounded sample of the replay workload ----
     cpu = None
     if rank == 0 and ws == 1 and not args.no_cpu:
@@ -409,10 +449,10 @@ def run_native(args):
         }
         if cpu is not None:
             out["cpu_baseline"] = cpu
-        return json.dumps(out)
-    return None
+        out["other_configs"] = others
     if ws > 1:
         dist.destroy_process_group()
+    return json.dumps(out) if rank == 0 else None
 
 
 def main():
