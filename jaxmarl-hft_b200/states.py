@@ -119,6 +119,28 @@ def pack_buffers(cfg: abi.LobStepConfig, arrays: dict, params: dict) -> abi.LobS
     return b
 
 
+def field_offset(cfg: abi.LobStepConfig, name: str) -> int:
+    """Byte offset, inside ``LobStepBuffers``, of the pointer field that the leaf ``name`` (a ``leaf_specs`` or ``PARAMS``
+    name) fills -- the table a table-driven binding (the XLA-FFI handler) passes next to its operands."""
+    import re
+    F, P = abi.LobStepBuffers, C.sizeof(C.c_void_p)
+    if name in WORLD_I32 or name in WORLD_F32 or name in PARAMS or name in (
+            "perm", "reset_window", "reset_is_sell", "cancel_u", "done_all", "info_world_i32", "info_world_f32"):
+        return getattr(F, name).offset
+    m = re.fullmatch(r"a(\d+)_(\w+)", name)
+    if m:
+        t, leaf = int(m.group(1)), m.group(2)
+        li, lf = abi.state_leaves(cfg.agent[t].kind)
+        if leaf in li:
+            return F.agent_i32.offset + (t * abi.LOB_MAX_AGENT_I32 + li.index(leaf)) * P
+        return F.agent_f32.offset + (t * abi.LOB_MAX_AGENT_F32 + lf.index(leaf)) * P
+    m = re.fullmatch(r"(actions|obs|reward|done_agents|info_i32_|info_f32_)(\d+)", name)
+    if not m:
+        raise KeyError(name)
+    field = {"info_i32_": "info_agent_i32", "info_f32_": "info_agent_f32"}.get(m.group(1), m.group(1))
+    return getattr(F, field).offset + int(m.group(2)) * P
+
+
 def pack_replay(asks, bids, trades, msgs, start, n_msgs, best_out=None, cancel_u=None) -> abi.LobReplayBuffers:
     r = abi.LobReplayBuffers()
     r.asks, r.bids, r.trades = _ptr(asks, C.c_int32), _ptr(bids, C.c_int32), _ptr(trades, C.c_int32)

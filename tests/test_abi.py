@@ -1,6 +1,7 @@
 """The C-ABI library (csrc/liblobstep.so) without a GPU: it loads, exports every symbol include/lobstep.h declares, its
 structs match the ctypes mirror, and its host-side validation rejects bad calls before touching the device."""
 import ctypes as C
+import numpy as np
 import os
 import re
 
@@ -111,3 +112,22 @@ def test_shipped_reference_env_configs_lower():
         except NotImplementedError:
             bad.append(os.path.basename(f))
     assert bad == ["exec_discrete_steps.json"] and len(ok) == 11
+
+
+def test_field_offsets_agree_with_pack_buffers():
+    """states.field_offset (the table of the table-driven XLA-FFI binding) against states.pack_buffers:
+    storing each leaf's address at its offset reproduces the packed struct byte for byte."""
+    from jaxmarl_hft_b200 import states
+    mac = H.load_mac("hetero_deep_book", cancel_mode=3)
+    cfg = Cfg.to_step_config(mac, 6, 30000)
+    arrays = states.alloc_numpy(cfg, 3)
+    params = {k: np.zeros(8, np.int32) for k in states.PARAMS}
+    packed = states.pack_buffers(cfg, arrays, params)
+    mine = abi.LobStepBuffers()
+    raw = (C.c_char * C.sizeof(mine)).from_address(C.addressof(mine))
+    for name, arr in list(arrays.items()) + list(params.items()):
+        off = states.field_offset(cfg, name)
+        C.c_void_p.from_address(C.addressof(mine) + off).value = arr.ctypes.data
+    assert bytes(raw) == bytes((C.c_char * C.sizeof(packed)).from_address(C.addressof(packed)))
+    with pytest.raises(KeyError):
+        states.field_offset(cfg, "nonsense")
