@@ -113,7 +113,7 @@ typedef struct LobAgentTypeConfig {
   /* market making */
   int32_t n_ticks_offset;
   int32_t tenth_action_market_order;    /* tenth_action == "MarketOrder" */
-  int32_t sell_buy_all_option;          /* only 0 supported */
+  int32_t sell_buy_all_option;          /* mm_env.py:1018-1024 (fixed_quants), :1144-1172 (simple) */
   int32_t fixed_action_setting;
   int32_t fixed_action;
   int32_t auto_liquidate_threshold;

@@ -270,8 +270,7 @@ def agent_type_config(cfg, n_agents: int, trader_id_start: int) -> abi.LobAgentT
         if cfg.action_space in ("bobRL", "bobStrategy") and cfg.bob_v0 not in _BOB_RL_ACTIONS and cfg.action_space == "bobRL":
             raise ValueError("cfg.bob_v0 must be one of [1,2,5,10]")  # mm:1522
         a.tenth_action_market_order = int(cfg.tenth_action == "MarketOrder")
-        if cfg.sell_buy_all_option:
-            raise NotImplementedError("sell_buy_all_option=True (mm:1018-1024) is not built")
+        a.sell_buy_all_option = int(cfg.sell_buy_all_option)
         a.fixed_action_setting = int(cfg.fixed_action_setting)
         a.fixed_action = cfg.fixed_action
         a.auto_liquidate_threshold = cfg.auto_liquidate_threshold

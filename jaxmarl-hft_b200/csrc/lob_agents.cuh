@@ -211,13 +211,21 @@ static __device__ __noinline__ MMOut mm_get_messages(BookCtx bk, const LobStepCo
     if (ac.fixed_action_setting) action = ac.fixed_action;
     const int ai = clamp_index(action, 10);
     // bid/ask offset tables mm:1012-1015
-    const float bid_offset = (float)((0x0152043210ull >> (4 * ai)) & 0xf);   // {0,1,2,3,4,0,2,5,1,0}
-    const float ask_offset = (float)((0x0510243210ull >> (4 * ai)) & 0xf);   // {0,1,2,3,4,2,0,1,5,0}
+    float bid_offset = (float)((0x0152043210ull >> (4 * ai)) & 0xf);   // {0,1,2,3,4,0,2,5,1,0}
+    float ask_offset = (float)((0x0510243210ull >> (4 * ai)) & 0xf);   // {0,1,2,3,4,2,0,1,5,0}
     const int unit = (ai == 9) ? 0 : 1;
     const float tickf = (float)tick;
     float half_spread_prev = jmaxf((float)(best_ask - best_bid) / 2.0f, (float)((double)tick / 2.0));
     float half_spread = (ffloordiv(half_spread_prev, tickf) + 1.0f) * tickf;
     int bid_quant = unit * ac.fixed_quant_value, ask_quant = unit * ac.fixed_quant_value;
+    if (ac.sell_buy_all_option) {   // mm:1018-1024: 9-entry tables {10,2,4,-1,0,2,-20,0,0} / {10,2,4,-1,2,0,0,-20,0};
+      const int a9 = clamp_index(action, 9);   // actions 6 / 7 post the whole inventory
+      const int inv_units = ifloordiv(inventory, ac.fixed_quant_value);
+      bid_offset = (a9 == 0) ? 10.f : (a9 == 1 || a9 == 5) ? 2.f : (a9 == 2) ? 4.f : (a9 == 3) ? -1.f : (a9 == 6) ? -20.f : 0.f;
+      ask_offset = (a9 == 0) ? 10.f : (a9 == 1 || a9 == 4) ? 2.f : (a9 == 2) ? 4.f : (a9 == 3) ? -1.f : (a9 == 7) ? -20.f : 0.f;
+      bid_quant = ((a9 <= 5) ? 1 : (a9 == 6 ? inv_units : 0)) * ac.fixed_quant_value;
+      ask_quant = ((a9 <= 5) ? 1 : (a9 == 7 ? inv_units : 0)) * ac.fixed_quant_value;
+    }
     if (empty_book) { bid_quant = 0; ask_quant = 0; }
     float bid_price_f = (float)best_bid - bid_offset * half_spread;
     float ask_price_f = (float)best_ask + ask_offset * half_spread;
@@ -260,7 +268,7 @@ static __device__ __noinline__ MMOut mm_get_messages(BookCtx bk, const LobStepCo
     o.posted_bid_price = 0; o.posted_ask_price = 0; o.bid_dist = 0; o.ask_dist = 0;
     o.bid_quant = bid_quant; o.ask_quant = ask_quant;
   } else if (ac.action_space == LOB_MM_ACT_SIMPLE || ac.action_space == LOB_MM_ACT_SPREAD_SKEW) {
-    // mm:1123-1246 (sell_buy_all_option == False) / mm:1667-1808: quotes around the last forward-filled best prices
+    // mm:1123-1246 / mm:1667-1808: quotes around the last forward-filled best prices
     const float tickf = (float)tick;
     const int ba = ifloordiv(w.old_ba_last, tick) * tick, bb = ifloordiv(w.old_bb_last, tick) * tick;
     int bid_price, ask_price, bid_quant, ask_quant;
@@ -270,6 +278,12 @@ static __device__ __noinline__ MMOut mm_get_messages(BookCtx bk, const LobStepCo
       const float bid_offset = (ai == 1) ? -2000.f : 0.f, ask_offset = (ai == 2) ? -2000.f : 0.f;
       bid_quant = ((ai == 0 || ai == 1) ? 1 : 0) * ac.fixed_quant_value;
       ask_quant = ((ai == 0 || ai == 2) ? 1 : 0) * ac.fixed_quant_value;
+      if (ac.sell_buy_all_option) {   // mm:1144-1172: one-sided actions post max(|inventory|, fixed quant) on the flattening side
+        const int big = max(abs(inventory), ac.fixed_quant_value);
+        const int aq = (inventory > 0) ? big : ac.fixed_quant_value, bq = (inventory > 0) ? ac.fixed_quant_value : big;
+        bid_quant = (ai == 0) ? ac.fixed_quant_value : (ai == 1 ? bq : 0);
+        ask_quant = (ai == 0) ? ac.fixed_quant_value : (ai == 2 ? aq : 0);
+      }
       const float tick_offset = (float)(ac.n_ticks_offset * tick);
       const float bp = (float)bb - bid_offset * tick_offset, ap = (float)ba + ask_offset * tick_offset;
       bid_price = f2i(ffloordiv(jmaxf(bp, 0.f), tickf) * tickf);

@@ -72,7 +72,6 @@ int check_step_cfg(const LobStepConfig* c) {
           (a->bob_v0 < 1 || a->bob_v0 > 1000))
         return fail(LOB_E_INVALID, "agent[%d].bob_v0=%d", t, a->bob_v0);
       if (ka != 2) return fail(LOB_E_INVALID, "agent[%d]: MM action spaces built here post 2 messages", t);
-      if (a->sell_buy_all_option) return fail(LOB_E_UNSUPPORTED, "agent[%d]: sell_buy_all_option is not built", t);
       if (a->reward_function < 0 || a->reward_function > LOB_MM_REW_DELTA_PORTFOLIO_VALUE)
         return fail(LOB_E_INVALID, "agent[%d].reward_function=%d", t, a->reward_function);
     } else {

@@ -512,6 +512,14 @@ static void mm_action_fixed_quant(const LobStepConfig* c, const LobAgentTypeConf
   float bid_offset = bid_offsets[ai], ask_offset = ask_offsets[ai];
   int32_t bid_quant = quants_tab[ai] * ac->fixed_quant_value;
   int32_t ask_quant = quants_tab[ai] * ac->fixed_quant_value;
+  if (ac->sell_buy_all_option) { /* mm:1018-1024: 9-entry tables, actions 6 / 7 post the whole inventory */
+    static const float bo[9] = {10, 2, 4, -1, 0, 2, -20, 0, 0}, ao[9] = {10, 2, 4, -1, 2, 0, 0, -20, 0};
+    const int32_t inv_units = ifloordiv(st->inventory, ac->fixed_quant_value);
+    ai = clamp_index(action, 9);
+    bid_offset = bo[ai]; ask_offset = ao[ai];
+    bid_quant = ((ai <= 5) ? 1 : (ai == 6 ? inv_units : 0)) * ac->fixed_quant_value;
+    ask_quant = ((ai <= 5) ? 1 : (ai == 7 ? inv_units : 0)) * ac->fixed_quant_value;
+  }
   if (empty_book) { bid_quant = 0; ask_quant = 0; }
   float bid_price_f = (float)best_bid - bid_offset * half_spread;
   float ask_price_f = (float)best_ask + ask_offset * half_spread;
@@ -621,10 +629,10 @@ static void mm_action_bob(const LobStepConfig* c, const LobAgentTypeConfig* ac, 
 /* jnp.remainder on int32: sign follows the divisor */
 static inline int32_t imod(int32_t a, int32_t b) { int32_t r = a % b; if (r != 0 && ((r < 0) != (b < 0))) r += b; return r; }
 
-/* mm:1123-1246 _getActionMsgs_simple (sell_buy_all_option == False) and mm:1667-1808 _getActionMsgs_spread_skew: both
+/* mm:1123-1246 _getActionMsgs_simple and mm:1667-1808 _getActionMsgs_spread_skew: both
  * quote around the last forward-filled best prices of the world state */
 static void mm_action_simple_or_skew(const LobStepConfig* c, const LobAgentTypeConfig* ac, int32_t action, const World* w,
-                                     int32_t trader_id, int32_t* out, MMExtras* ex) {
+                                     const MMState* st, int32_t trader_id, int32_t* out, MMExtras* ex) {
   const int32_t tick = c->tick_size;
   const float tickf = (float)tick;
   const int N = lob_num_msgs_per_step(c);
@@ -638,6 +646,14 @@ static void mm_action_simple_or_skew(const LobStepConfig* c, const LobAgentTypeC
     const float bid_offset = (ai == 1) ? -2000.f : 0.f, ask_offset = (ai == 2) ? -2000.f : 0.f;
     bid_quant = ((ai == 0 || ai == 1) ? 1 : 0) * ac->fixed_quant_value;
     ask_quant = ((ai == 0 || ai == 2) ? 1 : 0) * ac->fixed_quant_value;
+    if (ac->sell_buy_all_option) { /* mm:1144-1172: the one-sided actions post max(|inventory|, fixed quant) on the
+                                      side that flattens the inventory */
+      const int32_t big = imax32(iabs32(st->inventory), ac->fixed_quant_value);
+      const int32_t aq = (st->inventory > 0) ? big : ac->fixed_quant_value;
+      const int32_t bq = (st->inventory > 0) ? ac->fixed_quant_value : big;
+      bid_quant = (ai == 0) ? ac->fixed_quant_value : (ai == 1 ? bq : 0);
+      ask_quant = (ai == 0) ? ac->fixed_quant_value : (ai == 2 ? aq : 0);
+    }
     const float tick_offset = (float)(ac->n_ticks_offset * tick);
     float bp = (float)best_bid - bid_offset * tick_offset;
     float ap = (float)best_ask + ask_offset * tick_offset;
@@ -725,7 +741,7 @@ static void mm_get_messages(const LobStepConfig* c, const LobAgentTypeConfig* ac
   if (ac->action_space == LOB_MM_ACT_FIXED_QUANTS) mm_action_fixed_quant(c, ac, action, w, st, trader_id, act, ex);
   else if (ac->action_space == LOB_MM_ACT_DIRECTIONAL) mm_action_directional(c, ac, action, w, trader_id, act, ex);
   else if (ac->action_space == LOB_MM_ACT_SIMPLE || ac->action_space == LOB_MM_ACT_SPREAD_SKEW)
-    mm_action_simple_or_skew(c, ac, action, w, trader_id, act, ex);
+    mm_action_simple_or_skew(c, ac, action, w, st, trader_id, act, ex);
   else if (ac->action_space == LOB_MM_ACT_AVST) mm_action_avst(c, ac, action, w, st, trader_id, act, ex);
   else mm_action_bob(c, ac, action, w, st, trader_id, act, ex);
   int sz = ac->num_messages_by_agent / 4;
@@ -1611,7 +1627,6 @@ static int check_cfg(const LobStepConfig* c) {
     total += a->n_agents;
     int kc = a->num_messages_by_agent - a->num_action_messages_by_agent;
     if (kc != a->num_action_messages_by_agent || kc > 16) return LOB_E_INVALID;
-    if (a->kind == LOB_AGENT_MM && a->sell_buy_all_option) return LOB_E_UNSUPPORTED;
   }
   if (total > 64) return LOB_E_INVALID;
   if (lob_num_msgs_per_step(c) > LOB_ORACLE_MAX_N) return LOB_E_INVALID;

@@ -190,7 +190,23 @@ def fixed_time_agents(mac):
                             number_of_agents_per_type=[1, 1, 2, 1])
 
 
-MUTATORS = {"fixed_time": fixed_time_agents, "fixed_prices": fixed_prices_agents, "simple_skew_avst": simple_skew_avst_agents, "hetero": hetero_agents, "mm_complex": mm_complex_agents, "bob_twap": bob_twap_agents,
+def sell_buy_all_agents(mac):
+    """sell_buy_all_option=True in the two action spaces that read it (mm_env.py:1018-1024, :1144-1172)."""
+    from gymnax_exchange.jaxob.jaxob_config import MultiAgentConfig
+    d = dict(mac.dict_of_agents_configs)
+    mm, ex = d["MarketMaking"], d["Execution"]
+    agents = {
+        "MarketMaking": dataclasses.replace(mm, sell_buy_all_option=True, fixed_quant_value=3, observation_space="engineered"),
+        "Simple": dataclasses.replace(mm, short_name="SI", action_space="simple", n_actions=4, sell_buy_all_option=True,
+                                      fixed_quant_value=2),
+        "Simple3": dataclasses.replace(mm, short_name="S3", action_space="simple", n_actions=3, simple_nothing_action=False,
+                                       sell_buy_all_option=True, fixed_quant_value=4),
+        "Execution": ex,
+    }
+    return MultiAgentConfig(world_config=mac.world_config, dict_of_agents_configs=agents, number_of_agents_per_type=[2, 1, 1, 1])
+
+
+MUTATORS = {"sell_buy_all": sell_buy_all_agents, "fixed_time": fixed_time_agents, "fixed_prices": fixed_prices_agents, "simple_skew_avst": simple_skew_avst_agents, "hetero": hetero_agents, "mm_complex": mm_complex_agents, "bob_twap": bob_twap_agents,
             "bobstrat_1msg": bobstrat_1msg_agents}
 
 
@@ -406,6 +422,8 @@ if __name__ == "__main__":
         # the last window's nominal start wraps to day_start (base:288-290), so every data message is past the end
         run_env_case("env_fixed_time_masked", "2_player_fq_fqc.json", seed=22, B=2, steps=24, mutate="fixed_time",
                      ep_type="fixed_time", episode_time=1800, start_resolution=900, window_selector=25)
+    if "env_sba" in which:
+        run_env_case("env_sell_buy_all", "2_player_fq_fqc.json", seed=24, B=2, steps=66, mutate="sell_buy_all")
     if "env_cnl" in which:
         run_env_case("env_cancel_uniform_large", "2_player_fq_fqc.json", seed=23, B=3, steps=40, stress=True, mutate="hetero",
                      nOrders=40, nTrades=24, cancel_mode=3)

@@ -241,6 +241,17 @@ def _mutate(mac, how):
                                          observation_space="simplest_case", task="buy", task_size=40, fixed_quant_value=9),
         }
         return H.with_agents(mac, agents, [1, 2, 1])
+    if how == "sell_buy_all":
+        agents = {
+            "MarketMaking": dataclasses.replace(mm, sell_buy_all_option=True, fixed_quant_value=3,
+                                                observation_space="engineered"),
+            "Simple": dataclasses.replace(mm, short_name="SI", action_space="simple", n_actions=4, sell_buy_all_option=True,
+                                          fixed_quant_value=2),
+            "Simple3": dataclasses.replace(mm, short_name="S3", action_space="simple", n_actions=3,
+                                           simple_nothing_action=False, sell_buy_all_option=True, fixed_quant_value=4),
+            "Execution": ex,
+        }
+        return H.with_agents(mac, agents, [2, 1, 1, 1])
     if how == "fixed_time":
         agents = {
             "MarketMaking": dataclasses.replace(mm, observation_space="engineered"),

@@ -248,6 +248,21 @@ def test_step_fixed_time_episodes(oracle, episode_time, resolution):
     assert len(set(ref.params["init_max_steps"].tolist())) > 1   # windows really differ in length
 
 
+def test_step_sell_buy_all_option(oracle):
+    """sell_buy_all_option=True (mm_env.py:1018-1024 in fixed_quants, :1144-1172 in simple): inventory-sized orders, the
+    9-entry offset tables with negative offsets, out-of-range actions."""
+    import dataclasses
+    mac = H.load_mac("2_player_fq_fqc")
+    agents = dict(mac.dict_of_agents_configs)
+    mm, ex = agents["MarketMaking"], agents["Execution"]
+    agents = {"MarketMaking": dataclasses.replace(mm, sell_buy_all_option=True, fixed_quant_value=3),
+              "Simple": dataclasses.replace(mm, short_name="SI", action_space="simple", n_actions=4, sell_buy_all_option=True,
+                                            fixed_quant_value=5, reward_function="spooner"),
+              "Execution": ex}
+    _rollout_parity(oracle, H.with_agents(mac, agents, [2, 2, 1]), H.small_day(n_events=30000), B=48, steps=66, seed=19,
+                    stress_actions=True)
+
+
 def test_step_fixed_prices_vector_actions(oracle):
     """EXE fixed_prices (exec_env.py:1001): the action is a vector of quantities per price level ([B,n_i,n_actions])."""
     import dataclasses
