@@ -131,3 +131,11 @@ def test_field_offsets_agree_with_pack_buffers():
     assert bytes(raw) == bytes((C.c_char * C.sizeof(packed)).from_address(C.addressof(packed)))
     with pytest.raises(KeyError):
         states.field_offset(cfg, "nonsense")
+
+
+def test_graft_entry_build_runs():
+    """The driver's build check: __graft_entry__.build() compiles (or finds up to date) the CUDA library and the oracle,
+    loads the library and checks its ABI version."""
+    import importlib
+    g = importlib.import_module("__graft_entry__")
+    g.build()

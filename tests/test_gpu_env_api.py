@@ -189,3 +189,9 @@ def test_capture_rollout_graph_equals_eager_steps():
     for k in a:
         np.testing.assert_array_equal(a[k], b[k], err_msg=k)
     assert int(a["step_counter"].max()) == T + 1
+
+
+def test_graft_entry_smoke_runs():
+    """The driver's smoke check on cuda:0."""
+    import importlib
+    importlib.import_module("__graft_entry__").smoke()
