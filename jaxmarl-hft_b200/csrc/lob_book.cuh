@@ -38,6 +38,21 @@ __device__ __forceinline__ int wsum(int v) { return __reduce_add_sync(kFull, v);
 __device__ __forceinline__ int wsub(int a, int b) { return (int)((unsigned)a - (unsigned)b); }
 __device__ __forceinline__ int wadd(int a, int b) { return (int)((unsigned)a + (unsigned)b); }
 
+// Shared-memory accesses of the fast paths by explicit 32-bit shared-window address.  The addresses (book base, this
+// lane's first row) are made opaque once per book (keep()), so ptxas holds them in two registers instead of
+// re-deriving them from %tid / the kernel parameters for every message (13 instructions per message in ncu).
+__device__ __forceinline__ unsigned keep(unsigned v) { asm volatile("mov.b32 %0, %0;" : "+r"(v)); return v; }
+__device__ __forceinline__ int lds32(unsigned a) {
+  int v; asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v;
+}
+__device__ __forceinline__ int2 lds64(unsigned a) {
+  int2 v; asm volatile("ld.shared.v2.s32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a) : "memory"); return v;
+}
+__device__ __forceinline__ void sts32(unsigned a, int v) { asm volatile("st.shared.s32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts64(unsigned a, int x, int y) {
+  asm volatile("st.shared.v2.s32 [%0], {%1, %2};" ::"r"(a), "r"(x), "r"(y) : "memory");
+}
+
 enum { F_P = 0, F_Q = 1, F_OID = 2, F_TID = 3, F_TS = 4, F_TNS = 5 };
 enum { ASK = 0, BID = 1 };
 
@@ -372,7 +387,17 @@ struct Book {
     // padding rows [no, kRows) of both sides are blank for the whole kernel
     for (int i = lane_id(); i < 2 * kRows * 6; i += 32) smem_book[i] = -1;
     __syncwarp();
+    bind();
   }
+  unsigned book_sa, lane_sa;   // shared-window byte address of row 0 of the ASK side / of this lane's first row
+  __device__ __forceinline__ void bind() {   // after c.rows_off is known
+    const unsigned base = (unsigned)__cvta_generic_to_shared(dyn_smem() + c.rows_off);
+    book_sa = keep(base);
+    lane_sa = keep(base + (unsigned)lane_id() * 24u);
+  }
+  // byte address of row r (any r, warp-uniform or not) / of this lane's row k*32+lane of side s
+  __device__ __forceinline__ unsigned row_sa(int s, int r) const { return book_sa + (unsigned)((s * kRows + r) * 24); }
+  __device__ __forceinline__ unsigned lane_row_sa(int s, int k) const { return lane_sa + (unsigned)((s * kRows + k * 32) * 24); }
   __device__ __forceinline__ int* row(int s, int r) const { return dyn_smem() + c.rows_off + (s * kRows + r) * 6; }
   __device__ __forceinline__ int* side_base(int s) const { return dyn_smem() + c.rows_off + s * kRows * 6; }
 
@@ -454,8 +479,8 @@ struct Book {
   template <int S>
   __device__ __forceinline__ void blank_live(int r, int rp, int rq) {
     if (lane_id() == (r & 31)) {
-      int2* p = reinterpret_cast<int2*>(row(S, r));
-      p[0] = make_int2(-1, -1); p[1] = make_int2(-1, -1); p[2] = make_int2(-1, -1);
+      const unsigned a = row_sa(S, r);
+      sts64(a, -1, -1); sts64(a + 8, -1, -1); sts64(a + 16, -1, -1);
       flag[S] |= 1u << (r >> 5);
     }
     nneg[S] += (rp >= 0);
@@ -478,10 +503,10 @@ struct Book {
       bool degenerate = false;   // a best-level order stamped time_s == maxint: job:242-268 then ranks EVERY row
       if (bestn[OPP] == 1) {
 #pragma unroll
-        for (int k = SLOTS - 1; k >= 0; --k) { const int r = k * 32 + lane; if (row(OPP, r)[F_P] == tp) top = r; }
+        for (int k = SLOTS - 1; k >= 0; --k) if (lds32(lane_row_sa(OPP, k)) == tp) top = k * 32 + lane;
         top = wmin(top);
         if (top < c.no) {
-          const int2 tt = *reinterpret_cast<const int2*>(row(OPP, top) + F_TS);
+          const int2 tt = lds64(row_sa(OPP, top) + F_TS * 4);
           degenerate = (tt.x == c.maxint) | (tt.y == c.maxint);
         } else degenerate = true;
       } else {   // job:242-268: min time_s, then min time_ns, then lowest row
@@ -489,9 +514,9 @@ struct Book {
         int mt = c.maxint;
 #pragma unroll
         for (int k = 0; k < SLOTS; ++k) {
-          const int* p = row(OPP, k * 32 + lane);
-          const int2 tt = *reinterpret_cast<const int2*>(p + F_TS);
-          t[k] = (p[F_P] == tp) ? tt.x : c.maxint;
+          const unsigned a = lane_row_sa(OPP, k);
+          const int2 tt = lds64(a + F_TS * 4);
+          t[k] = (lds32(a) == tp) ? tt.x : c.maxint;
           n[k] = tt.y;
           mt = min(mt, t[k]);
         }
@@ -515,9 +540,9 @@ struct Book {
         scan_trades();
         return qtm;
       }
-      const int* o = row(OPP, top);
-      const int2 pq = *reinterpret_cast<const int2*>(o);
-      const int2 ot = *reinterpret_cast<const int2*>(o + F_OID);
+      const unsigned oa = row_sa(OPP, top);
+      const int2 pq = lds64(oa);
+      const int2 ot = lds64(oa + F_OID * 4);
       const int oq = pq.y;
       const int newq = max(0, wsub(oq, qtm));
       qtm = wsub(qtm, oq);
@@ -529,7 +554,7 @@ struct Book {
       }
       if (ntr < c.nt && m.ts != -1) ntr += 1;
       if (newq > 0) {
-        if (lane == (top & 31)) row(OPP, top)[F_Q] = newq;
+        if (lane == (top & 31)) sts32(oa + F_Q * 4, newq);
         bestq[OPP] = wadd(bestq[OPP], wsub(newq, oq));
       } else {
         blank_live<OPP>(top, tp, oq);
@@ -568,8 +593,8 @@ struct Book {
       return;
     }
     if (lane_id() == (r & 31)) {            // the blank row r takes the order
-      int2* p = reinterpret_cast<int2*>(row(OWN, r));
-      p[0] = make_int2(m.price, q); p[1] = make_int2(m.oid, m.tid); p[2] = make_int2(m.ts, m.tns);
+      const unsigned a = row_sa(OWN, r);
+      sts64(a, m.price, q); sts64(a + 8, m.oid, m.tid); sts64(a + 16, m.ts, m.tns);
       flag[OWN] &= ~(1u << (r >> 5));
     }
     nneg[OWN] -= 1;
@@ -588,15 +613,15 @@ struct Book {
     const int lane = lane_id();
     int idx = kBig;
 #pragma unroll
-    for (int k = SLOTS - 1; k >= 0; --k) { const int r = k * 32 + lane; if (row(S, r)[F_OID] == m.oid) idx = r; }
+    for (int k = SLOTS - 1; k >= 0; --k) if (lds32(lane_row_sa(S, k) + F_OID * 4) == m.oid) idx = k * 32 + lane;
     idx = wmin(idx);
     if (idx >= c.no) {   // no such order id (padding rows carry -1 and are not rows of the book)
       int j = kBig;
 #pragma unroll
       for (int k = SLOTS - 1; k >= 0; --k) {
-        const int* p = row(S, k * 32 + lane);
-        const int2 pq = *reinterpret_cast<const int2*>(p);
-        const int o = p[F_OID];
+        const unsigned a = lane_row_sa(S, k);
+        const int2 pq = lds64(a);
+        const int o = lds32(a + F_OID * 4);
         if (pq.x == m.price && o <= c.init_id && o >= c.init_lo && pq.y >= m.qty) j = k * 32 + lane;
       }
       j = wmin(j);
@@ -608,7 +633,7 @@ struct Book {
       }
       idx = (j < c.no) ? j : c.no - 1;
     }
-    const int2 pq = *reinterpret_cast<const int2*>(row(S, idx));
+    const int2 pq = lds64(row_sa(S, idx));
     if (pq.x == -1) {        // a blank row takes the cancel: qty = -1 - q stays <= 0 and the row is blanked again
       if (m.qty >= 0) return;
       __syncwarp();
@@ -618,7 +643,7 @@ struct Book {
     }
     const int nq = wsub(pq.y, m.qty);
     if (nq > 0) {
-      if (lane == (idx & 31)) row(S, idx)[F_Q] = nq;
+      if (lane == (idx & 31)) sts32(row_sa(S, idx) + F_Q * 4, nq);
       if (valid[S] && pq.x == bestp[S]) bestq[S] = wsub(bestq[S], m.qty);
     } else {
       blank_live<S>(idx, pq.x, pq.y);

@@ -300,6 +300,7 @@ __device__ __noinline__ ScanOut scan_messages(BookCtx ctx, int* msgs, int N, int
                                               int prev_a, int prev_b) {
   Book<SLOTS> bk;
   bk.c = ctx;
+  bk.bind();
   bk.oddm = (ctx.t4 == 2) ? Book<SLOTS>::kOddMkt : 0u;
   bk.scan_side(ASK);
   bk.scan_side(BID);
