@@ -438,6 +438,13 @@ struct Book {
     ntr = t.ntr; set_bit(kOddTrades, t.odd != 0);
   }
   __device__ __forceinline__ void rescan() { scan_side(ASK); scan_side(BID); scan_trades(); }
+  // Before a call into the literal path: drop both best-level caches.  They are then not live across the call (the
+  // register allocator otherwise keeps a local-memory copy of them up to date on EVERY message for the sake of these
+  // rare calls: 6 st.local per message in ncu); the next ensure() rebuilds what is needed.
+  __device__ __forceinline__ void drop_best() {
+    valid[ASK] = false; valid[BID] = false;
+    bestp[ASK] = 0; bestp[BID] = 0; bestq[ASK] = 0; bestq[BID] = 0; bestn[ASK] = 0; bestn[BID] = 0;
+  }
 
   // job:933-984 on a side without odd rows: live prices are >= 0, every other row (blank or padding) has price -1
   static __device__ __noinline__ Best best_scan(int side_off, int is_bid, int maxint, int n_blank) {
@@ -535,6 +542,7 @@ struct Book {
       }
       if (degenerate) {          // the literal loop from here on (it may stop at a blank row), then rebuild the summaries
         __syncwarp();
+        drop_best();
         qtm = g_match(c, OPP, m, qtm);
         scan_side(OPP);
         scan_trades();
@@ -566,6 +574,7 @@ struct Book {
 
   __device__ __forceinline__ void generic(const Msg& m) {
     __syncwarp();
+    drop_best();
     g_process(c, m);
     rescan();
   }
@@ -576,6 +585,7 @@ struct Book {
     constexpr int OPP = 1 - OWN;
     const int qtm = match<OPP>(m, m.qty);
     if (c.check_fill && nneg[OWN] == 0) {   // job:395-401: full side -> the worst price level is evicted
+      drop_best();
       g_evict(c, OWN);
       scan_side(OWN);
     }
@@ -588,6 +598,7 @@ struct Book {
       Msg a = m;
       a.qty = qtm;
       __syncwarp();
+      drop_best();
       g_add(c, OWN, a);
       scan_side(OWN);
       return;
@@ -627,6 +638,7 @@ struct Book {
       j = wmin(j);
       if (j >= c.no && c.cmode >= 2) {   // the random same-price fallbacks (job:142-164) live in the generic path
         __syncwarp();
+        drop_best();
         g_cancel(c, S, m);
         scan_side(S);
         return;
@@ -637,6 +649,7 @@ struct Book {
     if (pq.x == -1) {        // a blank row takes the cancel: qty = -1 - q stays <= 0 and the row is blanked again
       if (m.qty >= 0) return;
       __syncwarp();
+      drop_best();
       g_cancel(c, S, m);
       scan_side(S);
       return;
