@@ -121,42 +121,52 @@ static __device__ __noinline__ void cancel_msgs(BookCtx bk, int s, int agent, in
   __syncwarp();
 }
 
-// mm:520-582 == exe:413-475 _filter_messages; one lane, k <= 16
+// mm:520-582 == exe:413-475 _filter_messages (ka == kc <= 16, checked on the host): an action re-posting at the price of
+// one of the agent's own cancels is netted against it.  Lane i holds action i and cancel i; the k-th MASKED action is
+// paired with the k-th masked cancel by rank (not by price), rel = (cancel qty >= action qty) ? action qty : 0 is taken
+// off both, and an action left with quantity 0 becomes an all-zero row (-> doNothing).
 static __device__ __noinline__ void filter_messages(int* act, int ka, int* cnl, int kc) {
-  bool a_mask[16], c_mask[16];
-  int a_i[16], c_i[16], a[16], cq[16], rel[16];
+  const int lane = lane_id();
+  const bool ia = lane < ka, ic = lane < kc;
+  const int ap = ia ? act[lane * 8 + 3] : 0, aq = ia ? act[lane * 8 + 2] : 0;
+  const int cp = ic ? cnl[lane * 8 + 3] : 0, cq = ic ? cnl[lane * 8 + 2] : 0;
+  bool a_hit = false, c_hit = false;
 #pragma unroll 1
-  for (int i = 0; i < ka; ++i) a_mask[i] = false;
+  for (int j = 0; j < kc; ++j) { const int pj = __shfl_sync(kFull, cp, j); a_hit |= ia && (pj == ap) && (ap != 0); }
 #pragma unroll 1
-  for (int j = 0; j < kc; ++j) c_mask[j] = false;
+  for (int i = 0; i < ka; ++i) { const int pi = __shfl_sync(kFull, ap, i); c_hit |= ic && (cp == pi) && (pi != 0); }
+  const unsigned am = __ballot_sync(kFull, a_hit), cm = __ballot_sync(kFull, c_hit);
+  const int na = __popc(am), nc = __popc(cm);
+  int a_k = 0, c_k = 0;   // lane k: quantity of the k-th masked action / cancel (0 beyond the masked ones)
 #pragma unroll 1
-  for (int i = 0; i < ka; ++i)
+  for (int i = 0; i < ka; ++i) {
+    const int q = __shfl_sync(kFull, aq, i);
+    if (((am >> i) & 1u) && __popc(am & ((1u << i) - 1u)) == lane) a_k = q;
+  }
 #pragma unroll 1
-    for (int j = 0; j < kc; ++j)
-      if (cnl[j * 8 + 3] == act[i * 8 + 3] && act[i * 8 + 3] != 0) { a_mask[i] = true; c_mask[j] = true; }
-  int na = 0, nc = 0;
-#pragma unroll 1
-  for (int i = 0; i < ka; ++i) if (a_mask[i]) a_i[na++] = i;
-#pragma unroll 1
-  for (int j = 0; j < kc; ++j) if (c_mask[j]) c_i[nc++] = j;
-#pragma unroll 1
-  for (int k = 0; k < ka; ++k) a[k] = (k < na) ? act[a_i[k] * 8 + 2] : 0;
-#pragma unroll 1
-  for (int k = 0; k < kc; ++k) cq[k] = (k < nc) ? cnl[c_i[k] * 8 + 2] : 0;
-#pragma unroll 1
-  for (int k = 0; k < ka; ++k) rel[k] = (cq[k] >= a[k]) ? a[k] : 0;
-  int rt = 0, rf = na;
-#pragma unroll 1
-  for (int i = 0; i < ka; ++i) { int rank = a_mask[i] ? rt++ : rf++; act[i * 8 + 2] -= rel[rank]; }
-#pragma unroll 1
-  for (int i = 0; i < ka; ++i)
-    if (act[i * 8 + 2] == 0) {
-      reinterpret_cast<int4*>(act + i * 8)[0] = make_int4(0, 0, 0, 0);
-      reinterpret_cast<int4*>(act + i * 8)[1] = make_int4(0, 0, 0, 0);
+  for (int j = 0; j < kc; ++j) {
+    const int q = __shfl_sync(kFull, cq, j);
+    if (((cm >> j) & 1u) && __popc(cm & ((1u << j) - 1u)) == lane) c_k = q;
+  }
+  const int rel = (c_k >= a_k) ? a_k : 0;
+  const unsigned lt = (1u << lane) - 1u;
+  // rank among the masked ones, the unmasked ones follow (jnp.argsort of the negated mask, stable)
+  const int rank_a = a_hit ? __popc(am & lt) : na + __popc(~am & lt);
+  const int rank_c = c_hit ? __popc(cm & lt) : nc + __popc(~cm & lt);
+  const int rel_a = __shfl_sync(kFull, rel, ia ? rank_a : 0);
+  const int rel_c = __shfl_sync(kFull, rel, ic ? rank_c : 0);
+  __syncwarp();
+  if (ia) {
+    const int nq = (int)((unsigned)aq - (unsigned)rel_a);
+    if (nq == 0) {
+      reinterpret_cast<int4*>(act + lane * 8)[0] = make_int4(0, 0, 0, 0);
+      reinterpret_cast<int4*>(act + lane * 8)[1] = make_int4(0, 0, 0, 0);
+    } else {
+      act[lane * 8 + 2] = nq;
     }
-  rt = 0; rf = nc;
-#pragma unroll 1
-  for (int j = 0; j < kc; ++j) { int rank = c_mask[j] ? rt++ : rf++; cnl[j * 8 + 2] -= rel[rank]; }
+  }
+  if (ic) cnl[lane * 8 + 2] = (int)((unsigned)cq - (unsigned)rel_c);
+  __syncwarp();
 }
 
 // Old-world scalars every agent function needs (warp-uniform)
@@ -341,9 +351,9 @@ static __device__ __noinline__ MMOut mm_get_messages(BookCtx bk, const LobStepCo
       m[0] = make_int4(types[k], sides[k], quants[k], prices[k]);
       m[1] = make_int4(c.placeholder_order_id, tid, w.time0 + ac.time_delay_obs_act, w.time1 + ac.time_delay_obs_act);
     }
-    filter_messages(act, ac.num_action_messages_by_agent, cnl, 2 * sz);
   }
   __syncwarp();
+  filter_messages(act, ac.num_action_messages_by_agent, cnl, 2 * sz);   // all lanes
   return o;
 }
 
@@ -452,9 +462,9 @@ static __device__ __noinline__ void exe_get_messages(BookCtx bk, const LobStepCo
         m[1] = make_int4(c.placeholder_order_id, tid, w.time0 + ac.time_delay_obs_act, w.time1 + ac.time_delay_obs_act);
       }
     }
-    filter_messages(act, ka, cnl, sz);
   }
   __syncwarp();
+  filter_messages(act, ka, cnl, sz);   // all lanes
 }
 
 // Per-step market summary the rewards need (from the scan)
