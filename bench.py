@@ -409,7 +409,7 @@ def run_native(args):
         while True:
             oracle.replay(bc, ca, cbid, ct, ld.msgs, (cstart + reps * WINDOW) % (M - WINDOW), WINDOW, n_threads=threads)
             reps += 1
-            if time.perf_counter() - t0 > args.cpu_seconds or reps >= 50:
+            if time.perf_counter() - t0 > args.cpu_seconds or reps >= 400:
                 break
         dt = time.perf_counter() - t0
         cpu = {"value": cb * WINDOW * reps / dt, "unit": UNIT, "cores": threads, "kind": "port",
