@@ -4,7 +4,8 @@
 // in HBM (order row = 6 ints, trade row = 8 ints), so they are moved by the bulk-copy engine without a transpose.
 // Row r of a side belongs to lane r % 32 (slot r / 32); a field scan is SLOTS loads per lane (64-bit loads at a
 // 24-byte stride are bank-conflict free) followed by one REDUX.  Each side is padded to SLOTS*32 rows with blank
-// (-1) rows, so scans need no bounds checks.
+// (-1) rows, so scans need no bounds checks.  The fast paths address the book through two per-book registers (shared
+// address of the book, of this lane's first row) with explicit ld/st.shared; the generic functions use plain pointers.
 //
 // Two tiers:
 //   * FAST paths (inlined, small): the cases that make up a real message flow on books the reference itself produced
@@ -398,7 +399,6 @@ struct Book {
   // byte address of row r (any r, warp-uniform or not) / of this lane's row k*32+lane of side s
   __device__ __forceinline__ unsigned row_sa(int s, int r) const { return book_sa + (unsigned)((s * kRows + r) * 24); }
   __device__ __forceinline__ unsigned lane_row_sa(int s, int k) const { return lane_sa + (unsigned)((s * kRows + k * 32) * 24); }
-  __device__ __forceinline__ int* row(int s, int r) const { return dyn_smem() + c.rows_off + (s * kRows + r) * 6; }
   __device__ __forceinline__ int* side_base(int s) const { return dyn_smem() + c.rows_off + s * kRows * 6; }
 
   // ---- plain (non-bulk) global <-> shared copies: same layout on both sides ----
