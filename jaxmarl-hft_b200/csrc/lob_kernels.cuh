@@ -24,7 +24,7 @@ constexpr int kWarps = 4;            // warps (= environments in flight) per CTA
 #define LOB_REPLAY_MINB 6
 #endif
 constexpr int kReplayChunk = LOB_REPLAY_CHUNK;   // messages per staged chunk of the replay kernel (double buffered)
-constexpr int kMaxAgents = 16;       // agents per environment, all types
+constexpr int kMaxAgents = 64;       // agents per environment, all types (validation bound; all per-agent storage is sized at launch)
 
 // ---- bulk-copy engine + mbarrier (PTX) ----------------------------------------------------------------------
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }

@@ -248,6 +248,28 @@ def test_step_fixed_time_episodes(oracle, episode_time, resolution):
     assert len(set(ref.params["init_max_steps"].tolist())) > 1   # windows really differ in length
 
 
+def test_step_ten_plus_ten_agents(oracle):
+    """The reference's largest shipped trainer config steps 10 market makers + 10 execution agents per environment
+    (config/rl_configs/PMAP_ippo_rnn_JAXMARL_2player.yaml): 20 agents, 120 agent messages + 100 data messages per step,
+    a 60-row permutation."""
+    mac = H.load_mac("2_player_fq_fqc")
+    agents = dict(mac.dict_of_agents_configs)
+    ref, n_done = _rollout_parity(oracle, H.with_agents(mac, agents, [10, 10]), H.small_day(n_events=30000), B=24, steps=66,
+                                  seed=23, stress_actions=True)
+    assert ref.cfg.n_agent_types == 2 and C.num_msgs_per_step(ref.cfg) == 100 + 10 * 4 + 10 * 8
+    assert n_done == 24
+
+
+def test_step_mm_only_single_data_message(oracle):
+    """The shipped MM-only configs step ONE data message at a time (n_data_msg_per_step = 1): a 32-byte data slice, N = 5."""
+    import dataclasses
+    mac = H.load_mac("2_player_fq_fqc", n_data_msg_per_step=1, episode_time=50, start_resolution=50)   # as mm_bobRL.json, shorter
+    agents = {"MarketMaking": dataclasses.replace(mac.dict_of_agents_configs["MarketMaking"], action_space="bobRL", bob_v0=5)}
+    ref, n_done = _rollout_parity(oracle, H.with_agents(mac, agents, [1]), H.small_day(n_events=6000), B=64, steps=80,
+                                  seed=29, stress_actions=True)
+    assert C.num_msgs_per_step(ref.cfg) == 5 and n_done >= 64
+
+
 def test_step_sell_buy_all_option(oracle):
     """sell_buy_all_option=True (mm_env.py:1018-1024 in fixed_quants, :1144-1172 in simple): inventory-sized orders, the
     9-entry offset tables with negative offsets, out-of-range actions."""
