@@ -5,8 +5,8 @@ Field order and types follow the header exactly; ``check_sizes`` compares ``ctyp
 """
 import ctypes as C
 
-LOB_ABI_VERSION = 6
-LOB_MAX_AGENT_TYPES = 4
+LOB_ABI_VERSION = 7
+LOB_MAX_AGENT_TYPES = 8
 LOB_MAX_AGENT_I32 = 4
 LOB_MAX_AGENT_F32 = 10
 

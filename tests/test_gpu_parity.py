@@ -260,6 +260,23 @@ def test_step_ten_plus_ten_agents(oracle):
     assert n_done == 24
 
 
+def test_step_six_agent_types(oracle):
+    """MultiAgentConfig takes any number of agent types (marl_env.py:71-79); six different ones in one environment."""
+    import dataclasses
+    mac = H.load_mac("2_player_fq_fqc")
+    d = dict(mac.dict_of_agents_configs)
+    mm, ex = d["MarketMaking"], d["Execution"]
+    agents = {"MarketMaking": mm,
+              "Skew": dataclasses.replace(mm, short_name="SK", action_space="spread_skew", fixed_quant_value=3),
+              "Directional": dataclasses.replace(mm, short_name="DIR", action_space="directional_trading", fixed_quant_value=7),
+              "Execution": ex,
+              "Twap": dataclasses.replace(ex, short_name="TW", action_space="twap", task_size=150),
+              "Prices": dataclasses.replace(ex, short_name="FP", action_space="fixed_prices", n_actions=3, fixed_quant_value=5,
+                                            task="sell", task_size=90)}
+    _rollout_parity(oracle, H.with_agents(mac, agents, [1, 2, 1, 1, 2, 1]), H.small_day(n_events=30000), B=32, steps=66,
+                    seed=37)
+
+
 def test_step_mm_only_single_data_message(oracle):
     """The shipped MM-only configs step ONE data message at a time (n_data_msg_per_step = 1): a 32-byte data slice, N = 5."""
     import dataclasses
