@@ -62,6 +62,19 @@ class MultiAgentState:
 
 
 @dataclass
+class LoadedEnvState:
+    """base_env.py:45-58 (batched: every leaf has a leading ``[B]``)."""
+    ask_raw_orders: Any
+    bid_raw_orders: Any
+    trades: Any
+    init_time: Any
+    window_index: Any
+    step_counter: Any
+    max_steps_in_episode: Any
+    start_index: Any
+
+
+@dataclass
 class LoadedEnvParams:
     message_data: Any
     book_data: Any
@@ -186,6 +199,49 @@ class BaseLOBEnv:
     def replay(self, asks, bids, trades, start, n_msgs, best_out=None):
         """base_env.py:189-216 for a batch of books: scan ``n_msgs`` data messages from ``start[b]``."""
         replay_books(self.book_cfg, asks, bids, trades, self.device_params()["message_data"], start, n_msgs, best_out)
+
+    # ---- the reference's own method pair (base_env.py:189-234), batched ----
+    def reset_env(self, key=None, params: LoadedEnvParams = None, num_envs: int = 1, seed: int = 0):
+        """base_env.py:218-227 -> (0, LoadedEnvState): every environment starts from the precomputed state of a data
+        window -- ``cfg.window_selector`` if it is >= 0, else drawn uniformly (a torch CUDA generator seeded with
+        ``seed`` stands in for ``jax.random.randint(key, ...)``)."""
+        import torch
+        p = self.device_params() if params is None else {**self.device_params(), **params.init_states_array}
+        if self.cfg.window_selector >= 0:
+            w = torch.full((num_envs,), int(self.cfg.window_selector), dtype=torch.int64, device=self.device)
+        else:
+            g = torch.Generator(device=self.device)
+            g.manual_seed(int(seed))
+            w = torch.randint(0, self.n_windows, (num_envs,), generator=g, device=self.device)
+        state = LoadedEnvState(
+            ask_raw_orders=p["init_asks"][w].clone(), bid_raw_orders=p["init_bids"][w].clone(),
+            trades=p["init_trades"][w].clone(), init_time=p["init_init_time"][w].clone(),
+            window_index=w.to(torch.int32), step_counter=torch.zeros(num_envs, dtype=torch.int32, device=self.device),
+            max_steps_in_episode=p["init_max_steps"][w].clone(), start_index=p["init_start_index"][w].clone())
+        return 0, state
+
+    def step_env(self, key, state: "LoadedEnvState", action=None, params: LoadedEnvParams = None):
+        """base_env.py:189-216 -> (obs 0, state, reward 0, done [B] bool, {"info": 0}): the next ``n_data_msg_per_step``
+        data messages of every environment go through the book (one ``lob_replay_launch``; the state's buffers are
+        updated in place), ``done`` = the last message is ``episode_time`` seconds past ``init_time`` (base:232-234)."""
+        import torch
+        msgs = self.device_params()["message_data"] if params is None else params.message_data
+        Nd, M = self.n_data_msg_per_step, msgs.shape[0]
+        off = (state.start_index.to(torch.int64) + Nd * state.step_counter.to(torch.int64)).clamp(0, max(M - Nd, 0))
+        if self.cfg.ep_type == "fixed_time":     # base:358-368: messages past the episode end keep only their time stamp
+            idx = off[:, None] + torch.arange(Nd, device=off.device)[None, :]
+            sl = msgs[idx]                                                           # [B, Nd, 8]
+            late = sl[:, :, 6] >= (state.init_time[:, 0] + self.cfg.episode_time)[:, None]
+            sl = torch.where(late[:, :, None] & (torch.arange(8, device=off.device) < 6)[None, None, :],
+                             torch.zeros_like(sl), sl).reshape(-1, 8).contiguous()
+            start = torch.arange(off.shape[0], dtype=torch.int64, device=off.device) * Nd
+            replay_books(self.book_cfg, state.ask_raw_orders, state.bid_raw_orders, state.trades, sl, start, Nd)
+        else:
+            replay_books(self.book_cfg, state.ask_raw_orders, state.bid_raw_orders, state.trades, msgs, off, Nd)
+        t_last = msgs[off + Nd - 1, 6]
+        state.step_counter += 1
+        done = (t_last - state.init_time[:, 0]) >= self.cfg.episode_time
+        return 0, state, 0, done, {"info": 0}
 
 
 class MARLEnv:

@@ -195,3 +195,37 @@ def test_graft_entry_smoke_runs():
     """The driver's smoke check on cuda:0."""
     import importlib
     importlib.import_module("__graft_entry__").smoke()
+
+
+@pytest.mark.parametrize("ep_type", ["fixed_steps", "fixed_time"])
+def test_base_env_reset_step_pair(oracle, ep_type):
+    """BaseLOBEnv.reset_env / step_env (base_env.py:189-234), batched, against the oracle's replay of the same slices."""
+    import torch
+    over = dict(ep_type="fixed_time", episode_time=1800, start_resolution=900) if ep_type == "fixed_time" else {}
+    mac = H.load_mac("2_player_fq_fqc", **over)
+    ld = H.load_for(mac, H.small_day(n_events=30000))
+    w = mac.world_config
+    be = E.BaseLOBEnv(w, loaded=ld, device="cuda:0")
+    B = 40
+    _, st = be.reset_env(None, be.default_params, num_envs=B, seed=3)
+    widx = st.window_index.cpu().numpy()
+    assert len(set(widx.tolist())) > 3
+    P = be._params_np
+    ra, rb, rt = P["init_asks"][widx].copy(), P["init_bids"][widx].copy(), P["init_trades"][widx].copy()
+    np.testing.assert_array_equal(st.ask_raw_orders.cpu().numpy(), ra)
+    init_t = P["init_init_time"][widx]
+    Nd = w.n_data_msg_per_step
+    for k in range(5):
+        obs, st, rew, done, info = be.step_env(None, st, None, be.default_params)
+        off = np.clip(P["init_start_index"][widx].astype(np.int64) + Nd * k, 0, ld.msgs.shape[0] - Nd)
+        if ep_type == "fixed_time":
+            sl = ld.msgs[off[:, None] + np.arange(Nd)[None, :]].copy()
+            late = sl[:, :, 6] >= (init_t[:, 0] + w.episode_time)[:, None]
+            sl[late, :6] = 0
+            oracle.replay(be.book_cfg, ra, rb, rt, sl.reshape(-1, 8), np.arange(B, dtype=np.int64) * Nd, Nd)
+        else:
+            oracle.replay(be.book_cfg, ra, rb, rt, ld.msgs, off, Nd)
+        np.testing.assert_array_equal(st.ask_raw_orders.cpu().numpy(), ra); np.testing.assert_array_equal(st.bid_raw_orders.cpu().numpy(), rb)
+        np.testing.assert_array_equal(st.trades.cpu().numpy(), rt)
+        np.testing.assert_array_equal(done.cpu().numpy(), (ld.msgs[off + Nd - 1, 6] - init_t[:, 0]) >= w.episode_time)
+        assert obs == 0 and rew == 0 and info == {"info": 0} and int(st.step_counter[0]) == k + 1
