@@ -119,6 +119,57 @@ def pack_buffers(cfg: abi.LobStepConfig, arrays: dict, params: dict) -> abi.LobS
     return b
 
 
+# ---- the reference's pytrees <-> leaf names (for a binding that sits under the reference's own MARLEnv) ------------
+# StatesandParams.py:14-44 field -> leaf name of leaf_specs / pack_buffers
+WORLD_FIELD_OF_LEAF = {"asks": "ask_raw_orders", "bids": "bid_raw_orders", "trades": "trades", "init_time": "init_time",
+                       "window_index": "window_index", "max_steps": "max_steps_in_episode", "start_index": "start_index",
+                       "step_counter": "step_counter", "best_bids": "best_bids", "best_asks": "best_asks", "time": "time",
+                       "order_id_counter": "order_id_counter", "mid_price": "mid_price", "delta_time": "delta_time"}
+_PARAM_FIELD = {"init_asks": "ask_raw_orders", "init_bids": "bid_raw_orders", "init_trades": "trades",
+                "init_init_time": "init_time", "init_max_steps": "max_steps_in_episode", "init_start_index": "start_index"}
+
+
+def _get(obj, name):
+    return obj[name] if isinstance(obj, dict) else getattr(obj, name)
+
+
+def flatten(cfg: abi.LobStepConfig, state) -> dict:
+    """``MultiAgentState`` (the reference's flax struct, or this package's view) -> {leaf name: array} in the order of
+    ``leaf_specs``' state leaves: ``state.world_state.<field>`` then ``state.agent_states[t].<field>``."""
+    out = {leaf: _get(state.world_state, field) for leaf, field in WORLD_FIELD_OF_LEAF.items()}
+    for t in range(cfg.n_agent_types):
+        li, lf = abi.state_leaves(cfg.agent[t].kind)
+        for name in li + lf:
+            out[f"a{t}_{name}"] = _get(state.agent_states[t], name)
+    return out
+
+
+def unflatten(cfg: abi.LobStepConfig, state, leaves: dict):
+    """The inverse: a copy of ``state`` (any object with ``.replace``: flax structs, or dataclasses via
+    ``dataclasses.replace``) whose leaves are taken from ``leaves``."""
+    import dataclasses
+
+    def repl(obj, **kw):
+        if isinstance(obj, dict):
+            return {**obj, **kw}
+        return obj.replace(**kw) if hasattr(obj, "replace") else dataclasses.replace(obj, **kw)
+    ws = repl(state.world_state, **{field: leaves[leaf] for leaf, field in WORLD_FIELD_OF_LEAF.items()})
+    agents = []
+    for t in range(cfg.n_agent_types):
+        li, lf = abi.state_leaves(cfg.agent[t].kind)
+        agents.append(repl(state.agent_states[t], **{n: leaves[f"a{t}_{n}"] for n in li + lf}))
+    return repl(state, world_state=ws, agent_states=agents)
+
+
+def flatten_params(params) -> dict:
+    """``MultiAgentParams`` (marl_env.py:96-127) -> {PARAMS name: array}: the day tensor and the stacked reset states."""
+    lp = params.loaded_params
+    init = lp.init_states_array
+    if isinstance(init, dict) and "init_asks" in init:     # this package's own LoadedEnvParams
+        return {"message_data": lp.message_data, **{k: init[k] for k in PARAMS if k != "message_data"}}
+    return {"message_data": lp.message_data, **{k: _get(init, f) for k, f in _PARAM_FIELD.items()}}
+
+
 def field_offset(cfg: abi.LobStepConfig, name: str) -> int:
     """Byte offset, inside ``LobStepBuffers``, of the pointer field that the leaf ``name`` (a ``leaf_specs`` or ``PARAMS``
     name) fills -- the table a table-driven binding (the XLA-FFI handler) passes next to its operands."""

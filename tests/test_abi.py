@@ -139,3 +139,40 @@ def test_graft_entry_build_runs():
     import importlib
     g = importlib.import_module("__graft_entry__")
     g.build()
+
+
+def test_reference_pytree_flatten_roundtrip():
+    """states.flatten / unflatten / flatten_params on objects shaped like the reference's flax structs
+    (StatesandParams.py): the helpers the INTEGRATION.md stub uses to feed the table-driven FFI call."""
+    import dataclasses
+    from types import SimpleNamespace as NS
+    from jaxmarl_hft_b200 import states
+    mac = H.load_mac("2_player_fq_fqc")
+    cfg = Cfg.to_step_config(mac, 6, 30000)
+    arrays = states.alloc_numpy(cfg, 2)
+
+    @dataclasses.dataclass(frozen=True)
+    class Rec:                       # stands in for a flax struct: attribute access + .replace
+        d: dict
+        def __getattr__(self, k):
+            return self.d[k]
+        def replace(self, **kw):
+            return Rec({**self.d, **kw})
+    ws = Rec({f: arrays[l] for l, f in states.WORLD_FIELD_OF_LEAF.items()})
+    ags = []
+    for t in range(cfg.n_agent_types):
+        li, lf = abi.state_leaves(cfg.agent[t].kind)
+        ags.append(Rec({n: arrays[f"a{t}_{n}"] for n in li + lf}))
+    state = Rec({"world_state": ws, "agent_states": ags})
+    flat = states.flatten(cfg, state)
+    want = [k for k, (_, _, role) in states.leaf_specs(cfg, 2).items() if role == "s"]
+    assert sorted(flat) == sorted(want) and all(flat[k] is arrays[k] for k in want)
+    new = {k: v + 1 for k, v in flat.items()}
+    st2 = states.unflatten(cfg, state, new)
+    assert (st2.world_state.ask_raw_orders == arrays["asks"] + 1).all()
+    assert (st2.agent_states[1].quant_executed == arrays["a1_quant_executed"] + 1).all()
+    assert (state.world_state.ask_raw_orders == arrays["asks"]).all()          # functional
+    init = NS(ask_raw_orders=1, bid_raw_orders=2, trades=3, init_time=4, max_steps_in_episode=5, start_index=6,
+              window_index=7, step_counter=8)
+    p = states.flatten_params(NS(loaded_params=NS(message_data=0, book_data=None, init_states_array=init)))
+    assert list(p) == list(states.PARAMS) and p["init_trades"] == 3 and p["init_start_index"] == 6
