@@ -322,6 +322,8 @@ def to_step_config(mac: MultiAgentConfig, n_windows: int, n_messages: int) -> ab
         raise NotImplementedError('Use either "fixed_time" or "fixed_steps"')      # ldr:998
     if w.any_message_obs_space or w.debug_mode:
         raise NotImplementedError("message-based observation spaces / debug_mode logging are not built")
+    if w.save_raw_observations:
+        raise NotImplementedError("save_raw_observations=True (info['agents'][i]['obs_raw'], marl_env.py:673-674) is not built")
     types = list(mac.dict_of_agents_configs.values())
     if len(types) != len(mac.number_of_agents_per_type):
         raise ValueError("number_of_agents_per_type must have one entry per agent config")
