@@ -309,6 +309,8 @@ def agent_type_config(cfg, n_agents: int, trader_id_start: int) -> abi.LobAgentT
             raise ValueError("Invalid reference price type.")  # exe:1576-1580
         a.reference_price = abi.REF_PRICES[cfg.reference_price]
         a.reward_lambda = cfg.reward_lambda
+        if cfg.action_space == "fixed_prices" and cfg.action_type not in ("delta", "pure"):
+            raise ValueError("Invalid action_type specified.")  # exe:2168-2173
         if cfg.action_space == "fixed_prices" and not (1 <= cfg.n_actions <= 4):
             raise ValueError("fixed_prices supports 1 to 4 price levels (exec_env.py:1047-1054)")
     else:
