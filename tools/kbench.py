@@ -23,10 +23,13 @@ def main():
     ap.add_argument("--iters", type=int, default=5)
     ap.add_argument("--config", default="2_player_fq_fqc")
     ap.add_argument("--skip-replay", action="store_true")
+    ap.add_argument("--agents", default="", help="agents per type override, e.g. 10,10")
     a = ap.parse_args()
     dev = torch.device("cuda:0")
     L = _lib.lib()
     mac = H.load_mac(a.config)
+    if a.agents:
+        mac = H.with_agents(mac, dict(mac.dict_of_agents_configs), [int(x) for x in a.agents.split(",")])
     ld = Bn._load_day(mac)
     bc = C.book_config(mac.world_config)
     base_env = E.BaseLOBEnv(mac.world_config, loaded=ld, device=dev)
