@@ -138,6 +138,21 @@ def run_reference(args):
     total = sum(times)
     value = B * WINDOW * len(times) / total
     sample = f"{B} books x {WINDOW} msgs per step, {len(times)} steps, OpenMP over books"
+    # the same for MARLEnv.step (2_player_fq_fqc): the oracle's step over 1024 environments, all host threads
+    nenv = 1024
+    oenv = H.OracleEnv(oracle, mac, ld, nenv)
+    rng = np.random.default_rng(0)
+    H.draw_prng(rng, oenv.cfg, oenv.arrays)
+    oenv.reset()
+    st = []
+    for k in range(args.warmup + args.steps):
+        H.draw_prng(rng, oenv.cfg, oenv.arrays)
+        H.draw_actions(rng, oenv.cfg, oenv.arrays)
+        t0 = time.perf_counter()
+        oenv.step(n_threads=threads)
+        if k >= args.warmup:
+            st.append(time.perf_counter() - t0)
+    env_value = nenv * len(st) / sum(st)
     return json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
@@ -146,6 +161,8 @@ def run_reference(args):
                                "bounded sample", "books": B, "msgs_per_book_per_step": WINDOW},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "env_step": {"metric": "env_steps_per_sec", "value": env_value, "unit": "env-steps/s",
+                     "sample": f"{nenv} envs x {len(st)} steps of MARLEnv.step 2_player_fq_fqc, oracle, OpenMP over envs"},
     })
 
 
