@@ -385,9 +385,11 @@ lob_step_kernel(const __grid_constant__ LobStepConfig c, const __grid_constant__
   const int no = c.book.n_orders, nt = c.book.n_trades, Nd = c.n_data_msg_per_step, T = c.n_agent_types;
   const bool bulk_books = (no & 1) == 0;   // a side is no*24 bytes: 16-byte granular iff no is even
   const unsigned side_bytes = (unsigned)no * 24u;
+  // Environments are dealt CTA-fastest (env = pass * gridDim * nwarps + warp * gridDim + blockIdx), so that a partial last
+  // pass leaves every SM with the same number of active warps instead of some SMs full and the others idle.
   const long long stride = (long long)gridDim.x * nwarps;
-  for (long long base = (long long)blockIdx.x * nwarps; base < batch; base += stride) {
-    const long long e = base + warp;
+  for (long long base = blockIdx.x; base < batch; base += stride) {   // CTA-uniform trip count (warp 0 has the lowest index)
+    const long long e = base + (long long)warp * gridDim.x;
     const bool active = e < batch;
     WorldIn w;
     int oid_counter = 0, window_index = 0;
