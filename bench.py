@@ -369,9 +369,35 @@ def run_native(args):
     step_e2e_eager_value = ws * args.envs * K / (max_over_ranks(p0.elapsed_time(p1)) * 1e-3)
     step_h2d = sum(a.numel() * 4 for a in acts_in)
     step_d2h = sum(h.numel() * h.element_size() for h in outs_h)
+    # a 64-step rollout as ONE CUDA graph (MARLEnv.capture_rollout: the trainer's jit(scan(vmap(env.step))), state resident
+    # for the whole rollout; pre-sampled actions as the policy, Speed_test.py:165-214), trajectory read back per rollout
+    RT = 64
+    pol = [torch.randint(0, n_act_space[t], (RT, args.envs, n_i[t]), generator=g, device=dev, dtype=torch.int32)
+           for t in range(T)]
+    rgraph, traj = env.capture_rollout(state, lambda k, obs: [pol[t][k] for t in range(T)], RT, envp)
+    traj_dev = list(traj["obs"]) + list(traj["reward"]) + [traj["done"]]
+    traj_host = [torch.empty(x.shape, dtype=x.dtype).pin_memory() for x in traj_dev]
+    n_roll = max(1, K // 8)
+
+    def rollout_once():
+        rgraph.replay()
+        for h, x in zip(traj_host, traj_dev):
+            h.copy_(x, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    rollout_once()
+    barrier()
+    r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    r0.record()
+    for _ in range(n_roll):
+        rollout_once()
+    r1.record()
+    barrier()
+    rollout_value = ws * args.envs * RT * n_roll / (max_over_ranks(r0.elapsed_time(r1)) * 1e-3)
+    rollout_d2h = sum(h.numel() * h.element_size() for h in traj_host)
 
     # ---- (3b) the other env.step configurations of BASELINE.json, kernel-only (same timing rules) ----
-    del env, state, obs, graph
+    del env, state, obs, graph, rgraph, traj, traj_dev
     others = []
     for cfg_name, n_envs, label in (("exec_longrun_fixed_quants_complex", 8192, "BASELINE configs[2]: single execution agent"),
                                     ("hetero_deep_book", 16384, "BASELINE configs[4] shapes: 3 MM + 2 EXE + 2 directional, "
@@ -461,7 +487,10 @@ def run_native(args):
                                  "d2h_bytes_per_step": step_d2h,
                                  "api": "MARLEnv.capture_step: actions from pinned host memory, PRNG draw, step kernel, "
                                         "obs / rewards / done read back -- one CUDA graph launch per step",
-                                 "eager_value": step_e2e_eager_value},
+                                 "eager_value": step_e2e_eager_value,
+                                 "rollout_value": rollout_value,
+                                 "rollout": f"MARLEnv.capture_rollout: {RT} steps + pre-sampled policy as one CUDA graph, "
+                                            f"{rollout_d2h} B of trajectory (obs, rewards, done) read back per rollout"},
                          "gpu_launches": step_launches},
         }
         if cpu is not None:
