@@ -520,6 +520,17 @@ lob_step_kernel(const __grid_constant__ LobStepConfig c, const __grid_constant__
       const float new_dt = (float)ft0 + (float)ft1 / 1e9f - (float)w.time0 - (float)w.time1 / 1e9f;
       const int new_oid_counter = oid_counter - n_act;
       const int vol_a = bk.volume(ASK), vol_b = bk.volume(BID);
+      // The agents' reward passes read the step's trade log several times each: stage it once in the message buffer, which
+      // is dead from here on (when it fits; the log itself stays in global memory, fictional end-of-episode trades are
+      // inserted into / removed from the copy).
+      int* trp = bk.c.tr;
+      if (nt <= N) {
+        const int4* g4 = reinterpret_cast<const int4*>(bk.c.tr);
+        int4* s4 = reinterpret_cast<int4*>(msgs);
+        for (int i = lane; i < nt * 2; i += 32) s4[i] = g4[i];
+        __syncwarp();
+        trp = msgs;
+      }
 
       // ---- (E)+(G)+(I)+(J)+(K) per agent: reward, state, done, info, obs ----
       const ObsTime ot = {c.ep_type_fixed_time, c.episode_time, ft0, ft1, w.init_time0, w.init_time1, new_dt};
@@ -533,7 +544,7 @@ lob_step_kernel(const __grid_constant__ LobStepConfig c, const __grid_constant__
           float* obs = b.obs[t] + idx * d;
           if (ac.kind == LOB_AGENT_MM) {
             MMState s; load_mm_state(b, t, idx, s);
-            const MMReward R = mm_get_reward(bk.c.tr, nt, c, ac, w, so, s, tid);
+            const MMReward R = mm_get_reward(trp, nt, c, ac, w, so, s, tid);
             const int* x = scr + flat * 8;
             MMState ns;   // mm:2677-2736
             ns.posted_distance_bid = x[2]; ns.posted_distance_ask = x[3];
@@ -558,7 +569,7 @@ lob_step_kernel(const __grid_constant__ LobStepConfig c, const __grid_constant__
               mm_write_obs(ac, obs, ns.inventory, new_mid, so.ba_last, so.bb_last, vol_a, vol_b, new_step, false, ot);
           } else {
             EXEState s; load_exe_state(b, t, idx, s);
-            const EXEReward R = exe_get_reward(bk.c.tr, nt, c, ac, w, so, s, tid);
+            const EXEReward R = exe_get_reward(trp, nt, c, ac, w, so, s, tid);
             EXEState ns = s;   // exe:1771-1839
             ns.quant_executed = s.quant_executed + R.agentQuant;
             ns.p_vwap = R.p_vwap;
