@@ -609,11 +609,14 @@ struct Book {
       flag[OWN] &= ~(1u << (r >> 5));
     }
     nneg[OWN] -= 1;
-    if (valid[OWN]) {
+    {   // keep the cached best level exact (branch-free: the scan is a latency chain, a select is cheaper than a branch)
       const int bp = bestp[OWN];
-      const bool better = (bp == -1) | ((OWN == ASK) ? (m.price < bp) : (m.price > bp));
-      if (better) { bestp[OWN] = m.price; bestq[OWN] = q; bestn[OWN] = 1; }
-      else if (m.price == bp) { bestq[OWN] = wadd(bestq[OWN], q); bestn[OWN] += 1; }
+      const bool v = valid[OWN];
+      const bool better = v & ((bp == -1) | ((OWN == ASK) ? (m.price < bp) : (m.price > bp)));
+      const bool same = v & !better & (m.price == bp);
+      bestp[OWN] = better ? m.price : bp;
+      bestq[OWN] = better ? q : (same ? wadd(bestq[OWN], q) : bestq[OWN]);
+      bestn[OWN] = better ? 1 : bestn[OWN] + (same ? 1 : 0);
     }
   }
 
