@@ -654,6 +654,11 @@ struct ObsTime {
   }
 };
 
+// x / c.  div.rn.f32 takes a ~30-instruction slow path when the numerator's exponent field is 0, and many observation
+// inputs are exactly 0 (inventory, executed quantity, time_ns, ...): for a positive c, +-0 / c == +-0, returned as is
+// (c <= 0 or NaN keeps the division: 0 / 0 must stay NaN).
+__device__ __forceinline__ float fdivz(float x, float c) { return (x == 0.0f && c > 0.0f) ? x : x / c; }
+
 // mm:2963-3154 observation, alphabetical key order
 static __device__ __noinline__ void mm_write_obs(const LobAgentTypeConfig& ac, float* obs, int inventory, float mid_price,
                                                  int ba, int bb, int qa, int qb, int step_counter, bool zero,
@@ -662,25 +667,25 @@ static __device__ __noinline__ void mm_write_obs(const LobAgentTypeConfig& ac, f
   const bool nz = ac.normalize;
   const int spread = abs(ba - bb);
   if (ac.observation_space == LOB_OBS_BASIC) {
-    obs[0] = zero ? 0.f : (nz ? (float)inventory / 10.0f : (float)inventory);
-    obs[1] = zero ? 0.f : (nz ? (float)spread / 1e4f : (float)spread);
+    obs[0] = zero ? 0.f : (nz ? fdivz((float)inventory, 10.0f) : (float)inventory);
+    obs[1] = zero ? 0.f : (nz ? fdivz((float)spread, 1e4f) : (float)spread);
     return;
   }
   if (ot.fixed_time) {   // mm:3032-3069: + delta_time (first) and time_remaining (last)
     const float rem = ot.remaining();
-    obs[0] = zero ? 0.f : (nz ? ot.delta_time / 10.0f : ot.delta_time);
-    obs[9] = zero ? 0.f : (nz ? rem / (float)ot.episode_time : rem);
+    obs[0] = zero ? 0.f : (nz ? fdivz(ot.delta_time, 10.0f) : ot.delta_time);
+    obs[9] = zero ? 0.f : (nz ? fdivz(rem, (float)ot.episode_time) : rem);
     obs += 1;
   }
   float v[8];
-  v[0] = nz ? (float)inventory / 10.0f : (float)inventory;
-  v[1] = nz ? mid_price / 1e6f : mid_price;
-  v[2] = nz ? (float)ba / 1e6f : (float)ba;
-  v[3] = nz ? (float)bb / 1e6f : (float)bb;
-  v[4] = nz ? (float)qa / 1000.0f : (float)qa;
-  v[5] = nz ? (float)qb / 1000.0f : (float)qb;
-  v[6] = nz ? (float)spread / 1e4f : (float)spread;
-  v[7] = nz ? (float)step_counter / 10.0f : (float)step_counter;
+  v[0] = nz ? fdivz((float)inventory, 10.0f) : (float)inventory;
+  v[1] = nz ? fdivz(mid_price, 1e6f) : mid_price;
+  v[2] = nz ? fdivz((float)ba, 1e6f) : (float)ba;
+  v[3] = nz ? fdivz((float)bb, 1e6f) : (float)bb;
+  v[4] = nz ? fdivz((float)qa, 1000.0f) : (float)qa;
+  v[5] = nz ? fdivz((float)qb, 1000.0f) : (float)qb;
+  v[6] = nz ? fdivz((float)spread, 1e4f) : (float)spread;
+  v[7] = nz ? fdivz((float)step_counter, 10.0f) : (float)step_counter;
 #pragma unroll
   for (int k = 0; k < 8; ++k) obs[k] = zero ? 0.f : v[k];
 }
@@ -803,15 +808,15 @@ static __device__ __noinline__ void exe_write_obs(const LobAgentTypeConfig& ac, 
     const float time_used = (float)(ot.t0 - ot.i0) + (float)(ot.t1 - ot.i1) / 1e9f;
     const float ptime = (ep - time_used) / ep;
     const float pquant = (float)rem / (float)st.task_to_execute;
-    obs[0] = zero ? 0.f : (nz ? (mid_price - 7560000.0f) / 1e3f : mid_price);
-    obs[1] = zero ? 0.f : (nz ? (pquant - 0.5f) / 1.0f : pquant);
-    obs[2] = zero ? 0.f : (nz ? (ptime - 0.5f) / 1.0f : ptime);
+    obs[0] = zero ? 0.f : (nz ? fdivz((mid_price - 7560000.0f), 1e3f) : mid_price);
+    obs[1] = zero ? 0.f : (nz ? fdivz((pquant - 0.5f), 1.0f) : pquant);
+    obs[2] = zero ? 0.f : (nz ? fdivz((ptime - 0.5f), 1.0f) : ptime);
     return;
   }
   if (ac.observation_space == LOB_OBS_BASIC) {
-    obs[0] = zero ? 0.f : (nz ? (float)(ba - 1550000) / 1e3f : (float)ba);
-    obs[1] = zero ? 0.f : (nz ? (float)(bb - 1550000) / 1e3f : (float)bb);
-    obs[2] = zero ? 0.f : (nz ? (float)rem / ts : (float)rem);
+    obs[0] = zero ? 0.f : (nz ? fdivz((float)(ba - 1550000), 1e3f) : (float)ba);
+    obs[1] = zero ? 0.f : (nz ? fdivz((float)(bb - 1550000), 1e3f) : (float)bb);
+    obs[2] = zero ? 0.f : (nz ? fdivz((float)rem, ts) : (float)rem);
     return;
   }
   const int p_aggr = st.is_sell_task ? bb : ba, p_pass = st.is_sell_task ? ba : bb;
@@ -820,24 +825,24 @@ static __device__ __noinline__ void exe_write_obs(const LobAgentTypeConfig& ac, 
   const int spread = abs(p_aggr - p_pass);
   if (ot.fixed_time) {   // exe:1943-2010: + delta_time (first), time and time_remaining (last two)
     const float now = ot.now(), left = ot.remaining();
-    obs[0] = zero ? 0.f : (nz ? ot.delta_time / 10.0f : ot.delta_time);
-    obs[13] = zero ? 0.f : (nz ? now / 1e5f : now);
-    obs[14] = zero ? 0.f : (nz ? left / (float)ot.episode_time : left);
+    obs[0] = zero ? 0.f : (nz ? fdivz(ot.delta_time, 10.0f) : ot.delta_time);
+    obs[13] = zero ? 0.f : (nz ? fdivz(now, 1e5f) : now);
+    obs[14] = zero ? 0.f : (nz ? fdivz(left, (float)ot.episode_time) : left);
     obs += 1;
   }
   float v[12];
-  v[0] = nz ? (float)st.quant_executed / ts : (float)st.quant_executed;
-  v[1] = nz ? st.init_price / 1e7f : st.init_price;
-  v[2] = nz ? (float)st.is_sell_task / 1.0f : (float)st.is_sell_task;
-  v[3] = nz ? ((float)p_aggr - st.init_price) / 1e5f : (float)p_aggr;
-  v[4] = nz ? ((float)p_pass - st.init_price) / 1e5f : (float)p_pass;
-  v[5] = nz ? (float)q_aggr / 1000.0f : (float)q_aggr;
-  v[6] = nz ? (float)q_pass / 1000.0f : (float)q_pass;
-  v[7] = nz ? (float)rem / ts : (float)rem;
-  v[8] = nz ? ratio / 1.0f : ratio;
-  v[9] = nz ? (float)spread / 1e4f : (float)spread;
-  v[10] = nz ? (float)step_counter / 30.0f : (float)step_counter;
-  v[11] = nz ? (float)st.task_to_execute / ts : (float)st.task_to_execute;
+  v[0] = nz ? fdivz((float)st.quant_executed, ts) : (float)st.quant_executed;
+  v[1] = nz ? fdivz(st.init_price, 1e7f) : st.init_price;
+  v[2] = nz ? fdivz((float)st.is_sell_task, 1.0f) : (float)st.is_sell_task;
+  v[3] = nz ? fdivz(((float)p_aggr - st.init_price), 1e5f) : (float)p_aggr;
+  v[4] = nz ? fdivz(((float)p_pass - st.init_price), 1e5f) : (float)p_pass;
+  v[5] = nz ? fdivz((float)q_aggr, 1000.0f) : (float)q_aggr;
+  v[6] = nz ? fdivz((float)q_pass, 1000.0f) : (float)q_pass;
+  v[7] = nz ? fdivz((float)rem, ts) : (float)rem;
+  v[8] = nz ? fdivz(ratio, 1.0f) : ratio;
+  v[9] = nz ? fdivz((float)spread, 1e4f) : (float)spread;
+  v[10] = nz ? fdivz((float)step_counter, 30.0f) : (float)step_counter;
+  v[11] = nz ? fdivz((float)st.task_to_execute, ts) : (float)st.task_to_execute;
 #pragma unroll
   for (int k = 0; k < 12; ++k) obs[k] = zero ? 0.f : v[k];
 }
