@@ -66,23 +66,29 @@ __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wa
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // ---- shared-memory layout of one warp (in 32-bit words) -----------------------------------------------------
+constexpr int kInPlaceActs = 64;   // action messages (8 words each) a warp permutes through 16 registers per lane
 struct WarpLayout {
   int book;      // 2 sides * nrows * 6 (nrows = SLOTS * 32, padded with blank rows)
   int msgs;      // step: N * 8 ; replay: 2 * kReplayChunk * 8      (16-byte aligned)
-  int act;       // step: n_act * 8
+  int act;       // step: n_act * 8 staging for the action messages
   int scratch;   // step: n_agents * 8 (what the action phase leaves for the info / state update)
+                 // Deep books ("diet": shared memory decides the warps per SM) drop both: the actions are built in their
+                 // slots of `msgs` and permuted in place through registers (n_act <= kInPlaceActs), the scratch values go
+                 // straight into the info rows in global memory.
   int bar;       // 2 mbarriers (4 words, 8-byte aligned)
   int words;     // per-warp total, multiple of 4
 };
+__host__ __device__ constexpr bool layout_diet(int nrows) { return nrows >= 256; }
 __host__ __device__ inline WarpLayout make_layout(int nrows, int msg_words, int n_act, int n_agents) {
+  const bool diet = layout_diet(nrows);
   WarpLayout L;
   int o = 0;
   L.book = o; o += 12 * nrows;
   o = (o + 3) & ~3;
   L.msgs = o; o += msg_words;
   o = (o + 3) & ~3;
-  L.act = o; o += n_act * 8;
-  L.scratch = o; o += n_agents * 8;
+  L.act = o; o += (diet && n_act <= kInPlaceActs) ? 0 : n_act * 8;
+  L.scratch = o; o += diet ? 0 : n_agents * 8;
   o = (o + 3) & ~3;
   L.bar = o; o += 4;
   L.words = (o + 3) & ~3;
@@ -362,7 +368,7 @@ __device__ __noinline__ ScanOut scan_messages(BookCtx ctx, int* msgs, int N, int
 constexpr int kStepCtasPerSm = LOB_STEP_CTAS;                 // phase-synchronous groups per SM
 constexpr int kStepMaxWarps = LOB_STEP_MAXW / LOB_STEP_CTAS;  // warps per CTA (book capacity classes up to 128 rows)
 // deeper books are shared-memory limited to fewer warps anyway: give them the registers
-__host__ __device__ constexpr int step_max_warps(int slots) { return slots <= 4 ? kStepMaxWarps : slots == 8 ? 12 : 7; }
+__host__ __device__ constexpr int step_max_warps(int slots) { return slots <= 4 ? kStepMaxWarps : slots == 8 ? 12 : 8; }
 
 template <int SLOTS>
 __global__ void __launch_bounds__(step_max_warps(SLOTS) * 32, kStepCtasPerSm)
@@ -374,7 +380,9 @@ lob_step_kernel(const __grid_constant__ LobStepConfig c, const __grid_constant__
   int* ws = smem + warp * L.words;
   uint64_t* bar = reinterpret_cast<uint64_t*>(ws + L.bar);
   int* msgs = ws + L.msgs;
-  int* act_all = ws + L.act;
+  constexpr bool kDiet = layout_diet(SLOTS * 32);
+  const bool acts_in_place = kDiet && n_act <= kInPlaceActs;
+  int* act_all = acts_in_place ? msgs + n_cnl * 8 : ws + L.act;
   int* scr = ws + L.scratch;
   if (lane == 0) mbar_init(&bar[0], 1);
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -471,10 +479,10 @@ lob_step_kernel(const __grid_constant__ LobStepConfig c, const __grid_constant__
             const int action = av[0];
             const int inventory = b.agent_i32[t][2][idx];
             MMOut o = mm_get_messages(bk.c, c, ac, action, w, inventory, tid, act_all + ai * 8, msgs + ci * 8);
-            if (lane == 0) {
-              int* s = scr + flat * 8;
-              s[0] = o.posted_bid_price; s[1] = o.posted_ask_price; s[2] = o.bid_dist; s[3] = o.ask_dist;
-              s[4] = o.bid_quant; s[5] = o.ask_quant;
+            if (lane == 0) {   // (diet: straight into the info row, mm:2695-2730; phase 3 reads the two distances back)
+              int* x = kDiet ? b.info_agent_i32[t] + idx * LOB_MMINFO_I32_COLS + 3 : scr + flat * 8;
+              x[0] = o.posted_bid_price; x[1] = o.posted_ask_price; x[2] = o.bid_dist; x[3] = o.ask_dist;
+              x[4] = o.ask_quant; x[5] = o.bid_quant;
             }
           } else {
             exe_get_messages(bk.c, c, ac, av, b.best_asks + e * N * 2, b.best_bids + e * N * 2, N, w,
@@ -487,11 +495,28 @@ lob_step_kernel(const __grid_constant__ LobStepConfig c, const __grid_constant__
       __syncwarp();
       for (int i = lane; i < n_act; i += 32) act_all[i * 8 + 4] = oid_counter - i;   // marl:285-289
       __syncwarp();
-      for (int j = lane; j < n_act * 8; j += 32) {   // marl:293-295 permutation(key, x) == x[perm]
-        const int i = j >> 3, k = j & 7;
-        int src = i;
-        if (c.shuffle_action_messages && b.perm) src = max(0, min(b.perm[e * n_act + i], n_act - 1));
-        msgs[(n_cnl + i) * 8 + k] = act_all[src * 8 + k];
+      // marl:293-295 permutation(key, x) == x[perm]
+      const bool shuffle = c.shuffle_action_messages && b.perm;
+      if (!acts_in_place) {
+        for (int j = lane; j < n_act * 8; j += 32) {
+          const int i = j >> 3, k = j & 7;
+          const int src = shuffle ? max(0, min(b.perm[e * n_act + i], n_act - 1)) : i;
+          msgs[(n_cnl + i) * 8 + k] = act_all[src * 8 + k];
+        }
+      } else if (shuffle) {   // in place: every lane gathers its (up to 16) words first, then all store
+        int v[kInPlaceActs * 8 / 32];
+#pragma unroll
+        for (int q = 0; q < kInPlaceActs * 8 / 32; ++q) {
+          const int j = lane + 32 * q;
+          v[q] = 0;
+          if (j < n_act * 8) v[q] = act_all[max(0, min(b.perm[e * n_act + (j >> 3)], n_act - 1)) * 8 + (j & 7)];
+        }
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < kInPlaceActs * 8 / 32; ++q) {
+          const int j = lane + 32 * q;
+          if (j < n_act * 8) act_all[j] = v[q];
+        }
       }
       __syncwarp();
     }
@@ -545,7 +570,7 @@ lob_step_kernel(const __grid_constant__ LobStepConfig c, const __grid_constant__
           if (ac.kind == LOB_AGENT_MM) {
             MMState s; load_mm_state(b, t, idx, s);
             const MMReward R = mm_get_reward(trp, nt, c, ac, w, so, s, tid);
-            const int* x = scr + flat * 8;
+            const int* x = kDiet ? b.info_agent_i32[t] + idx * LOB_MMINFO_I32_COLS + 3 : scr + flat * 8;   // from phase 1
             MMState ns;   // mm:2677-2736
             ns.posted_distance_bid = x[2]; ns.posted_distance_ask = x[3];
             ns.inventory = R.end_inventory;
@@ -557,8 +582,8 @@ lob_step_kernel(const __grid_constant__ LobStepConfig c, const __grid_constant__
               if (!so.ep_done) store_mm_state(b, t, idx, ns);
               int* ii = b.info_agent_i32[t] + idx * LOB_MMINFO_I32_COLS;
               float* fi = b.info_agent_f32[t] + idx * LOB_MMINFO_F32_COLS;
-              ii[0] = 0; ii[1] = ns.inventory; ii[2] = R.forced_unwind; ii[3] = x[0]; ii[4] = x[1]; ii[5] = x[2];
-              ii[6] = x[3]; ii[7] = x[5]; ii[8] = x[4];
+              ii[0] = 0; ii[1] = ns.inventory; ii[2] = R.forced_unwind;
+              if (!kDiet) { ii[3] = x[0]; ii[4] = x[1]; ii[5] = x[2]; ii[6] = x[3]; ii[7] = x[4]; ii[8] = x[5]; }
               fi[0] = R.reward; fi[1] = R.reward_portfolio_value; fi[2] = R.reward_spooner; fi[3] = R.end_of_ep_pv;
               fi[4] = R.reward_spooner_damped; fi[5] = R.reward_spooner_asym_damped;
               fi[6] = R.reward_spooner_asym_damped2; fi[7] = R.reward_delta_pv; fi[8] = ns.total_PnL;
