@@ -368,7 +368,10 @@ __device__ __noinline__ ScanOut scan_messages(BookCtx ctx, int* msgs, int N, int
 constexpr int kStepCtasPerSm = LOB_STEP_CTAS;                 // phase-synchronous groups per SM
 constexpr int kStepMaxWarps = LOB_STEP_MAXW / LOB_STEP_CTAS;  // warps per CTA (book capacity classes up to 128 rows)
 // deeper books are shared-memory limited to fewer warps anyway: give them the registers
-__host__ __device__ constexpr int step_max_warps(int slots) { return slots <= 4 ? kStepMaxWarps : slots == 8 ? 12 : 8; }
+#ifndef LOB_STEP_MAXW8
+#define LOB_STEP_MAXW8 14
+#endif
+__host__ __device__ constexpr int step_max_warps(int slots) { return slots <= 4 ? kStepMaxWarps : slots == 8 ? LOB_STEP_MAXW8 : 8; }
 
 template <int SLOTS>
 __global__ void __launch_bounds__(step_max_warps(SLOTS) * 32, kStepCtasPerSm)

@@ -24,10 +24,11 @@ def main():
     ap.add_argument("--config", default="2_player_fq_fqc")
     ap.add_argument("--skip-replay", action="store_true")
     ap.add_argument("--agents", default="", help="agents per type override, e.g. 10,10")
+    ap.add_argument("--norders", type=int, default=0, help="book rows per side override")
     a = ap.parse_args()
     dev = torch.device("cuda:0")
     L = _lib.lib()
-    mac = H.load_mac(a.config)
+    mac = H.load_mac(a.config, **({"nOrders": a.norders} if a.norders else {}))
     if a.agents:
         mac = H.with_agents(mac, dict(mac.dict_of_agents_configs), [int(x) for x in a.agents.split(",")])
     ld = Bn._load_day(mac)
