@@ -9,7 +9,7 @@
  *
  * PARITY PIN: the reference is 100 % JAX and `import jax` fails in the build
  * container, so this restatement is pinned against (a) hand-worked
- * known-answer cases (tests/test_oracle_kat.py) and (b) golden vectors
+ * known-answer cases (tests/test_quirks.py) and (b) golden vectors
  * produced by executing the UNMODIFIED reference sources under a numpy-backed
  * JAX emulation (tests/golden/make_golden.py, tests/golden/jaxshim/).  It has
  * NOT been compared with a real jaxlib run: "parity unpinned against real JAX".
