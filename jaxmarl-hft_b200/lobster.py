@@ -374,9 +374,11 @@ def load_or_generate(world, seed=20220103, n_events=400_000, stress=False, cache
                        day_start=world.day_start, day_end=world.day_end, stress=stress)
     ld = load_days([day], world.episode_time, world.n_data_msg_per_step, world.start_resolution,
                    world.day_start, world.day_end, window_type=world.ep_type)
-    if path is not None:
-        np.savez_compressed(path, msgs=ld.msgs, starts=ld.starts, ends=ld.ends, obs=ld.books,
+    if path is not None:   # atomic: several ranks of one job may generate the same day at the same time
+        tmp = f"{path}.{os.getpid()}.tmp.npz"
+        np.savez_compressed(tmp, msgs=ld.msgs, starts=ld.starts, ends=ld.ends, obs=ld.books,
                             max_msgs_in_windows_arr=ld.max_msgs)
+        os.replace(tmp, path)
     return ld
 
 
