@@ -668,7 +668,7 @@ lob_reset_kernel(const __grid_constant__ LobStepConfig c, const __grid_constant_
   int* ws = smem + warp * L.words;
   Book<SLOTS> bk;
   bk.init(c.book, ws + L.book);
-  const int no = c.book.n_orders, nt = c.book.n_trades;
+  const int no = c.book.n_orders;
   const long long stride = (long long)gridDim.x * kWarps;
   for (long long e = (long long)blockIdx.x * kWarps + warp; e < batch; e += stride) {
     reset_env(c, b, e, bk, N);
