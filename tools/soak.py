@@ -54,6 +54,7 @@ def main():
     cases.append(("2_player", base, dict(n_events=60000)))
     cases.append(("2_player stress small book", H.load_mac("2_player_fq_fqc", nOrders=40, nTrades=24), dict(seed=9, n_events=60000, stress=True)))
     cases.append(("hetero deep", H.load_mac("hetero_deep_book"), dict(n_events=60000)))
+    cases.append(("2_player 200-row book", H.load_mac("2_player_fq_fqc", nOrders=200, nTrades=150), dict(n_events=60000)))
     cases.append(("cancel mode 3 + MKT", H.load_mac("2_player_fq_fqc", nOrders=48, nTrades=20, cancel_mode=3, type_4_interpretation=2),
                   dict(seed=9, n_events=60000, stress=True)))
     cases.append(("fixed_time", H.load_mac("2_player_fq_fqc", ep_type="fixed_time", episode_time=900, start_resolution=300), dict(n_events=60000)))
