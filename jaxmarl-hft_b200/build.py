@@ -15,6 +15,7 @@ INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 SO = os.path.join(CSRC, "liblobstep.so")
 OBJ = os.path.join(CSRC, "build")
 SLOTS = (1, 2, 4, 8, 16)
+GROUPED = ((8, 14),)   # (lanes per book, rows per lane) classes of the grouped kernels
 # --fmad=false: a*b+c stays two roundings, as in the XLA lowering of the reference's float32 expressions
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--fmad=false",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v"] + os.environ.get("LOB_NVCC_EXTRA", "").split()
@@ -25,7 +26,7 @@ def _nvcc():
 
 
 def _sources():
-    return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh"))) + [
+    return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h"))) + [
         os.path.join(INCLUDE, "lobstep.h")]
 
 
@@ -47,6 +48,9 @@ def build_cuda(force=False, verbose=False):
     jobs = [(os.path.join(CSRC, "lobstep.cu"), os.path.join(OBJ, "lobstep.o"), [])]
     for s in SLOTS:
         jobs.append((os.path.join(CSRC, "lob_inst.cu"), os.path.join(OBJ, f"lob_inst_s{s}.o"), [f"-DLOB_SLOTS={s}"]))
+
+    for l, r in GROUPED:
+        jobs.append((os.path.join(CSRC, "lob_ginst.cu"), os.path.join(OBJ, f"lob_ginst_l{l}r{r}.o"), [f"-DLOB_GL={l}", f"-DLOB_GR={r}"]))
 
     def compile_one(job):
         src, obj, extra = job

@@ -5,23 +5,10 @@
 #include <stdarg.h>
 #include <stdio.h>
 
-#include "../../include/lobstep.h"
+#include "lob_glaunch.h"
 #include "lob_kernels.cuh"
 
 namespace lobhost {
-
-char* err_buf();            // thread-local message buffer (512 bytes), defined in lobstep.cu
-void count_launch();        // thread-local launch counter, defined in lobstep.cu
-
-inline int fail(int code, const char* fmt, ...) {
-  va_list ap;
-  va_start(ap, fmt);
-  vsnprintf(err_buf(), 512, fmt, ap);
-  va_end(ap);
-  return code;
-}
-
-struct DevInfo { int sms; int max_smem_optin; };
 
 // persistent grid: a multiple of the SM count, capped by the work
 inline int grid_for(long long n_items, int sms, int ctas_per_sm) {
@@ -42,13 +29,6 @@ int prepare(K kernel, size_t smem_bytes, const DevInfo& d, int* ctas_per_sm) {
   e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, lob::kWarps * 32, smem_bytes);
   if (e != cudaSuccess) return fail(LOB_E_CUDA, "occupancy query: %s", cudaGetErrorString(e));
   *ctas_per_sm = n < 1 ? 1 : n;
-  return LOB_OK;
-}
-
-inline int launched(const char* what) {
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) return fail(LOB_E_CUDA, "%s: %s", what, cudaGetErrorString(e));
-  count_launch();
   return LOB_OK;
 }
 

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/lobstep.h"
@@ -136,6 +137,14 @@ int slots_for(int n_orders) {
   return p;
 }
 
+// Book-capacity class of the grouped kernels (lob_gbook.cuh): 1 = 8 lanes x 14 rows (up to 112 rows per side), 0 = none
+// (the one-warp-per-book kernels).  LOB_ONE_WARP_PER_BOOK=1 forces the latter (A/B measurements).
+int grouped_class(int n_orders) {
+  static const bool off = [] { const char* e = getenv("LOB_ONE_WARP_PER_BOOK"); return e && e[0] == '1'; }();
+  if (off) return 0;
+  return n_orders <= 112 ? 1 : 0;
+}
+
 #define DISPATCH_SLOTS(slots, CALL)                                   \
   switch (slots) {                                                    \
     case 1: { constexpr int S = 1; CALL; } break;                     \
@@ -207,6 +216,7 @@ int lob_replay_launch(const LobBookConfig* cfg, const LobReplayBuffers* bufs, in
   DevInfo d;
   if ((rc = device_info(&d))) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  if (grouped_class(cfg->n_orders) == 1) return launch_greplay<8, 14>(cfg, bufs, n_books, st, d);
   DISPATCH_SLOTS(slots_for(cfg->n_orders), rc = launch_replay<S>(cfg, bufs, n_books, st, d));
   return rc;
 }
