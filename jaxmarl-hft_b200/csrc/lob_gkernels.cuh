@@ -24,7 +24,7 @@ lob_greplay_kernel(const __grid_constant__ LobBookConfig cfg, const __grid_const
   constexpr int G = BK::G;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   BK bk;
-  bk.bind(cfg, dyn_smem() + warp * BK::kWarpWords);
+  bk.bind(cfg, dyn_smem() + warp * BK::kWarpWords, (long long)(B.bids - B.asks));
   const int g = lane / L;
   const int no = cfg.n_orders, nt = cfg.n_trades;
   const long long n_units = (n_books + G - 1) / G;
@@ -41,21 +41,24 @@ lob_greplay_kernel(const __grid_constant__ LobBookConfig cfg, const __grid_const
       T = B.n_msgs;
       if (st < 0 || avail <= 0) T = 0; else if (avail < T) T = (int)avail;
       mp = reinterpret_cast<const int4*>(B.msgs) + st * 2;
-      bk.rows[ASK] = B.asks + b * no * 6; bk.rows[BID] = B.bids + b * no * 6;
+      bk.rows0 = B.asks + b * no * 6;
       bk.tr = B.trades + b * nt * 8;
       bk.cu = B.cancel_u + b * (long long)B.n_msgs * 2;   // only dereferenced under cancel_mode 2/3
     }
     bk.load(cfg, have);
     bk.scan_trades(cfg, have);
-    const int Tmax = wmax(T);
-    int4 lo = make_int4(0, 0, 0, 0), hi = lo;
+    bk.ensure_both(cfg);   // micro() expects both best levels valid on entry
+    // every group runs through its own message stream, one row micro-op per iteration (lob_gbook.cuh), one message ahead
+    int idx = 0;
+    int4 lo = make_int4(0, 0, 0, 0), hi = lo, nlo = lo, nhi = lo;
     if (0 < T) { lo = ldg_msg(mp); hi = ldg_msg(mp + 1); }
-#pragma unroll 1
-    for (int i = 0; i < Tmax; ++i) {
-      int4 nlo = make_int4(0, 0, 0, 0), nhi = nlo;
-      if (i + 1 < T) { nlo = ldg_msg(mp + 2 * (i + 1)); nhi = ldg_msg(mp + 2 * (i + 1) + 1); }
-      bk.template process<false>(cfg, lo, hi, i < T, i);
-      lo = nlo; hi = nhi;
+    if (1 < T) { nlo = ldg_msg(mp + 2); nhi = ldg_msg(mp + 3); }
+    while (__any_sync(kFull, idx < T)) {
+      const bool fin = bk.template micro<false>(cfg, lo, hi, idx < T, idx);
+      if (fin & (idx < T)) {
+        lo = nlo; hi = nhi; idx += 1;
+        if (idx + 1 < T) { nlo = ldg_msg(mp + 2 * (idx + 1)); nhi = ldg_msg(mp + 2 * (idx + 1) + 1); }
+      }
     }
     if (B.best_out) {
       bk.settle(cfg);
