@@ -266,6 +266,8 @@ const char* lob_last_error(void);
 int lob_step_launch(const LobStepConfig* cfg, const LobStepBuffers* bufs, int64_t batch, void* cuda_stream);
 int lob_reset_launch(const LobStepConfig* cfg, const LobStepBuffers* bufs, int64_t batch, void* cuda_stream);
 int lob_replay_launch(const LobBookConfig* cfg, const LobReplayBuffers* bufs, int64_t n_books, void* cuda_stream);
+/* Measurement variant of lob_replay_launch (4 books per warp; n_orders <= 112): same results, slower -- see DESIGN.md 6 */
+int lob_replay_launch_grouped(const LobBookConfig* cfg, const LobReplayBuffers* bufs, int64_t n_books, void* cuda_stream);
 /* asks/bids [B,No,6] -> l2 [B,4*n_levels] = [ask_p,ask_q,bid_p,bid_q] x n_levels   job:1232-1264 */
 int lob_l2_launch(const LobBookConfig* cfg, const int32_t* asks, const int32_t* bids, int32_t* l2,
                   int32_t n_levels, int64_t n_books, void* cuda_stream);

@@ -35,6 +35,7 @@ def lib():
         L.lob_draw_launch_dev.argtypes = [C.POINTER(abi.LobStepConfig), C.POINTER(abi.LobStepBuffers), C.c_int64, C.c_int32,
                                           C.c_uint64, vp, vp]
         L.lob_replay_launch.argtypes = [C.POINTER(abi.LobBookConfig), C.POINTER(abi.LobReplayBuffers), C.c_int64, vp]
+        L.lob_replay_launch_grouped.argtypes = L.lob_replay_launch.argtypes
         L.lob_l2_launch.argtypes = [C.POINTER(abi.LobBookConfig), abi.p_i32, abi.p_i32, abi.p_i32, C.c_int32,
                                     C.c_int64, vp]
         L.lob_host_replay_create.argtypes = [C.POINTER(abi.LobBookConfig), C.c_int64, C.c_int64, C.c_int]
@@ -59,6 +60,14 @@ def check(rc, what):
         raise LobError(f"{what} failed ({rc}): {msg.decode() if msg else ''}")
 
 
-def current_stream_ptr():
+def current_stream_ptr(device=None):
+    """The current torch stream of ``device`` (default: the current device) as the ``void*`` the C ABI takes."""
     import torch
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def on_device(device):
+    """Context manager: make ``device`` the current CUDA device for the launches inside (the C entry points launch on the
+    current device and refuse buffers that live on another one)."""
+    import torch
+    return torch.cuda.device(torch.device(device))

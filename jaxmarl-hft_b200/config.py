@@ -331,6 +331,10 @@ def to_step_config(mac: MultiAgentConfig, n_windows: int, n_messages: int) -> ab
         raise ValueError("number_of_agents_per_type must have one entry per agent config")
     if len(types) > abi.LOB_MAX_AGENT_TYPES:
         raise ValueError(f"at most {abi.LOB_MAX_AGENT_TYPES} agent types")
+    if w.episode_time < 1:
+        raise ValueError(f"episode_time={w.episode_time}: must be >= 1")
+    if w.window_selector < -1:
+        raise ValueError(f"window_selector={w.window_selector}: -1 (random) or a window index")   # base:222-225
     c = abi.LobStepConfig()
     c.book = book_config(w)
     c.n_data_msg_per_step = w.n_data_msg_per_step
@@ -348,6 +352,13 @@ def to_step_config(mac: MultiAgentConfig, n_windows: int, n_messages: int) -> ab
     tid = w.trader_id_range_start  # marl:103-115: ids count down across types
     for i, (cfg, n) in enumerate(zip(types, mac.number_of_agents_per_type)):
         c.agent[i] = agent_type_config(cfg, n, tid)
+        # the values the kernels divide by (mirrors check_step_cfg in csrc/lobstep.cu)
+        if c.agent[i].reward_scaling_quo == 0:
+            raise ValueError(f"{cfg.short_name}: reward_scaling_quo must not be 0")
+        if c.agent[i].kind == abi.AGENT_MM and c.agent[i].sell_buy_all_option and c.agent[i].fixed_quant_value < 1:
+            raise ValueError(f"{cfg.short_name}: sell_buy_all_option needs fixed_quant_value >= 1")   # mm:1018
+        if c.agent[i].kind == abi.AGENT_EXE and c.agent[i].task_size < 1:
+            raise ValueError(f"{cfg.short_name}: task_size must be >= 1")
         if (c.ep_type_fixed_time and c.agent[i].kind == abi.AGENT_EXE
                 and c.agent[i].action_space == abi.EXE_ACTION_SPACES["twap"]):
             raise NotImplementedError("TWAP not implemented for fixed time episodes")   # exe:1141-1142

@@ -57,12 +57,17 @@ int check_step_cfg(const LobStepConfig* c) {
   if (c->tick_size < 1) return fail(LOB_E_INVALID, "tick_size=%d", c->tick_size);
   if (c->n_windows < 1) return fail(LOB_E_INVALID, "n_windows=%d", c->n_windows);
   if (c->n_messages < c->n_data_msg_per_step) return fail(LOB_E_INVALID, "n_messages < n_data_msg_per_step");
+  if (c->episode_time < 1) return fail(LOB_E_INVALID, "episode_time=%d", c->episode_time);
   int total = 0;
   for (int t = 0; t < c->n_agent_types; ++t) {
     const LobAgentTypeConfig* a = &c->agent[t];
     if (a->kind != LOB_AGENT_MM && a->kind != LOB_AGENT_EXE) return fail(LOB_E_INVALID, "agent[%d].kind=%d", t, a->kind);
     if (a->n_agents < 0) return fail(LOB_E_INVALID, "agent[%d].n_agents=%d", t, a->n_agents);
     total += a->n_agents;
+    if (a->reward_scaling_quo == 0.0) return fail(LOB_E_INVALID, "agent[%d].reward_scaling_quo is 0 (the reward is divided by it)", t);
+    if (a->kind == LOB_AGENT_MM && a->sell_buy_all_option && a->fixed_quant_value < 1)   // mm:1018: inventory // fixed_quant_value
+      return fail(LOB_E_INVALID, "agent[%d].fixed_quant_value=%d with sell_buy_all_option (an integer divisor)", t, a->fixed_quant_value);
+    if (a->kind == LOB_AGENT_EXE && a->task_size < 1) return fail(LOB_E_INVALID, "agent[%d].task_size=%d", t, a->task_size);
     const int ka = a->num_action_messages_by_agent, kc = a->num_messages_by_agent - ka;
     if (kc != ka || ka < 1 || ka > 16)
       return fail(LOB_E_INVALID, "agent[%d]: cancel (%d) and action (%d) message counts must match and be in [1,16]", t, kc, ka);
@@ -101,6 +106,28 @@ int check_step_cfg(const LobStepConfig* c) {
 
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
+// The kernels are launched on the CURRENT device: a buffer that lives on another GPU would be an illegal access that
+// poisons the context, so it is refused here (one driver query per launch, on the first state buffer).
+int check_on_current_device(const void* p, const char* what) {
+  cudaPointerAttributes at;
+  int dev = -1;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess || cudaGetDevice(&dev) != cudaSuccess) {
+    cudaGetLastError();
+    return fail(LOB_E_CUDA, "%s: cannot query the buffer's device", what);
+  }
+  if (at.type != cudaMemoryTypeDevice && at.type != cudaMemoryTypeManaged)
+    return fail(LOB_E_INVALID, "%s is not device memory", what);
+  if (at.type == cudaMemoryTypeDevice && at.device != dev)
+    return fail(LOB_E_INVALID, "%s lives on device %d but the current device is %d (set the device before the launch)", what, at.device, dev);
+  return LOB_OK;
+}
+
+struct DeviceGuard {   // cudaSetDevice for the scope of a host-replay call, restored on exit
+  int prev = -1;
+  explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
 int check_step_bufs(const LobStepConfig* c, const LobStepBuffers* b, bool step) {
   if (!b) return fail(LOB_E_INVALID, "null buffers");
 #define REQ(f) if (!b->f) return fail(LOB_E_INVALID, "buffer '" #f "' is null")
@@ -135,14 +162,6 @@ int slots_for(int n_orders) {
   int p = 1;
   while (p < s) p <<= 1;
   return p;
-}
-
-// Book-capacity class of the grouped kernels (lob_gbook.cuh): 1 = 8 lanes x 14 rows (up to 112 rows per side), 0 = none
-// (the one-warp-per-book kernels).  LOB_ONE_WARP_PER_BOOK=1 forces the latter (A/B measurements).
-int grouped_class(int n_orders) {
-  static const bool off = [] { const char* e = getenv("LOB_ONE_WARP_PER_BOOK"); return e && e[0] == '1'; }();
-  if (off) return 0;
-  return n_orders <= 112 ? 1 : 0;
 }
 
 #define DISPATCH_SLOTS(slots, CALL)                                   \
@@ -198,7 +217,7 @@ int32_t lob_info_f32_cols(const LobStepConfig* c, int32_t t) {
   return c->agent[t].kind == LOB_AGENT_MM ? LOB_MMINFO_F32_COLS : LOB_EXEINFO_F32_COLS;
 }
 
-int lob_replay_launch(const LobBookConfig* cfg, const LobReplayBuffers* bufs, int64_t n_books, void* cuda_stream) {
+static int check_replay(const LobBookConfig* cfg, const LobReplayBuffers* bufs, int64_t n_books) {
   int rc = check_book(cfg);
   if (rc) return rc;
   if (!bufs || !bufs->asks || !bufs->bids || !bufs->trades || !bufs->start)
@@ -212,13 +231,31 @@ int lob_replay_launch(const LobBookConfig* cfg, const LobReplayBuffers* bufs, in
       (bufs->best_out && !aligned16(bufs->best_out)))
     return fail(LOB_E_INVALID, "replay buffers must be 16-byte aligned");
   if (n_books < 0) return fail(LOB_E_INVALID, "n_books=%lld", (long long)n_books);
+  if (n_books > 0 && (rc = check_on_current_device(bufs->asks, "replay buffer 'asks'"))) return rc;
+  return LOB_OK;
+}
+
+int lob_replay_launch(const LobBookConfig* cfg, const LobReplayBuffers* bufs, int64_t n_books, void* cuda_stream) {
+  int rc = check_replay(cfg, bufs, n_books);
+  if (rc) return rc;
   if (n_books == 0) return LOB_OK;
   DevInfo d;
   if ((rc = device_info(&d))) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
-  if (grouped_class(cfg->n_orders) == 1) return launch_greplay<8, 14>(cfg, bufs, n_books, st, d);
   DISPATCH_SLOTS(slots_for(cfg->n_orders), rc = launch_replay<S>(cfg, bufs, n_books, st, d));
   return rc;
+}
+
+/* The A/B variant of the replay: 4 books per warp, 8 lanes per book (lob_gbook.cuh).  Same results, measured SLOWER than
+ * one warp per book (profiles/r2_ncu_greplay_grouped_*.txt); kept as the evidence of that measurement, not dispatched to. */
+int lob_replay_launch_grouped(const LobBookConfig* cfg, const LobReplayBuffers* bufs, int64_t n_books, void* cuda_stream) {
+  int rc = check_replay(cfg, bufs, n_books);
+  if (rc) return rc;
+  if (cfg->n_orders > 112) return fail(LOB_E_UNSUPPORTED, "grouped replay: n_orders=%d > 112", cfg->n_orders);
+  if (n_books == 0) return LOB_OK;
+  DevInfo d;
+  if ((rc = device_info(&d))) return rc;
+  return launch_greplay<8, 14>(cfg, bufs, n_books, static_cast<cudaStream_t>(cuda_stream), d);
 }
 
 int lob_step_launch(const LobStepConfig* cfg, const LobStepBuffers* bufs, int64_t batch, void* cuda_stream) {
@@ -227,6 +264,7 @@ int lob_step_launch(const LobStepConfig* cfg, const LobStepBuffers* bufs, int64_
   if ((rc = check_step_bufs(cfg, bufs, true))) return rc;
   if (batch < 0) return fail(LOB_E_INVALID, "batch=%lld", (long long)batch);
   if (batch == 0) return LOB_OK;
+  if ((rc = check_on_current_device(bufs->asks, "buffer 'asks'"))) return rc;
   DevInfo d;
   if ((rc = device_info(&d))) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
@@ -243,6 +281,7 @@ int lob_reset_launch(const LobStepConfig* cfg, const LobStepBuffers* bufs, int64
   DevInfo d;
   if ((rc = device_info(&d))) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  if ((rc = check_on_current_device(bufs->asks, "buffer 'asks'"))) return rc;
   DISPATCH_SLOTS(slots_for(cfg->book.n_orders), rc = launch_reset<S>(cfg, bufs, batch, st, d));
   return rc;
 }
@@ -269,7 +308,8 @@ static int draw_impl(const LobStepConfig* cfg, const LobStepBuffers* bufs, int64
   if (!cfg || !bufs) return fail(LOB_E_INVALID, "null argument");
   if (cfg->n_agent_types < 0 || cfg->n_agent_types > LOB_MAX_AGENT_TYPES || cfg->n_windows < 1)
     return fail(LOB_E_INVALID, "bad configuration for lob_draw_launch");
-  if (window_selector >= cfg->n_windows) return fail(LOB_E_INVALID, "window_selector=%d outside [0,%d)", window_selector, cfg->n_windows);
+  if (window_selector < -1 || window_selector >= cfg->n_windows)   // base:222-225: -1 = draw, else a window index
+    return fail(LOB_E_INVALID, "window_selector=%d outside [-1,%d)", window_selector, cfg->n_windows);
   if (batch < 0) return fail(LOB_E_INVALID, "batch=%lld", (long long)batch);
   if (batch == 0) return LOB_OK;
   const int n_act = lob_num_action_msgs(cfg);
@@ -319,7 +359,9 @@ LobHostReplay* lob_host_replay_create(const LobBookConfig* cfg, int64_t max_book
     return nullptr;
   }
   if (max_books < 1 || max_msgs_total < 1) { fail(LOB_E_INVALID, "host replay: empty capacity"); return nullptr; }
-  if (cudaSetDevice(device) != cudaSuccess) { fail(LOB_E_CUDA, "cudaSetDevice(%d) failed", device); return nullptr; }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) { fail(LOB_E_CUDA, "host replay: no CUDA device %d", device); return nullptr; }
+  DeviceGuard guard(device);
   LobHostReplay* h = new LobHostReplay();
   memset(h, 0, sizeof(*h));
   h->cfg = *cfg; h->max_books = max_books; h->max_msgs = max_msgs_total; h->device = device;
@@ -341,7 +383,7 @@ LobHostReplay* lob_host_replay_create(const LobBookConfig* cfg, int64_t max_book
 int lob_host_replay_set_messages(LobHostReplay* h, const int32_t* msgs_host, int64_t n_msgs_total) {
   if (!h || !msgs_host) return fail(LOB_E_INVALID, "host replay: null argument");
   if (n_msgs_total < 0 || n_msgs_total > h->max_msgs) return fail(LOB_E_INVALID, "host replay: %lld messages exceed capacity", (long long)n_msgs_total);
-  cudaSetDevice(h->device);
+  DeviceGuard guard(h->device);
   cudaError_t e = cudaMemcpyAsync(h->d_msgs, msgs_host, (size_t)n_msgs_total * 32, cudaMemcpyHostToDevice, h->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
   if (e != cudaSuccess) return fail(LOB_E_CUDA, "host replay set_messages: %s", cudaGetErrorString(e));
@@ -354,7 +396,12 @@ int lob_host_replay_run(LobHostReplay* h, int32_t* asks_host, int32_t* bids_host
                         int64_t* d2h_bytes) {
   if (!h || !asks_host || !bids_host || !trades_host || !start_host) return fail(LOB_E_INVALID, "host replay: null argument");
   if (n_books < 0 || n_books > h->max_books) return fail(LOB_E_INVALID, "host replay: %lld books exceed capacity", (long long)n_books);
-  cudaSetDevice(h->device);
+  if (n_msgs < 0 || n_msgs > h->n_msgs_resident) return fail(LOB_E_INVALID, "host replay: n_msgs=%d outside [0,%lld]", n_msgs, (long long)h->n_msgs_resident);
+  for (int64_t b = 0; b < n_books; ++b)   // a bad offset is an error here, not a silently unprocessed book
+    if (start_host[b] < 0 || start_host[b] + n_msgs > h->n_msgs_resident)
+      return fail(LOB_E_INVALID, "host replay: start[%lld]=%lld + %d messages leaves the %lld resident messages", (long long)b,
+                  (long long)start_host[b], n_msgs, (long long)h->n_msgs_resident);
+  DeviceGuard guard(h->device);
   const size_t side = (size_t)n_books * h->cfg.n_orders * 6 * 4, tr = (size_t)n_books * h->cfg.n_trades * 8 * 4;
   cudaError_t e = cudaMemcpyAsync(h->d_asks, asks_host, side, cudaMemcpyHostToDevice, h->stream);
   if (e == cudaSuccess) e = cudaMemcpyAsync(h->d_bids, bids_host, side, cudaMemcpyHostToDevice, h->stream);
@@ -379,7 +426,7 @@ int lob_host_replay_run(LobHostReplay* h, int32_t* asks_host, int32_t* bids_host
 
 void lob_host_replay_destroy(LobHostReplay* h) {
   if (!h) return;
-  cudaSetDevice(h->device);
+  DeviceGuard guard(h->device);
   if (h->d_asks) cudaFree(h->d_asks);
   if (h->d_bids) cudaFree(h->d_bids);
   if (h->d_trades) cudaFree(h->d_trades);

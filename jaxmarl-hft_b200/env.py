@@ -125,13 +125,17 @@ def build_reset_params(loaded: lobster.LoadedDay, world, replay_fn):
 
 
 # ---- device-side replay -------------------------------------------------------------------------------------
-def replay_books(book_cfg: abi.LobBookConfig, asks, bids, trades, msgs, start, n_msgs, best_out=None, cancel_u=None):
+def replay_books(book_cfg: abi.LobBookConfig, asks, bids, trades, msgs, start, n_msgs, best_out=None, cancel_u=None,
+                 grouped=False):
     """``job.scan_through_entire_array`` for every book (torch CUDA tensors, in place).  ``cancel_u`` float32
-    [B, n_msgs, 2]: the uniform draws of the random cancel fallbacks (cancel_mode 2/3, job:142-164)."""
+    [B, n_msgs, 2]: the uniform draws of the random cancel fallbacks (cancel_mode 2/3, job:142-164).  ``grouped`` selects
+    the 4-books-per-warp measurement variant (same results, slower)."""
     L = _lib.lib()
     r = states.pack_replay(asks, bids, trades, msgs, start, n_msgs, best_out, cancel_u)
-    _lib.check(L.lob_replay_launch(C.byref(book_cfg), C.byref(r), asks.shape[0], _lib.current_stream_ptr()),
-               "lob_replay_launch")
+    fn = L.lob_replay_launch_grouped if grouped else L.lob_replay_launch
+    with _lib.on_device(asks.device):
+        _lib.check(fn(C.byref(book_cfg), C.byref(r), asks.shape[0], _lib.current_stream_ptr(asks.device)),
+                   "lob_replay_launch")
 
 
 def l2_state(book_cfg: abi.LobBookConfig, asks, bids, n_levels):
@@ -140,8 +144,9 @@ def l2_state(book_cfg: abi.LobBookConfig, asks, bids, n_levels):
     L = _lib.lib()
     out = torch.empty((asks.shape[0], 4 * n_levels), dtype=torch.int32, device=asks.device)
     p = lambda t: C.cast(t.data_ptr(), abi.p_i32)
-    _lib.check(L.lob_l2_launch(C.byref(book_cfg), p(asks), p(bids), p(out), n_levels, asks.shape[0],
-                               _lib.current_stream_ptr()), "lob_l2_launch")
+    with _lib.on_device(asks.device):
+        _lib.check(L.lob_l2_launch(C.byref(book_cfg), p(asks), p(bids), p(out), n_levels, asks.shape[0],
+                                   _lib.current_stream_ptr(asks.device)), "lob_l2_launch")
     return out
 
 
@@ -310,10 +315,11 @@ class MARLEnv:
         if self._counter_dev is None:
             import torch
             self._counter_dev = torch.ones(1, dtype=torch.int64, device=self.device)   # device-resident: graph-capturable
-        _lib.check(_lib.lib().lob_draw_launch_dev(C.byref(self.cfg), C.byref(bufs), self.num_envs,
-                                                  int(self.multi_agent_config.world_config.window_selector), self._seed,
-                                                  C.c_void_p(self._counter_dev.data_ptr()), _lib.current_stream_ptr()),
-                   "lob_draw_launch_dev")
+        with _lib.on_device(self.device):
+            _lib.check(_lib.lib().lob_draw_launch_dev(C.byref(self.cfg), C.byref(bufs), self.num_envs,
+                                                      int(self.multi_agent_config.world_config.window_selector), self._seed,
+                                                      C.c_void_p(self._counter_dev.data_ptr()),
+                                                      _lib.current_stream_ptr(self.device)), "lob_draw_launch_dev")
 
     def reset(self, key=None, params: MultiAgentParams = None, arrays=None, draw=True):
         """marl_env.py:764 -> (obs list [B,n_i,d_i], MultiAgentState)."""
@@ -325,8 +331,9 @@ class MARLEnv:
         _, bufs, obs, _, _, _, state = self._bound(arrays)
         if draw:
             self._draw(arrays, bufs)
-        _lib.check(L.lob_reset_launch(C.byref(self.cfg), C.byref(bufs), self.num_envs, _lib.current_stream_ptr()),
-                   "lob_reset_launch")
+        with _lib.on_device(self.device):
+            _lib.check(L.lob_reset_launch(C.byref(self.cfg), C.byref(bufs), self.num_envs,
+                                          _lib.current_stream_ptr(self.device)), "lob_reset_launch")
         return obs, state
 
     def step(self, key, state: MultiAgentState, actions, params: MultiAgentParams = None, draw=True):
@@ -335,13 +342,16 @@ class MARLEnv:
         L = _lib.lib()
         arrays = state.arrays
         _, bufs, obs, rewards, dones, info, view = self._bound(arrays)
+        if len(actions) != self.cfg.n_agent_types:
+            raise ValueError(f"actions: one entry per agent type expected ({self.cfg.n_agent_types}), got {len(actions)}")
         for t, a in enumerate(actions):
             dst = arrays[f"actions{t}"]
             dst.copy_(a.reshape(dst.shape), non_blocking=True)
         if draw:
             self._draw(arrays, bufs)
-        _lib.check(L.lob_step_launch(C.byref(self.cfg), C.byref(bufs), self.num_envs, _lib.current_stream_ptr()),
-                   "lob_step_launch")
+        with _lib.on_device(self.device):
+            _lib.check(L.lob_step_launch(C.byref(self.cfg), C.byref(bufs), self.num_envs,
+                                         _lib.current_stream_ptr(self.device)), "lob_step_launch")
         return obs, view, rewards, dones, info
 
     def capture_step(self, state: MultiAgentState, actions, params: MultiAgentParams = None, pre=None, post=None):
@@ -351,24 +361,41 @@ class MARLEnv:
         enqueue copies (e.g. pinned host -> ``actions``, results -> pinned host).  Returns (graph, outputs) where outputs
         is what ``step`` returns (views of the in-place buffers)."""
         import torch
-        s = torch.cuda.Stream()
-        s.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(s):                      # warm-up outside capture (allocations, attribute queries)
-            if pre:
-                pre()
-            out = self.step(None, state, actions, params)
-            if post:
-                post(out)
-        torch.cuda.current_stream().wait_stream(s)
-        torch.cuda.synchronize()
-        g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
-            if pre:
-                pre()
-            out = self.step(None, state, actions, params)
-            if post:
-                post(out)
+        with torch.cuda.device(self.device):
+            snap = self._snapshot(state.arrays)
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):                  # warm-up outside capture (allocations, attribute queries)
+                if pre:
+                    pre()
+                out = self.step(None, state, actions, params)
+                if post:
+                    post(out)
+            torch.cuda.current_stream().wait_stream(s)
+            torch.cuda.synchronize()
+            self._restore(state.arrays, snap)           # the warm-up transition is undone: the caller's episode is untouched
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                if pre:
+                    pre()
+                out = self.step(None, state, actions, params)
+                if post:
+                    post(out)
         return g, out
+
+    def _snapshot(self, arrays):
+        """Copies of every leaf of the buffer table and of the device PRNG counter (the warm-up of a graph capture runs a
+        real step on them)."""
+        if self._counter_dev is None:
+            import torch
+            self._counter_dev = torch.ones(1, dtype=torch.int64, device=self.device)
+        return {k: v.clone() for k, v in arrays.items()}, self._counter_dev.clone()
+
+    def _restore(self, arrays, snap):
+        leaves, counter = snap
+        for k, v in leaves.items():
+            arrays[k].copy_(v)
+        self._counter_dev.copy_(counter)
 
     def capture_rollout(self, state: MultiAgentState, policy, n_steps: int, params: MultiAgentParams = None):
         """``n_steps`` env steps with the policy in between as ONE CUDA graph -- the ``jit(lax.scan(vmap(env.step)))`` of
@@ -400,15 +427,18 @@ class MARLEnv:
                     traj["done_agents"][t][k].copy_(arrays[f"done_agents{t}"])
                 traj["done"][k].copy_(arrays["done_all"])
 
-        s = torch.cuda.Stream()
-        s.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(s):
-            body(1)                                       # warm-up outside capture: runs ONE step
-        torch.cuda.current_stream().wait_stream(s)
-        torch.cuda.synchronize()
-        g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
-            body(n_steps)
+        with torch.cuda.device(self.device):
+            snap = self._snapshot(arrays)
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                body(1)                                   # warm-up outside capture: runs ONE step ...
+            torch.cuda.current_stream().wait_stream(s)
+            torch.cuda.synchronize()
+            self._restore(arrays, snap)                   # ... which is undone (state, outputs and the PRNG counter)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                body(n_steps)
         return g, traj
 
     def unpack_info(self, arrays):

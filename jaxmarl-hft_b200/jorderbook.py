@@ -75,6 +75,8 @@ class OrderBook:
         if l2_book is not None:
             l2 = np.asarray(l2_book)
             rows = l2.reshape(1, -1) if l2.ndim == 1 else l2
+            if rows.shape[0] not in (1, self.n_books):
+                raise ValueError(f"l2_book: one row or one row per book ({self.n_books}) expected, got {rows.shape[0]}")
             time = (0, 0) if time is None else time                                       # jorderbook.py:49-50
             m = np.stack([init_msgs_from_l2(self.cfg, r, time) for r in rows])            # [R, 2L, 8]
             msgs = torch.from_numpy(np.ascontiguousarray(m.reshape(-1, 8))).to(self.device)
@@ -95,8 +97,9 @@ class OrderBook:
             cu = (torch.randint(0, 2 ** 23, (self.n_books, n_msgs, 2), generator=g, device=self.device)
                   .to(torch.float32) / 2.0 ** 23)
         r = states.pack_replay(state.asks, state.bids, state.trades, msgs, start, n_msgs, best_out, cu)
-        _lib.check(_lib.lib().lob_replay_launch(C.byref(self.book_cfg), C.byref(r), self.n_books,
-                                                _lib.current_stream_ptr()), "lob_replay_launch")
+        with _lib.on_device(self.device):
+            _lib.check(_lib.lib().lob_replay_launch(C.byref(self.book_cfg), C.byref(r), self.n_books,
+                                                    _lib.current_stream_ptr(self.device)), "lob_replay_launch")
         return state._replace(key=state.key + 1)
 
     def _as_msgs(self, msgs):
@@ -177,8 +180,9 @@ class OrderBook:
                                torch.zeros(self.n_books, dtype=torch.int64, device=self.device), 0, best)
         cfg1 = abi.LobBookConfig.from_buffer_copy(self.book_cfg)
         cfg1.cancel_mode = min(int(cfg1.cancel_mode), 1)      # nothing is processed: no draws needed
-        _lib.check(_lib.lib().lob_replay_launch(C.byref(cfg1), C.byref(r), self.n_books, _lib.current_stream_ptr()),
-                   "lob_replay_launch")
+        with _lib.on_device(self.device):
+            _lib.check(_lib.lib().lob_replay_launch(C.byref(cfg1), C.byref(r), self.n_books,
+                                                    _lib.current_stream_ptr(self.device)), "lob_replay_launch")
         return best[:, 0:2], best[:, 2:4]
 
     def get_best_ask(self, state: LobState):
@@ -196,8 +200,9 @@ class OrderBook:
         import torch
         out = torch.empty((self.n_books, 4 * n_levels), dtype=torch.int32, device=self.device)
         p = lambda t: C.cast(t.data_ptr(), abi.p_i32)
-        _lib.check(_lib.lib().lob_l2_launch(C.byref(self.book_cfg), p(state.asks), p(state.bids), p(out), n_levels,
-                                            self.n_books, _lib.current_stream_ptr()), "lob_l2_launch")
+        with _lib.on_device(self.device):
+            _lib.check(_lib.lib().lob_l2_launch(C.byref(self.book_cfg), p(state.asks), p(state.bids), p(out), n_levels,
+                                                self.n_books, _lib.current_stream_ptr(self.device)), "lob_l2_launch")
         return out
 
     def get_side_ids(self, state: LobState, side: int):

@@ -92,8 +92,8 @@ def copy_inputs(src, dst):
 
 
 def assert_arrays_match(ref: dict, got: dict, cfg, rtol=1e-5, atol=1e-6, float_exact=False, skip=()):
-    """ints / bytes bit-exact; floats bit-exact where ``float_exact`` else rel 1e-5 (north_star's tolerance).
-    NaN == NaN (market_share is 0/0 when nothing traded, mm:2408)."""
+    """ints / bytes bit-exact; floats where ``float_exact``: the same BIT PATTERN (so +0.0 != -0.0), any NaN == any NaN
+    (market_share is 0/0 when nothing traded, mm:2408); else rel 1e-5 (north_star's tolerance)."""
     for k, r in ref.items():
         if k in skip:
             continue
@@ -101,7 +101,10 @@ def assert_arrays_match(ref: dict, got: dict, cfg, rtol=1e-5, atol=1e-6, float_e
         if r.dtype.kind in "iu":
             np.testing.assert_array_equal(g, r, err_msg=k)
         elif float_exact:
-            np.testing.assert_array_equal(g.view(np.uint32) if False else g, r, err_msg=k)
+            g32, r32 = np.ascontiguousarray(g, np.float32), np.ascontiguousarray(r, np.float32)
+            nan = np.isnan(g32) & np.isnan(r32)
+            np.testing.assert_array_equal(np.where(nan, 0, g32.view(np.uint32)), np.where(nan, 0, r32.view(np.uint32)),
+                                          err_msg=f"{k} (bit patterns)")
         else:
             np.testing.assert_allclose(g, r, rtol=rtol, atol=atol, equal_nan=True, err_msg=k)
 

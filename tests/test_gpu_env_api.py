@@ -94,8 +94,11 @@ def test_capture_step_graph_replays_like_eager_steps(oracle):
     states_ = [e.reset(None, p)[1] for e, p in zip(envs, params)]
     rng = np.random.default_rng(1)
     acts = [torch.zeros((B, 1), dtype=torch.int32, device="cuda") for _ in range(2)]
-    graph, out = envs[0].capture_step(states_[0], acts, params[0])     # the warm-up runs ONE step (capture itself runs nothing)
-    envs[1].step(None, states_[1], acts, params[1])
+    before = H.to_numpy(states_[0].arrays)
+    graph, out = envs[0].capture_step(states_[0], acts, params[0])     # the warm-up step is undone: capturing leaves no trace
+    after = H.to_numpy(states_[0].arrays)
+    for k in before:
+        np.testing.assert_array_equal(before[k], after[k], err_msg=k)
     for k in range(5):
         a_np = [rng.integers(0, sp.n, size=(B, 1)).astype(np.int32) for sp in envs[0].action_spaces]
         for t in range(2):
@@ -106,7 +109,7 @@ def test_capture_step_graph_replays_like_eager_steps(oracle):
     a, b = H.to_numpy(states_[0].arrays), H.to_numpy(states_[1].arrays)
     for k in a:
         np.testing.assert_array_equal(a[k], b[k], err_msg=k)
-    assert int(a["step_counter"].max()) == 6
+    assert int(a["step_counter"].max()) == 5
 
 
 def test_marl_env_fixed_time_episodes():
@@ -170,9 +173,8 @@ def test_capture_rollout_graph_equals_eager_steps():
     def policy(k, obs):    # a deterministic function of the observation: capturable device work only
         return [((obs[t].abs().sum(-1) * 1000.0).to(torch.int64) % n[t]).to(torch.int32) for t in range(2)]
 
-    graph, traj = envs[0].capture_rollout(states_[0], policy, T, params[0])          # warm-up ran ONE step
+    graph, traj = envs[0].capture_rollout(states_[0], policy, T, params[0])          # (the warm-up step is undone)
     obs1 = [states_[1].arrays[f"obs{t}"] for t in range(2)]
-    envs[1].step(None, states_[1], policy(0, obs1), params[1])
     graph.replay()
     ref = {"obs": [[], []], "reward": [[], []], "done": []}
     for k in range(T):
@@ -188,7 +190,7 @@ def test_capture_rollout_graph_equals_eager_steps():
     a, b = H.to_numpy(states_[0].arrays), H.to_numpy(states_[1].arrays)
     for k in a:
         np.testing.assert_array_equal(a[k], b[k], err_msg=k)
-    assert int(a["step_counter"].max()) == T + 1
+    assert int(a["step_counter"].max()) == T
 
 
 def test_graft_entry_smoke_runs():
