@@ -366,6 +366,26 @@ def to_step_config(mac: MultiAgentConfig, n_windows: int, n_messages: int) -> ab
     return c
 
 
+CONFIG_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "configs")
+
+
+def load_named_config(name: str, **world_overrides) -> MultiAgentConfig:
+    """One of the env JSONs shipped under ``configs/`` (the reference's config/env_configs/*.json), with optional
+    overrides of world-config fields."""
+    mac = load_config_from_file(os.path.join(CONFIG_DIR, name + ".json"))
+    if world_overrides:
+        mac = MultiAgentConfig(world_config=dataclasses.replace(mac.world_config, **world_overrides),
+                               dict_of_agents_configs=mac.dict_of_agents_configs,
+                               number_of_agents_per_type=mac.number_of_agents_per_type)
+    return mac
+
+
+def with_agents(mac: MultiAgentConfig, agents: dict, n_per_type) -> MultiAgentConfig:
+    """The same world with another set of agent types / counts."""
+    return MultiAgentConfig(world_config=mac.world_config, dict_of_agents_configs=agents,
+                            number_of_agents_per_type=list(n_per_type))
+
+
 def num_action_msgs(c: abi.LobStepConfig) -> int:
     return sum(c.agent[i].n_agents * c.agent[i].num_action_messages_by_agent for i in range(c.n_agent_types))
 

@@ -89,9 +89,20 @@ static inline int32_t f2i(float x) {
   return (int32_t)x;
 }
 
-/* The fixed reduction order of float sums over the trade log (see the header): 32 interleaved partial sums, then a
- * butterfly.  term[r] is the r-th addend. */
+/* The reduction order of float sums over the trade log (see the header).  Mode 0 (default, shared bit for bit with the
+ * CUDA path): 32 interleaved partial sums, then a butterfly.  Mode 1: strictly left to right -- the order in which the
+ * golden vectors were produced (tests/golden/jaxshim/jax/_core.py:_seq_sum), used by tests/test_golden.py to check this
+ * restatement against them at 1e-5 relative on EVERY float leaf, including the ill-conditioned EXE reward family
+ * (exe:1627-1665) whose value moves with the summation order.  term[r] is the r-th addend. */
+static int g_sum_order = 0;
+void lob_oracle_set_sum_order(int left_to_right) { g_sum_order = left_to_right ? 1 : 0; }
+int lob_oracle_get_sum_order(void) { return g_sum_order; }
 static float wsumf(const float* term, int n) {
+  if (g_sum_order) {
+    float s = 0.f;
+    for (int r = 0; r < n; ++r) s = s + term[r];
+    return s;
+  }
   float acc[32], nxt[32];
   for (int l = 0; l < 32; ++l) acc[l] = 0.f;
   for (int r = 0; r < n; ++r) acc[r & 31] = acc[r & 31] + term[r];

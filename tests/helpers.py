@@ -1,26 +1,18 @@
 """Shared test scaffolding: configs, a numpy env driven by the CPU oracle, seeded PRNG products."""
-import dataclasses
 import os
+import sys
 
 import numpy as np
 
 from jaxmarl_hft_b200 import abi, config as C, env as E, lobster, states
 
-CONFIG_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "jaxmarl-hft_b200", "configs")
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
+from oracle.harness import OracleEnv, draw_actions, draw_prng, oracle_replay_fn  # noqa: F401  (re-exported)
 
-def load_mac(name, **world_overrides) -> C.MultiAgentConfig:
-    mac = C.load_config_from_file(os.path.join(CONFIG_DIR, name + ".json"))
-    if world_overrides:
-        mac = C.MultiAgentConfig(world_config=dataclasses.replace(mac.world_config, **world_overrides),
-                                 dict_of_agents_configs=mac.dict_of_agents_configs,
-                                 number_of_agents_per_type=mac.number_of_agents_per_type)
-    return mac
-
-
-def with_agents(mac, agents: dict, n_per_type) -> C.MultiAgentConfig:
-    return C.MultiAgentConfig(world_config=mac.world_config, dict_of_agents_configs=agents,
-                              number_of_agents_per_type=list(n_per_type))
+CONFIG_DIR = C.CONFIG_DIR
+load_mac = C.load_named_config
+with_agents = C.with_agents
 
 
 _DAY_CACHE = {}
@@ -37,52 +29,6 @@ def load_for(mac, day):
     w = mac.world_config
     return lobster.load_days([day], w.episode_time, w.n_data_msg_per_step, w.start_resolution, w.day_start, w.day_end,
                              window_type=w.ep_type)
-
-
-def oracle_replay_fn(oracle, book_cfg):
-    book_cfg = E.limit_only_book_config(book_cfg)
-
-    def fn(asks, bids, trades, msgs, start, n_msgs):
-        oracle.replay(book_cfg, asks, bids, trades, msgs, start, n_msgs)
-        return asks, bids, trades
-    return fn
-
-
-class OracleEnv:
-    """MARLEnv over numpy arrays, computed by the oracle.  Mirrors jaxmarl_hft_b200.env.MARLEnv's buffer handling."""
-
-    def __init__(self, oracle, mac, loaded, num_envs):
-        self.oracle, self.mac, self.loaded, self.B = oracle, mac, loaded, num_envs
-        w = mac.world_config
-        self.book_cfg = C.book_config(w)
-        self.params = E.build_reset_params(loaded, w, oracle_replay_fn(oracle, self.book_cfg))
-        self.cfg = C.to_step_config(mac, loaded.starts.shape[0], loaded.msgs.shape[0])
-        self.arrays = states.alloc_numpy(self.cfg, num_envs)
-
-    def reset(self):
-        self.oracle.reset(self.cfg, self.arrays, self.params)
-
-    def step(self, n_threads=1):
-        self.oracle.step(self.cfg, self.arrays, self.params, n_threads)
-
-
-def draw_prng(rng, cfg, arrays):
-    """Seeded stand-ins for the jax.random products (perm, reset window, is_sell)."""
-    B = arrays["asks"].shape[0]
-    arrays["reset_window"][:] = rng.integers(0, cfg.n_windows, size=B)
-    arrays["reset_is_sell"][:] = rng.integers(0, 2, size=arrays["reset_is_sell"].shape)
-    n_act = C.num_action_msgs(cfg)
-    if n_act:
-        arrays["perm"][:] = np.argsort(rng.random((B, n_act)), axis=1)
-    if "cancel_u" in arrays:   # jax.random.uniform: multiples of 2^-23 in [0, 1)
-        arrays["cancel_u"][:] = rng.integers(0, 2 ** 23, size=arrays["cancel_u"].shape).astype(np.float32) / np.float32(2 ** 23)
-
-
-def draw_actions(rng, cfg, arrays):
-    for t in range(cfg.n_agent_types):
-        a = cfg.agent[t]
-        hi = a.fixed_quant_value if abi.action_width(a) > 1 else a.n_actions   # fixed_prices: a vector of quantities
-        arrays[f"actions{t}"][:] = rng.integers(0, hi, size=arrays[f"actions{t}"].shape)
 
 
 def copy_inputs(src, dst):

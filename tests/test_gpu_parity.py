@@ -400,3 +400,111 @@ def test_step_on_adversarial_day(oracle):
             H.assert_arrays_match(ref.arrays, gpu.numpy(), ref.cfg)
         except AssertionError as e:
             raise AssertionError(f"step {s}: {e}") from None
+
+
+# ---- BASELINE.json sizes, CUDA vs the oracle (OpenMP over books / envs on the box's host cores) ----------------------
+def _bench_day(mac):
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    return lobster.load_or_generate(mac.world_config, seed=20220103, n_events=400_000, cache_dir=os.path.join(root, ".cache"))
+
+
+def _full_size_rollout(oracle, mac, B, steps, seed):
+    """env.reset + ``steps`` x env.step on B environments of the bench's synthetic day: every state, output and info leaf of
+    every environment after EVERY step (ints bit-exact, floats rel 1e-5)."""
+    ld = _bench_day(mac)
+    ref = H.OracleEnv(oracle, mac, ld, B)
+    gpu = H.CudaEnv(mac, ld, B, ref.params)
+    threads = oracle.max_threads()
+    rng = np.random.default_rng(seed)
+    H.draw_prng(rng, ref.cfg, ref.arrays)
+    gpu.set_inputs(ref.arrays)
+    ref.reset(); gpu.reset()
+    H.assert_arrays_match(ref.arrays, gpu.numpy(), ref.cfg)
+    n_done = 0
+    for s in range(steps):
+        H.draw_prng(rng, ref.cfg, ref.arrays)
+        H.draw_actions(rng, ref.cfg, ref.arrays)
+        gpu.set_inputs(ref.arrays)
+        gpu.step(); ref.step(n_threads=threads)      # (the launch is asynchronous: both sides work at the same time)
+        try:
+            H.assert_arrays_match(ref.arrays, gpu.numpy(), ref.cfg)
+        except AssertionError as e:
+            raise AssertionError(f"step {s}: {e}") from None
+        n_done += int(ref.arrays["done_all"].sum())
+    return ref, n_done
+
+
+def test_baseline_config2_exec_8192_envs(oracle):
+    """BASELINE configs[2] AS WRITTEN: single execution agent (exec_longrun_fixed_quants_complex), NUM_ENVS = 8192,
+    a whole 64-step episode plus the first step after the auto-reset."""
+    mac = H.load_mac("exec_longrun_fixed_quants_complex")
+    ref, n_done = _full_size_rollout(oracle, mac, 8192, 65, seed=21)
+    assert n_done == 8192
+
+
+def test_baseline_config3_2player_16384_envs(oracle):
+    """BASELINE configs[3] shapes at the bench's per-GPU batch: 2_player_fq_fqc, 16384 envs, 66 steps (crosses the
+    auto-reset: done on the 64th step, quirk Q14)."""
+    mac = H.load_mac("2_player_fq_fqc")
+    ref, n_done = _full_size_rollout(oracle, mac, 16384, 66, seed=22)
+    assert n_done == 16384
+
+
+def test_baseline_config1_replay_16384_books(oracle):
+    """BASELINE configs[1] AS WRITTEN: 16384 books x 6400 messages of the bench's day, from the windows' reset states:
+    books, trade logs and best prices against the oracle's replay (105 M messages on the host cores)."""
+    mac = H.load_mac("2_player_fq_fqc")
+    ld = _bench_day(mac)
+    bc = C.book_config(mac.world_config)
+    params = E.build_reset_params(ld, mac.world_config, H.oracle_replay_fn(oracle, bc))
+    B, W, M, T = 16384, ld.starts.shape[0], ld.msgs.shape[0], 6400
+    widx = np.arange(B) % W
+    a0, b0, t0 = params["init_asks"][widx].copy(), params["init_bids"][widx].copy(), params["init_trades"][widx].copy()
+    start = ((ld.starts[widx].astype(np.int64) + (np.arange(B) // W) % 100) % (M - T)).astype(np.int64)   # bench.py's offsets
+    ra, rb, rt = a0.copy(), b0.copy(), t0.copy()
+    rbest = np.zeros((B, 4), np.int32)
+    oracle.replay(bc, ra, rb, rt, ld.msgs, start, T, best_out=rbest, n_threads=oracle.max_threads())
+    ga, gb, gt, gbest = H.cuda_replay(bc, a0, b0, t0, ld.msgs, start, T, want_best=True)
+    np.testing.assert_array_equal(ga, ra); np.testing.assert_array_equal(gb, rb)
+    np.testing.assert_array_equal(gt, rt); np.testing.assert_array_equal(gbest, rbest)
+
+
+def test_grouped_replay_variant_bit_exact(oracle):
+    """The measurement variant lob_replay_launch_grouped (4 books per warp) gives the same books as the oracle."""
+    import torch
+    rng = np.random.default_rng(77)
+    bc = _book_cfg(100, 100)
+    B, T = 70, 900
+    msgs = H.random_messages(rng, B * T, bc)
+    start = np.arange(B, dtype=np.int64) * T
+    a0 = np.full((B, 100, 6), -1, np.int32); b0 = a0.copy(); t0 = np.full((B, 100, 8), -1, np.int32)
+    ra, rb, rt = a0.copy(), b0.copy(), t0.copy()
+    oracle.replay(bc, ra, rb, rt, msgs, start, T)
+    dev = torch.device("cuda:0")
+    ta, tb, tt = (torch.from_numpy(x).to(dev) for x in (a0, b0, t0))
+    E.replay_books(bc, ta, tb, tt, torch.from_numpy(msgs).to(dev), torch.from_numpy(start).to(dev), T, grouped=True)
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(ta.cpu().numpy(), ra); np.testing.assert_array_equal(tb.cpu().numpy(), rb)
+    np.testing.assert_array_equal(tt.cpu().numpy(), rt)
+
+
+def test_launch_follows_the_envs_device(oracle):
+    """an env on cuda:1 while the current device is 0 must launch on GPU 1 (needs two GPUs), and the C entry
+    point refuses buffers of another device instead of faulting."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from jaxmarl_hft_b200 import _lib
+    mac = H.load_mac("2_player_fq_fqc")
+    ld = H.load_for(mac, H.small_day(n_events=30000))
+    torch.cuda.set_device(0)
+    env = E.MARLEnv(None, mac, num_envs=64, loaded=ld, device="cuda:1", seed=5)
+    obs, state = env.reset(None, env.default_params)
+    acts = [torch.zeros((64, 1), dtype=torch.int32, device="cuda:1") for _ in range(2)]
+    env.step(None, state, acts, env.default_params)
+    torch.cuda.synchronize(1)
+    assert state.arrays["asks"].device.index == 1 and int(state.arrays["step_counter"].max()) == 1
+    bufs = states.pack_buffers(env.cfg, state.arrays, env.base_env.device_params())
+    rc = _lib.lib().lob_step_launch(ctypes.byref(env.cfg), ctypes.byref(bufs), 64, _lib.current_stream_ptr())   # current device 0
+    assert rc == abi.LOB_E_INVALID and b"device" in _lib.lib().lob_last_error()
