@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define LOB_ABI_VERSION 7
+#define LOB_ABI_VERSION 8
 #define LOB_MAX_AGENT_TYPES 8
 #define LOB_MAX_AGENT_I32 4  /* int32 state leaves per agent type */
 #define LOB_MAX_AGENT_F32 10 /* float32 state leaves per agent type */
@@ -244,6 +244,13 @@ typedef struct LobStepBuffers {
   float*   info_world_f32;                   /* [B,LOB_WINFO_F32_COLS] */
   int32_t* info_agent_i32[LOB_MAX_AGENT_TYPES]; /* [B,n_i,Ki] */
   float*   info_agent_f32[LOB_MAX_AGENT_TYPES]; /* [B,n_i,Kf] */
+  /* optional workspace of lob_step_launch (both NULL = not used; contents are scratch, not state).  With it, books deeper
+   * than 128 rows per side are stepped on a 128-row shared-memory window (the reference rests an order in the LOWEST blank
+   * row, JaxOrderBookArrays.py:73, so the live orders sit in the first rows); the environments whose book does not fit
+   * are listed here and redone at full capacity by a second launch of the same call.  Results are identical either way. */
+  int32_t* work_redo_list;                   /* [B] environment indices of the second pass */
+  int32_t* work_redo_count;                  /* [4] word 0: environments in the second pass of the LAST call; word 1: running
+                                                total over all calls (statistics); 16-byte aligned */
 } LobStepBuffers;
 
 /* ---- pure replay: every book b scans msgs[start[b] .. start[b]+n_msgs) -- */

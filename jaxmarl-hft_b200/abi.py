@@ -5,7 +5,7 @@ Field order and types follow the header exactly; ``check_sizes`` compares ``ctyp
 """
 import ctypes as C
 
-LOB_ABI_VERSION = 7
+LOB_ABI_VERSION = 8
 LOB_MAX_AGENT_TYPES = 8
 LOB_MAX_AGENT_I32 = 4
 LOB_MAX_AGENT_F32 = 10
@@ -89,7 +89,8 @@ class LobStepBuffers(C.Structure):
         ("obs", p_f32 * LOB_MAX_AGENT_TYPES), ("reward", p_f32 * LOB_MAX_AGENT_TYPES),
         ("done_all", p_u8), ("done_agents", p_u8 * LOB_MAX_AGENT_TYPES),
         ("info_world_i32", p_i32), ("info_world_f32", p_f32),
-        ("info_agent_i32", p_i32 * LOB_MAX_AGENT_TYPES), ("info_agent_f32", p_f32 * LOB_MAX_AGENT_TYPES)]
+        ("info_agent_i32", p_i32 * LOB_MAX_AGENT_TYPES), ("info_agent_f32", p_f32 * LOB_MAX_AGENT_TYPES),
+        ("work_redo_list", p_i32), ("work_redo_count", p_i32)]
 
 
 class LobReplayBuffers(C.Structure):

@@ -73,6 +73,8 @@ struct BookCtx {
   int cmode;   // cst CancelMode; 2 / 3 add the random same-price fallbacks of job:142-164
   int mi;      // index of the current message in the scan (selects its pair of uniform draws)
   const float* cu;   // [n_msgs][2] uniform draws of this book's scan (cancel_mode 2/3), else unused
+  int extra_blank;   // WINDOW mode (Book<SLOTS, true>): rows of the real book beyond the `no` rows held in shared memory, all
+                     // of them blank (checked when the book is staged); 0 otherwise
 };
 __device__ __forceinline__ int* dyn_smem() { extern __shared__ __align__(128) int lob_dyn_smem[]; return lob_dyn_smem; }
 __device__ __forceinline__ int* rowp(const BookCtx& c, int s, int r) { return dyn_smem() + c.rows_off + (s * c.nrows + r) * 6; }
@@ -310,6 +312,7 @@ static __device__ __noinline__ Best g_best(BookCtx c, int s) {
   }
   Best b;
   b.p = bp; b.q = wsum(q); b.n = wsum(n);
+  if (bp == -1) { b.q -= c.extra_blank; b.n += c.extra_blank; }   // the blank rows beyond the window count too (quirk Q7)
   return b;
 }
 // job:920-930 get_volume
@@ -360,7 +363,13 @@ static __device__ __noinline__ TradeScan g_scan_trades(BookCtx c) {
 }
 
 // ======================================================================================= fast path =============
-template <int SLOTS>
+// WIN = true: the WINDOW mode of deep books.  Shared memory holds only the first kRows rows of each side; the rows beyond
+// (c.extra_blank of them) were all blank when the book was staged.  The reference always rests an order in the LOWEST
+// blank row (job:73), so a book whose live orders fit the window never touches the rows beyond it, and every fast path
+// is exact on the window alone.  Whatever would need them -- an order that finds no blank row in the window, any call
+// into the literal path -- sets kAborted instead: the caller drops the step of this environment (nothing of it has been
+// written back) and hands it to the full-size kernel.
+template <int SLOTS, bool WIN = false>
 struct Book {
   static constexpr int kRows = SLOTS * 32;
   BookCtx c;
@@ -373,14 +382,16 @@ struct Book {
   //   bit 2: the trade rows after ntr are not all free -> the trade slot must be searched
   //   bit 3: type-4 messages are MKT orders (Type4Interpretation.MKT): prices are rewritten, always generic
   unsigned oddm;
-  static constexpr unsigned kOddTrades = 4u, kOddMkt = 8u;
+  static constexpr unsigned kOddTrades = 4u, kOddMkt = 8u, kAborted = 16u;
+  __device__ __forceinline__ bool aborted() const { return WIN && (oddm & kAborted) != 0u; }
   int ntr;            // next trade row: first row whose time_s column is -1
   __device__ __forceinline__ bool odd(int s) const { return (oddm >> s) & 1u; }
   __device__ __forceinline__ void set_bit(unsigned bit, bool on) { oddm = on ? (oddm | bit) : (oddm & ~bit); }
 
   __device__ __forceinline__ void init(const LobBookConfig& cfg, int* smem_book) {
     c.rows_off = (int)(smem_book - dyn_smem()); c.tr = nullptr; c.nrows = kRows;
-    c.no = cfg.n_orders; c.nt = cfg.n_trades;
+    c.no = WIN ? kRows : cfg.n_orders; c.nt = cfg.n_trades;
+    c.extra_blank = WIN ? cfg.n_orders - kRows : 0;
     c.maxint = cfg.maxint; c.init_id = cfg.init_id; c.init_lo = cfg.init_id - 2 * cfg.book_depth;
     c.t4 = cfg.type_4_interpretation; c.check_fill = cfg.check_book_fill;
     c.cmode = cfg.cancel_mode; c.mi = 0; c.cu = nullptr;
@@ -431,7 +442,7 @@ struct Book {
   // ---- derive the register-resident summaries from shared memory ----
   __device__ __forceinline__ void scan_side(int s) {
     const SideScan r = g_scan_side(c, s);
-    flag[s] = r.flag; nneg[s] = r.nneg; set_bit(1u << s, r.odd != 0); valid[s] = false;
+    flag[s] = r.flag; nneg[s] = r.nneg + (WIN ? c.extra_blank : 0); set_bit(1u << s, r.odd != 0); valid[s] = false;
   }
   __device__ __forceinline__ void scan_trades() {
     const TradeScan t = g_scan_trades(c);
@@ -541,6 +552,7 @@ struct Book {
         }
       }
       if (degenerate) {          // the literal loop from here on (it may stop at a blank row), then rebuild the summaries
+        if (WIN) { oddm |= kAborted; return qtm; }
         __syncwarp();
         drop_best();
         qtm = g_match(c, OPP, m, qtm);
@@ -573,6 +585,7 @@ struct Book {
   }
 
   __device__ __forceinline__ void generic(const Msg& m) {
+    if (WIN) { oddm |= kAborted; return; }
     __syncwarp();
     drop_best();
     g_process(c, m);
@@ -584,7 +597,9 @@ struct Book {
   __device__ __forceinline__ void limit(const Msg& m) {
     constexpr int OPP = 1 - OWN;
     const int qtm = match<OPP>(m, m.qty);
+    if (WIN && aborted()) return;
     if (c.check_fill && nneg[OWN] == 0) {   // job:395-401: full side -> the worst price level is evicted
+      if (WIN) { oddm |= kAborted; return; }   // (unreachable: the rows beyond the window are blank)
       drop_best();
       g_evict(c, OWN);
       scan_side(OWN);
@@ -595,6 +610,7 @@ struct Book {
     if (q == 0 && r != kBig && !odd(OWN)) return;   // written into a blank row and blanked again (job:83): no-op
     const bool neg1 = (m.price == -1) | (m.oid == -1) | (m.tid == -1) | (m.ts == -1) | (m.tns == -1);
     if (q == 0 || r == kBig || odd(OWN) || neg1 || m.price <= 0 || m.price == c.maxint) {   // (an ask AT maxint reads as "empty", job:940)
+      if (WIN) { oddm |= kAborted; return; }   // in particular r == kBig: the window is full, the order rests beyond it
       Msg a = m;
       a.qty = qtm;
       __syncwarp();
@@ -640,10 +656,15 @@ struct Book {
       }
       j = wmin(j);
       if (j >= c.no && c.cmode >= 2) {   // the random same-price fallbacks (job:142-164) live in the generic path
+        if (WIN) { oddm |= kAborted; return; }
         __syncwarp();
         drop_best();
         g_cancel(c, S, m);
         scan_side(S);
+        return;
+      }
+      if (WIN && j >= c.no) {   // the LAST row of the real book takes the cancel: it is blank (beyond the window)
+        if (m.qty < 0) oddm |= kAborted;
         return;
       }
       idx = (j < c.no) ? j : c.no - 1;
@@ -651,6 +672,7 @@ struct Book {
     const int2 pq = lds64(row_sa(S, idx));
     if (pq.x == -1) {        // a blank row takes the cancel: qty = -1 - q stays <= 0 and the row is blanked again
       if (m.qty >= 0) return;
+      if (WIN) { oddm |= kAborted; return; }
       __syncwarp();
       drop_best();
       g_cancel(c, S, m);

@@ -18,8 +18,9 @@ int launch_replay(const LobBookConfig* cfg, const LobReplayBuffers* bufs, int64_
   return launched("lob_replay_kernel");
 }
 
-template <int S>
-int launch_step(const LobStepConfig* c, const LobStepBuffers* b, int64_t batch, cudaStream_t st, const DevInfo& d) {
+// WIN: the shared-memory window pass of deep books (see lob_step_kernel); LIST: walk b->work_redo_list (second pass).
+template <int S, bool WIN, bool LIST>
+static int launch_step_impl(const LobStepConfig* c, const LobStepBuffers* b, int64_t batch, cudaStream_t st, const DevInfo& d) {
   const int N = lob_num_msgs_per_step(c), n_act = lob_num_action_msgs(c), n_cnl = lob_num_cancel_msgs(c);
   int n_agents = 0;
   for (int t = 0; t < c->n_agent_types; ++t) n_agents += c->agent[t].n_agents;
@@ -27,8 +28,9 @@ int launch_step(const LobStepConfig* c, const LobStepBuffers* b, int64_t batch, 
   if (((n_cnl + n_act) * 8) % 4 != 0) return fail(LOB_E_INVALID, "internal: data slice misaligned");
   // one persistent CTA per SM; as many warps (= environments in flight) as shared memory and registers allow
   const size_t per_warp = (size_t)L.words * 4;
+  auto kernel = lob::lob_step_kernel<S, WIN>;
   cudaFuncAttributes fa;
-  cudaError_t e = cudaFuncGetAttributes(&fa, lob::lob_step_kernel<S>);
+  cudaError_t e = cudaFuncGetAttributes(&fa, kernel);
   if (e != cudaSuccess) return fail(LOB_E_CUDA, "cudaFuncGetAttributes: %s", cudaGetErrorString(e));
   const int G = lob::kStepCtasPerSm;   // CTAs (phase-synchronous groups) per SM
   int warps = (int)((((size_t)d.max_smem_optin + 1024) / G - 1024 - fa.sharedSizeBytes) / per_warp);
@@ -39,16 +41,31 @@ int launch_step(const LobStepConfig* c, const LobStepBuffers* b, int64_t batch, 
     return fail(LOB_E_INVALID, "configuration needs %zu B of shared memory per environment (device limit %d)", per_warp,
                 d.max_smem_optin);
   const size_t smem = per_warp * warps;
-  e = cudaFuncSetAttribute(lob::lob_step_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return fail(LOB_E_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
   int need_extreme = 0;
   for (int t = 0; t < c->n_agent_types; ++t)
     if (c->agent[t].kind == LOB_AGENT_MM && c->agent[t].exclude_extreme_spreads) need_extreme = 1;
-  long long ctas = (batch + warps - 1) / warps;
+  long long ctas = (batch + warps - 1) / warps;   // (LIST: the count is only known on the device -> at most `batch`)
   if (ctas > (long long)d.sms * G) ctas = (long long)d.sms * G;
-  lob::lob_step_kernel<S><<<(int)ctas, warps * 32, smem, st>>>(*c, *b, batch, L, N, n_act, n_cnl, need_extreme);
+  kernel<<<(int)ctas, warps * 32, smem, st>>>(*c, *b, batch, L, N, n_act, n_cnl, need_extreme,
+                                              LIST ? b->work_redo_list : nullptr, LIST ? b->work_redo_count : nullptr);
   return launched("lob_step_kernel");
 }
+
+template <int S>
+int launch_step(const LobStepConfig* c, const LobStepBuffers* b, int64_t batch, cudaStream_t st, const DevInfo& d) {
+  return launch_step_impl<S, false, false>(c, b, batch, st, d);
+}
+template <int S>
+int launch_step_redo(const LobStepConfig* c, const LobStepBuffers* b, int64_t batch, cudaStream_t st, const DevInfo& d) {
+  return launch_step_impl<S, false, true>(c, b, batch, st, d);
+}
+#if LOB_SLOTS == LOB_WINDOW_SLOTS
+int launch_step_window(const LobStepConfig* c, const LobStepBuffers* b, int64_t batch, cudaStream_t st, const DevInfo& d) {
+  return launch_step_impl<LOB_SLOTS, true, false>(c, b, batch, st, d);
+}
+#endif
 
 template <int S>
 int launch_reset(const LobStepConfig* c, const LobStepBuffers* b, int64_t batch, cudaStream_t st, const DevInfo& d) {
@@ -72,6 +89,7 @@ int launch_l2(const LobBookConfig* cfg, const int32_t* asks, const int32_t* bids
 
 template int launch_replay<LOB_SLOTS>(const LobBookConfig*, const LobReplayBuffers*, int64_t, cudaStream_t, const DevInfo&);
 template int launch_step<LOB_SLOTS>(const LobStepConfig*, const LobStepBuffers*, int64_t, cudaStream_t, const DevInfo&);
+template int launch_step_redo<LOB_SLOTS>(const LobStepConfig*, const LobStepBuffers*, int64_t, cudaStream_t, const DevInfo&);
 template int launch_reset<LOB_SLOTS>(const LobStepConfig*, const LobStepBuffers*, int64_t, cudaStream_t, const DevInfo&);
 template int launch_l2<LOB_SLOTS>(const LobBookConfig*, const int32_t*, const int32_t*, int32_t*, int32_t, int64_t, cudaStream_t, const DevInfo&);
 

@@ -225,8 +225,8 @@ __device__ __forceinline__ int obs_dim_of(const LobAgentTypeConfig& a, int fixed
 
 // marl_env.py:130-207 reset_env for env e: the precomputed state of window reset_window[e] replaces every leaf.
 // The book / trade log are left in shared memory (the caller stores them); everything else is written here.
-template <int SLOTS>
-__device__ __noinline__ void reset_env(const LobStepConfig& c, const LobStepBuffers& b, long long e, Book<SLOTS>& bk,
+template <int SLOTS, bool WIN>
+__device__ __noinline__ void reset_env(const LobStepConfig& c, const LobStepBuffers& b, long long e, Book<SLOTS, WIN>& bk,
                                           int N) {
   const int lane = lane_id();
   const int no = c.book.n_orders, nt = c.book.n_trades, T = c.n_agent_types;
@@ -236,6 +236,16 @@ __device__ __noinline__ void reset_env(const LobStepConfig& c, const LobStepBuff
   __syncwarp();
   bk.load_side(ASK, b.init_asks + (long long)wdx * no * 6);
   bk.load_side(BID, b.init_bids + (long long)wdx * no * 6);
+  if (WIN) {   // the rows beyond the shared-memory window go straight to the state (if they are not blank, the next step of
+               // this environment finds out when it stages the book and runs on the full-size kernel)
+    constexpr int W = Book<SLOTS, WIN>::kRows;
+    const int tail2 = (no - W) * 3;   // int2 per side
+    const int2* sa = reinterpret_cast<const int2*>(b.init_asks + ((long long)wdx * no + W) * 6);
+    const int2* sb = reinterpret_cast<const int2*>(b.init_bids + ((long long)wdx * no + W) * 6);
+    int2* da = reinterpret_cast<int2*>(b.asks + (e * no + W) * 6);
+    int2* db = reinterpret_cast<int2*>(b.bids + (e * no + W) * 6);
+    for (int i = lane; i < tail2; i += 32) { da[i] = sa[i]; db[i] = sb[i]; }
+  }
   bk.c.tr = b.trades + e * nt * 8;
   bk.load_trades(b.init_trades + (long long)wdx * nt * 8);   // straight into the state buffer
   __syncwarp();
@@ -282,7 +292,7 @@ __device__ __noinline__ void reset_env(const LobStepConfig& c, const LobStepBuff
 // marl:348-364 the scan of one step's message list, with the per-message best bid/ask (job:792-823) and the forward
 // fill (marl:723-749) done online.  A function of its own so that the hot loop gets its own register allocation:
 // nothing of the surrounding step (world scalars, agent bookkeeping) is live in it.
-struct ScanOut { float avg_sum, sum_a, sum_b; int prev_a, prev_b, abort_episode; };
+struct ScanOut { float avg_sum, sum_a, sum_b; int prev_a, prev_b, abort_episode, overflow; };
 
 // marl:723-749 _ffill_best_prices for the 32 messages held one per lane: a price of -1 takes the last valid price before
 // it (carry = the last valid price of the previous messages / of the previous step) and its quantity becomes 0.
@@ -301,13 +311,13 @@ __device__ __forceinline__ void ffill32(int& price, int& qty, int& carry, bool i
   carry = __shfl_sync(kFull, price, last_lane);
 }
 
-template <int SLOTS>
+template <int SLOTS, bool WIN>
 __device__ __noinline__ ScanOut scan_messages(BookCtx ctx, int* msgs, int N, int* best_asks, int* best_bids,
                                               int prev_a, int prev_b) {
-  Book<SLOTS> bk;
+  Book<SLOTS, WIN> bk;
   bk.c = ctx;
   bk.bind();
-  bk.oddm = (ctx.t4 == 2) ? Book<SLOTS>::kOddMkt : 0u;
+  bk.oddm = (ctx.t4 == 2) ? Book<SLOTS, WIN>::kOddMkt : 0u;
   bk.scan_side(ASK);
   bk.scan_side(BID);
   bk.ntr = 0;                      // the trade log was re-initialised for this step (bit kOddTrades stays clear)
@@ -319,13 +329,19 @@ __device__ __noinline__ ScanOut scan_messages(BookCtx ctx, int* msgs, int N, int
   for (int i = 0; i < N; ++i) {
     bk.c.mi = i;
     bk.process(m4[2 * i], m4[2 * i + 1]);
+    if (WIN && bk.aborted()) break;   // the book left its shared-memory window: the full-size kernel redoes this step
     if (!(bk.valid[ASK] & bk.valid[BID])) { bk.ensure(ASK); bk.ensure(BID); }
     if (lane == 0) m4[2 * i] = make_int4(bk.bestp[ASK], bk.bestq[ASK], bk.bestp[BID], bk.bestq[BID]);
   }
   __syncwarp();
+  if (WIN && bk.aborted()) {   // nothing of this step may reach global memory (the old best pairs are inputs of the redo)
+    ScanOut o;
+    o.avg_sum = o.sum_a = o.sum_b = 0.f; o.prev_a = prev_a; o.prev_b = prev_b; o.abort_episode = 0; o.overflow = 1;
+    return o;
+  }
   // ---- the data-parallel part, 32 messages at a time: abort flag, forward fill, means, the [N,2] state rows ----
   ScanOut o;
-  o.avg_sum = 0.f; o.abort_episode = 0;
+  o.avg_sum = 0.f; o.abort_episode = 0; o.overflow = 0;
   float pa = 0.f, pb = 0.f;
   int2* ga = reinterpret_cast<int2*>(best_asks);
   int2* gb = reinterpret_cast<int2*>(best_bids);
@@ -373,10 +389,16 @@ constexpr int kStepMaxWarps = LOB_STEP_MAXW / LOB_STEP_CTAS;  // warps per CTA (
 #endif
 __host__ __device__ constexpr int step_max_warps(int slots) { return slots <= 4 ? kStepMaxWarps : slots == 8 ? LOB_STEP_MAXW8 : 8; }
 
-template <int SLOTS>
+// WIN = true (deep books, n_orders > 32 * SLOTS): the environments run on a shared-memory WINDOW of the first 32 * SLOTS
+// rows of each side (Book<SLOTS, true>); an environment whose book does not fit -- a non-blank row beyond the window when
+// it is staged, or an order that has to rest beyond it during the scan -- writes nothing and is appended to
+// b.work_redo_list for the second pass: the same kernel with WIN = false at the book's full capacity class, walking that
+// list (env_list / env_count) instead of 0 .. batch-1.
+template <int SLOTS, bool WIN>
 __global__ void __launch_bounds__(step_max_warps(SLOTS) * 32, kStepCtasPerSm)
 lob_step_kernel(const __grid_constant__ LobStepConfig c, const __grid_constant__ LobStepBuffers b, long long batch,
-                WarpLayout L, int N, int n_act, int n_cnl, int need_extreme) {
+                WarpLayout L, int N, int n_act, int n_cnl, int need_extreme, const int* __restrict__ env_list,
+                const int* __restrict__ env_count) {
   int* const smem = dyn_smem();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nwarps = blockDim.x >> 5;
@@ -391,17 +413,23 @@ lob_step_kernel(const __grid_constant__ LobStepConfig c, const __grid_constant__
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   unsigned phase = 0u;
 
-  Book<SLOTS> bk;
+  Book<SLOTS, WIN> bk;
   bk.init(c.book, ws + L.book);
   const int no = c.book.n_orders, nt = c.book.n_trades, Nd = c.n_data_msg_per_step, T = c.n_agent_types;
-  const bool bulk_books = (no & 1) == 0;   // a side is no*24 bytes: 16-byte granular iff no is even
-  const unsigned side_bytes = (unsigned)no * 24u;
+  const bool bulk_books = (no & 1) == 0;   // a side is no*24 bytes: 16-byte granular iff no is even (WIN: required)
+  const unsigned side_bytes = (unsigned)bk.c.no * 24u;   // (WIN: the window's rows)
+  if (env_list) {                          // second pass: the environments the window pass handed over
+    batch = *env_count;
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(b.work_redo_count + 1, (int)batch);   // statistics
+  }
   // Environments are dealt CTA-fastest (env = pass * gridDim * nwarps + warp * gridDim + blockIdx), so that a partial last
   // pass leaves every SM with the same number of active warps instead of some SMs full and the others idle.
   const long long stride = (long long)gridDim.x * nwarps;
   for (long long base = blockIdx.x; base < batch; base += stride) {   // CTA-uniform trip count (warp 0 has the lowest index)
-    const long long e = base + (long long)warp * gridDim.x;
-    const bool active = e < batch;
+    const long long slot = base + (long long)warp * gridDim.x;
+    bool active = slot < batch;
+    const long long e = (env_list && active) ? (long long)env_list[slot] : slot;
+    bool overflow = false;
     WorldIn w;
     int oid_counter = 0, window_index = 0;
     float avg_sum = 0.f, sum_a = 0.f, sum_b = 0.f;
@@ -441,6 +469,18 @@ lob_step_kernel(const __grid_constant__ LobStepConfig c, const __grid_constant__
         __syncwarp();
       }
       if (!bulk_books) { bk.load_side(ASK, b.asks + e * no * 6); bk.load_side(BID, b.bids + e * no * 6); }
+      if (WIN) {   // every row beyond the window must be blank (all six fields -1), else this book needs the full-size kernel
+        constexpr int W = Book<SLOTS, WIN>::kRows;
+        const int tail4 = (no - W) * 6 / 4;   // int4 per side (no and W even)
+        const int4* ta = reinterpret_cast<const int4*>(b.asks + (e * no + W) * 6);
+        const int4* tb = reinterpret_cast<const int4*>(b.bids + (e * no + W) * 6);
+        int acc = -1;
+        for (int i = lane; i < tail4; i += 32) {
+          const int4 u = ta[i], v = tb[i];
+          acc &= u.x & u.y & u.z & u.w & v.x & v.y & v.z & v.w;
+        }
+        overflow = !__all_sync(kFull, acc == -1);
+      }
       bk.c.tr = b.trades + e * nt * 8;   // the trade log is worked on in place (HBM / L2): a row is one 32-byte sector
       bk.c.cu = b.cancel_u + e * N * 2;  // only dereferenced under cancel_mode 2/3
       bk.fill_trades_empty();            // marl:348: the trade log is re-initialised every step
@@ -526,11 +566,16 @@ lob_step_kernel(const __grid_constant__ LobStepConfig c, const __grid_constant__
     __syncthreads();
 
     // =================================================== phase 2: the message scan ===============================
-    if (active) {
-      const ScanOut so2 = scan_messages<SLOTS>(bk.c, msgs, N, b.best_asks + e * N * 2,
-                                               b.best_bids + e * N * 2, w.old_ba_last, w.old_bb_last);
+    if (active && !overflow) {
+      const ScanOut so2 = scan_messages<SLOTS, WIN>(bk.c, msgs, N, b.best_asks + e * N * 2,
+                                                    b.best_bids + e * N * 2, w.old_ba_last, w.old_bb_last);
       avg_sum = so2.avg_sum; sum_a = so2.sum_a; sum_b = so2.sum_b;
       prev_a = so2.prev_a; prev_b = so2.prev_b; abort_episode = so2.abort_episode != 0;
+      if (WIN) overflow = so2.overflow != 0;
+    }
+    if (WIN && active && overflow) {   // hand the environment to the second pass; nothing of this step was written back
+      if (lane == 0) b.work_redo_list[atomicAdd(b.work_redo_count, 1)] = (int)e;
+      active = false;
     }
     __syncthreads();
 

@@ -268,7 +268,19 @@ int lob_step_launch(const LobStepConfig* cfg, const LobStepBuffers* bufs, int64_
   DevInfo d;
   if ((rc = device_info(&d))) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
-  DISPATCH_SLOTS(slots_for(cfg->book.n_orders), rc = launch_step<S>(cfg, bufs, batch, st, d));
+  const int slots = slots_for(cfg->book.n_orders);
+  // Deep books (more rows per side than the window): pass 1 steps every environment on a shared-memory window of the
+  // first 32 * LOB_WINDOW_SLOTS rows (the reference keeps the live orders in the lowest rows, job:73); pass 2 redoes, at
+  // full capacity, the environments whose book did not fit.  Needs the workspace buffers; LOB_NO_WINDOW=1 disables it.
+  static const bool no_window = [] { const char* e = getenv("LOB_NO_WINDOW"); return e && e[0] == '1'; }();
+  if (slots > LOB_WINDOW_SLOTS && bufs->work_redo_list && bufs->work_redo_count && (cfg->book.n_orders & 1) == 0 && !no_window) {
+    cudaError_t e = cudaMemsetAsync(bufs->work_redo_count, 0, sizeof(int32_t), st);
+    if (e != cudaSuccess) return fail(LOB_E_CUDA, "cudaMemsetAsync: %s", cudaGetErrorString(e));
+    if ((rc = launch_step_window(cfg, bufs, batch, st, d))) return rc;
+    DISPATCH_SLOTS(slots, rc = launch_step_redo<S>(cfg, bufs, batch, st, d));
+    return rc;
+  }
+  DISPATCH_SLOTS(slots, rc = launch_step<S>(cfg, bufs, batch, st, d));
   return rc;
 }
 

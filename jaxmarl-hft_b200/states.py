@@ -19,7 +19,7 @@ PARAMS = ("message_data", "init_asks", "init_bids", "init_trades", "init_init_ti
 
 
 def leaf_specs(cfg: abi.LobStepConfig, batch: int):
-    """name -> (shape, dtype, role) for state ('s'), input ('i') and output ('o') leaves."""
+    """name -> (shape, dtype, role) for state ('s'), input ('i'), output ('o') and workspace ('w') leaves."""
     B, No, Nt, N = batch, cfg.book.n_orders, cfg.book.n_trades, num_msgs_per_step(cfg)
     T = cfg.n_agent_types
     sp = {
@@ -36,6 +36,9 @@ def leaf_specs(cfg: abi.LobStepConfig, batch: int):
         "info_world_i32": ((B, len(abi.WINFO_I32)), np.int32, "o"),
         "info_world_f32": ((B, len(abi.WINFO_F32)), np.float32, "o"),
     }
+    if No > 128:   # workspace of lob_step_launch's window pass for deep books (scratch, not state; see include/lobstep.h)
+        sp["work_redo_list"] = ((B,), np.int32, "w")
+        sp["work_redo_count"] = ((4,), np.int32, "w")
     if cfg.book.cancel_mode >= 2:   # job:142-164: the uniform draws of the two random-cancel fallbacks, per message
         sp["cancel_u"] = ((B, N, 2), np.float32, "i")
     for t in range(T):
@@ -116,6 +119,8 @@ def pack_buffers(cfg: abi.LobStepConfig, arrays: dict, params: dict) -> abi.LobS
     b.done_all = _ptr(arrays["done_all"], C.c_uint8)
     b.info_world_i32 = _ptr(arrays["info_world_i32"], C.c_int32)
     b.info_world_f32 = _ptr(arrays["info_world_f32"], C.c_float)
+    b.work_redo_list = _ptr(arrays.get("work_redo_list"), C.c_int32)
+    b.work_redo_count = _ptr(arrays.get("work_redo_count"), C.c_int32)
     return b
 
 
@@ -176,7 +181,8 @@ def field_offset(cfg: abi.LobStepConfig, name: str) -> int:
     import re
     F, P = abi.LobStepBuffers, C.sizeof(C.c_void_p)
     if name in WORLD_I32 or name in WORLD_F32 or name in PARAMS or name in (
-            "perm", "reset_window", "reset_is_sell", "cancel_u", "done_all", "info_world_i32", "info_world_f32"):
+            "perm", "reset_window", "reset_is_sell", "cancel_u", "done_all", "info_world_i32", "info_world_f32",
+            "work_redo_list", "work_redo_count"):
         return getattr(F, name).offset
     m = re.fullmatch(r"a(\d+)_(\w+)", name)
     if m:

@@ -508,3 +508,31 @@ def test_launch_follows_the_envs_device(oracle):
     bufs = states.pack_buffers(env.cfg, state.arrays, env.base_env.device_params())
     rc = _lib.lib().lob_step_launch(ctypes.byref(env.cfg), ctypes.byref(bufs), 64, _lib.current_stream_ptr())   # current device 0
     assert rc == abi.LOB_E_INVALID and b"device" in _lib.lib().lob_last_error()
+
+
+def test_step_deep_book_window_and_second_pass(oracle):
+    """Deep books run on a 128-row shared-memory window; a book that outgrows it is redone at full capacity by the second
+    pass of the same lob_step_launch.  A 200-row book on the capacity-stress day: both passes are exercised (some
+    environments fit the window, some do not), every leaf equals the oracle's after every step."""
+    mac = H.load_mac("2_player_fq_fqc", nOrders=200, nTrades=128)
+    ld = H.load_for(mac, H.small_day(seed=9, n_events=30000, stress=True))
+    B = 96
+    ref = H.OracleEnv(oracle, mac, ld, B)
+    gpu = H.CudaEnv(mac, ld, B, ref.params)
+    assert "work_redo_list" in gpu.arrays
+    rng = np.random.default_rng(6)
+    H.draw_prng(rng, ref.cfg, ref.arrays)
+    gpu.set_inputs(ref.arrays)
+    ref.reset(); gpu.reset()
+    redone = []
+    for s in range(70):
+        H.draw_prng(rng, ref.cfg, ref.arrays)
+        H.draw_actions(rng, ref.cfg, ref.arrays)
+        gpu.set_inputs(ref.arrays)
+        ref.step(n_threads=8); gpu.step()
+        got = gpu.numpy()
+        H.assert_arrays_match(ref.arrays, got, ref.cfg)
+        redone.append(int(got["work_redo_count"][0]))
+    live = np.maximum((ref.arrays["asks"] != -1).any(axis=2).sum(axis=1), (ref.arrays["bids"] != -1).any(axis=2).sum(axis=1))
+    assert 0 < max(redone) and min(redone) < B, (redone, live.max())
+    assert int(got["work_redo_count"][1]) == sum(redone)
