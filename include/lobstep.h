@@ -312,6 +312,14 @@ int64_t lob_sizeof_agent_type_config(void);
 int64_t lob_sizeof_step_config(void);
 int64_t lob_sizeof_step_buffers(void);
 int64_t lob_sizeof_replay_buffers(void);
+/* Byte offsets of sentinel fields, in the fixed order below, so that a mirror of these structs (ctypes, cgo, ...) can check
+ * its LAYOUT and not only its size: LobBookConfig.{cancel_mode, check_book_fill}; LobAgentTypeConfig.{fixed_quant_value,
+ * task_size, doom_price_penalty, reward_scaling_quo, reward_lambda}; LobStepConfig.{tick_size, episode_time,
+ * n_agent_types, n_messages, agent}; LobStepBuffers.{best_asks, mid_price, agent_f32, perm, message_data, obs, done_all,
+ * info_agent_f32, work_redo_count}; LobReplayBuffers.{start, n_msgs, best_out, cancel_u}.  Writes min(n, 25) values,
+ * returns 25. */
+#define LOB_ABI_N_OFFSETS 25
+int32_t lob_abi_offsets(int64_t* out, int32_t n);
 
 #ifdef __cplusplus
 }

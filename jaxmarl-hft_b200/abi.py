@@ -104,14 +104,40 @@ _SIZEOF = {"lob_sizeof_book_config": LobBookConfig, "lob_sizeof_agent_type_confi
            "lob_sizeof_replay_buffers": LobReplayBuffers}
 
 
+# the sentinel fields of lob_abi_offsets (include/lobstep.h), in its order
+_SENTINELS = [(LobBookConfig, "cancel_mode"), (LobBookConfig, "check_book_fill"),
+              (LobAgentTypeConfig, "fixed_quant_value"), (LobAgentTypeConfig, "task_size"),
+              (LobAgentTypeConfig, "doom_price_penalty"), (LobAgentTypeConfig, "reward_scaling_quo"),
+              (LobAgentTypeConfig, "reward_lambda"),
+              (LobStepConfig, "tick_size"), (LobStepConfig, "episode_time"), (LobStepConfig, "n_agent_types"),
+              (LobStepConfig, "n_messages"), (LobStepConfig, "agent"),
+              (LobStepBuffers, "best_asks"), (LobStepBuffers, "mid_price"), (LobStepBuffers, "agent_f32"),
+              (LobStepBuffers, "perm"), (LobStepBuffers, "message_data"), (LobStepBuffers, "obs"),
+              (LobStepBuffers, "done_all"), (LobStepBuffers, "info_agent_f32"), (LobStepBuffers, "work_redo_count"),
+              (LobReplayBuffers, "start"), (LobReplayBuffers, "n_msgs"), (LobReplayBuffers, "best_out"),
+              (LobReplayBuffers, "cancel_u")]
+
+
 def check_sizes(lib):
-    """Raise if the loaded library's structs differ in size from this mirror."""
+    """Raise if the loaded library's structs differ from this mirror: in size, or (the CUDA library) in the byte offset of
+    the sentinel fields ``lob_abi_offsets`` reports -- two same-sized fields swapped on one side would pass the size check."""
     for fn, cls in _SIZEOF.items():
         f = getattr(lib, fn)
         f.restype = C.c_int64
         got = int(f())
         if got != C.sizeof(cls):
             raise RuntimeError(f"ABI mismatch: {fn}() = {got}, ctypes mirror = {C.sizeof(cls)}")
+    if hasattr(lib, "lob_abi_offsets"):
+        n = len(_SENTINELS)
+        out = (C.c_int64 * n)()
+        lib.lob_abi_offsets.argtypes = [C.POINTER(C.c_int64), C.c_int32]
+        lib.lob_abi_offsets.restype = C.c_int32
+        if int(lib.lob_abi_offsets(out, n)) != n:
+            raise RuntimeError("ABI mismatch: lob_abi_offsets reports another number of sentinel fields")
+        for (cls, name), got in zip(_SENTINELS, out):
+            if getattr(cls, name).offset != int(got):
+                raise RuntimeError(f"ABI mismatch: offsetof({cls.__name__}, {name}) = {int(got)} in the library, "
+                                   f"{getattr(cls, name).offset} in the ctypes mirror")
 
 
 def action_width(a) -> int:

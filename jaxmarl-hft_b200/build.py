@@ -38,16 +38,27 @@ def _digest():
     return h.hexdigest()
 
 
-def build_cuda(force=False, verbose=False):
+def build_variant(name, defines=(), slots=SLOTS):
+    """A development build with extra ``-D`` flags -> csrc/variants/liblobstep_<name>.so (git-ignored; travels with gpurun).
+    Use it with ``LOB_SO=<path> python tools/kbench.py`` to A/B a kernel change against the committed build."""
+    vdir = os.path.join(CSRC, "variants")
+    return build_cuda(force=True, so=os.path.join(vdir, f"liblobstep_{name}.so"), obj=os.path.join(vdir, f"obj_{name}"),
+                      extra=[f"-D{d}" for d in defines], slots=slots)
+
+
+def build_cuda(force=False, verbose=False, so=SO, obj=OBJ, extra=(), slots=SLOTS):
     """Compile csrc/*.cu -> csrc/liblobstep.so.  Skipped when the sources are unchanged since the last build."""
+    SO, OBJ = so, obj   # noqa: N806  (the variant build reuses the body below with its own paths)
     stamp = os.path.join(OBJ, "digest.txt")
-    digest = _digest()
+    digest = _digest() + " ".join(extra)
     if not force and os.path.exists(SO) and os.path.exists(stamp) and open(stamp).read() == digest:
         return SO
     os.makedirs(OBJ, exist_ok=True)
-    jobs = [(os.path.join(CSRC, "lobstep.cu"), os.path.join(OBJ, "lobstep.o"), [])]
-    for s in SLOTS:
-        jobs.append((os.path.join(CSRC, "lob_inst.cu"), os.path.join(OBJ, f"lob_inst_s{s}.o"), [f"-DLOB_SLOTS={s}"]))
+    extra = list(extra)
+    jobs = [(os.path.join(CSRC, "lobstep.cu"), os.path.join(OBJ, "lobstep.o"), extra)]
+    for s in SLOTS:   # (every capacity class is linked; `slots` only says which ones get the extra flags)
+        jobs.append((os.path.join(CSRC, "lob_inst.cu"), os.path.join(OBJ, f"lob_inst_s{s}.o"),
+                     [f"-DLOB_SLOTS={s}"] + (extra if s in slots else [])))
 
     for l, r in GROUPED:
         jobs.append((os.path.join(CSRC, "lob_ginst.cu"), os.path.join(OBJ, f"lob_ginst_l{l}r{r}.o"), [f"-DLOB_GL={l}", f"-DLOB_GR={r}"]))

@@ -430,6 +430,9 @@ lob_step_kernel(const __grid_constant__ LobStepConfig c, const __grid_constant__
     bool active = slot < batch;
     const long long e = (env_list && active) ? (long long)env_list[slot] : slot;
     bool overflow = false;
+#ifdef LOB_PHASE_TIMING
+    const long long tp0 = clock64();
+#endif
     WorldIn w;
     int oid_counter = 0, window_index = 0;
     float avg_sum = 0.f, sum_a = 0.f, sum_b = 0.f;
@@ -563,7 +566,13 @@ lob_step_kernel(const __grid_constant__ LobStepConfig c, const __grid_constant__
       }
       __syncwarp();
     }
+#ifdef LOB_PHASE_TIMING
+    const long long tp1 = clock64();
+#endif
     __syncthreads();
+#ifdef LOB_PHASE_TIMING
+    const long long tp1b = clock64();
+#endif
 
     // =================================================== phase 2: the message scan ===============================
     if (active && !overflow) {
@@ -577,7 +586,13 @@ lob_step_kernel(const __grid_constant__ LobStepConfig c, const __grid_constant__
       if (lane == 0) b.work_redo_list[atomicAdd(b.work_redo_count, 1)] = (int)e;
       active = false;
     }
+#ifdef LOB_PHASE_TIMING
+    const long long tp2 = clock64();
+#endif
     __syncthreads();
+#ifdef LOB_PHASE_TIMING
+    const long long tp2b = clock64();
+#endif
 
     // =================================================== phase 3: rewards, state, observations, write-back ========
     if (active) {
@@ -699,6 +714,13 @@ lob_step_kernel(const __grid_constant__ LobStepConfig c, const __grid_constant__
         bulk_commit();
       }
     }
+#ifdef LOB_PHASE_TIMING
+    if (lane == 0 && (blockIdx.x % 37) == 0 && (warp == 0 || warp == nwarps - 1)) {
+      const long long tp3 = clock64();
+      printf("phase cycles cta %d warp %d env %lld: p1 %lld wait1 %lld scan %lld wait2 %lld p3 %lld\n", (int)blockIdx.x, warp, e,
+             tp1 - tp0, tp1b - tp1, tp2 - tp1b, tp2b - tp2, tp3 - tp2b);
+    }
+#endif
   }
   if (lane == 0) bulk_wait_all();
 }

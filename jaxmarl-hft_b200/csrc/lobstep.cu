@@ -2,6 +2,7 @@
 // allocation and no synchronisation in the *_launch entry points (the host-replay handle owns its own scratch).
 #include <cuda_runtime.h>
 #include <stdarg.h>
+#include <stddef.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -187,6 +188,22 @@ int64_t lob_sizeof_agent_type_config(void) { return (int64_t)sizeof(LobAgentType
 int64_t lob_sizeof_step_config(void) { return (int64_t)sizeof(LobStepConfig); }
 int64_t lob_sizeof_step_buffers(void) { return (int64_t)sizeof(LobStepBuffers); }
 int64_t lob_sizeof_replay_buffers(void) { return (int64_t)sizeof(LobReplayBuffers); }
+int32_t lob_abi_offsets(int64_t* out, int32_t n) {
+  const int64_t off[LOB_ABI_N_OFFSETS] = {
+      offsetof(LobBookConfig, cancel_mode), offsetof(LobBookConfig, check_book_fill),
+      offsetof(LobAgentTypeConfig, fixed_quant_value), offsetof(LobAgentTypeConfig, task_size),
+      offsetof(LobAgentTypeConfig, doom_price_penalty), offsetof(LobAgentTypeConfig, reward_scaling_quo),
+      offsetof(LobAgentTypeConfig, reward_lambda),
+      offsetof(LobStepConfig, tick_size), offsetof(LobStepConfig, episode_time), offsetof(LobStepConfig, n_agent_types),
+      offsetof(LobStepConfig, n_messages), offsetof(LobStepConfig, agent),
+      offsetof(LobStepBuffers, best_asks), offsetof(LobStepBuffers, mid_price), offsetof(LobStepBuffers, agent_f32),
+      offsetof(LobStepBuffers, perm), offsetof(LobStepBuffers, message_data), offsetof(LobStepBuffers, obs),
+      offsetof(LobStepBuffers, done_all), offsetof(LobStepBuffers, info_agent_f32), offsetof(LobStepBuffers, work_redo_count),
+      offsetof(LobReplayBuffers, start), offsetof(LobReplayBuffers, n_msgs), offsetof(LobReplayBuffers, best_out),
+      offsetof(LobReplayBuffers, cancel_u)};
+  for (int i = 0; i < n && i < LOB_ABI_N_OFFSETS && out; ++i) out[i] = off[i];
+  return LOB_ABI_N_OFFSETS;
+}
 
 /* marl_env.py:85-94 */
 int32_t lob_num_action_msgs(const LobStepConfig* c) {

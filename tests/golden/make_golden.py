@@ -410,8 +410,8 @@ if __name__ == "__main__":
         run_replay_case("replay_cancel_large_adversarial", seed=19, B=4, T=400, no=33, nt=16, t4=1, fill=True,
                         adversarial=True, cancel_mode=3)
     if "env" in which:
-        run_env_case("env_2player", "2_player_fq_fqc.json", seed=3, B=3, steps=68)
-        run_env_case("env_exec", "exec_longrun_fixed_quants_complex.json", seed=4, B=2, steps=20)
+        run_env_case("env_2player", "2_player_fq_fqc.json", seed=3, B=16, steps=66)
+        run_env_case("env_exec", "exec_longrun_fixed_quants_complex.json", seed=4, B=16, steps=20)
     if "env2" in which:
         run_env_case("env_hetero_smallbook", "2_player_fq_fqc.json", seed=6, B=2, steps=66, stress=True, mutate="hetero",
                      nOrders=40, nTrades=24)

@@ -231,3 +231,36 @@ def test_base_env_reset_step_pair(oracle, ep_type):
         np.testing.assert_array_equal(st.trades.cpu().numpy(), rt)
         np.testing.assert_array_equal(done.cpu().numpy(), (ld.msgs[off + Nd - 1, 6] - init_t[:, 0]) >= w.episode_time)
         assert obs == 0 and rew == 0 and info == {"info": 0} and int(st.step_counter[0]) == k + 1
+
+
+def test_host_buffer_replay_matches_oracle(oracle):
+    """lob_host_replay_* (the C ABI's HOST-buffer path: H2D + replay + D2H inside one call, bench.py's e2e leg) against the
+    oracle; bad offsets are an error, not a silently unprocessed book."""
+    import ctypes
+    from jaxmarl_hft_b200 import _lib, abi
+    L = _lib.lib()
+    rng = np.random.default_rng(12)
+    bc = C.book_config(C.World_EnvironmentConfig(nOrders=100, nTrades=100))
+    B, T, M = 200, 333, 200 * 333 + 50
+    msgs = H.random_messages(rng, M, bc)
+    start = rng.integers(0, M - T + 1, size=B).astype(np.int64)
+    a = np.full((B, 100, 6), -1, np.int32); b = a.copy(); t = np.full((B, 100, 8), -1, np.int32)
+    ra, rb, rt = a.copy(), b.copy(), t.copy()
+    oracle.replay(bc, ra, rb, rt, msgs, start, T)
+    h = L.lob_host_replay_create(ctypes.byref(bc), B, M, 0)
+    assert h, L.lob_last_error()
+    p = lambda x: x.ctypes.data_as(abi.p_i32)
+    try:
+        _lib.check(L.lob_host_replay_set_messages(h, p(msgs), M), "set_messages")
+        h2d, d2h = ctypes.c_int64(0), ctypes.c_int64(0)
+        for _ in range(2):      # two calls continue the same books: replay twice on the host side too
+            _lib.check(L.lob_host_replay_run(h, p(a), p(b), p(t), start.ctypes.data_as(abi.p_i64), T, B,
+                                             ctypes.byref(h2d), ctypes.byref(d2h)), "run")
+        oracle.replay(bc, ra, rb, rt, msgs, start, T)
+        np.testing.assert_array_equal(a, ra); np.testing.assert_array_equal(b, rb); np.testing.assert_array_equal(t, rt)
+        assert h2d.value == 2 * a.nbytes + t.nbytes + start.nbytes and d2h.value == 2 * a.nbytes + t.nbytes
+        bad = start.copy(); bad[7] = M - T + 1
+        rc = L.lob_host_replay_run(h, p(a), p(b), p(t), bad.ctypes.data_as(abi.p_i64), T, B, None, None)
+        assert rc == abi.LOB_E_INVALID and b"start[7]" in L.lob_last_error()
+    finally:
+        L.lob_host_replay_destroy(h)
