@@ -292,7 +292,11 @@ __device__ __noinline__ void reset_env(const LobStepConfig& c, const LobStepBuff
 // marl:348-364 the scan of one step's message list, with the per-message best bid/ask (job:792-823) and the forward
 // fill (marl:723-749) done online.  A function of its own so that the hot loop gets its own register allocation:
 // nothing of the surrounding step (world scalars, agent bookkeeping) is live in it.
-struct ScanOut { float avg_sum, sum_a, sum_b; int prev_a, prev_b, abort_episode, overflow; };
+struct ScanOut {
+  float avg_sum, sum_a, sum_b;
+  int prev_a, prev_b, abort_episode, overflow;
+  int trade_rows;   // every row of the step's trade log from this one on is still blank (all -1): the reward passes stop here
+};
 
 // marl:723-749 _ffill_best_prices for the 32 messages held one per lane: a price of -1 takes the last valid price before
 // it (carry = the last valid price of the previous messages / of the previous step) and its quantity becomes 0.
@@ -337,11 +341,15 @@ __device__ __noinline__ ScanOut scan_messages(BookCtx ctx, int* msgs, int N, int
   if (WIN && bk.aborted()) {   // nothing of this step may reach global memory (the old best pairs are inputs of the redo)
     ScanOut o;
     o.avg_sum = o.sum_a = o.sum_b = 0.f; o.prev_a = prev_a; o.prev_b = prev_b; o.abort_episode = 0; o.overflow = 1;
+    o.trade_rows = ctx.nt;
     return o;
   }
   // ---- the data-parallel part, 32 messages at a time: abort flag, forward fill, means, the [N,2] state rows ----
   ScanOut o;
   o.avg_sum = 0.f; o.abort_episode = 0; o.overflow = 0;
+  // The log was blank before the scan and trades are appended at row ntr (job:205); a trade stamped time_s == -1 is written
+  // without advancing ntr (quirk Q3), hence the + 1.  After the literal path the rows may be anywhere (kOddTrades).
+  o.trade_rows = (bk.oddm & Book<SLOTS, WIN>::kOddTrades) ? ctx.nt : min(ctx.nt, bk.ntr + 1);
   float pa = 0.f, pb = 0.f;
   int2* ga = reinterpret_cast<int2*>(best_asks);
   int2* gb = reinterpret_cast<int2*>(best_bids);
@@ -436,7 +444,7 @@ lob_step_kernel(const __grid_constant__ LobStepConfig c, const __grid_constant__
     WorldIn w;
     int oid_counter = 0, window_index = 0;
     float avg_sum = 0.f, sum_a = 0.f, sum_b = 0.f;
-    int prev_a = 0, prev_b = 0;
+    int prev_a = 0, prev_b = 0, trade_rows = 0;
     bool abort_episode = false;
 
     // =================================================== phase 1: stage state, build the agent messages ==========
@@ -580,6 +588,7 @@ lob_step_kernel(const __grid_constant__ LobStepConfig c, const __grid_constant__
                                                     b.best_bids + e * N * 2, w.old_ba_last, w.old_bb_last);
       avg_sum = so2.avg_sum; sum_a = so2.sum_a; sum_b = so2.sum_b;
       prev_a = so2.prev_a; prev_b = so2.prev_b; abort_episode = so2.abort_episode != 0;
+      trade_rows = so2.trade_rows;
       if (WIN) overflow = so2.overflow != 0;
     }
     if (WIN && active && overflow) {   // hand the environment to the second pass; nothing of this step was written back
@@ -608,18 +617,28 @@ lob_step_kernel(const __grid_constant__ LobStepConfig c, const __grid_constant__
       const float new_dt = (float)ft0 + (float)ft1 / 1e9f - (float)w.time0 - (float)w.time1 / 1e9f;
       const int new_oid_counter = oid_counter - n_act;
       const int vol_a = bk.volume(ASK), vol_b = bk.volume(BID);
+#ifdef LOB_PHASE_TIMING
+      const long long tq0 = clock64();
+#endif
       // The agents' reward passes read the step's trade log several times each: stage it once in the message buffer, which
       // is dead from here on (when it fits; the log itself stays in global memory, fictional end-of-episode trades are
       // inserted into / removed from the copy).
+      // Only the first nt_r rows can hold a trade: the rows behind them are blank and add exactly +0 to every sum of the
+      // reward passes (a blank row is nobody's trade), so the passes -- and the fictional end-of-episode trade, which
+      // takes the first row holding a -1 (job:886-889) -- work on nt_r rows: one more than the scan left non-blank.
+      const int nt_r = min(nt, trade_rows + 1);
       int* trp = bk.c.tr;
-      if (nt <= N) {
+      if (nt_r <= N) {
         const int4* g4 = reinterpret_cast<const int4*>(bk.c.tr);
         int4* s4 = reinterpret_cast<int4*>(msgs);
-        for (int i = lane; i < nt * 2; i += 32) s4[i] = g4[i];
+        for (int i = lane; i < nt_r * 2; i += 32) s4[i] = g4[i];
         __syncwarp();
         trp = msgs;
       }
 
+#ifdef LOB_PHASE_TIMING
+      const long long tq1 = clock64();
+#endif
       // ---- (E)+(G)+(I)+(J)+(K) per agent: reward, state, done, info, obs ----
       const ObsTime ot = {c.ep_type_fixed_time, c.episode_time, ft0, ft1, w.init_time0, w.init_time1, new_dt};
       int flat = 0;
@@ -632,7 +651,7 @@ lob_step_kernel(const __grid_constant__ LobStepConfig c, const __grid_constant__
           float* obs = b.obs[t] + idx * d;
           if (ac.kind == LOB_AGENT_MM) {
             MMState s; load_mm_state(b, t, idx, s);
-            const MMReward R = mm_get_reward(trp, nt, c, ac, w, so, s, tid);
+            const MMReward R = mm_get_reward(trp, nt_r, c, ac, w, so, s, tid);
             const int* x = kDiet ? b.info_agent_i32[t] + idx * LOB_MMINFO_I32_COLS + 3 : scr + flat * 8;   // from phase 1
             MMState ns;   // mm:2677-2736
             ns.posted_distance_bid = x[2]; ns.posted_distance_ask = x[3];
@@ -657,7 +676,7 @@ lob_step_kernel(const __grid_constant__ LobStepConfig c, const __grid_constant__
               mm_write_obs(ac, obs, ns.inventory, new_mid, so.ba_last, so.bb_last, vol_a, vol_b, new_step, false, ot);
           } else {
             EXEState s; load_exe_state(b, t, idx, s);
-            const EXEReward R = exe_get_reward(trp, nt, c, ac, w, so, s, tid);
+            const EXEReward R = exe_get_reward(trp, nt_r, c, ac, w, so, s, tid);
             EXEState ns = s;   // exe:1771-1839
             ns.quant_executed = s.quant_executed + R.agentQuant;
             ns.p_vwap = R.p_vwap;
@@ -682,6 +701,11 @@ lob_step_kernel(const __grid_constant__ LobStepConfig c, const __grid_constant__
           }
         }
       }
+#ifdef LOB_PHASE_TIMING
+      const long long tq2 = clock64();
+      if (lane == 0 && (blockIdx.x % 37) == 0 && (warp == 0 || warp == nwarps - 1))
+        printf("phase3 cta %d warp %d: volumes %lld tradecopy %lld agents %lld\n", (int)blockIdx.x, warp, tq0 - tp2b, tq1 - tq0, tq2 - tq1);
+#endif
       // ---- world info marl:618-639 ----
       if (lane == 0) {
         b.done_all[e] = so.ep_done ? 1 : 0;
