@@ -279,6 +279,18 @@ int lob_replay_launch_grouped(const LobBookConfig* cfg, const LobReplayBuffers* 
 int lob_l2_launch(const LobBookConfig* cfg, const int32_t* asks, const int32_t* bids, int32_t* l2,
                   int32_t n_levels, int64_t n_books, void* cuda_stream);
 
+/* ---- the loader's day preprocessing on the device (lobster_loader.py:891-945 _pre_process_msg_ob, :1073-1132
+ * merge_market_orders).  raw = the parsed LOBSTER message table, float64 [n,6] row-major (time, type, order_id, size, price,
+ * direction), time-sorted.  Call lob_loader_flags_launch, take the EXCLUSIVE prefix sum `pos` of `keep` (M = pos[n-1] +
+ * keep[n-1] rows survive), then lob_loader_scatter_launch: msgs int32 [M-1,8] in the env's column order, time_out f64
+ * [M-1], rows i64 [M] = original row of every kept message (book[j] = orderbook[rows[j]], j < M-1, is the book BEFORE
+ * msgs[j]).  flags[0]: bit 0 = the table is not time-sorted, bit 1 = a field does not fit int32 -- both are errors. */
+int lob_loader_flags_launch(const double* raw, int64_t n, int32_t day_start, int32_t day_end, int64_t* keep, int64_t* mqty,
+                            int64_t* mprice, int32_t* flags, void* cuda_stream);
+int lob_loader_scatter_launch(const double* raw, int64_t n, int32_t day_start, int32_t day_end, const int64_t* keep,
+                              const int64_t* pos, const int64_t* mqty, const int64_t* mprice, int32_t* msgs, double* time_out,
+                              int64_t* rows, int32_t* flags, void* cuda_stream);
+
 /* The PRNG products of one step, drawn on the device by a counter-based generator: perm [B,n_action] (a uniform
  * random permutation per environment, marl_env.py:293-295), reset_window [B] in [0, n_windows) or window_selector when it
  * is >= 0 (base_env.py:222-225), reset_is_sell [B,n_agent_types] in {0,1} (exec_env.py:221) and, under cancel_mode 2/3,

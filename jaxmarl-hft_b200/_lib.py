@@ -45,6 +45,10 @@ def lib():
                                           abi.p_i64, abi.p_i64]
         L.lob_host_replay_destroy.argtypes = [vp]
         L.lob_host_replay_destroy.restype = None
+        p_f64, p64 = C.POINTER(C.c_double), abi.p_i64
+        L.lob_loader_flags_launch.argtypes = [p_f64, C.c_int64, C.c_int32, C.c_int32, p64, p64, p64, abi.p_i32, vp]
+        L.lob_loader_scatter_launch.argtypes = [p_f64, C.c_int64, C.c_int32, C.c_int32, p64, p64, p64, p64, abi.p_i32, p_f64,
+                                                p64, abi.p_i32, vp]
         L.lob_launch_count.restype = C.c_int64
         L.lob_launch_count_reset.restype = None
         for fn in ("lob_num_msgs_per_step", "lob_num_action_msgs", "lob_num_cancel_msgs"):

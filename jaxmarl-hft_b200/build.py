@@ -55,7 +55,8 @@ def build_cuda(force=False, verbose=False, so=SO, obj=OBJ, extra=(), slots=SLOTS
         return SO
     os.makedirs(OBJ, exist_ok=True)
     extra = list(extra)
-    jobs = [(os.path.join(CSRC, "lobstep.cu"), os.path.join(OBJ, "lobstep.o"), extra)]
+    jobs = [(os.path.join(CSRC, "lobstep.cu"), os.path.join(OBJ, "lobstep.o"), extra),
+            (os.path.join(CSRC, "lob_loader.cu"), os.path.join(OBJ, "lob_loader.o"), [])]
     for s in SLOTS:   # (every capacity class is linked; `slots` only says which ones get the extra flags)
         jobs.append((os.path.join(CSRC, "lob_inst.cu"), os.path.join(OBJ, f"lob_inst_s{s}.o"),
                      [f"-DLOB_SLOTS={s}"] + (extra if s in slots else [])))

@@ -59,15 +59,16 @@ def local_episode_stats(x: torch.Tensor, mask: torch.Tensor = None) -> torch.Ten
 
 
 def reduce_episode_stats(stats: torch.Tensor) -> dict:
-    """All-reduce per-rank [K,5] (or [5]) statistics: SUM for count / sum / sumsq, MIN / MAX for the extremes.
-    Three tiny collectives (latency-bound; off the step path).  Returns mean / std / min / max / count tensors."""
+    """Combine per-rank [K,5] (or [5]) statistics over the ranks: SUM for count / sum / sumsq, MIN / MAX for the extremes.
+    ONE tiny collective (an all-gather of K*5 doubles per rank, combined locally; latency-bound, off the step path).
+    Returns mean / std / min / max / count tensors."""
     s = stats.reshape(-1, 5).clone()
     if dist.is_initialized() and dist.get_world_size() > 1:
-        add = s[:, 0:3].contiguous(); mn = s[:, 3].contiguous(); mx = s[:, 4].contiguous()
-        dist.all_reduce(add, op=dist.ReduceOp.SUM)
-        dist.all_reduce(mn, op=dist.ReduceOp.MIN)
-        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
-        s = torch.cat([add, mn[:, None], mx[:, None]], dim=1)
+        parts = [torch.empty_like(s) for _ in range(dist.get_world_size())]
+        dist.all_gather(parts, s.contiguous())
+        g = torch.stack(parts)                       # [world, K, 5]
+        s = torch.cat([g[:, :, 0:3].sum(dim=0), g[:, :, 3].min(dim=0).values[:, None], g[:, :, 4].max(dim=0).values[:, None]],
+                      dim=1)
     n = s[:, 0].clamp(min=1.0)
     mean = s[:, 1] / n
     var = (s[:, 2] / n - mean * mean).clamp(min=0.0)

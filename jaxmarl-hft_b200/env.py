@@ -181,7 +181,7 @@ class BaseLOBEnv:
         self.n_data_msg_per_step = cfg.n_data_msg_per_step
         if cfg.ep_type not in ("fixed_steps", "fixed_time"):
             raise NotImplementedError('Use either "fixed_time" or "fixed_steps"')   # ldr:998
-        self.loaded = loaded if loaded is not None else lobster.load_or_generate(cfg, **(synth or {}))
+        self.loaded = loaded if loaded is not None else lobster.load_or_generate(cfg, device=device, **(synth or {}))
         self.n_windows = int(self.loaded.starts.shape[0])
         self.start_indeces, self.end_indeces = self.loaded.starts, self.loaded.ends
         self.max_messages_in_episode_arr = self.loaded.max_msgs
@@ -192,7 +192,10 @@ class BaseLOBEnv:
         """The whole day + reset states, resident in HBM once."""
         if self._params_dev is None:
             import torch
-            self._params_dev = {k: torch.from_numpy(v).to(self.device) for k, v in self._params_np.items()}
+            md = getattr(self.loaded, "msgs_device", None)     # preprocessed on the device: already resident
+            keep = md is not None and md.device == torch.device(self.device) and md.is_contiguous()
+            self._params_dev = {k: (md if (k == "message_data" and keep) else torch.from_numpy(v).to(self.device))
+                                for k, v in self._params_np.items()}
         return self._params_dev
 
     @property

@@ -37,6 +37,7 @@ class LoadedDay:
     ends: np.ndarray        # int64 [W]
     books: np.ndarray       # int64 [W,4*levels]  L2 row BEFORE msgs[starts[w]]
     max_msgs: np.ndarray    # int64 [W]
+    msgs_device: object = None   # the same msgs as a CUDA tensor when the day was preprocessed on the device (stays in HBM)
 
 
 class _SynthBook:
@@ -297,6 +298,47 @@ def preprocess_day(day: RawDay, day_start=34200, day_end=57600, return_time=Fals
     return out[1:], book[:-1]                                           # ldr:941-942
 
 
+def preprocess_day_cuda(day: RawDay, day_start=34200, day_end=57600, device="cuda"):
+    """``preprocess_day`` on the device (csrc/lob_loader.cu through lob_loader_*_launch): the parsed message table goes to
+    HBM once and the day's message tensor is produced there.  Returns (msgs int32 CUDA tensor [M,8], rows int64 CUDA tensor
+    [M]: original row of the message BEFORE which ``orderbook[rows[j]]`` is the book state, time float64 CUDA tensor [M]).
+    The table must be time-sorted (LOBSTER files are); an unsorted one is refused."""
+    import ctypes as C
+
+    import torch
+
+    from . import _lib, abi
+    L = _lib.lib()
+    dev = torch.device(device)
+    raw = torch.from_numpy(np.ascontiguousarray(day.messages[:, :6], np.float64)).to(dev)
+    n = raw.shape[0]
+    keep = torch.empty(n, dtype=torch.int64, device=dev)
+    mq, mp = torch.empty_like(keep), torch.empty_like(keep)
+    flags = torch.zeros(4, dtype=torch.int32, device=dev)
+    p64 = lambda t: C.cast(t.data_ptr(), abi.p_i64)
+    pf = lambda t: C.cast(t.data_ptr(), C.POINTER(C.c_double))
+    p32 = lambda t: C.cast(t.data_ptr(), abi.p_i32)
+    with _lib.on_device(dev):
+        st = _lib.current_stream_ptr(dev)
+        _lib.check(L.lob_loader_flags_launch(pf(raw), n, int(day_start), int(day_end), p64(keep), p64(mq), p64(mp), p32(flags), st),
+                   "lob_loader_flags_launch")
+        pos = torch.cumsum(keep, 0) - keep                     # exclusive prefix sum (plumbing)
+        M = int((pos[-1] + keep[-1]).item()) if n else 0
+        if M < 2:
+            raise ValueError("the day holds fewer than two usable messages")
+        msgs = torch.empty((M - 1, 8), dtype=torch.int32, device=dev)
+        tm = torch.empty(M - 1, dtype=torch.float64, device=dev)
+        rows = torch.empty(M, dtype=torch.int64, device=dev)
+        _lib.check(L.lob_loader_scatter_launch(pf(raw), n, int(day_start), int(day_end), p64(keep), p64(pos), p64(mq), p64(mp),
+                                               p32(msgs), pf(tm), p64(rows), p32(flags), st), "lob_loader_scatter_launch")
+        f = int(flags[0].item())
+    if f & 1:
+        raise ValueError("the message table is not time-sorted: merge_market_orders groups by time stamp (ldr:1073-1132)")
+    if f & 2:
+        raise ValueError("message field does not fit int32 (base:184 narrows silently; refuse instead)")
+    return msgs, rows[:-1], tm
+
+
 def window_indices(n_msgs, window_length, n_data_msg_per_step, window_resolution):
     """fixed_steps branch of ldr:971-1002 / :1019-1038."""
     if n_data_msg_per_step <= 0:
@@ -324,11 +366,16 @@ def window_indices_fixed_time(time, window_length, window_resolution, day_start,
 
 
 def load_days(days, window_length, n_data_msg_per_step, window_resolution, day_start=34200, day_end=57600,
-              window_type="fixed_steps") -> LoadedDay:
+              window_type="fixed_steps", device=None) -> LoadedDay:
     """ldr:626-695 ``run_loading`` over one or more days, concatenated with cumulative message offsets
-    (ldr:664-679).  ``window_type`` is the reference's ``type_`` ("fixed_steps" | "fixed_time")."""
+    (ldr:664-679).  ``window_type`` is the reference's ``type_`` ("fixed_steps" | "fixed_time").  With ``device`` (a CUDA
+    device) the per-day preprocessing runs there (``preprocess_day_cuda``) and the message tensor stays in HBM
+    (``LoadedDay.msgs_device``); the window bookkeeping (a few hundred indices) is host arithmetic either way."""
     if window_type not in ("fixed_steps", "fixed_time"):
         raise NotImplementedError('Use either "fixed_time" or "fixed_steps"')      # ldr:998
+    if device is not None:
+        return _load_days_cuda(days, window_length, n_data_msg_per_step, window_resolution, day_start, day_end, window_type,
+                               device)
     all_m, all_s, all_e, all_b, all_x = [], [], [], [], []
     offset = 0
     for d in days:
@@ -353,6 +400,28 @@ def load_days(days, window_length, n_data_msg_per_step, window_resolution, day_s
                      books=np.concatenate(all_b, 0), max_msgs=np.concatenate(all_x))
 
 
+def _load_days_cuda(days, window_length, n_data_msg_per_step, window_resolution, day_start, day_end, window_type, device):
+    import torch
+    all_m, all_s, all_e, all_b, all_x = [], [], [], [], []
+    offset = 0
+    for d in days:
+        m, rows, tm = preprocess_day_cuda(d, day_start, day_end, device)
+        if window_type == "fixed_time":
+            tmh = tm.cpu().numpy()
+            s, e = window_indices_fixed_time(tmh, window_length, window_resolution, day_start, day_end)
+        else:
+            s, e = window_indices(m.shape[0], window_length, n_data_msg_per_step, window_resolution)
+        all_b.append(d.orderbook[rows[torch.from_numpy(s).to(rows.device)].cpu().numpy()])   # W rows of the book table
+        all_x.append(e - s)
+        all_s.append(s + offset)
+        all_e.append(e + offset)
+        all_m.append(m)
+        offset += m.shape[0]
+    msgs_dev = torch.cat(all_m, 0) if len(all_m) > 1 else all_m[0]
+    return LoadedDay(msgs=msgs_dev.cpu().numpy(), starts=np.concatenate(all_s), ends=np.concatenate(all_e),
+                     books=np.concatenate(all_b, 0), max_msgs=np.concatenate(all_x), msgs_device=msgs_dev)
+
+
 def cache_suffix(world) -> str:
     """base:398-411 ``_get_filename_suffix``."""
     return "_".join(str(x) for x in (world.stock, world.timePeriod, world.book_depth, world.ep_type,
@@ -360,8 +429,9 @@ def cache_suffix(world) -> str:
                                      world.day_start, world.day_end))
 
 
-def load_or_generate(world, seed=20220103, n_events=400_000, stress=False, cache_dir=None) -> LoadedDay:
-    """Loader entry point used by the env: npz cache with the reference's key names (ldr:686-693), else generate."""
+def load_or_generate(world, seed=20220103, n_events=400_000, stress=False, cache_dir=None, device=None) -> LoadedDay:
+    """Loader entry point used by the env: npz cache with the reference's key names (ldr:686-693), else generate (and, with
+    a CUDA ``device``, preprocess the day there)."""
     path = None
     if cache_dir is not None:
         os.makedirs(cache_dir, exist_ok=True)
@@ -373,7 +443,7 @@ def load_or_generate(world, seed=20220103, n_events=400_000, stress=False, cache
     day = generate_day(seed=seed, n_events=n_events, levels=world.book_depth, tick=world.tick_size,
                        day_start=world.day_start, day_end=world.day_end, stress=stress)
     ld = load_days([day], world.episode_time, world.n_data_msg_per_step, world.start_resolution,
-                   world.day_start, world.day_end, window_type=world.ep_type)
+                   world.day_start, world.day_end, window_type=world.ep_type, device=device)
     if path is not None:   # atomic: several ranks of one job may generate the same day at the same time
         tmp = f"{path}.{os.getpid()}.tmp.npz"
         np.savez_compressed(tmp, msgs=ld.msgs, starts=ld.starts, ends=ld.ends, obs=ld.books,

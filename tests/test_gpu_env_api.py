@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 
 import helpers as H
-from jaxmarl_hft_b200 import abi, config as C, env as E
+from jaxmarl_hft_b200 import abi, config as C, env as E, lobster
 
 pytestmark = pytest.mark.gpu
 
@@ -264,3 +264,49 @@ def test_host_buffer_replay_matches_oracle(oracle):
         assert rc == abi.LOB_E_INVALID and b"start[7]" in L.lob_last_error()
     finally:
         L.lob_host_replay_destroy(h)
+
+
+def _day_with_everything(seed):
+    """A synthetic day plus what a real LOBSTER file also holds: rows of types 5 / 6 / 7 (dropped), rows outside the trading
+    window, bursts of same-time-stamp executions in BOTH directions interleaved with other rows (merge_market_orders)."""
+    rng = np.random.default_rng(seed)
+    day = H.small_day(seed=seed, n_events=20000)
+    m, ob = day.messages.copy(), day.orderbook.copy()
+    n = m.shape[0]
+    for i in rng.choice(np.arange(50, n - 50), size=300, replace=False):    # same-time-stamp bursts of executions
+        k = int(rng.integers(2, 6))
+        m[i:i + k, 0] = m[i, 0]
+        m[i:i + k, 1] = rng.choice([4, 4, 4, 1, 5], size=k)
+        m[i:i + k, 5] = rng.choice([-1, 1], size=k)
+    odd = rng.choice(n, size=200, replace=False)
+    m[odd, 1] = rng.choice([5, 6, 7], size=200)
+    m[:40, 0] = 34100.0 + np.arange(40) * 0.5            # before day_start
+    m[-30:, 0] = 57601.0 + np.arange(30) * 0.25          # after day_end
+    assert (np.diff(m[:, 0]) >= 0).all()
+    return lobster.RawDay(messages=m, orderbook=ob, levels=day.levels)
+
+
+@pytest.mark.parametrize("seed", [3, 4])
+def test_loader_preprocessing_on_the_device_matches_the_host_loader(seed):
+    """csrc/lob_loader.cu (lobster_loader.py:891-945, :1073-1132 on the device) == lobster.preprocess_day, which
+    tests/test_loader_vs_reference.py pins against the reference's own pandas loader."""
+    import torch
+    from jaxmarl_hft_b200 import lobster
+    day = _day_with_everything(seed)
+    m_ref, ob_ref, t_ref = lobster.preprocess_day(day, return_time=True)
+    msgs, rows, tm = lobster.preprocess_day_cuda(day, device="cuda:0")
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(msgs.cpu().numpy().astype(np.int64), m_ref)
+    np.testing.assert_array_equal(day.orderbook[rows.cpu().numpy()], ob_ref)
+    np.testing.assert_array_equal(tm.cpu().numpy(), t_ref)
+    assert (m_ref[:, 0] == 4).sum() > 100
+    for kind, kw in (("fixed_steps", {}), ("fixed_time", dict(window_length=1800, window_resolution=900))):
+        a = lobster.load_days([day], kw.get("window_length", 64), 100, kw.get("window_resolution", 64), window_type=kind)
+        b = lobster.load_days([day], kw.get("window_length", 64), 100, kw.get("window_resolution", 64), window_type=kind,
+                              device="cuda:0")
+        for f in ("msgs", "starts", "ends", "books", "max_msgs"):
+            np.testing.assert_array_equal(getattr(a, f), getattr(b, f), err_msg=f"{kind} {f}")
+        assert b.msgs_device is not None and b.msgs_device.is_cuda
+    bad = lobster.RawDay(messages=day.messages[::-1].copy(), orderbook=day.orderbook, levels=day.levels)
+    with pytest.raises(ValueError, match="time-sorted"):
+        lobster.preprocess_day_cuda(bad, device="cuda:0")

@@ -13,7 +13,7 @@ import numpy as np
 import torch
 
 import bench as Bn
-import helpers as H
+import helpers as H  # noqa: E402  (development aid: shares the tests' config helpers)
 from jaxmarl_hft_b200 import _lib, config as C, env as E, states
 
 
@@ -25,6 +25,8 @@ def main():
     ap.add_argument("--skip-replay", action="store_true")
     ap.add_argument("--agents", default="", help="agents per type override, e.g. 10,10")
     ap.add_argument("--norders", type=int, default=0, help="book rows per side override")
+    ap.add_argument("--replay-msgs", type=int, default=6400, help="messages per book per replay launch (bench.py: 38400)")
+    ap.add_argument("--grouped", action="store_true", help="replay through the 4-books-per-warp measurement variant")
     a = ap.parse_args()
     dev = torch.device("cuda:0")
     L = _lib.lib()
@@ -43,15 +45,16 @@ def main():
         asks = torch.from_numpy(P["init_asks"][widx]).to(dev); bids = torch.from_numpy(P["init_bids"][widx]).to(dev)
         trades = torch.from_numpy(P["init_trades"][widx]).to(dev)
         base = ld.starts[widx].astype(np.int64) + (np.arange(B) // W) % 100
-        starts = torch.from_numpy(np.stack([(base + k * 6400) % (M - 6400) for k in range(a.iters + 2)])).to(dev)
+        TW = a.replay_msgs
+        starts = torch.from_numpy(np.stack([(base + k * TW) % (M - TW) for k in range(a.iters + 2)])).to(dev)
         for k in range(2):
-            E.replay_books(bc, asks, bids, trades, msgs_d, starts[k], 6400)
+            E.replay_books(bc, asks, bids, trades, msgs_d, starts[k], TW, grouped=a.grouped)
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.iters)]
         for k in range(a.iters):
-            ev[k][0].record(); E.replay_books(bc, asks, bids, trades, msgs_d, starts[2 + k], 6400); ev[k][1].record()
+            ev[k][0].record(); E.replay_books(bc, asks, bids, trades, msgs_d, starts[2 + k], TW, grouped=a.grouped); ev[k][1].record()
         torch.cuda.synchronize()
         ms = float(np.mean([x.elapsed_time(y) for x, y in ev]))
-        out["replay_ms"] = round(ms, 3); out["replay_msgs_per_s"] = f"{B * 6400 / ms * 1e3:.3e}"
+        out["replay_ms"] = round(ms, 3); out["replay_msgs_per_s"] = f"{B * TW / ms * 1e3:.3e}"
     env = E.MARLEnv(None, mac, num_envs=B, loaded=ld, device=dev, seed=1)
     envp = env.default_params
     obs, state = env.reset(None, envp)
