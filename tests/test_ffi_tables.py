@@ -77,3 +77,55 @@ def test_ffi_needs_jax_and_says_so():
     except ImportError:
         with pytest.raises(RuntimeError, match="jax"):
             ffi_stub.build_ffi()
+
+
+def test_lob_ffi_cc_compiles_and_fills_the_struct(tmp_path):
+    """csrc/lob_ffi.cc against a MOCK of xla/ffi/api/ffi.h (tests/ffi_mock: same names and call shapes; the real header
+    ships with jaxlib) linked with csrc/liblobstep.so: the table-driven Fill() puts every fake operand / result pointer at
+    the offset the stub's table names, and a bad table is an error, not a wild store."""
+    import os
+    import shutil
+    import subprocess
+    import textwrap
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    csrc = os.path.join(root, "jaxmarl-hft_b200", "csrc")
+    if not (shutil.which("g++") and os.path.exists(os.path.join(csrc, "liblobstep.so"))):
+        pytest.skip("needs g++ and the built liblobstep.so")
+    cfg = Cfg.to_step_config(H.load_mac("2_player_fq_fqc"), 62, 400000)
+    tab = ffi_stub.step_table(cfg)
+    drv = tmp_path / "drv.cc"
+    drv.write_text(textwrap.dedent(f'''
+        #include <cstdio>
+        #include <cstring>
+        #include "{os.path.join(csrc, "lob_ffi.cc")}"
+        int main() {{
+          const int arg_off[] = {{{", ".join(map(str, tab.arg_off.tolist()))}}};
+          const int ret_off[] = {{{", ".join(map(str, tab.ret_off.tolist()))}}};
+          const size_t na = sizeof(arg_off) / 4, nr = sizeof(ret_off) / 4;
+          ffi::RemainingArgs args; ffi::RemainingRets rets;
+          for (size_t i = 0; i < na; ++i) args.ptrs.push_back(reinterpret_cast<void*>(0x1000 + 16 * i));
+          for (size_t i = 0; i < nr; ++i) rets.ptrs.push_back(reinterpret_cast<void*>(0x900000 + 16 * i));
+          LobStepBuffers b;
+          ffi::Error e = Fill(&b, ffi::Span<const int32_t>(arg_off, na), ffi::Span<const int32_t>(ret_off, nr), args, rets);
+          if (e.failure()) {{ std::printf("fill failed: %s\\n", e.message().c_str()); return 1; }}
+          const char* raw = reinterpret_cast<const char*>(&b);
+          for (size_t i = 0; i < nr; ++i) {{   // results win where a state leaf is both operand and result (aliased)
+            void* p; std::memcpy(&p, raw + ret_off[i], sizeof(p));
+            if (p != rets.ptrs[i]) {{ std::printf("result %zu misplaced\\n", i); return 2; }}
+          }}
+          if (b.message_data == nullptr || b.asks != rets.ptrs[0]) return 3;
+          const int bad[] = {{(int)sizeof(LobStepBuffers)}};
+          ffi::RemainingArgs one; one.ptrs.push_back(nullptr);
+          ffi::RemainingRets none;
+          if (!Fill(&b, ffi::Span<const int32_t>(bad, 1), ffi::Span<const int32_t>(bad, 0), one, none).failure()) return 4;
+          if (!Fill(&b, ffi::Span<const int32_t>(arg_off, 2), ffi::Span<const int32_t>(ret_off, 0), one, none).failure()) return 5;
+          std::printf("ok %zu %zu\\n", na, nr);
+          return LobStep() && LobReplay() ? 0 : 6;
+        }}'''))
+    exe = tmp_path / "drv"
+    cmd = ["g++", "-std=c++17", "-O1", f"-I{os.path.join(root, 'tests', 'ffi_mock')}", f"-I{os.path.join(root, 'include')}",
+           "-I/usr/local/cuda/include", str(drv), f"-L{csrc}", "-llobstep", f"-Wl,-rpath,{csrc}", "-o", str(exe)]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.startswith("ok"), (r.returncode, r.stdout, r.stderr)
