@@ -27,13 +27,10 @@
  *   - python scalars are weakly typed (float scalar (+) int32 array -> float32);
  *   - float32 `//` is jnp.floor_divide == round((x - fmod(x,y)) / y) with the
  *     sign fix-up of jax._src.numpy.ufuncs._float_divmod;
- *   - float reductions: XLA leaves the order unspecified.  Reductions over the
- *     trade log use ONE fixed order, shared bit for bit with the CUDA path:
- *     row r is accumulated into partial sum r % 32 in increasing r, then the
- *     32 partial sums are combined by a butterfly (xor 16, 8, 4, 2, 1) --
- *     wsumf() below (trade log rows; the per-message best-price means of the
- *     world info with "row" = message index).  The per-message mid-price mean is
- *     summed left-to-right in message order.
+ *   - float reductions: XLA leaves the order unspecified.  Sums over the trade log run left to right in row order
+ *     (tsumf: the goldens' order); the per-message best-price means of the world info use 32 interleaved partial sums
+ *     and a butterfly (wsumf); the per-message mid-price mean is summed left to right in message order.  The CUDA path
+ *     uses the same three orders, so it agrees with this file bit for bit on every float leaf.
  * Compile: gcc -O2 -fwrapv -ffp-contract=off -fno-fast-math (see Makefile).
  */
 #include <math.h>
@@ -89,20 +86,19 @@ static inline int32_t f2i(float x) {
   return (int32_t)x;
 }
 
-/* The reduction order of float sums over the trade log (see the header).  Mode 0 (default, shared bit for bit with the
- * CUDA path): 32 interleaved partial sums, then a butterfly.  Mode 1: strictly left to right -- the order in which the
- * golden vectors were produced (tests/golden/jaxshim/jax/_core.py:_seq_sum), used by tests/test_golden.py to check this
- * restatement against them at 1e-5 relative on EVERY float leaf, including the ill-conditioned EXE reward family
- * (exe:1627-1665) whose value moves with the summation order.  term[r] is the r-th addend. */
-static int g_sum_order = 0;
-void lob_oracle_set_sum_order(int left_to_right) { g_sum_order = left_to_right ? 1 : 0; }
-int lob_oracle_get_sum_order(void) { return g_sum_order; }
+/* Float sums over the TRADE LOG (rewards, exe:1627-1712, mm:2318-2450): strictly left to right in row order -- the order
+ * the golden vectors were produced with (tests/golden/jaxshim/jax/_core.py:_seq_sum), so this restatement reproduces every
+ * float leaf of the goldens, including the ill-conditioned EXE reward family whose value moves with the summation order.
+ * The CUDA path sums in the same order (one lane per agent walks the rows the scan filled).  term[r] is the r-th addend. */
+static float tsumf(const float* term, int n) {
+  float s = 0.f;
+  for (int r = 0; r < n; ++r) s = s + term[r];
+  return s;
+}
+/* Float sums over the step's MESSAGES (the per-message best-price means of the world info): 32 interleaved partial sums,
+ * then a butterfly (xor 16, 8, 4, 2, 1) -- the order of the CUDA path's 32-messages-at-a-time epilogue.  These means are
+ * well conditioned: any order agrees with the goldens to ~1e-7 relative. */
 static float wsumf(const float* term, int n) {
-  if (g_sum_order) {
-    float s = 0.f;
-    for (int r = 0; r < n; ++r) s = s + term[r];
-    return s;
-  }
   float acc[32], nxt[32];
   for (int l = 0; l < 32; ++l) acc[l] = 0.f;
   for (int r = 0; r < n; ++r) acc[r & 31] = acc[r & 31] + term[r];
@@ -805,10 +801,10 @@ static int32_t sum_abs_q(const int32_t* t, int nt) {
   for (int r = 0; r < nt; ++r) s += iabs32(t[r * 8 + 1]);
   return s;
 }
-/* sum_r( f32(p)/tick * |q| ) in the wsumf order; ft = scratch [nt] */
+/* sum_r( f32(p)/tick * |q| ) left to right (tsumf); ft = scratch [nt] */
 static float sum_pq_over_tick(const int32_t* t, int nt, int32_t tick, float* ft) {
   for (int r = 0; r < nt; ++r) ft[r] = (float)t[r * 8 + 0] / (float)tick * (float)iabs32(t[r * 8 + 1]);
-  return wsumf(ft, nt);
+  return tsumf(ft, nt);
 }
 
 /* mm:2247-2673 get_reward */
@@ -878,7 +874,7 @@ static float mm_get_reward(const LobStepConfig* c, const LobAgentTypeConfig* ac,
     ft[r] = db / tickf * (float)iabs32(s.agent_buys[r * 8 + 1]);
     ft[nt + r] = ds / tickf * (float)iabs32(s.agent_sells[r * 8 + 1]);
   }
-  float buyPnL = wsumf(ft, nt), sellPnL = wsumf(ft + nt, nt);
+  float buyPnL = tsumf(ft, nt), sellPnL = tsumf(ft + nt, nt);
   const float eta = (float)ac->inventoryPnL_eta, gamma = (float)ac->inventoryPnL_gamma;
   float reward_spooner = buyPnL + sellPnL + rebate_income + InventoryPnL;
   float reward_spooner_damped = buyPnL + sellPnL + rebate_income + InventoryPnL - (eta * InventoryPnL);
@@ -894,11 +890,11 @@ static float mm_get_reward(const LobStepConfig* c, const LobAgentTypeConfig* ac,
   float avg_buy_price = 0.f, avg_sell_price = 0.f;
   if (buyQuant > 0) {
     for (int r = 0; r < nt; ++r) ft[r] = (float)s.agent_buys[r * 8] / (float)buyQuant * (float)iabs32(s.agent_buys[r * 8 + 1]);
-    avg_buy_price = wsumf(ft, nt);
+    avg_buy_price = tsumf(ft, nt);
   }
   if (sellQuant > 0) {
     for (int r = 0; r < nt; ++r) ft[r] = (float)s.agent_sells[r * 8] / (float)sellQuant * (float)iabs32(s.agent_sells[r * 8 + 1]);
-    avg_sell_price = wsumf(ft, nt);
+    avg_sell_price = tsumf(ft, nt);
   }
   float approx_realized_pnl = (float)imin32(buyQuant, sellQuant) * (avg_sell_price - avg_buy_price);
   float approx_unrealized_pnl = (inventory_change > 0) ? (float)inventory_change * (averageMidprice - avg_buy_price)
@@ -1182,7 +1178,7 @@ static float exe_get_reward(const LobStepConfig* c, const LobAgentTypeConfig* ac
   else { /* exe:1630-1632 */
     for (int r = 0; r < nt; ++r)
       ft[r] = (float)ifloordiv(other[r * 8], tick) * ((float)iabs32(other[r * 8 + 1]) / (float)otherQuant);
-    P_vwap = wsumf(ft, nt);
+    P_vwap = tsumf(ft, nt);
   }
   int32_t direction_switch = isign32(st->is_sell_task * 2 - 1);
   int32_t QP_agent = 0;
@@ -1199,7 +1195,7 @@ static float exe_get_reward(const LobStepConfig* c, const LobAgentTypeConfig* ac
   float reward = advantage + (float)ac->reward_lambda * drift;
   for (int r = 0; r < nt; ++r) /* exe:1710-1712; rows that are not the agent's contribute 0/task * (0 - t0) == 0 */
     ft[r] = (float)iabs32(agent[r * 8 + 1]) / (float)st->task_to_execute * (float)(agent[r * 8 + 4] - w->init_time[0]);
-  ex->trade_duration = st->trade_duration + wsumf(ft, nt);
+  ex->trade_duration = st->trade_duration + tsumf(ft, nt);
   int32_t quant_left2 = st->task_to_execute - st->quant_executed - agentQuant;
   ex->reward = reward;
   ex->agentQuant = agentQuant;
@@ -1218,7 +1214,7 @@ static float exe_get_reward(const LobStepConfig* c, const LobAgentTypeConfig* ac
       if (!st->is_sell_task) slip = -slip;
       ft[k] = slip * (float)iabs32(agent[k * 8 + 1]);
     }
-    reward_scaled = wsumf(ft, nt) / (float)ac->reward_scaling_quo;
+    reward_scaled = tsumf(ft, nt) / (float)ac->reward_scaling_quo;
   }
   return reward_scaled;
 }

@@ -76,11 +76,6 @@ class Oracle:
         self._check(self.lib.lob_oracle_l2(C.byref(book_cfg), p(asks), p(bids), p(out), n_levels, nb), "lob_oracle_l2")
         return out
 
-    def set_sum_order(self, left_to_right: bool):
-        """Float sums over the trade log: False = the butterfly order shared with the CUDA path (default), True = strictly
-        left to right (the order the golden vectors were produced with)."""
-        self.lib.lob_oracle_set_sum_order(1 if left_to_right else 0)
-
     def max_threads(self):
         """Host threads the OpenMP legs may use: the CPUs this process may run on (libgomp alone reports 1 when the
         environment pins OMP_NUM_THREADS)."""

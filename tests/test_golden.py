@@ -4,13 +4,10 @@ sources under the NumPy JAX emulation (tests/golden/make_golden.py, tests/golden
 What is pinned: job.scan_through_entire_array_save_bidask + get_L2_state on adversarial streams (full books, eviction,
 the -1 wrap, trade-log overflow, IOC / LIM / MKT type-4 interpretation), and MARLEnv.reset / MARLEnv.step rollouts through
 the reference's own loader, reset-state precompute, agent message construction, rewards, observations, info dicts and
-auto-reset.  Integer leaves are compared bit for bit.  Float leaves: rel 1e-5 (north_star) on EVERY leaf when the oracle
-sums the trade log left to right, the order the golden vectors were produced with (``Oracle.set_sum_order(True)``).  In
-the butterfly order the oracle shares bit for bit with the CUDA path, the EXE quantities the reference computes by
-cancelling two ~1e7-sized float32 products (advantage / drift / reward and their running means, exe:1627-1665) move with
-the summation order of ``P_vwap``; they get an absolute tolerance of K ulp(P_vwap) x the quantity the agent traded IN
-THAT STEP (``_exe_tolerances``; K = 4, twice the largest error measured over all goldens), everything else stays at
-rel 1e-5 (see DESIGN.md "Float parity").
+auto-reset.  Integer leaves are compared bit for bit.  Float leaves: rel 1e-5 (north_star) on EVERY leaf, with no exception
+list: the oracle and the CUDA path sum the trade log left to right in row order, the order the golden vectors were produced
+with, so even the EXE quantities the reference computes by cancelling two ~1e7-sized float32 products (advantage / drift /
+reward and their running means, exe:1627-1665) are reproduced (see DESIGN.md "Float parity").
 """
 import ast
 import glob
@@ -25,16 +22,6 @@ from jaxmarl_hft_b200 import abi, config as C, env as E, lobster, states
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 REPLAY_CASES = sorted(glob.glob(os.path.join(GOLDEN, "replay_*.npz")))
 ENV_CASES = sorted(glob.glob(os.path.join(GOLDEN, "env_*.npz")))
-
-def _ulp32(x):
-    """Spacing of float32 at |x| (elementwise)."""
-    x = np.maximum(np.abs(np.asarray(x, np.float64)), 2.0 ** -126)
-    return 2.0 ** (np.floor(np.log2(x)) - 23)
-
-
-K_ULP = 4.0      # measured over all goldens (oracle butterfly vs golden): advantage / drift <= 2.07 x (u*Q + ulp(P*Q))
-K_ULP_RM = 6.0   # ... and the per-unit price_adv / price_drift means <= 3.2 ulp(P_vwap)   (P_vwap itself: <= 5 ulp)
-
 
 def _book_cfg(z):
     return C.book_config(C.World_EnvironmentConfig(nOrders=int(z["no"]), nTrades=int(z["nt"]),
@@ -113,67 +100,8 @@ def _set_draws(arrays, trace, B, n_act, T, kinds, n_agents=None, random_task=Non
 _STATE_ALIAS = {}
 
 
-class ExeTolerance:
-    """Absolute tolerances of the EXE leaves whose value moves with the summation order of P_vwap (exe:1627-1665), when the
-    trade log is NOT summed left to right.  With u = ulp(P_vwap) and Q = the quantity agent a traded in this step
-    (incl. the forced end-of-episode trade), from the golden state / info leaves:
-        advantage = +-(QP - P_vwap * Q),  drift = +-Q * (P_vwap - init_price // tick)   ->  tol = K (u Q + ulp(P_vwap Q))
-        slippage (info revenue_direction_normalised) = advantage + drift                 ->  2 tol
-        reward (info, unscaled) = advantage + lambda drift -> (1 + |lambda|) tol;  reward{t} = that / reward_scaling_quo
-        advantage_return / drift_return: running sums  ->  the error this leaf HAD after the previous step + tol (+ 1 ulp of
-                                                           the sum): only the step's own increment gets slack
-        price_adv_rm / price_drift_rm / slippage_rm: running means m' = (m k + v) / (k + 1) of v = advantage / Q, drift / Q,
-                                                           slippage -> the same running mean of the per-step slack
-                                                           (K_rm u, K_rm u, 2 tol; none when Q = 0)
-    A step in which the agent traded nothing (Q = 0) therefore gets NO slack on its per-step leaves."""
-
-    def __init__(self, cfg, B):
-        self.cfg, self.B = cfg, B
-        self.err = {}      # (t, leaf) -> |got - ref| of the running sums after the previous step
-        self.rm = {}       # (t, leaf) -> propagated slack of the running means
-
-    def step(self, z, prev, pre, arrays):
-        """Returns ({(t, leaf): atol array [B, n]}) for the leaves of step ``pre`` (``prev`` = prefix of the state it started from)."""
-        cfg, B, out = self.cfg, self.B, {}
-        done = np.asarray(z[f"{pre}done_all"]).reshape(B).astype(bool)
-        for t in range(cfg.n_agent_types):
-            a = cfg.agent[t]
-            if a.kind != abi.AGENT_EXE:
-                continue
-            ex_prev = z[f"{prev}state/a{t}_quant_executed"].reshape(B, -1).astype(np.int64)
-            task = z[f"{prev}state/a{t}_task_to_execute"].reshape(B, -1).astype(np.int64)
-            q_left = z[f"{pre}info{t}/quant_left"].reshape(B, -1).astype(np.int64)
-            Q = (task - ex_prev - q_left).astype(np.float64)                 # exe:1786: quant_left = task - executed - agentQuant
-            P = np.maximum(np.abs(z[f"{prev}state/a{t}_p_vwap"].reshape(B, -1)),
-                           np.abs(np.asarray(arrays[f"a{t}_p_vwap"]).reshape(B, -1))).astype(np.float64)
-            u = _ulp32(P)
-            tol = K_ULP * (u * Q + np.where(Q > 0, _ulp32(P * Q), 0.0))
-            lam, quo = abs(float(a.reward_lambda)), abs(float(a.reward_scaling_quo))
-            out[(t, "advantage")] = tol
-            out[(t, "drift")] = tol
-            out[(t, "revenue_direction_normalised")] = 2 * tol
-            out[(t, "reward")] = (1 + lam) * tol
-            out[(t, f"reward{t}")] = (1 + lam) * tol / quo
-            # state leaves: after an auto-reset they hold the reset values (exactly 0)
-            live = ~done[:, None]
-            k = z[f"{prev}state/step_counter"].reshape(B, 1).astype(np.float64)        # exe:1760-1762: the OLD step counter
-            for leaf in ("advantage_return", "drift_return"):
-                ref = z[f"{pre}state/a{t}_{leaf}"].reshape(B, -1).astype(np.float64)
-                got = np.asarray(arrays[f"a{t}_{leaf}"]).reshape(B, -1).astype(np.float64)
-                out[(t, leaf)] = np.where(live, self.err.get((t, leaf), 0.0) + tol + _ulp32(ref), 0.0)
-                self.err[(t, leaf)] = np.where(live, np.abs(got - ref), 0.0)
-            for leaf, slack in (("price_adv_rm", np.where(Q > 0, K_ULP_RM * u, 0.0)),
-                                ("price_drift_rm", np.where(Q > 0, K_ULP_RM * u, 0.0)), ("slippage_rm", 2 * tol)):
-                m = (self.rm.get((t, leaf), 0.0) * k + slack) / (k + 1)
-                out[(t, leaf)] = np.where(live, m, 0.0)
-                self.rm[(t, leaf)] = np.where(live, m, 0.0)
-        return out
-
-
-def _compare(z, prefix, arrays, cfg, what, tol=None):
-    """Every golden leaf under ``prefix`` against our buffer table.  ``tol``: {(t, leaf): atol} of ExeTolerance, or None
-    (rel 1e-5 on everything)."""
-    tol = tol or {}
+def _compare(z, prefix, arrays, cfg, what):
+    """Every golden leaf under ``prefix`` against our buffer table: ints bit for bit, floats rel 1e-5 (atol 1e-6)."""
     T = cfg.n_agent_types
     errs = []
 
@@ -185,15 +113,10 @@ def _compare(z, prefix, arrays, cfg, what, tol=None):
                 errs.append(f"{what} {name}: int mismatch at {np.argwhere(got.astype(np.int64) != ref.astype(np.int64))[:4].tolist()} "
                             f"got {got.ravel()[:6]} ref {ref.ravel()[:6]}")
         else:
-            t = next((int(c) for c in name if c.isdigit()), -1)
-            leaf_key = name[len(f"a{t}_"):] if name.startswith(f"a{t}_") else name
-            atol = tol.get((t, leaf_key))
-            atol = 1e-6 if atol is None else np.asarray(atol).reshape(ref.shape) + 1e-6
-            ok = np.isclose(got, ref, rtol=1e-5, atol=atol, equal_nan=True)
+            ok = np.isclose(got, ref, rtol=1e-5, atol=1e-6, equal_nan=True)
             if not ok.all():
                 bad = np.argwhere(~ok)[0]
-                errs.append(f"{what} {name}: float mismatch at {bad.tolist()} got {got[tuple(bad)]!r} ref {ref[tuple(bad)]!r} "
-                            f"atol {np.broadcast_to(atol, ref.shape)[tuple(bad)]:.3g}")
+                errs.append(f"{what} {name}: float mismatch at {bad.tolist()} got {got[tuple(bad)]!r} ref {ref[tuple(bad)]!r}")
 
     for k in z.files:
         if not k.startswith(prefix):
@@ -212,8 +135,7 @@ def _compare(z, prefix, arrays, cfg, what, tol=None):
     return errs
 
 
-def _compare_info(z, prefix, arrays, cfg, tol=None):
-    tol = tol or {}
+def _compare_info(z, prefix, arrays, cfg):
     errs = []
     wi, wf = arrays["info_world_i32"], arrays["info_world_f32"]
     world = {k: wi[:, j] for j, k in enumerate(abi.WINFO_I32)}
@@ -241,10 +163,8 @@ def _compare_info(z, prefix, arrays, cfg, tol=None):
                     if not np.array_equal(got.astype(np.int64), ref.astype(np.int64)):
                         errs.append(f"info{t} {name}: got {got.ravel()} ref {ref.ravel()}")
                 else:
-                    atol = tol.get((t, name))
-                    atol = 1e-6 if atol is None else np.asarray(atol).reshape(ref.shape) + 1e-6
-                    if not np.isclose(got, ref, rtol=1e-5, atol=atol, equal_nan=True).all():
-                        errs.append(f"info{t} {name}: got {got.ravel()} ref {ref.ravel()} atol {np.ravel(atol)}")
+                    if not np.isclose(got, ref, rtol=1e-5, atol=1e-6, equal_nan=True).all():
+                        errs.append(f"info{t} {name}: got {got.ravel()} ref {ref.ravel()}")
     return errs
 
 
@@ -339,9 +259,7 @@ def _setup(z):
     return mac, ld
 
 
-def _rollout(z, env, step_fn, reset_fn, get_arrays, set_inputs, left_to_right):
-    """``left_to_right``: the path under test sums the trade log in the goldens' order -> rel 1e-5 on every leaf; else the
-    EXE reward family gets the ExeTolerance bound."""
+def _rollout(z, env, step_fn, reset_fn, get_arrays, set_inputs):
     cfg = env.cfg
     overrides = dict(ast.literal_eval(str(z["world_overrides"]))) if "world_overrides" in z.files else {}
     wsel = int(overrides.get("window_selector", -1))
@@ -356,8 +274,6 @@ def _rollout(z, env, step_fn, reset_fn, get_arrays, set_inputs, left_to_right):
     reset_fn()
     errs = _compare(z, "reset/", get_arrays(), cfg, "reset")
     assert not errs, "\n".join(errs[:10])
-    exe_tol = None if left_to_right else ExeTolerance(cfg, B)
-    prev = "reset/"
     for s in range(steps):
         _set_draws(inp, _parse_trace(z[f"step{s}/trace"]), B, n_act, T, kinds, n_agents, rnd, wsel)
         for t in range(T):
@@ -367,10 +283,8 @@ def _rollout(z, env, step_fn, reset_fn, get_arrays, set_inputs, left_to_right):
         set_inputs(inp)
         step_fn()
         arr = get_arrays()
-        tol = exe_tol.step(z, prev, f"step{s}/", arr) if exe_tol else None
-        errs = _compare(z, f"step{s}/", arr, cfg, f"step {s}", tol) + _compare_info(z, f"step{s}/", arr, cfg, tol)
+        errs = _compare(z, f"step{s}/", arr, cfg, f"step {s}") + _compare_info(z, f"step{s}/", arr, cfg)
         assert not errs, f"step {s}:\n" + "\n".join(errs[:12])
-        prev = f"step{s}/"
 
 
 @pytest.mark.parametrize("path", ENV_CASES, ids=[os.path.basename(p) for p in ENV_CASES])
@@ -379,21 +293,7 @@ def test_oracle_env_matches_reference(oracle, path):
     mac, ld = _setup(z)
     env = H.OracleEnv(oracle, mac, ld, int(z["B"]))
     assert env.cfg.n_windows == int(z["n_windows"])
-    oracle.set_sum_order(True)      # the goldens' order: every float leaf within rel 1e-5, no exception
-    try:
-        _rollout(z, env, env.step, env.reset, lambda: env.arrays, lambda inp: H.copy_inputs(inp, env.arrays), True)
-    finally:
-        oracle.set_sum_order(False)
-
-
-@pytest.mark.parametrize("path", ENV_CASES, ids=[os.path.basename(p) for p in ENV_CASES])
-def test_oracle_butterfly_order_within_bound(oracle, path):
-    """The oracle in the summation order it shares with the CUDA path (CUDA == oracle bit for bit in tests/test_gpu_parity.py)
-    against the same goldens: rel 1e-5, the EXE reward family within the ExeTolerance bound."""
-    z = np.load(path)
-    mac, ld = _setup(z)
-    env = H.OracleEnv(oracle, mac, ld, int(z["B"]))
-    _rollout(z, env, env.step, env.reset, lambda: env.arrays, lambda inp: H.copy_inputs(inp, env.arrays), False)
+    _rollout(z, env, env.step, env.reset, lambda: env.arrays, lambda inp: H.copy_inputs(inp, env.arrays))
 
 
 @pytest.mark.gpu
@@ -404,4 +304,4 @@ def test_cuda_env_matches_reference(oracle, path):
     bc = C.book_config(mac.world_config)
     params = E.build_reset_params(ld, mac.world_config, E._cuda_replay_fn(bc, "cuda:0"))
     gpu = H.CudaEnv(mac, ld, int(z["B"]), params)
-    _rollout(z, gpu, gpu.step, gpu.reset, gpu.numpy, gpu.set_inputs, False)
+    _rollout(z, gpu, gpu.step, gpu.reset, gpu.numpy, gpu.set_inputs)

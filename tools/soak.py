@@ -25,7 +25,7 @@ def rollout(oracle, mac, day, B, steps, seed, threads):
     H.draw_prng(rng, ref.cfg, ref.arrays)
     gpu.set_inputs(ref.arrays)
     ref.reset(); gpu.reset()
-    H.assert_arrays_match(ref.arrays, gpu.numpy(), ref.cfg)
+    H.assert_arrays_match(ref.arrays, gpu.numpy(), ref.cfg, float_exact=True)
     for s in range(steps):
         H.draw_prng(rng, ref.cfg, ref.arrays)
         H.draw_actions(rng, ref.cfg, ref.arrays)
@@ -36,7 +36,7 @@ def rollout(oracle, mac, day, B, steps, seed, threads):
         gpu.set_inputs(ref.arrays)
         ref.step(n_threads=threads); gpu.step()
         try:
-            H.assert_arrays_match(ref.arrays, gpu.numpy(), ref.cfg)
+            H.assert_arrays_match(ref.arrays, gpu.numpy(), ref.cfg, float_exact=True)   # bit patterns, floats included
         except AssertionError as e:
             raise AssertionError(f"seed {seed} step {s}: {e}") from None
 
@@ -55,6 +55,9 @@ def main():
     cases.append(("2_player stress small book", H.load_mac("2_player_fq_fqc", nOrders=40, nTrades=24), dict(seed=9, n_events=60000, stress=True)))
     cases.append(("hetero deep", H.load_mac("hetero_deep_book"), dict(n_events=60000)))
     cases.append(("2_player 200-row book", H.load_mac("2_player_fq_fqc", nOrders=200, nTrades=150), dict(n_events=60000)))
+    # deep books on the capacity-stress day: the books outgrow the 128-row shared-memory window -> both passes of the step
+    cases.append(("hetero deep, stress day (2 passes)", H.load_mac("hetero_deep_book"), dict(seed=9, n_events=60000, stress=True)))
+    cases.append(("2_player 300-row book, stress day", H.load_mac("2_player_fq_fqc", nOrders=300, nTrades=64), dict(seed=9, n_events=60000, stress=True)))
     cases.append(("cancel mode 3 + MKT", H.load_mac("2_player_fq_fqc", nOrders=48, nTrades=20, cancel_mode=3, type_4_interpretation=2),
                   dict(seed=9, n_events=60000, stress=True)))
     cases.append(("fixed_time", H.load_mac("2_player_fq_fqc", ep_type="fixed_time", episode_time=900, start_resolution=300), dict(n_events=60000)))
