@@ -38,11 +38,25 @@ __device__ __forceinline__ int clamp_index(int a, int n) { if (a < 0) a += n; re
 __device__ __forceinline__ int isign(int a) { return (a > 0) - (a < 0); }
 __device__ __forceinline__ int imod(int a, int b) { int r = a % b; if (r != 0 && ((r < 0) != (b < 0))) r += b; return r; }  // jnp.remainder
 
-// butterfly combine of the 32 per-lane partial sums (see the header note)
+// butterfly combine of the 32 per-lane partial sums: the per-message means of the world info (oracle: wsumf)
 __device__ __forceinline__ float wsumf(float v) {
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) v = v + __shfl_xor_sync(kFull, v, off);
   return v;
+}
+// Float sums over the TRADE LOG run strictly left to right in row order (oracle: tsumf; the order the golden vectors were
+// produced with, so the ill-conditioned EXE reward family -- differences of two ~1e7-sized float32 products -- comes out
+// as in the reference's eager evaluation).  Lane l holds the terms of row base + l; `rows` = the lanes whose terms can be
+// non-zero (every other row adds exactly +0, and a running sum that starts at +0 never becomes -0, so skipping them is
+// bit-identical).  Every lane ends up with the same sums.
+template <int K>
+__device__ __forceinline__ void seq_add(float (&acc)[K], const float (&term)[K], unsigned rows) {
+  while (rows) {
+    const int l = __ffs(rows) - 1;
+    rows &= rows - 1u;
+#pragma unroll
+    for (int k = 0; k < K; ++k) acc[k] = acc[k] + __shfl_sync(kFull, term[k], l);
+  }
 }
 
 // One trade row classified against a trader id (job:895-904, mm:2214-2243)
@@ -490,42 +504,44 @@ struct MMSums {
 static __device__ __noinline__ MMSums mm_trade_sums(const int* tr, int nt, int tid, float tickf, bool ref_is_int,
                                                     int ref_buy_i, int ref_sell_i, float ref_f) {
   MMSums s = {0, 0, 0, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // outgoing, income, rebate_buy, rebate_sell, buyPnL, sellPnL
 #pragma unroll 1
-  for (int r = lane_id(); r < nt; r += 32) {
-    const TradeRow t = classify(tr, r, tid);
+  for (int base = 0; base < nt; base += 32) {
+    const int r = base + lane_id();
+    const bool in = r < nt;
+    const TradeRow t = classify(tr, in ? r : 0, tid);
     const int aq = abs(t.q);
     const float fq = (float)aq;
     const float pq = (float)t.p / tickf * fq;
-    const bool buy = t.agent && t.buy, sell = t.agent && t.sell;
+    const bool mine = in && t.agent;
+    const bool buy = mine && t.buy, sell = mine && t.sell;
     s.buyQ += buy ? aq : 0;
     s.sellQ += sell ? aq : 0;
-    s.otherQ += t.agent ? 0 : aq;
-    s.outgoing = s.outgoing + (buy ? pq : 0.f);
-    s.income = s.income + (sell ? pq : 0.f);
-    s.rebate_buy = s.rebate_buy + ((t.agent && t.pass_buy) ? pq : 0.f);
-    s.rebate_sell = s.rebate_sell + ((t.agent && t.pass_sell) ? pq : 0.f);
+    s.otherQ += (in && !t.agent) ? aq : 0;
     // rows that are not buys contribute (ref - 0)/tick * 0 == 0 (mm:2416-2417)
     const float db = ref_is_int ? (float)(ref_buy_i - t.p) : (ref_f - (float)t.p);
     const float ds = ref_is_int ? (float)(t.p - ref_sell_i) : ((float)t.p - ref_f);
-    s.buyPnL = s.buyPnL + (buy ? db / tickf * fq : 0.f);
-    s.sellPnL = s.sellPnL + (sell ? ds / tickf * fq : 0.f);
+    const float term[6] = {buy ? pq : 0.f, sell ? pq : 0.f, (mine && t.pass_buy) ? pq : 0.f, (mine && t.pass_sell) ? pq : 0.f,
+                           buy ? db / tickf * fq : 0.f, sell ? ds / tickf * fq : 0.f};
+    seq_add(acc, term, __ballot_sync(kFull, mine));
   }
   s.buyQ = wsum(s.buyQ); s.sellQ = wsum(s.sellQ); s.otherQ = wsum(s.otherQ);
-  s.income = wsumf(s.income); s.outgoing = wsumf(s.outgoing);
-  s.rebate_buy = wsumf(s.rebate_buy); s.rebate_sell = wsumf(s.rebate_sell);
-  s.buyPnL = wsumf(s.buyPnL); s.sellPnL = wsumf(s.sellPnL);
+  s.outgoing = acc[0]; s.income = acc[1]; s.rebate_buy = acc[2]; s.rebate_sell = acc[3]; s.buyPnL = acc[4]; s.sellPnL = acc[5];
   return s;
 }
 // mm:2441-2442: sum_r p_r / Q * |q_r| over the agent's buys (want_buy) or sells
 static __device__ __noinline__ float mm_avg_price(const int* tr, int nt, int tid, bool want_buy, int Q) {
-  float acc = 0.f;
+  float acc[1] = {0.f};
 #pragma unroll 1
-  for (int r = lane_id(); r < nt; r += 32) {
-    const TradeRow t = classify(tr, r, tid);
-    const bool hit = t.agent && (want_buy ? t.buy : t.sell);
-    acc = acc + (hit ? (float)t.p / (float)Q * (float)abs(t.q) : 0.f);
+  for (int base = 0; base < nt; base += 32) {
+    const int r = base + lane_id();
+    const bool in = r < nt;
+    const TradeRow t = classify(tr, in ? r : 0, tid);
+    const bool hit = in && t.agent && (want_buy ? t.buy : t.sell);
+    const float term[1] = {hit ? (float)t.p / (float)Q * (float)abs(t.q) : 0.f};
+    seq_add(acc, term, __ballot_sync(kFull, hit));
   }
-  return wsumf(acc);
+  return acc[0];
 }
 
 // mm:2247-2673 get_reward
@@ -713,32 +729,41 @@ struct EXESums {
 static __device__ __noinline__ EXESums exe_trade_sums(const int* tr, int nt, int tid, int tick, int task_to_execute,
                                                       int init_time0, float init_price, int is_sell) {
   EXESums s = {0, 0, 0, 0, 0.f, 0.f};
+  float acc[2] = {0.f, 0.f};   // tds, simplest
 #pragma unroll 1
-  for (int r = lane_id(); r < nt; r += 32) {
-    const TradeRow t = classify(tr, r, tid);
+  for (int base = 0; base < nt; base += 32) {
+    const int r = base + lane_id();
+    const bool in = r < nt;
+    const TradeRow t = classify(tr, in ? r : 0, tid);
     const int aq = abs(t.q);
-    s.qsum += t.agent ? t.q : 0;
-    s.agentQ += t.agent ? aq : 0;
-    s.otherQ += t.agent ? 0 : aq;
-    s.QP += t.agent ? ifloordiv(t.p, tick) * aq : 0;
-    s.tds = s.tds + (t.agent ? (float)aq / (float)task_to_execute * (float)(t.ts - init_time0) : 0.f);
+    const bool mine = in && t.agent;
+    s.qsum += mine ? t.q : 0;
+    s.agentQ += mine ? aq : 0;
+    s.otherQ += (in && !t.agent) ? aq : 0;
+    s.QP += mine ? ifloordiv(t.p, tick) * aq : 0;
     float slip = (float)t.p - init_price;   // exe:1744-1752 (|q| == 0 for rows that are not the agent's)
     if (!is_sell) slip = -slip;
-    s.simplest = s.simplest + (t.agent ? slip * (float)aq : 0.f);
+    const float term[2] = {mine ? (float)aq / (float)task_to_execute * (float)(t.ts - init_time0) : 0.f,
+                           mine ? slip * (float)aq : 0.f};
+    seq_add(acc, term, __ballot_sync(kFull, mine));
   }
   s.qsum = wsum(s.qsum); s.agentQ = wsum(s.agentQ); s.otherQ = wsum(s.otherQ); s.QP = wsum(s.QP);
-  s.tds = wsumf(s.tds); s.simplest = wsumf(s.simplest);
+  s.tds = acc[0]; s.simplest = acc[1];
   return s;
 }
 // exe:1630-1632: sum_r (p_r // tick) * (|q_r| / otherQ) over the OTHER traders' trades
 static __device__ __noinline__ float exe_vwap(const int* tr, int nt, int tid, int tick, int otherQ) {
-  float acc = 0.f;
+  float acc[1] = {0.f};
 #pragma unroll 1
-  for (int r = lane_id(); r < nt; r += 32) {
-    const TradeRow t = classify(tr, r, tid);
-    acc = acc + (t.agent ? 0.f : (float)ifloordiv(t.p, tick) * ((float)abs(t.q) / (float)otherQ));
+  for (int base = 0; base < nt; base += 32) {
+    const int r = base + lane_id();
+    const bool in = r < nt;
+    const TradeRow t = classify(tr, in ? r : 0, tid);
+    const bool other = in && !t.agent && t.q != 0;   // (a row without quantity adds p * 0 == +0: prices are >= 0 here)
+    const float term[1] = {other ? (float)ifloordiv(t.p, tick) * ((float)abs(t.q) / (float)otherQ) : 0.f};
+    seq_add(acc, term, __ballot_sync(kFull, other));
   }
-  return wsumf(acc);
+  return acc[0];
 }
 
 // exe:1511-1758 get_reward
