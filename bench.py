@@ -417,6 +417,16 @@ def run_native(args):
     rollout_d2h = sum(h.numel() * h.element_size() for h in traj_host)
     reduce_us = max_over_ranks(float(np.mean([a.elapsed_time(b) for a, b in red_ev[:n_roll]]))) * 1e3
     stats_count = float(stats_out["count"].sum().item())
+    # the same 64-step rollout as ONE kernel launch (MARLEnv.rollout -> lob_rollout_launch: the books stay in shared memory
+    # for the whole rollout), PRNG draws included, trajectory read back
+    def rollout_kernel_once(k):
+        tk, _ = env.rollout(state, pol, RT, envp)
+        for h, x in zip(traj_host, list(tk["obs"]) + list(tk["reward"]) + [tk["done"]]):
+            h.copy_(x, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    rollout_kernel_once(0)
+    rollout_kernel_value = ws * args.envs * RT * n_roll / (timed(rollout_kernel_once, n_roll) * 1e-3)
     del env, state, graph, rgraph, traj, traj_dev, traj_host, pol
 
     # ---- (3a) STRONG scaling of BASELINE configs[3]: args.total_envs environments over the N GPUs (contiguous blocks,
@@ -519,6 +529,10 @@ def run_native(args):
                                  "rollout": f"MARLEnv.capture_rollout: {RT} steps + pre-sampled policy as one CUDA graph, "
                                             f"{rollout_d2h} B of trajectory (obs, rewards, done) read back per rollout, then "
                                             "dist.reduce_episode_stats over the ranks",
+                                 "rollout_kernel_value": rollout_kernel_value,
+                                 "rollout_kernel": f"MARLEnv.rollout: the same {RT} steps as ONE launch of lob_rollout_launch "
+                                                   "(books resident in shared memory across the steps), draws and "
+                                                   "trajectory read-back included",
                                  "episode_stat_reduce_us": reduce_us if ws > 1 else None,
                                  "episode_stat_samples": stats_count},
                          "strong_scaling": strong,

@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define LOB_ABI_VERSION 8
+#define LOB_ABI_VERSION 9
 #define LOB_MAX_AGENT_TYPES 8
 #define LOB_MAX_AGENT_I32 4  /* int32 state leaves per agent type */
 #define LOB_MAX_AGENT_F32 10 /* float32 state leaves per agent type */
@@ -253,6 +253,26 @@ typedef struct LobStepBuffers {
                                                 total over all calls (statistics); 16-byte aligned */
 } LobStepBuffers;
 
+/* ---- rollout: n_steps consecutive steps of every environment in ONE launch (lob_rollout_launch), the books resident in
+ *      shared memory in between -- the trainer's jit(lax.scan(vmap(env.step))) with the actions given up front
+ *      (ippo_rnn_JAXMARL.py:616-661 with a pre-sampled policy, Speed_test.py:165-214).  Step ts reads row ts of the
+ *      trajectory inputs and writes row ts of the trajectory outputs; a NULL input falls back to the LobStepBuffers field
+ *      (the same values every step), a NULL output is not recorded.  T = n_steps, B = batch.                          */
+typedef struct LobRolloutBuffers {
+  int32_t n_steps;                                    /* T >= 1 */
+  int32_t _pad0;
+  int64_t batch;                                      /* B: the leading dimension after T of every buffer below */
+  const int32_t* actions[LOB_MAX_AGENT_TYPES];        /* [T,B,n_i] ([T,B,n_i,n_actions] for EXE fixed_prices) */
+  const int32_t* perm;                                /* [T,B,n_action] */
+  const int32_t* reset_window;                        /* [T,B] */
+  const int32_t* reset_is_sell;                       /* [T,B,n_agent_types] */
+  const float*   cancel_u;                            /* [T,B,N,2] (cancel_mode 2/3) */
+  float*   obs[LOB_MAX_AGENT_TYPES];                  /* [T,B,n_i,d_i] */
+  float*   reward[LOB_MAX_AGENT_TYPES];               /* [T,B,n_i] */
+  uint8_t* done_agents[LOB_MAX_AGENT_TYPES];          /* [T,B,n_i] */
+  uint8_t* done_all;                                  /* [T,B] */
+} LobRolloutBuffers;
+
 /* ---- pure replay: every book b scans msgs[start[b] .. start[b]+n_msgs) -- */
 typedef struct LobReplayBuffers {
   int32_t* asks;               /* [B,No,6] in/out */
@@ -272,6 +292,10 @@ const char* lob_last_error(void);
 
 int lob_step_launch(const LobStepConfig* cfg, const LobStepBuffers* bufs, int64_t batch, void* cuda_stream);
 int lob_reset_launch(const LobStepConfig* cfg, const LobStepBuffers* bufs, int64_t batch, void* cuda_stream);
+/* roll->n_steps steps of every environment, equal to that many lob_step_launch calls fed row by row (state leaves, the
+ * LobStepBuffers outputs and info hold what the LAST step left).  roll->batch must equal batch. */
+int lob_rollout_launch(const LobStepConfig* cfg, const LobStepBuffers* bufs, const LobRolloutBuffers* roll, int64_t batch,
+                       void* cuda_stream);
 int lob_replay_launch(const LobBookConfig* cfg, const LobReplayBuffers* bufs, int64_t n_books, void* cuda_stream);
 /* Measurement variant of lob_replay_launch (4 books per warp; n_orders <= 112): same results, slower -- see DESIGN.md 6 */
 int lob_replay_launch_grouped(const LobBookConfig* cfg, const LobReplayBuffers* bufs, int64_t n_books, void* cuda_stream);
@@ -324,6 +348,7 @@ int64_t lob_sizeof_agent_type_config(void);
 int64_t lob_sizeof_step_config(void);
 int64_t lob_sizeof_step_buffers(void);
 int64_t lob_sizeof_replay_buffers(void);
+int64_t lob_sizeof_rollout_buffers(void);
 /* Byte offsets of sentinel fields, in the fixed order below, so that a mirror of these structs (ctypes, cgo, ...) can check
  * its LAYOUT and not only its size: LobBookConfig.{cancel_mode, check_book_fill}; LobAgentTypeConfig.{fixed_quant_value,
  * task_size, doom_price_penalty, reward_scaling_quo, reward_lambda}; LobStepConfig.{tick_size, episode_time,

@@ -30,6 +30,8 @@ def lib():
         vp = C.c_void_p
         L.lob_step_launch.argtypes = [C.POINTER(abi.LobStepConfig), C.POINTER(abi.LobStepBuffers), C.c_int64, vp]
         L.lob_reset_launch.argtypes = [C.POINTER(abi.LobStepConfig), C.POINTER(abi.LobStepBuffers), C.c_int64, vp]
+        L.lob_rollout_launch.argtypes = [C.POINTER(abi.LobStepConfig), C.POINTER(abi.LobStepBuffers),
+                                         C.POINTER(abi.LobRolloutBuffers), C.c_int64, vp]
         L.lob_draw_launch.argtypes = [C.POINTER(abi.LobStepConfig), C.POINTER(abi.LobStepBuffers), C.c_int64, C.c_int32,
                                       C.c_uint64, C.c_uint64, vp]
         L.lob_draw_launch_dev.argtypes = [C.POINTER(abi.LobStepConfig), C.POINTER(abi.LobStepBuffers), C.c_int64, C.c_int32,

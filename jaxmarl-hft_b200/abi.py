@@ -5,7 +5,7 @@ Field order and types follow the header exactly; ``check_sizes`` compares ``ctyp
 """
 import ctypes as C
 
-LOB_ABI_VERSION = 8
+LOB_ABI_VERSION = 9
 LOB_MAX_AGENT_TYPES = 8
 LOB_MAX_AGENT_I32 = 4
 LOB_MAX_AGENT_F32 = 10
@@ -93,6 +93,13 @@ class LobStepBuffers(C.Structure):
         ("work_redo_list", p_i32), ("work_redo_count", p_i32)]
 
 
+class LobRolloutBuffers(C.Structure):
+    _fields_ = [("n_steps", i32), ("_pad0", i32), ("batch", i64),
+                ("actions", p_i32 * LOB_MAX_AGENT_TYPES), ("perm", p_i32), ("reset_window", p_i32), ("reset_is_sell", p_i32),
+                ("cancel_u", p_f32), ("obs", p_f32 * LOB_MAX_AGENT_TYPES), ("reward", p_f32 * LOB_MAX_AGENT_TYPES),
+                ("done_agents", p_u8 * LOB_MAX_AGENT_TYPES), ("done_all", p_u8)]
+
+
 class LobReplayBuffers(C.Structure):
     _fields_ = [("asks", p_i32), ("bids", p_i32), ("trades", p_i32), ("msgs", p_i32), ("start", p_i64),
                 ("n_msgs_total", i64), ("n_msgs", i32), ("_pad0", i32), ("best_out", p_i32),
@@ -101,7 +108,7 @@ class LobReplayBuffers(C.Structure):
 
 _SIZEOF = {"lob_sizeof_book_config": LobBookConfig, "lob_sizeof_agent_type_config": LobAgentTypeConfig,
            "lob_sizeof_step_config": LobStepConfig, "lob_sizeof_step_buffers": LobStepBuffers,
-           "lob_sizeof_replay_buffers": LobReplayBuffers}
+           "lob_sizeof_replay_buffers": LobReplayBuffers, "lob_sizeof_rollout_buffers": LobRolloutBuffers}
 
 
 # the sentinel fields of lob_abi_offsets (include/lobstep.h), in its order

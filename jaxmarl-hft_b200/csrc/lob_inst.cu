@@ -3,6 +3,7 @@
 #ifndef LOB_SLOTS
 #error "compile with -DLOB_SLOTS=<1|2|4|8|16>"
 #endif
+#include <string.h>
 #include "lob_launch.cuh"
 
 namespace lobhost {
@@ -20,7 +21,8 @@ int launch_replay(const LobBookConfig* cfg, const LobReplayBuffers* bufs, int64_
 
 // WIN: the shared-memory window pass of deep books (see lob_step_kernel); LIST: walk b->work_redo_list (second pass).
 template <int S, bool WIN, bool LIST>
-static int launch_step_impl(const LobStepConfig* c, const LobStepBuffers* b, int64_t batch, cudaStream_t st, const DevInfo& d) {
+static int launch_step_impl(const LobStepConfig* c, const LobStepBuffers* b, int64_t batch, cudaStream_t st, const DevInfo& d,
+                            const LobRolloutBuffers* roll = nullptr) {
   const int N = lob_num_msgs_per_step(c), n_act = lob_num_action_msgs(c), n_cnl = lob_num_cancel_msgs(c);
   int n_agents = 0;
   for (int t = 0; t < c->n_agent_types; ++t) n_agents += c->agent[t].n_agents;
@@ -48,14 +50,22 @@ static int launch_step_impl(const LobStepConfig* c, const LobStepBuffers* b, int
     if (c->agent[t].kind == LOB_AGENT_MM && c->agent[t].exclude_extreme_spreads) need_extreme = 1;
   long long ctas = (batch + warps - 1) / warps;   // (LIST: the count is only known on the device -> at most `batch`)
   if (ctas > (long long)d.sms * G) ctas = (long long)d.sms * G;
+  LobRolloutBuffers rb;
+  memset(&rb, 0, sizeof(rb));
+  if (roll) rb = *roll;
   kernel<<<(int)ctas, warps * 32, smem, st>>>(*c, *b, batch, L, N, n_act, n_cnl, need_extreme,
-                                              LIST ? b->work_redo_list : nullptr, LIST ? b->work_redo_count : nullptr);
+                                              LIST ? b->work_redo_list : nullptr, LIST ? b->work_redo_count : nullptr, rb);
   return launched("lob_step_kernel");
 }
 
 template <int S>
 int launch_step(const LobStepConfig* c, const LobStepBuffers* b, int64_t batch, cudaStream_t st, const DevInfo& d) {
   return launch_step_impl<S, false, false>(c, b, batch, st, d);
+}
+template <int S>
+int launch_rollout(const LobStepConfig* c, const LobStepBuffers* b, const LobRolloutBuffers* roll, int64_t batch, cudaStream_t st,
+                   const DevInfo& d) {
+  return launch_step_impl<S, false, false>(c, b, batch, st, d, roll);
 }
 template <int S>
 int launch_step_redo(const LobStepConfig* c, const LobStepBuffers* b, int64_t batch, cudaStream_t st, const DevInfo& d) {
@@ -90,6 +100,8 @@ int launch_l2(const LobBookConfig* cfg, const int32_t* asks, const int32_t* bids
 template int launch_replay<LOB_SLOTS>(const LobBookConfig*, const LobReplayBuffers*, int64_t, cudaStream_t, const DevInfo&);
 template int launch_step<LOB_SLOTS>(const LobStepConfig*, const LobStepBuffers*, int64_t, cudaStream_t, const DevInfo&);
 template int launch_step_redo<LOB_SLOTS>(const LobStepConfig*, const LobStepBuffers*, int64_t, cudaStream_t, const DevInfo&);
+template int launch_rollout<LOB_SLOTS>(const LobStepConfig*, const LobStepBuffers*, const LobRolloutBuffers*, int64_t, cudaStream_t,
+                                       const DevInfo&);
 template int launch_reset<LOB_SLOTS>(const LobStepConfig*, const LobStepBuffers*, int64_t, cudaStream_t, const DevInfo&);
 template int launch_l2<LOB_SLOTS>(const LobBookConfig*, const int32_t*, const int32_t*, int32_t*, int32_t, int64_t, cudaStream_t, const DevInfo&);
 

@@ -225,12 +225,13 @@ __device__ __forceinline__ int obs_dim_of(const LobAgentTypeConfig& a, int fixed
 
 // marl_env.py:130-207 reset_env for env e: the precomputed state of window reset_window[e] replaces every leaf.
 // The book / trade log are left in shared memory (the caller stores them); everything else is written here.
+// reset_window / reset_is_sell: the draws of THIS call ([B] / [B,n_types]; the rollout launch passes the rows of its step)
 template <int SLOTS, bool WIN>
 __device__ __noinline__ void reset_env(const LobStepConfig& c, const LobStepBuffers& b, long long e, Book<SLOTS, WIN>& bk,
-                                          int N) {
+                                          int N, const int* __restrict__ reset_window, const int* __restrict__ reset_is_sell) {
   const int lane = lane_id();
   const int no = c.book.n_orders, nt = c.book.n_trades, T = c.n_agent_types;
-  int wdx = b.reset_window[e];
+  int wdx = reset_window[e];
   if (wdx < 0) wdx += c.n_windows;
   wdx = max(0, min(wdx, c.n_windows - 1));
   __syncwarp();
@@ -278,7 +279,7 @@ __device__ __noinline__ void reset_env(const LobStepConfig& c, const LobStepBuff
         mm_write_obs(ac, b.obs[t] + idx * d, 0, mid, ap, bp, qa, qb, 0, false, ot);
       } else {                          // exe:210-266
         EXEState s = {};
-        s.is_sell_task = (ac.task == LOB_TASK_RANDOM) ? b.reset_is_sell[e * T + t] : (ac.task == LOB_TASK_BUY ? 0 : 1);
+        s.is_sell_task = (ac.task == LOB_TASK_RANDOM) ? reset_is_sell[e * T + t] : (ac.task == LOB_TASK_BUY ? 0 : 1);
         s.init_price = mid;
         s.task_to_execute = ac.task_size;
         s.p_vwap = mid / (float)c.tick_size;
@@ -397,6 +398,11 @@ constexpr int kStepMaxWarps = LOB_STEP_MAXW / LOB_STEP_CTAS;  // warps per CTA (
 #endif
 __host__ __device__ constexpr int step_max_warps(int slots) { return slots <= 4 ? kStepMaxWarps : slots == 8 ? LOB_STEP_MAXW8 : 8; }
 
+// ROLLOUT (rb.n_steps > 1, lob_rollout_launch): every warp takes its environment through rb.n_steps consecutive steps
+// before it moves on -- the books stay in shared memory in between (staged before the first step, written back after the
+// last one), step ts reads its actions / PRNG products from row ts of the trajectory inputs and its observations, rewards
+// and dones also land in row ts of the trajectory outputs.  Everything else is the plain step, so the result equals
+// rb.n_steps launches of it.
 // WIN = true (deep books, n_orders > 32 * SLOTS): the environments run on a shared-memory WINDOW of the first 32 * SLOTS
 // rows of each side (Book<SLOTS, true>); an environment whose book does not fit -- a non-blank row beyond the window when
 // it is staged, or an order that has to rest beyond it during the scan -- writes nothing and is appended to
@@ -406,7 +412,7 @@ template <int SLOTS, bool WIN>
 __global__ void __launch_bounds__(step_max_warps(SLOTS) * 32, kStepCtasPerSm)
 lob_step_kernel(const __grid_constant__ LobStepConfig c, const __grid_constant__ LobStepBuffers b, long long batch,
                 WarpLayout L, int N, int n_act, int n_cnl, int need_extreme, const int* __restrict__ env_list,
-                const int* __restrict__ env_count) {
+                const int* __restrict__ env_count, const __grid_constant__ LobRolloutBuffers rb) {
   int* const smem = dyn_smem();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nwarps = blockDim.x >> 5;
@@ -437,6 +443,13 @@ lob_step_kernel(const __grid_constant__ LobStepConfig c, const __grid_constant__
     const long long slot = base + (long long)warp * gridDim.x;
     bool active = slot < batch;
     const long long e = (env_list && active) ? (long long)env_list[slot] : slot;
+    const int n_steps = WIN ? 1 : max(rb.n_steps, 1);
+    for (int ts = 0; ts < n_steps; ++ts) {    // (CTA-uniform: the phases below are passed by all warps together)
+    const bool first_step = ts == 0, last_step = ts == n_steps - 1;
+    const long long toff = (long long)ts * rb.batch;      // row ts of a [T, B, ...] trajectory buffer (0 in the plain step)
+    const int* const perm_t = rb.perm ? rb.perm + toff * n_act : b.perm;
+    const int* const reset_window_t = rb.reset_window ? rb.reset_window + toff : b.reset_window;
+    const int* const reset_is_sell_t = rb.reset_is_sell ? rb.reset_is_sell + toff * T : b.reset_is_sell;
     bool overflow = false;
 #ifdef LOB_PHASE_TIMING
     const long long tp0 = clock64();
@@ -470,8 +483,9 @@ lob_step_kernel(const __grid_constant__ LobStepConfig c, const __grid_constant__
         if (lane == 0) {
           bulk_wait_read();        // the previous env's bulk stores have drained this warp's buffers
           fence_async_smem();
-          mbar_expect_tx(&bar[0], (bulk_books ? 2u * side_bytes : 0u) + (unsigned)Nd * 32u);
-          if (bulk_books) {
+          const bool books = bulk_books && first_step;   // (rollout: the books of the previous step are still in place)
+          mbar_expect_tx(&bar[0], (books ? 2u * side_bytes : 0u) + (unsigned)Nd * 32u);
+          if (books) {
             bulk_g2s(bk.side_base(ASK), b.asks + e * no * 6, side_bytes, &bar[0]);
             bulk_g2s(bk.side_base(BID), b.bids + e * no * 6, side_bytes, &bar[0]);
           }
@@ -479,7 +493,7 @@ lob_step_kernel(const __grid_constant__ LobStepConfig c, const __grid_constant__
         }
         __syncwarp();
       }
-      if (!bulk_books) { bk.load_side(ASK, b.asks + e * no * 6); bk.load_side(BID, b.bids + e * no * 6); }
+      if (!bulk_books && first_step) { bk.load_side(ASK, b.asks + e * no * 6); bk.load_side(BID, b.bids + e * no * 6); }
       if (WIN) {   // every row beyond the window must be blank (all six fields -1), else this book needs the full-size kernel
         constexpr int W = Book<SLOTS, WIN>::kRows;
         const int tail4 = (no - W) * 6 / 4;   // int4 per side (no and W even)
@@ -493,7 +507,7 @@ lob_step_kernel(const __grid_constant__ LobStepConfig c, const __grid_constant__
         overflow = !__all_sync(kFull, acc == -1);
       }
       bk.c.tr = b.trades + e * nt * 8;   // the trade log is worked on in place (HBM / L2): a row is one 32-byte sector
-      bk.c.cu = b.cancel_u + e * N * 2;  // only dereferenced under cancel_mode 2/3
+      bk.c.cu = (rb.cancel_u ? rb.cancel_u + toff * N * 2 : b.cancel_u) + e * N * 2;  // only dereferenced under cancel_mode 2/3
       bk.fill_trades_empty();            // marl:348: the trade log is re-initialised every step
       w.extreme_spread = false;
       if (need_extreme) {   // mm:2545-2553 over the OLD per-message bests
@@ -528,7 +542,7 @@ lob_step_kernel(const __grid_constant__ LobStepConfig c, const __grid_constant__
           const long long idx = e * ac.n_agents + a;
           const int tid = ac.trader_id_start - a;
           const int aw = (ac.kind == LOB_AGENT_EXE && ac.action_space == LOB_EXE_ACT_FIXED_PRICES) ? ac.n_actions : 1;
-          const int* av = b.actions[t] + idx * aw;
+          const int* av = (rb.actions[t] ? rb.actions[t] + toff * ac.n_agents * aw : b.actions[t]) + idx * aw;
           if (ac.kind == LOB_AGENT_MM) {
             const int action = av[0];
             const int inventory = b.agent_i32[t][2][idx];
@@ -550,11 +564,11 @@ lob_step_kernel(const __grid_constant__ LobStepConfig c, const __grid_constant__
       for (int i = lane; i < n_act; i += 32) act_all[i * 8 + 4] = oid_counter - i;   // marl:285-289
       __syncwarp();
       // marl:293-295 permutation(key, x) == x[perm]
-      const bool shuffle = c.shuffle_action_messages && b.perm;
+      const bool shuffle = c.shuffle_action_messages && perm_t;
       if (!acts_in_place) {
         for (int j = lane; j < n_act * 8; j += 32) {
           const int i = j >> 3, k = j & 7;
-          const int src = shuffle ? max(0, min(b.perm[e * n_act + i], n_act - 1)) : i;
+          const int src = shuffle ? max(0, min(perm_t[e * n_act + i], n_act - 1)) : i;
           msgs[(n_cnl + i) * 8 + k] = act_all[src * 8 + k];
         }
       } else if (shuffle) {   // in place: every lane gathers its (up to 16) words first, then all store
@@ -563,7 +577,7 @@ lob_step_kernel(const __grid_constant__ LobStepConfig c, const __grid_constant__
         for (int q = 0; q < kInPlaceActs * 8 / 32; ++q) {
           const int j = lane + 32 * q;
           v[q] = 0;
-          if (j < n_act * 8) v[q] = act_all[max(0, min(b.perm[e * n_act + (j >> 3)], n_act - 1)) * 8 + (j & 7)];
+          if (j < n_act * 8) v[q] = act_all[max(0, min(perm_t[e * n_act + (j >> 3)], n_act - 1)) * 8 + (j & 7)];
         }
         __syncwarp();
 #pragma unroll
@@ -717,7 +731,7 @@ lob_step_kernel(const __grid_constant__ LobStepConfig c, const __grid_constant__
         wf[0] = new_mid; wf[1] = sum_a / (float)N; wf[2] = sum_b / (float)N; wf[3] = new_dt;
       }
       if (so.ep_done) {   // marl:787-803 auto-reset, fused: the reset state is only touched when the episode ended
-        reset_env(c, b, e, bk, N);
+        reset_env(c, b, e, bk, N, reset_window_t, reset_is_sell_t);
       } else if (lane == 0) {
         b.step_counter[e] = new_step;
         b.time[e * 2] = ft0; b.time[e * 2 + 1] = ft1;
@@ -726,16 +740,32 @@ lob_step_kernel(const __grid_constant__ LobStepConfig c, const __grid_constant__
         b.delta_time[e] = new_dt;
       }
       __syncwarp();
-      // ---- write back: same layout in HBM, so the bulk-copy engine does it ----
-      if (!bulk_books) { bk.store_side(ASK, b.asks + e * no * 6); bk.store_side(BID, b.bids + e * no * 6); }
-      fence_async_smem();
-      __syncwarp();
-      if (lane == 0) {
-        if (bulk_books) {
-          bulk_s2g(b.asks + e * no * 6, bk.side_base(ASK), side_bytes);
-          bulk_s2g(b.bids + e * no * 6, bk.side_base(BID), side_bytes);
+      if (rb.n_steps > 1) {   // rollout: this step's outputs (just written: reset observations included) -> row ts
+        for (int t = 0; t < T; ++t) {
+          const LobAgentTypeConfig& ac = c.agent[t];
+          const int na = ac.n_agents, d = obs_dim_of(ac, c.ep_type_fixed_time);
+          const long long i0 = e * na, o0 = (toff + e) * na;
+          if (rb.obs[t]) for (int i = lane; i < na * d; i += 32) rb.obs[t][o0 * d + i] = b.obs[t][i0 * d + i];
+          for (int i = lane; i < na; i += 32) {
+            if (rb.reward[t]) rb.reward[t][o0 + i] = b.reward[t][i0 + i];
+            if (rb.done_agents[t]) rb.done_agents[t][o0 + i] = b.done_agents[t][i0 + i];
+          }
         }
-        bulk_commit();
+        if (lane == 0 && rb.done_all) rb.done_all[toff + e] = so.ep_done ? 1 : 0;
+        __syncwarp();
+      }
+      // ---- write back (rollout: after the last step only): same layout in HBM, so the bulk-copy engine does it ----
+      if (last_step) {
+        if (!bulk_books) { bk.store_side(ASK, b.asks + e * no * 6); bk.store_side(BID, b.bids + e * no * 6); }
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          if (bulk_books) {
+            bulk_s2g(b.asks + e * no * 6, bk.side_base(ASK), side_bytes);
+            bulk_s2g(b.bids + e * no * 6, bk.side_base(BID), side_bytes);
+          }
+          bulk_commit();
+        }
       }
     }
 #ifdef LOB_PHASE_TIMING
@@ -745,6 +775,7 @@ lob_step_kernel(const __grid_constant__ LobStepConfig c, const __grid_constant__
              tp1 - tp0, tp1b - tp1, tp2 - tp1b, tp2b - tp2, tp3 - tp2b);
     }
 #endif
+    }   // ts
   }
   if (lane == 0) bulk_wait_all();
 }
@@ -762,7 +793,7 @@ lob_reset_kernel(const __grid_constant__ LobStepConfig c, const __grid_constant_
   const int no = c.book.n_orders;
   const long long stride = (long long)gridDim.x * kWarps;
   for (long long e = (long long)blockIdx.x * kWarps + warp; e < batch; e += stride) {
-    reset_env(c, b, e, bk, N);
+    reset_env(c, b, e, bk, N, b.reset_window, b.reset_is_sell);
     __syncwarp();
     bk.store_side(ASK, b.asks + e * no * 6);
     bk.store_side(BID, b.bids + e * no * 6);

@@ -37,6 +37,7 @@ template <int S> int launch_step(const LobStepConfig* c, const LobStepBuffers* b
 // deep books: the window pass (Book<LOB_WINDOW_SLOTS, true>) and the second pass over b->work_redo_list at full capacity
 #define LOB_WINDOW_SLOTS 4
 int launch_step_window(const LobStepConfig* c, const LobStepBuffers* b, int64_t batch, cudaStream_t st, const DevInfo& d);
+template <int S> int launch_rollout(const LobStepConfig* c, const LobStepBuffers* b, const LobRolloutBuffers* roll, int64_t batch, cudaStream_t st, const DevInfo& d);
 template <int S> int launch_step_redo(const LobStepConfig* c, const LobStepBuffers* b, int64_t batch, cudaStream_t st, const DevInfo& d);
 template <int S> int launch_reset(const LobStepConfig* c, const LobStepBuffers* b, int64_t batch, cudaStream_t st, const DevInfo& d);
 template <int S> int launch_l2(const LobBookConfig* cfg, const int32_t* asks, const int32_t* bids, int32_t* l2, int32_t n_levels, int64_t n_books, cudaStream_t st, const DevInfo& d);

@@ -188,6 +188,7 @@ int64_t lob_sizeof_agent_type_config(void) { return (int64_t)sizeof(LobAgentType
 int64_t lob_sizeof_step_config(void) { return (int64_t)sizeof(LobStepConfig); }
 int64_t lob_sizeof_step_buffers(void) { return (int64_t)sizeof(LobStepBuffers); }
 int64_t lob_sizeof_replay_buffers(void) { return (int64_t)sizeof(LobReplayBuffers); }
+int64_t lob_sizeof_rollout_buffers(void) { return (int64_t)sizeof(LobRolloutBuffers); }
 int32_t lob_abi_offsets(int64_t* out, int32_t n) {
   const int64_t off[LOB_ABI_N_OFFSETS] = {
       offsetof(LobBookConfig, cancel_mode), offsetof(LobBookConfig, check_book_fill),
@@ -298,6 +299,27 @@ int lob_step_launch(const LobStepConfig* cfg, const LobStepBuffers* bufs, int64_
     return rc;
   }
   DISPATCH_SLOTS(slots, rc = launch_step<S>(cfg, bufs, batch, st, d));
+  return rc;
+}
+
+int lob_rollout_launch(const LobStepConfig* cfg, const LobStepBuffers* bufs, const LobRolloutBuffers* roll, int64_t batch,
+                       void* cuda_stream) {
+  int rc = check_step_cfg(cfg);
+  if (rc) return rc;
+  if ((rc = check_step_bufs(cfg, bufs, true))) return rc;
+  if (!roll) return fail(LOB_E_INVALID, "null rollout buffers");
+  if (roll->n_steps < 1) return fail(LOB_E_INVALID, "n_steps=%d", roll->n_steps);
+  if (batch < 0 || roll->batch != batch) return fail(LOB_E_INVALID, "rollout batch %lld != batch %lld", (long long)roll->batch, (long long)batch);
+  if (cfg->book.cancel_mode >= 2 && !roll->cancel_u && roll->n_steps > 1)
+    return fail(LOB_E_INVALID, "rollout buffer 'cancel_u' is null (cancel_mode %d draws per message and step)", cfg->book.cancel_mode);
+  if (batch == 0) return LOB_OK;
+  if ((rc = check_on_current_device(bufs->asks, "buffer 'asks'"))) return rc;
+  DevInfo d;
+  if ((rc = device_info(&d))) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  // (deep books run at their full capacity class here: the window pass hands environments to a second launch, which a
+  //  multi-step launch cannot do mid-rollout)
+  DISPATCH_SLOTS(slots_for(cfg->book.n_orders), rc = launch_rollout<S>(cfg, bufs, roll, batch, st, d));
   return rc;
 }
 

@@ -357,6 +357,65 @@ class MARLEnv:
                                          _lib.current_stream_ptr(self.device)), "lob_step_launch")
         return obs, view, rewards, dones, info
 
+    def rollout(self, state: MultiAgentState, actions, n_steps: int, params: MultiAgentParams = None, draw=True):
+        """``n_steps`` env steps in ONE kernel launch (``lob_rollout_launch``): every environment's books stay in shared
+        memory for the whole rollout -- the trainer's ``jit(lax.scan(vmap(env.step)))`` (ippo_rnn_JAXMARL.py:616-661) with
+        the actions given up front (a pre-sampled / open-loop policy: Speed_test.py:165-214).  ``actions``: one int32 CUDA
+        tensor ``[T, B, n_i]`` per agent type.  Equal, leaf for leaf, to ``n_steps`` calls of ``step`` (same PRNG counter
+        sequence).  Returns (traj, state) with ``traj = {"obs": [[T,B,n_i,d_i] per type], "reward": [[T,B,n_i]],
+        "done_agents": [[T,B,n_i] uint8], "done": [T,B] uint8}``; the state, the last step's outputs and info are in
+        ``state.arrays`` as after ``step``."""
+        import torch
+        T_, B, dev = int(n_steps), self.num_envs, self.device
+        nt = self.cfg.n_agent_types
+        if len(actions) != nt:
+            raise ValueError(f"actions: one [T, B, n_i] tensor per agent type expected ({nt}), got {len(actions)}")
+        arrays = state.arrays
+        _, bufs, _, _, _, _, view = self._bound(arrays)
+        key = ("roll", T_, id(arrays))
+        io = self._roll_cache.get(key) if hasattr(self, "_roll_cache") else None
+        if io is None:
+            z = lambda name, dt: torch.empty((T_,) + tuple(arrays[name].shape), dtype=dt, device=dev)
+            io = {"perm": z("perm", torch.int32), "reset_window": z("reset_window", torch.int32),
+                  "reset_is_sell": z("reset_is_sell", torch.int32),
+                  "obs": [z(f"obs{t}", torch.float32) for t in range(nt)],
+                  "reward": [z(f"reward{t}", torch.float32) for t in range(nt)],
+                  "done_agents": [z(f"done_agents{t}", torch.uint8) for t in range(nt)], "done": z("done_all", torch.uint8)}
+            if "cancel_u" in arrays:
+                io["cancel_u"] = z("cancel_u", torch.float32)
+            self._roll_cache = {key: io}
+        acts = []
+        for t, a in enumerate(actions):
+            want = (T_,) + tuple(arrays[f"actions{t}"].shape)
+            a = a.reshape(want).to(torch.int32).contiguous()
+            if a.device != arrays["asks"].device:
+                raise ValueError("actions must live on the environment's device")
+            acts.append(a)
+        if draw:      # the same counter sequence n_steps calls of step() would consume
+            for k in range(T_):
+                row = {**arrays, "perm": io["perm"][k], "reset_window": io["reset_window"][k],
+                       "reset_is_sell": io["reset_is_sell"][k]}
+                if "cancel_u" in io:
+                    row["cancel_u"] = io["cancel_u"][k]
+                self._draw(row, states.pack_buffers(self.cfg, row, self.base_env.device_params()))
+        rb = abi.LobRolloutBuffers()
+        rb.n_steps, rb.batch = T_, B
+        p32, pf, p8 = (lambda t: C.cast(t.data_ptr(), abi.p_i32)), (lambda t: C.cast(t.data_ptr(), abi.p_f32)), \
+            (lambda t: C.cast(t.data_ptr(), abi.p_u8))
+        for t in range(nt):
+            rb.actions[t] = p32(acts[t]); rb.obs[t] = pf(io["obs"][t]); rb.reward[t] = pf(io["reward"][t])
+            rb.done_agents[t] = p8(io["done_agents"][t])
+        rb.perm, rb.reset_window, rb.reset_is_sell = p32(io["perm"]), p32(io["reset_window"]), p32(io["reset_is_sell"])
+        if "cancel_u" in io:
+            rb.cancel_u = pf(io["cancel_u"])
+        rb.done_all = p8(io["done"])
+        with _lib.on_device(dev):
+            _lib.check(_lib.lib().lob_rollout_launch(C.byref(self.cfg), C.byref(bufs), C.byref(rb), B,
+                                                     _lib.current_stream_ptr(dev)), "lob_rollout_launch")
+        self._roll_keepalive = (acts, rb)     # the launch is asynchronous: keep the operands alive
+        traj = {"obs": io["obs"], "reward": io["reward"], "done_agents": io["done_agents"], "done": io["done"]}
+        return traj, view
+
     def capture_step(self, state: MultiAgentState, actions, params: MultiAgentParams = None, pre=None, post=None):
         """One step as a CUDA graph: [pre()] + actions copy + PRNG draw + step kernel [+ post()] captured on the current
         stream (the rollout-fusion row of SURVEY 8f-4: one graph launch per step instead of 4+ launches and their Python).

@@ -1773,3 +1773,4 @@ int64_t lob_sizeof_agent_type_config(void) { return (int64_t)sizeof(LobAgentType
 int64_t lob_sizeof_step_config(void) { return (int64_t)sizeof(LobStepConfig); }
 int64_t lob_sizeof_step_buffers(void) { return (int64_t)sizeof(LobStepBuffers); }
 int64_t lob_sizeof_replay_buffers(void) { return (int64_t)sizeof(LobReplayBuffers); }
+int64_t lob_sizeof_rollout_buffers(void) { return (int64_t)sizeof(LobRolloutBuffers); }

@@ -310,3 +310,40 @@ def test_loader_preprocessing_on_the_device_matches_the_host_loader(seed):
     bad = lobster.RawDay(messages=day.messages[::-1].copy(), orderbook=day.orderbook, levels=day.levels)
     with pytest.raises(ValueError, match="time-sorted"):
         lobster.preprocess_day_cuda(bad, device="cuda:0")
+
+
+@pytest.mark.parametrize("config,kw", [("2_player_fq_fqc", {}), ("2_player_fq_fqc", {"cancel_mode": 3, "nOrders": 48, "nTrades": 20}),
+                                       ("hetero_deep_book", {})])
+def test_rollout_kernel_equals_eager_steps(config, kw):
+    """MARLEnv.rollout (lob_rollout_launch: T steps per environment in one launch, books resident in shared memory) == T
+    calls of MARLEnv.step on a twin env with the same seed: trajectory outputs row by row, every state / output / info
+    leaf at the end.  70 steps cross the auto-reset."""
+    import torch
+    mac = H.load_mac(config, **kw)
+    ld = H.load_for(mac, H.small_day(n_events=30000, **({"seed": 9, "stress": True} if kw else {})))
+    B, T = 80, 70
+    envs = [E.MARLEnv(None, mac, num_envs=B, loaded=ld, device="cuda:0", seed=21) for _ in range(2)]
+    params = [e.default_params for e in envs]
+    states_ = [e.reset(None, p)[1] for e, p in zip(envs, params)]
+    nt = envs[0].cfg.n_agent_types
+    g = torch.Generator(device="cuda"); g.manual_seed(3)
+    acts = [torch.randint(0, envs[0].action_spaces[t].n, (T,) + tuple(states_[0].arrays[f"actions{t}"].shape), generator=g,
+                          device="cuda", dtype=torch.int32) for t in range(nt)]
+    traj, _ = envs[0].rollout(states_[0], acts, T, params[0])
+    ref = {"obs": [[] for _ in range(nt)], "reward": [[] for _ in range(nt)], "done": []}
+    for k in range(T):
+        o, _, r, d, _ = envs[1].step(None, states_[1], [a[k] for a in acts], params[1])
+        for t in range(nt):
+            ref["obs"][t].append(o[t].clone()); ref["reward"][t].append(r[t].clone())
+        ref["done"].append(d["__all__"].clone())
+    torch.cuda.synchronize()
+    for t in range(nt):
+        assert torch.equal(traj["obs"][t].view(torch.int32), torch.stack(ref["obs"][t]).view(torch.int32))
+        assert torch.equal(traj["reward"][t].view(torch.int32), torch.stack(ref["reward"][t]).view(torch.int32))
+    assert torch.equal(traj["done"].bool(), torch.stack(ref["done"]))
+    assert int(traj["done"].sum()) == B
+    a, b = H.to_numpy(states_[0].arrays), H.to_numpy(states_[1].arrays)
+    inputs = ("perm", "reset_window", "reset_is_sell", "cancel_u")     # the rollout reads its own [T, ...] copies of these
+    for k in a:
+        if not (k.startswith("work_") or k.startswith("actions") or k in inputs):
+            np.testing.assert_array_equal(a[k].view(np.uint8), b[k].view(np.uint8), err_msg=k)
