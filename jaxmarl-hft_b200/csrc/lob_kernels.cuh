@@ -381,8 +381,8 @@ __device__ __noinline__ ScanOut scan_messages(BookCtx ctx, int* msgs, int N, int
 // Phase-synchronous persistent CTA: ONE CTA per SM with as many warps as shared memory / registers allow (one
 // environment per warp).  The step has three code phases -- (1) stage state + build the agent messages, (2) the
 // message scan, (3) rewards / observations / write-back -- and the warps of the CTA pass them together
-// (__syncthreads between phases), so that at any time the SM's instruction cache serves ONE phase's code to all of its
-// warps instead of three phases to desynchronised warps (the L1.5 instruction cache is 32 KB; ncu showed the
+// (a __syncthreads after the scan), so that at any time the SM's instruction cache serves ONE phase's code to (nearly) all
+// of its warps instead of three phases to desynchronised warps (the L1.5 instruction cache is 32 KB; ncu showed the
 // unsynchronised version stalled on instruction fetch: smsp stall_no_instruction 8.2 of ~16 per issue).
 #ifndef LOB_STEP_MAXW
 #define LOB_STEP_MAXW 20
@@ -591,7 +591,13 @@ lob_step_kernel(const __grid_constant__ LobStepConfig c, const __grid_constant__
 #ifdef LOB_PHASE_TIMING
     const long long tp1 = clock64();
 #endif
+    // (No barrier here.  The warps' smem regions are private, so the barriers of this loop only exist to keep the SM's warps
+    //  in ONE code phase for the instruction cache.  Letting a warp start its scan as soon as its own phase 1 is done is
+    //  worth 1-2 % (0.574 -> 0.562 ms): phase 1 is short and the scans re-align at the barrier below every step; dropping
+    //  THAT barrier instead loses 24 %, dropping both 60 %.)
+#ifdef LOB_SYNC1
     __syncthreads();
+#endif
 #ifdef LOB_PHASE_TIMING
     const long long tp1b = clock64();
 #endif
