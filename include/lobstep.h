@@ -12,7 +12,13 @@
  *                           job.scan_through_entire_array jaxob/JaxOrderBookArrays.py:736
  *                           (also the reset-state precompute, base_env.py:245-296)
  *   lob_l2_launch      <->  job.get_L2_state              jaxob/JaxOrderBookArrays.py:1232
- *   lob_replay_host    <->  the same replay through HOST buffers (bench e2e leg)
+ *   lob_rollout_launch <->  lax.scan(vmap(env.step)) over T steps with the actions given up front
+ *                           jaxrl/MARL/ippo_rnn_JAXMARL.py:616-661, jaxen/Speed_test.py:165-214
+ *   lob_host_replay_*  <->  the same replay through HOST buffers (bench e2e leg)
+ *   lob_loader_*_launch <-> _pre_process_msg_ob + merge_market_orders
+ *                           jaxlobster/lobster_loader.py:891-945, :1073-1132
+ *   lob_draw_launch*   <->  the jax.random products of one step (marl_env.py:135, :294-295; base_env.py:222-225;
+ *                           exec_env.py:221), counter-based, for callers without JAX
  *
  * Conventions
  *   - plain pointers and sizes only; no torch / jax types.

@@ -383,6 +383,13 @@ class MARLEnv:
                   "done_agents": [z(f"done_agents{t}", torch.uint8) for t in range(nt)], "done": z("done_all", torch.uint8)}
             if "cancel_u" in arrays:
                 io["cancel_u"] = z("cancel_u", torch.float32)
+            io["draw_bufs"] = []      # step k's rows of the draw buffers, packed once (pointers never change)
+            for k in range(T_):
+                row = {**arrays, "perm": io["perm"][k], "reset_window": io["reset_window"][k],
+                       "reset_is_sell": io["reset_is_sell"][k]}
+                if "cancel_u" in io:
+                    row["cancel_u"] = io["cancel_u"][k]
+                io["draw_bufs"].append(states.pack_buffers(self.cfg, row, self.base_env.device_params()))
             self._roll_cache = {key: io}
         acts = []
         for t, a in enumerate(actions):
@@ -393,11 +400,7 @@ class MARLEnv:
             acts.append(a)
         if draw:      # the same counter sequence n_steps calls of step() would consume
             for k in range(T_):
-                row = {**arrays, "perm": io["perm"][k], "reset_window": io["reset_window"][k],
-                       "reset_is_sell": io["reset_is_sell"][k]}
-                if "cancel_u" in io:
-                    row["cancel_u"] = io["cancel_u"][k]
-                self._draw(row, states.pack_buffers(self.cfg, row, self.base_env.device_params()))
+                self._draw(arrays, io["draw_bufs"][k])
         rb = abi.LobRolloutBuffers()
         rb.n_steps, rb.batch = T_, B
         p32, pf, p8 = (lambda t: C.cast(t.data_ptr(), abi.p_i32)), (lambda t: C.cast(t.data_ptr(), abi.p_f32)), \
