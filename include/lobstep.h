@@ -46,7 +46,7 @@
 extern "C" {
 #endif
 
-#define LOB_ABI_VERSION 9
+#define LOB_ABI_VERSION 10
 #define LOB_MAX_AGENT_TYPES 8
 #define LOB_MAX_AGENT_I32 4  /* int32 state leaves per agent type */
 #define LOB_MAX_AGENT_F32 10 /* float32 state leaves per agent type */
@@ -181,6 +181,7 @@ typedef struct LobStepConfig {
 int32_t lob_num_msgs_per_step(const LobStepConfig* cfg);
 int32_t lob_num_action_msgs(const LobStepConfig* cfg);
 int32_t lob_num_cancel_msgs(const LobStepConfig* cfg);
+int64_t lob_split_workspace_words(const LobStepConfig* cfg, int64_t batch);   /* size of LobStepBuffers.work_split */
 int32_t lob_obs_dim(const LobStepConfig* cfg, int32_t agent_type);       /* mm_env.py:3195-3223 ; exec_env.py:2188-2202 */
 int32_t lob_info_i32_cols(const LobStepConfig* cfg, int32_t agent_type);
 int32_t lob_info_f32_cols(const LobStepConfig* cfg, int32_t agent_type);
@@ -257,6 +258,10 @@ typedef struct LobStepBuffers {
   int32_t* work_redo_list;                   /* [B] environment indices of the second pass */
   int32_t* work_redo_count;                  /* [4] word 0: environments in the second pass of the LAST call; word 1: running
                                                 total over all calls (statistics); 16-byte aligned */
+  /* optional workspace of lob_step_launch (NULL = not used): lob_split_workspace_words(cfg, B) 32-bit words.  With it the
+   * step kernel only collects what reads the trade log, and the agents' scalar arithmetic (rewards, new agent state, info
+   * rows, observations) runs as a second launch with ONE THREAD PER AGENT over the whole batch.  Same results. */
+  int32_t* work_split;
 } LobStepBuffers;
 
 /* ---- rollout: n_steps consecutive steps of every environment in ONE launch (lob_rollout_launch), the books resident in

@@ -5,7 +5,7 @@ Field order and types follow the header exactly; ``check_sizes`` compares ``ctyp
 """
 import ctypes as C
 
-LOB_ABI_VERSION = 9
+LOB_ABI_VERSION = 10
 LOB_MAX_AGENT_TYPES = 8
 LOB_MAX_AGENT_I32 = 4
 LOB_MAX_AGENT_F32 = 10
@@ -90,7 +90,7 @@ class LobStepBuffers(C.Structure):
         ("done_all", p_u8), ("done_agents", p_u8 * LOB_MAX_AGENT_TYPES),
         ("info_world_i32", p_i32), ("info_world_f32", p_f32),
         ("info_agent_i32", p_i32 * LOB_MAX_AGENT_TYPES), ("info_agent_f32", p_f32 * LOB_MAX_AGENT_TYPES),
-        ("work_redo_list", p_i32), ("work_redo_count", p_i32)]
+        ("work_redo_list", p_i32), ("work_redo_count", p_i32), ("work_split", p_i32)]
 
 
 class LobRolloutBuffers(C.Structure):
@@ -145,6 +145,15 @@ def check_sizes(lib):
             if getattr(cls, name).offset != int(got):
                 raise RuntimeError(f"ABI mismatch: offsetof({cls.__name__}, {name}) = {int(got)} in the library, "
                                    f"{getattr(cls, name).offset} in the ctypes mirror")
+
+
+SPLIT_ENV_WORDS, SPLIT_AGENT_WORDS = 24, 24     # csrc/lob_kernels.cuh kSplitEnvWords / kSplitAgentWords
+
+
+def split_workspace_words(cfg, batch: int) -> int:
+    """== lob_split_workspace_words: 32-bit words of ``LobStepBuffers.work_split``."""
+    n = sum(cfg.agent[t].n_agents for t in range(cfg.n_agent_types))
+    return int(batch) * (SPLIT_ENV_WORDS + SPLIT_AGENT_WORDS * n)
 
 
 def action_width(a) -> int:

@@ -544,10 +544,18 @@ static __device__ __noinline__ float mm_avg_price(const int* tr, int nt, int tid
   return acc[0];
 }
 
-// mm:2247-2673 get_reward
-static __device__ __noinline__ MMReward mm_get_reward(int* tr, int nt, const LobStepConfig& c, const LobAgentTypeConfig& ac,
-                                                      const WorldIn& w, const StepOut& so, const MMState& st, int tid) {
-  MMReward R;
+// mm:2247-2673 get_reward, in two stages.  COLLECT (the whole warp): everything that reads the trade log -- the masked
+// sums, the fictional end-of-episode trade, the average prices of the "complex" reward.  FINISH (any ONE thread): the scalar
+// arithmetic on those sums.  lob_step_launch with the split workspace runs FINISH for all agents of all environments as one
+// thread per agent (lob_agents_finish_kernel) instead of 32 lanes repeating it for one agent after the other.
+struct MMCollect {
+  MMSums s;
+  float avg_buy, avg_sell;
+  int forced_unwind;
+};
+static __device__ __noinline__ MMCollect mm_collect(int* tr, int nt, const LobStepConfig& c, const LobAgentTypeConfig& ac,
+                                                    const StepOut& so, int inventory, int tid) {
+  MMCollect K;
   const int tick = c.tick_size;
   const float tickf = (float)tick;
   const float last_mid = (float)(so.bb_last + so.ba_last) / 2.0f;
@@ -558,8 +566,8 @@ static __device__ __noinline__ MMReward mm_get_reward(int* tr, int nt, const Lob
   else if (ac.reference_price == LOB_REF_NEAR_TOUCH) { ref_buy_i = so.bb_last; ref_sell_i = so.ba_last; }
 
   MMSums s = mm_trade_sums(tr, nt, tid, tickf, ref_is_int, ref_buy_i, ref_sell_i, ref_f);
-  const int inv_before = st.inventory + s.buyQ - s.sellQ;
-  R.forced_unwind = inv_before * (so.ep_done ? 1 : 0);
+  const int inv_before = inventory + s.buyQ - s.sellQ;
+  K.forced_unwind = inv_before * (so.ep_done ? 1 : 0);
   const bool fict = so.ep_done && abs(inv_before) > 0;
   int saved = 0, frow = 0;
   if (fict) {   // mm:2294-2316 the inventory is unwound by a fictional trade at the unwind price
@@ -575,6 +583,28 @@ static __device__ __noinline__ MMReward mm_get_reward(int* tr, int nt, const Lob
                             make_int4(0, 0, c.artificial_trader_id_end_episode, tid), &saved);
     s = mm_trade_sums(tr, nt, tid, tickf, ref_is_int, ref_buy_i, ref_sell_i, ref_f);
   }
+  K.avg_buy = 0.f; K.avg_sell = 0.f;
+  if (ac.reward_function == LOB_MM_REW_COMPLEX) {  // mm:2441-2442
+    K.avg_buy = (s.buyQ > 0) ? mm_avg_price(tr, nt, tid, true, s.buyQ) : 0.f;
+    K.avg_sell = (s.sellQ > 0) ? mm_avg_price(tr, nt, tid, false, s.sellQ) : 0.f;
+  }
+  if (fict) restore_trade(tr, frow, saved);
+  K.s = s;
+  return K;
+}
+static __device__ __noinline__ MMReward mm_finish(const MMCollect& K, const LobStepConfig& c, const LobAgentTypeConfig& ac,
+                                                  const WorldIn& w, const StepOut& so, const MMState& st) {
+  MMReward R;
+  const MMSums s = K.s;
+  const int tick = c.tick_size;
+  const float tickf = (float)tick;
+  const float last_mid = (float)(so.bb_last + so.ba_last) / 2.0f;
+  const bool ref_is_int = (ac.reference_price == LOB_REF_FAR_TOUCH || ac.reference_price == LOB_REF_NEAR_TOUCH);
+  const float ref_f = (ac.reference_price == LOB_REF_MID_AVG) ? so.avg_mid : last_mid;
+  int ref_buy_i = 0, ref_sell_i = 0;
+  if (ac.reference_price == LOB_REF_FAR_TOUCH) { ref_buy_i = so.ba_last; ref_sell_i = so.bb_last; }
+  else if (ac.reference_price == LOB_REF_NEAR_TOUCH) { ref_buy_i = so.bb_last; ref_sell_i = so.ba_last; }
+  R.forced_unwind = K.forced_unwind;
   const int buyQ = s.buyQ, sellQ = s.sellQ;
   const int new_inventory = st.inventory + buyQ - sellQ;
   const float rebate_income = (s.rebate_buy + s.rebate_sell) * (float)(ac.rebate_bps / 10000.0);
@@ -598,14 +628,12 @@ static __device__ __noinline__ MMReward mm_get_reward(int* tr, int nt, const Lob
   float reward_complex = 0.f;
   if (ac.reward_function == LOB_MM_REW_COMPLEX) {  // mm:2437-2450
     const int inv_change = buyQ - sellQ;
-    const float avg_buy = (buyQ > 0) ? mm_avg_price(tr, nt, tid, true, buyQ) : 0.f;
-    const float avg_sell = (sellQ > 0) ? mm_avg_price(tr, nt, tid, false, sellQ) : 0.f;
+    const float avg_buy = K.avg_buy, avg_sell = K.avg_sell;
     const float realized = (float)min(buyQ, sellQ) * (avg_sell - avg_buy);
     const float unrealized = (inv_change > 0) ? (float)inv_change * (so.avg_mid - avg_buy)
                                               : (float)abs(inv_change) * (avg_sell - so.avg_mid);
     reward_complex = realized + (float)ac.unrealizedPnL_lambda * unrealized + eta * jminf(InvPnL, InvPnL * eta);
   }
-  if (fict) restore_trade(tr, frow, saved);
 
   R.reward_portfolio_value = ref_is_int ? (float)new_inventory * ((float)reference_i / tickf) + new_cash
                                         : (float)new_inventory * (ref_f / tickf) + new_cash;
@@ -659,6 +687,11 @@ static __device__ __noinline__ MMReward mm_get_reward(int* tr, int nt, const Lob
   return R;
 }
 
+static __device__ __forceinline__ MMReward mm_get_reward(int* tr, int nt, const LobStepConfig& c, const LobAgentTypeConfig& ac,
+                                                         const WorldIn& w, const StepOut& so, const MMState& st, int tid) {
+  return mm_finish(mm_collect(tr, nt, c, ac, so, st.inventory, tid), c, ac, w, so, st);
+}
+
 // The clock fields of the fixed_time observation variants (mm:3014-3015, exe:1936-1937): world time after the step,
 // the episode's init_time, the step's delta_time.
 struct ObsTime {
@@ -675,11 +708,10 @@ struct ObsTime {
 // (c <= 0 or NaN keeps the division: 0 / 0 must stay NaN).
 __device__ __forceinline__ float fdivz(float x, float c) { return (x == 0.0f && c > 0.0f) ? x : x / c; }
 
-// mm:2963-3154 observation, alphabetical key order
+// mm:2963-3154 observation, alphabetical key order (ONE thread writes; the callers pick it)
 static __device__ __noinline__ void mm_write_obs(const LobAgentTypeConfig& ac, float* obs, int inventory, float mid_price,
                                                  int ba, int bb, int qa, int qb, int step_counter, bool zero,
                                                  const ObsTime& ot) {
-  if (lane_id() != 0) return;
   const bool nz = ac.normalize;
   const int spread = abs(ba - bb);
   if (ac.observation_space == LOB_OBS_BASIC) {
@@ -766,15 +798,20 @@ static __device__ __noinline__ float exe_vwap(const int* tr, int nt, int tid, in
   return acc[0];
 }
 
-// exe:1511-1758 get_reward
-static __device__ __noinline__ EXEReward exe_get_reward(int* tr, int nt, const LobStepConfig& c, const LobAgentTypeConfig& ac,
-                                                        const WorldIn& w, const StepOut& so, const EXEState& st, int tid) {
-  EXEReward R;
+// exe:1511-1758 get_reward, in the same two stages as mm_collect / mm_finish
+struct EXECollect {
+  EXESums s;
+  float p_vwap;
+  int doom_quant;
+};
+static __device__ __noinline__ EXECollect exe_collect(int* tr, int nt, const LobStepConfig& c, const LobAgentTypeConfig& ac,
+                                                      const WorldIn& w, const StepOut& so, const EXEState& st, int tid) {
+  EXECollect K;
   const int tick = c.tick_size;
   const float tickf = (float)tick;
   EXESums s = exe_trade_sums(tr, nt, tid, tick, st.task_to_execute, w.init_time0, st.init_price, st.is_sell_task);
   const int quant_left0 = st.task_to_execute - (st.quant_executed + abs(s.qsum));
-  R.doom_quant = (so.ep_done ? 1 : 0) * quant_left0;
+  K.doom_quant = (so.ep_done ? 1 : 0) * quant_left0;
   const bool fict = so.ep_done && quant_left0 > 0;
   int saved = 0, frow = 0;
   if (fict) {   // exe:1564-1588 the remainder is executed by a fictional trade at the doom price
@@ -794,11 +831,20 @@ static __device__ __noinline__ EXEReward exe_get_reward(int* tr, int nt, const L
                             make_int4(0, 0, c.artificial_trader_id_end_episode, tid), &saved);
     s = exe_trade_sums(tr, nt, tid, tick, st.task_to_execute, w.init_time0, st.init_price, st.is_sell_task);
   }
-  const int agentQ = s.agentQ, otherQ = s.otherQ, QP = s.QP;
-  float P_vwap;
-  if (otherQ == 0) P_vwap = ffloordiv(so.avg_mid, tickf);
-  else P_vwap = exe_vwap(tr, nt, tid, tick, otherQ);
+  if (s.otherQ == 0) K.p_vwap = ffloordiv(so.avg_mid, tickf);
+  else K.p_vwap = exe_vwap(tr, nt, tid, tick, s.otherQ);
   if (fict) restore_trade(tr, frow, saved);
+  K.s = s;
+  return K;
+}
+static __device__ __noinline__ EXEReward exe_finish(const EXECollect& K, const LobStepConfig& c, const LobAgentTypeConfig& ac,
+                                                    const WorldIn& w, const EXEState& st) {
+  EXEReward R;
+  const EXESums s = K.s;
+  const float tickf = (float)c.tick_size;
+  const int agentQ = s.agentQ, QP = s.QP;
+  const float P_vwap = K.p_vwap;
+  R.doom_quant = K.doom_quant;
   const int ds = isign(st.is_sell_task * 2 - 1);
   const float advantage = (float)ds * ((float)QP - P_vwap * (float)agentQ);
   const float drift = (float)(ds * agentQ) * (P_vwap - ffloordiv(st.init_price, tickf));
@@ -820,11 +866,15 @@ static __device__ __noinline__ EXEReward exe_get_reward(int* tr, int nt, const L
   return R;
 }
 
+static __device__ __forceinline__ EXEReward exe_get_reward(int* tr, int nt, const LobStepConfig& c, const LobAgentTypeConfig& ac,
+                                                           const WorldIn& w, const StepOut& so, const EXEState& st, int tid) {
+  return exe_finish(exe_collect(tr, nt, c, ac, w, so, st, tid), c, ac, w, st);
+}
+
 // exe:1879-1906 / exe:1913-2079, alphabetical key order
 static __device__ __noinline__ void exe_write_obs(const LobAgentTypeConfig& ac, float* obs, const EXEState& st, int ba, int bb,
                                                   int ask_vol, int bid_vol, int step_counter, int max_steps, bool zero,
                                                   float mid_price, const ObsTime& ot) {
-  if (lane_id() != 0) return;
   const bool nz = ac.normalize;
   const float ts = (float)ac.task_size;
   const int rem = st.task_to_execute - st.quant_executed;

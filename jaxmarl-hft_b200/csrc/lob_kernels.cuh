@@ -276,7 +276,7 @@ __device__ __noinline__ void reset_env(const LobStepConfig& c, const LobStepBuff
       if (ac.kind == LOB_AGENT_MM) {   // mm:417-459
         MMState s = {0, 0, 0, 0.f, 0.f};
         if (lane == 0) store_mm_state(b, t, idx, s);
-        mm_write_obs(ac, b.obs[t] + idx * d, 0, mid, ap, bp, qa, qb, 0, false, ot);
+        if (lane == 0) mm_write_obs(ac, b.obs[t] + idx * d, 0, mid, ap, bp, qa, qb, 0, false, ot);
       } else {                          // exe:210-266
         EXEState s = {};
         s.is_sell_task = (ac.task == LOB_TASK_RANDOM) ? reset_is_sell[e * T + t] : (ac.task == LOB_TASK_BUY ? 0 : 1);
@@ -284,7 +284,7 @@ __device__ __noinline__ void reset_env(const LobStepConfig& c, const LobStepBuff
         s.task_to_execute = ac.task_size;
         s.p_vwap = mid / (float)c.tick_size;
         if (lane == 0) store_exe_state(b, t, idx, s);
-        exe_write_obs(ac, b.obs[t] + idx * d, s, ap, bp, qa, qb, 0, max_steps, false, mid, ot);
+        if (lane == 0) exe_write_obs(ac, b.obs[t] + idx * d, s, ap, bp, qa, qb, 0, max_steps, false, mid, ot);
       }
     }
   }
@@ -378,6 +378,19 @@ __device__ __noinline__ ScanOut scan_messages(BookCtx ctx, int* msgs, int N, int
   return o;
 }
 
+// ---- SPLIT mode of the step (b.work_split != NULL): the step kernel only COLLECTS what reads the trade log and parks it, with
+// the old agent state and the step's world scalars, in the workspace; lob_agents_finish_kernel then does the agents' scalar
+// arithmetic (reward variants, new state, info row, observation) with ONE THREAD PER AGENT over the whole batch -- warps of
+// 32 same-type agents, coalesced leaves -- instead of 32 lanes repeating it for one agent after the other inside the
+// latency-bound phase 3.  Workspace words (32-bit), B = batch, A = agents per environment:
+//   env record   e            at  e * kSplitEnvWords
+//   agent record (e, slot)    at  B * kSplitEnvWords + (e * A + slot) * kSplitAgentWords     (slot = type-major index)
+constexpr int kSplitEnvWords = 24, kSplitAgentWords = 24;
+enum { SE_MID = 0, SE_OLD_BA, SE_OLD_BB, SE_EXTREME, SE_STEP, SE_MAX_STEPS, SE_INIT0, SE_INIT1, SE_BA, SE_BB, SE_AVG_MID,
+       SE_EP_DONE, SE_NEW_MID, SE_NEW_STEP, SE_FT0, SE_FT1, SE_NEW_DT, SE_VOL_A, SE_VOL_B };
+__device__ __forceinline__ int f2bits(float x) { return __float_as_int(x); }
+__device__ __forceinline__ float bits2f(int x) { return __int_as_float(x); }
+
 // Phase-synchronous persistent CTA: ONE CTA per SM with as many warps as shared memory / registers allow (one
 // environment per warp).  The step has three code phases -- (1) stage state + build the agent messages, (2) the
 // message scan, (3) rewards / observations / write-back -- and the warps of the CTA pass them together
@@ -430,6 +443,11 @@ lob_step_kernel(const __grid_constant__ LobStepConfig c, const __grid_constant__
   Book<SLOTS, WIN> bk;
   bk.init(c.book, ws + L.book);
   const int no = c.book.n_orders, nt = c.book.n_trades, Nd = c.n_data_msg_per_step, T = c.n_agent_types;
+  int n_agents_total = 0;
+  for (int t = 0; t < T; ++t) n_agents_total += c.agent[t].n_agents;
+  const long long batch_total = batch;                          // (the launch's batch: `batch` becomes the list length below)
+  const bool split = b.work_split != nullptr && rb.n_steps == 0;   // see kSplitEnvWords (plain step only: a rollout launch,
+                                                                   // n_steps >= 1, finishes in the kernel)
   const bool bulk_books = (no & 1) == 0;   // a side is no*24 bytes: 16-byte granular iff no is even (WIN: required)
   const unsigned side_bytes = (unsigned)bk.c.no * 24u;   // (WIN: the window's rows)
   if (env_list) {                          // second pass: the environments the window pass handed over
@@ -548,7 +566,7 @@ lob_step_kernel(const __grid_constant__ LobStepConfig c, const __grid_constant__
             const int inventory = b.agent_i32[t][2][idx];
             MMOut o = mm_get_messages(bk.c, c, ac, action, w, inventory, tid, act_all + ai * 8, msgs + ci * 8);
             if (lane == 0) {   // (diet: straight into the info row, mm:2695-2730; phase 3 reads the two distances back)
-              int* x = kDiet ? b.info_agent_i32[t] + idx * LOB_MMINFO_I32_COLS + 3 : scr + flat * 8;
+              int* x = (kDiet || split) ? b.info_agent_i32[t] + idx * LOB_MMINFO_I32_COLS + 3 : scr + flat * 8;
               x[0] = o.posted_bid_price; x[1] = o.posted_ask_price; x[2] = o.bid_dist; x[3] = o.ask_dist;
               x[4] = o.ask_quant; x[5] = o.bid_quant;
             }
@@ -662,6 +680,46 @@ lob_step_kernel(const __grid_constant__ LobStepConfig c, const __grid_constant__
       // ---- (E)+(G)+(I)+(J)+(K) per agent: reward, state, done, info, obs ----
       const ObsTime ot = {c.ep_type_fixed_time, c.episode_time, ft0, ft1, w.init_time0, w.init_time1, new_dt};
       int flat = 0;
+      if (split) {   // collect only; lob_agents_finish_kernel does the rest (see kSplitEnvWords)
+        int* er = b.work_split + e * kSplitEnvWords;
+        if (lane == 0) {
+          er[SE_MID] = f2bits(w.mid_price); er[SE_OLD_BA] = w.old_ba_last; er[SE_OLD_BB] = w.old_bb_last;
+          er[SE_EXTREME] = w.extreme_spread ? 1 : 0; er[SE_STEP] = w.step_counter; er[SE_MAX_STEPS] = w.max_steps;
+          er[SE_INIT0] = w.init_time0; er[SE_INIT1] = w.init_time1; er[SE_BA] = so.ba_last; er[SE_BB] = so.bb_last;
+          er[SE_AVG_MID] = f2bits(so.avg_mid); er[SE_EP_DONE] = so.ep_done ? 1 : 0; er[SE_NEW_MID] = f2bits(new_mid);
+          er[SE_NEW_STEP] = new_step; er[SE_FT0] = ft0; er[SE_FT1] = ft1; er[SE_NEW_DT] = f2bits(new_dt);
+          er[SE_VOL_A] = vol_a; er[SE_VOL_B] = vol_b;
+        }
+        int* ar = b.work_split + batch_total * kSplitEnvWords + e * n_agents_total * kSplitAgentWords;
+        for (int t = 0; t < T; ++t) {
+          const LobAgentTypeConfig& ac = c.agent[t];
+          for (int a = 0; a < ac.n_agents; ++a, ++flat, ar += kSplitAgentWords) {
+            const long long idx = e * ac.n_agents + a;
+            const int tid = ac.trader_id_start - a;
+            if (ac.kind == LOB_AGENT_MM) {
+              MMState s; load_mm_state(b, t, idx, s);
+              const MMCollect K = mm_collect(trp, nt_r, c, ac, so, s.inventory, tid);
+              if (lane == 0) {
+                ar[0] = K.s.buyQ; ar[1] = K.s.sellQ; ar[2] = K.s.otherQ; ar[3] = f2bits(K.s.income); ar[4] = f2bits(K.s.outgoing);
+                ar[5] = f2bits(K.s.rebate_buy); ar[6] = f2bits(K.s.rebate_sell); ar[7] = f2bits(K.s.buyPnL);
+                ar[8] = f2bits(K.s.sellPnL); ar[9] = f2bits(K.avg_buy); ar[10] = f2bits(K.avg_sell); ar[11] = K.forced_unwind;
+                ar[12] = s.inventory; ar[13] = f2bits(s.total_PnL); ar[14] = f2bits(s.cash_balance);
+              }
+            } else {
+              EXEState s; load_exe_state(b, t, idx, s);
+              const EXECollect K = exe_collect(trp, nt_r, c, ac, w, so, s, tid);
+              if (lane == 0) {
+                ar[0] = K.s.qsum; ar[1] = K.s.agentQ; ar[2] = K.s.otherQ; ar[3] = K.s.QP; ar[4] = f2bits(K.s.tds);
+                ar[5] = f2bits(K.s.simplest); ar[6] = f2bits(K.p_vwap); ar[7] = K.doom_quant;
+                ar[8] = s.task_to_execute; ar[9] = s.quant_executed; ar[10] = s.is_sell_task; ar[11] = f2bits(s.init_price);
+                ar[12] = f2bits(s.p_vwap); ar[13] = f2bits(s.total_revenue); ar[14] = f2bits(s.drift_return);
+                ar[15] = f2bits(s.advantage_return); ar[16] = f2bits(s.slippage_rm); ar[17] = f2bits(s.price_adv_rm);
+                ar[18] = f2bits(s.price_drift_rm); ar[19] = f2bits(s.vwap_rm); ar[20] = f2bits(s.trade_duration);
+              }
+            }
+          }
+        }
+      } else
       for (int t = 0; t < T; ++t) {
         const LobAgentTypeConfig& ac = c.agent[t];
         const int d = obs_dim_of(ac, c.ep_type_fixed_time);
@@ -672,7 +730,7 @@ lob_step_kernel(const __grid_constant__ LobStepConfig c, const __grid_constant__
           if (ac.kind == LOB_AGENT_MM) {
             MMState s; load_mm_state(b, t, idx, s);
             const MMReward R = mm_get_reward(trp, nt_r, c, ac, w, so, s, tid);
-            const int* x = kDiet ? b.info_agent_i32[t] + idx * LOB_MMINFO_I32_COLS + 3 : scr + flat * 8;   // from phase 1
+            const int* x = (kDiet || split) ? b.info_agent_i32[t] + idx * LOB_MMINFO_I32_COLS + 3 : scr + flat * 8;   // from phase 1
             MMState ns;   // mm:2677-2736
             ns.posted_distance_bid = x[2]; ns.posted_distance_ask = x[3];
             ns.inventory = R.end_inventory;
@@ -685,14 +743,14 @@ lob_step_kernel(const __grid_constant__ LobStepConfig c, const __grid_constant__
               int* ii = b.info_agent_i32[t] + idx * LOB_MMINFO_I32_COLS;
               float* fi = b.info_agent_f32[t] + idx * LOB_MMINFO_F32_COLS;
               ii[0] = 0; ii[1] = ns.inventory; ii[2] = R.forced_unwind;
-              if (!kDiet) { ii[3] = x[0]; ii[4] = x[1]; ii[5] = x[2]; ii[6] = x[3]; ii[7] = x[4]; ii[8] = x[5]; }
+              if (!(kDiet || split)) { ii[3] = x[0]; ii[4] = x[1]; ii[5] = x[2]; ii[6] = x[3]; ii[7] = x[4]; ii[8] = x[5]; }
               fi[0] = R.reward; fi[1] = R.reward_portfolio_value; fi[2] = R.reward_spooner; fi[3] = R.end_of_ep_pv;
               fi[4] = R.reward_spooner_damped; fi[5] = R.reward_spooner_asym_damped;
               fi[6] = R.reward_spooner_asym_damped2; fi[7] = R.reward_delta_pv; fi[8] = ns.total_PnL;
               fi[9] = R.delta_mid_price; fi[10] = R.market_share; fi[11] = R.buyPnL; fi[12] = R.invPnL;
               fi[13] = R.sellPnL; fi[14] = R.inventoryValue;
             }
-            if (!so.ep_done)
+            if (!so.ep_done && lane == 0)
               mm_write_obs(ac, obs, ns.inventory, new_mid, so.ba_last, so.bb_last, vol_a, vol_b, new_step, false, ot);
           } else {
             EXEState s; load_exe_state(b, t, idx, s);
@@ -716,7 +774,7 @@ lob_step_kernel(const __grid_constant__ LobStepConfig c, const __grid_constant__
               ii[0] = R.quant_left; ii[1] = done ? 1 : 0; ii[2] = R.doom_quant; ii[3] = ns.is_sell_task;
               fi[0] = R.slippage; fi[1] = ns.vwap_rm; fi[2] = R.drift; fi[3] = R.advantage; fi[4] = R.reward;
             }
-            if (!so.ep_done)   // marl:690-698: a finished agent observes zeros until the episode ends
+            if (!so.ep_done && lane == 0)   // marl:690-698: a finished agent observes zeros until the episode ends
               exe_write_obs(ac, obs, ns, so.ba_last, so.bb_last, vol_a, vol_b, new_step, w.max_steps, done, new_mid, ot);
           }
         }
@@ -784,6 +842,102 @@ lob_step_kernel(const __grid_constant__ LobStepConfig c, const __grid_constant__
     }   // ts
   }
   if (lane == 0) bulk_wait_all();
+}
+
+// ================================================================================= agents' finish (split mode) ====
+// One THREAD per (environment, agent), type-major (thread g of type t handles the leaf index g - offset_t = e * n_t + a:
+// a warp is 32 consecutive agents of ONE type, its loads of the [B, n_t] leaves are coalesced).  Reads the records the
+// step kernel left in b.work_split; writes what the in-kernel path writes: reward, done, info row, and -- unless the
+// episode ended (then reset_env already wrote the reset state and observation) -- the new agent state and observation.
+static __global__ void __launch_bounds__(128)
+lob_agents_finish_kernel(const __grid_constant__ LobStepConfig c, const __grid_constant__ LobStepBuffers b, long long batch) {
+  const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int T = c.n_agent_types;
+  int t = 0, slot0 = 0, n_agents_total = 0;
+  long long off = 0;
+  for (int k = 0; k < T; ++k) n_agents_total += c.agent[k].n_agents;
+  for (; t < T; ++t) {
+    const long long cnt = batch * c.agent[t].n_agents;
+    if (g < off + cnt) break;
+    off += cnt; slot0 += c.agent[t].n_agents;
+  }
+  if (t >= T) return;
+  const LobAgentTypeConfig& ac = c.agent[t];
+  const long long idx = g - off;
+  const long long e = idx / ac.n_agents;
+  const int a = (int)(idx - e * ac.n_agents);
+  const int* er = b.work_split + e * kSplitEnvWords;
+  const int* ar = b.work_split + batch * kSplitEnvWords + (e * n_agents_total + slot0 + a) * kSplitAgentWords;
+  WorldIn w;
+  w.time0 = 0; w.time1 = 0;
+  w.mid_price = bits2f(er[SE_MID]); w.old_ba_last = er[SE_OLD_BA]; w.old_bb_last = er[SE_OLD_BB];
+  w.extreme_spread = er[SE_EXTREME] != 0; w.step_counter = er[SE_STEP]; w.max_steps = er[SE_MAX_STEPS];
+  w.init_time0 = er[SE_INIT0]; w.init_time1 = er[SE_INIT1];
+  StepOut so;
+  so.ba_last = er[SE_BA]; so.bb_last = er[SE_BB]; so.avg_mid = bits2f(er[SE_AVG_MID]); so.ep_done = er[SE_EP_DONE] != 0;
+  const float new_mid = bits2f(er[SE_NEW_MID]), new_dt = bits2f(er[SE_NEW_DT]);
+  const int new_step = er[SE_NEW_STEP], vol_a = er[SE_VOL_A], vol_b = er[SE_VOL_B];
+  const ObsTime ot = {c.ep_type_fixed_time, c.episode_time, er[SE_FT0], er[SE_FT1], w.init_time0, w.init_time1, new_dt};
+  const int d = obs_dim_of(ac, c.ep_type_fixed_time);
+  float* obs = b.obs[t] + idx * d;
+  if (ac.kind == LOB_AGENT_MM) {
+    MMCollect K;
+    K.s.buyQ = ar[0]; K.s.sellQ = ar[1]; K.s.otherQ = ar[2]; K.s.income = bits2f(ar[3]); K.s.outgoing = bits2f(ar[4]);
+    K.s.rebate_buy = bits2f(ar[5]); K.s.rebate_sell = bits2f(ar[6]); K.s.buyPnL = bits2f(ar[7]); K.s.sellPnL = bits2f(ar[8]);
+    K.avg_buy = bits2f(ar[9]); K.avg_sell = bits2f(ar[10]); K.forced_unwind = ar[11];
+    MMState s;
+    s.posted_distance_bid = 0; s.posted_distance_ask = 0;
+    s.inventory = ar[12]; s.total_PnL = bits2f(ar[13]); s.cash_balance = bits2f(ar[14]);
+    const MMReward R = mm_finish(K, c, ac, w, so, s);
+    const int* x = b.info_agent_i32[t] + idx * LOB_MMINFO_I32_COLS + 3;   // the step kernel's phase 1 left them there
+    MMState ns;   // mm:2677-2736
+    ns.posted_distance_bid = x[2]; ns.posted_distance_ask = x[3];
+    ns.inventory = R.end_inventory;
+    ns.total_PnL = s.total_PnL + R.PnL;
+    ns.cash_balance = R.cash_balance;
+    b.reward[t][idx] = R.reward_scaled;
+    b.done_agents[t][idx] = 0;
+    if (!so.ep_done) store_mm_state(b, t, idx, ns);
+    int* ii = b.info_agent_i32[t] + idx * LOB_MMINFO_I32_COLS;
+    float* fi = b.info_agent_f32[t] + idx * LOB_MMINFO_F32_COLS;
+    ii[0] = 0; ii[1] = ns.inventory; ii[2] = R.forced_unwind;
+    fi[0] = R.reward; fi[1] = R.reward_portfolio_value; fi[2] = R.reward_spooner; fi[3] = R.end_of_ep_pv;
+    fi[4] = R.reward_spooner_damped; fi[5] = R.reward_spooner_asym_damped;
+    fi[6] = R.reward_spooner_asym_damped2; fi[7] = R.reward_delta_pv; fi[8] = ns.total_PnL;
+    fi[9] = R.delta_mid_price; fi[10] = R.market_share; fi[11] = R.buyPnL; fi[12] = R.invPnL;
+    fi[13] = R.sellPnL; fi[14] = R.inventoryValue;
+    if (!so.ep_done)
+      mm_write_obs(ac, obs, ns.inventory, new_mid, so.ba_last, so.bb_last, vol_a, vol_b, new_step, false, ot);
+  } else {
+    EXECollect K;
+    K.s.qsum = ar[0]; K.s.agentQ = ar[1]; K.s.otherQ = ar[2]; K.s.QP = ar[3]; K.s.tds = bits2f(ar[4]);
+    K.s.simplest = bits2f(ar[5]); K.p_vwap = bits2f(ar[6]); K.doom_quant = ar[7];
+    EXEState s;
+    s.task_to_execute = ar[8]; s.quant_executed = ar[9]; s.is_sell_task = ar[10]; s.init_price = bits2f(ar[11]);
+    s.p_vwap = bits2f(ar[12]); s.total_revenue = bits2f(ar[13]); s.drift_return = bits2f(ar[14]);
+    s.advantage_return = bits2f(ar[15]); s.slippage_rm = bits2f(ar[16]); s.price_adv_rm = bits2f(ar[17]);
+    s.price_drift_rm = bits2f(ar[18]); s.vwap_rm = bits2f(ar[19]); s.trade_duration = bits2f(ar[20]);
+    const EXEReward R = exe_finish(K, c, ac, w, s);
+    EXEState ns = s;   // exe:1771-1839
+    ns.quant_executed = s.quant_executed + R.agentQuant;
+    ns.p_vwap = R.p_vwap;
+    ns.total_revenue = s.total_revenue + (float)R.qp_agent;
+    ns.drift_return = s.drift_return + R.drift;
+    ns.advantage_return = s.advantage_return + R.advantage;
+    ns.slippage_rm = R.slippage_rm; ns.price_adv_rm = R.price_adv_rm;
+    ns.price_drift_rm = R.price_drift_rm; ns.vwap_rm = R.vwap_rm;
+    ns.trade_duration = R.trade_duration;
+    const bool done = (ns.task_to_execute - ns.quant_executed) <= 0;   // exe:270-272
+    b.reward[t][idx] = R.reward_scaled;
+    b.done_agents[t][idx] = done ? 1 : 0;
+    if (!so.ep_done) store_exe_state(b, t, idx, ns);
+    int* ii = b.info_agent_i32[t] + idx * LOB_EXEINFO_I32_COLS;
+    float* fi = b.info_agent_f32[t] + idx * LOB_EXEINFO_F32_COLS;
+    ii[0] = R.quant_left; ii[1] = done ? 1 : 0; ii[2] = R.doom_quant; ii[3] = ns.is_sell_task;
+    fi[0] = R.slippage; fi[1] = ns.vwap_rm; fi[2] = R.drift; fi[3] = R.advantage; fi[4] = R.reward;
+    if (!so.ep_done)   // marl:690-698: a finished agent observes zeros until the episode ends
+      exe_write_obs(ac, obs, ns, so.ba_last, so.bb_last, vol_a, vol_b, new_step, w.max_steps, done, new_mid, ot);
+  }
 }
 
 // ================================================================================================= reset ====

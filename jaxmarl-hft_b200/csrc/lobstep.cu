@@ -165,6 +165,16 @@ int slots_for(int n_orders) {
   return p;
 }
 
+int launch_agents_finish(const LobStepConfig* c, const LobStepBuffers* b, int64_t batch, cudaStream_t st) {
+  long long n = 0;
+  for (int t = 0; t < c->n_agent_types; ++t) n += c->agent[t].n_agents;
+  n *= batch;
+  if (n == 0) return LOB_OK;
+  if (reinterpret_cast<uintptr_t>(b->work_split) & 15u) return fail(LOB_E_INVALID, "work_split must be 16-byte aligned");
+  lob::lob_agents_finish_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(*c, *b, batch);
+  return launched("lob_agents_finish_kernel");
+}
+
 #define DISPATCH_SLOTS(slots, CALL)                                   \
   switch (slots) {                                                    \
     case 1: { constexpr int S = 1; CALL; } break;                     \
@@ -217,6 +227,11 @@ int32_t lob_num_cancel_msgs(const LobStepConfig* c) {
   for (int t = 0; t < c->n_agent_types; ++t)
     n += c->agent[t].n_agents * (c->agent[t].num_messages_by_agent - c->agent[t].num_action_messages_by_agent);
   return n;
+}
+int64_t lob_split_workspace_words(const LobStepConfig* c, int64_t batch) {
+  int64_t n = 0;
+  for (int t = 0; t < c->n_agent_types; ++t) n += c->agent[t].n_agents;
+  return batch * (lob::kSplitEnvWords + lob::kSplitAgentWords * n);
 }
 int32_t lob_num_msgs_per_step(const LobStepConfig* c) {
   return c->n_data_msg_per_step + lob_num_action_msgs(c) + lob_num_cancel_msgs(c);
@@ -286,6 +301,12 @@ int lob_step_launch(const LobStepConfig* cfg, const LobStepBuffers* bufs, int64_
   DevInfo d;
   if ((rc = device_info(&d))) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  // Split mode (collect in the step kernel, the agents' arithmetic as one thread per agent afterwards) pays from two agents
+  // per environment on (measured: 1 agent -2 %, 2 agents +2.5 %, 7 agents +12 %, 20 agents +22 %)
+  LobStepBuffers local;
+  int n_agents_total = 0;
+  for (int t = 0; t < cfg->n_agent_types; ++t) n_agents_total += cfg->agent[t].n_agents;
+  if (bufs->work_split && n_agents_total < 2) { local = *bufs; local.work_split = nullptr; bufs = &local; }
   const int slots = slots_for(cfg->book.n_orders);
   // Deep books (more rows per side than the window): pass 1 steps every environment on a shared-memory window of the
   // first 32 * LOB_WINDOW_SLOTS rows (the reference keeps the live orders in the lowest rows, job:73); pass 2 redoes, at
@@ -296,9 +317,10 @@ int lob_step_launch(const LobStepConfig* cfg, const LobStepBuffers* bufs, int64_
     if (e != cudaSuccess) return fail(LOB_E_CUDA, "cudaMemsetAsync: %s", cudaGetErrorString(e));
     if ((rc = launch_step_window(cfg, bufs, batch, st, d))) return rc;
     DISPATCH_SLOTS(slots, rc = launch_step_redo<S>(cfg, bufs, batch, st, d));
-    return rc;
+  } else {
+    DISPATCH_SLOTS(slots, rc = launch_step<S>(cfg, bufs, batch, st, d));
   }
-  DISPATCH_SLOTS(slots, rc = launch_step<S>(cfg, bufs, batch, st, d));
+  if (!rc && bufs->work_split) rc = launch_agents_finish(cfg, bufs, batch, st);   // split mode: one thread per agent
   return rc;
 }
 

@@ -36,6 +36,7 @@ def leaf_specs(cfg: abi.LobStepConfig, batch: int):
         "info_world_i32": ((B, len(abi.WINFO_I32)), np.int32, "o"),
         "info_world_f32": ((B, len(abi.WINFO_F32)), np.float32, "o"),
     }
+    sp["work_split"] = ((max(abi.split_workspace_words(cfg, B), 4),), np.int32, "w")   # collect / finish split of the step
     if No > 128:   # workspace of lob_step_launch's window pass for deep books (scratch, not state; see include/lobstep.h)
         sp["work_redo_list"] = ((B,), np.int32, "w")
         sp["work_redo_count"] = ((4,), np.int32, "w")
@@ -121,6 +122,7 @@ def pack_buffers(cfg: abi.LobStepConfig, arrays: dict, params: dict) -> abi.LobS
     b.info_world_f32 = _ptr(arrays["info_world_f32"], C.c_float)
     b.work_redo_list = _ptr(arrays.get("work_redo_list"), C.c_int32)
     b.work_redo_count = _ptr(arrays.get("work_redo_count"), C.c_int32)
+    b.work_split = _ptr(arrays.get("work_split"), C.c_int32)
     return b
 
 
@@ -182,7 +184,7 @@ def field_offset(cfg: abi.LobStepConfig, name: str) -> int:
     F, P = abi.LobStepBuffers, C.sizeof(C.c_void_p)
     if name in WORLD_I32 or name in WORLD_F32 or name in PARAMS or name in (
             "perm", "reset_window", "reset_is_sell", "cancel_u", "done_all", "info_world_i32", "info_world_f32",
-            "work_redo_list", "work_redo_count"):
+            "work_redo_list", "work_redo_count", "work_split"):
         return getattr(F, name).offset
     m = re.fullmatch(r"a(\d+)_(\w+)", name)
     if m:
