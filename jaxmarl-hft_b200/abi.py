@@ -147,7 +147,7 @@ def check_sizes(lib):
                                    f"{getattr(cls, name).offset} in the ctypes mirror")
 
 
-SPLIT_ENV_WORDS, SPLIT_AGENT_WORDS = 24, 24     # csrc/lob_kernels.cuh kSplitEnvWords / kSplitAgentWords
+SPLIT_ENV_WORDS, SPLIT_AGENT_WORDS = 24, 0     # csrc/lob_kernels.cuh kSplitEnvWords / kSplitAgentWords
 
 
 def split_workspace_words(cfg, batch: int) -> int:

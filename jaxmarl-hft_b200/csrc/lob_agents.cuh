@@ -64,9 +64,8 @@ struct TradeRow {
   int p, q, ts;
   bool agent, buy, sell, pass_buy, pass_sell;
 };
-__device__ __forceinline__ TradeRow classify(const int* tr, int r, int tid) {
+__device__ __forceinline__ TradeRow classify_row(const int4 a, const int4 b, int tid) {
   TradeRow o;
-  const int4 a = reinterpret_cast<const int4*>(tr)[2 * r], b = reinterpret_cast<const int4*>(tr)[2 * r + 1];
   const bool valid = a.x >= 0;  // trades[:,0] >= 0
   const int p = valid ? a.x : 0, q = valid ? a.y : 0, ts = valid ? b.x : 0;
   const int ptid = valid ? b.z : 0, atid = valid ? b.w : 0;
@@ -80,6 +79,26 @@ __device__ __forceinline__ TradeRow classify(const int* tr, int r, int tid) {
   o.pass_buy = (aq >= 0) && (tid == aptid);
   o.pass_sell = (aq < 0) && (tid == aptid);
   return o;
+}
+__device__ __forceinline__ TradeRow classify(const int* tr, int r, int tid) {
+  return classify_row(reinterpret_cast<const int4*>(tr)[2 * r], reinterpret_cast<const int4*>(tr)[2 * r + 1], tid);
+}
+// ONE THREAD walking the log (lob_agents_finish_kernel): the agent's fictional end-of-episode trade (mm:2294-2316,
+// exe:1564-1588; job:886-889 add_trade overwrites the first row holding a -1, else the last row) is SUBSTITUTED while the
+// thread reads the rows -- the log itself is shared by the environment's agents and is not touched.
+struct FictTrade { int row; int4 lo, hi; };   // row < 0: none
+__device__ __forceinline__ TradeRow classify_sub(const int* tr, int r, int tid, const FictTrade& f) {
+  int4 a = reinterpret_cast<const int4*>(tr)[2 * r], b = reinterpret_cast<const int4*>(tr)[2 * r + 1];
+  if (r == f.row) { a = f.lo; b = f.hi; }
+  return classify_row(a, b, tid);
+}
+static __device__ __noinline__ int first_flagged_trade_row_thread(const int* tr, int nt) {
+#pragma unroll 1
+  for (int r = 0; r < nt; ++r) {
+    const int4 a = reinterpret_cast<const int4*>(tr)[2 * r], b = reinterpret_cast<const int4*>(tr)[2 * r + 1];
+    if ((a.x == -1) | (a.y == -1) | (a.z == -1) | (a.w == -1) | (b.x == -1) | (b.y == -1) | (b.z == -1) | (b.w == -1)) return r;
+  }
+  return nt - 1;
 }
 
 // job:886-889 add_trade for the reward only: overwrite the first row holding a -1 (else the last row); returns the
@@ -592,6 +611,84 @@ static __device__ __noinline__ MMCollect mm_collect(int* tr, int nt, const LobSt
   K.s = s;
   return K;
 }
+// The same collection by ONE THREAD: the rows in order, sums left to right (== seq_add's order: the rows it skips add +0)
+static __device__ __noinline__ MMSums mm_trade_sums_thread(const int* tr, int nt, int tid, float tickf, bool ref_is_int,
+                                                           int ref_buy_i, int ref_sell_i, float ref_f, FictTrade f) {
+  MMSums s = {0, 0, 0, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+  for (int r = 0; r < nt; ++r) {
+    const TradeRow t = classify_sub(tr, r, tid, f);
+    const int aq = abs(t.q);
+    const float fq = (float)aq;
+    s.otherQ += t.agent ? 0 : aq;
+    if (!t.agent) continue;
+    const float pq = (float)t.p / tickf * fq;
+    const bool buy = t.buy, sell = t.sell;
+    s.buyQ += buy ? aq : 0;
+    s.sellQ += sell ? aq : 0;
+    const float db = ref_is_int ? (float)(ref_buy_i - t.p) : (ref_f - (float)t.p);
+    const float ds = ref_is_int ? (float)(t.p - ref_sell_i) : ((float)t.p - ref_f);
+    s.outgoing = s.outgoing + (buy ? pq : 0.f);
+    s.income = s.income + (sell ? pq : 0.f);
+    s.rebate_buy = s.rebate_buy + (t.pass_buy ? pq : 0.f);
+    s.rebate_sell = s.rebate_sell + (t.pass_sell ? pq : 0.f);
+    s.buyPnL = s.buyPnL + (buy ? db / tickf * fq : 0.f);
+    s.sellPnL = s.sellPnL + (sell ? ds / tickf * fq : 0.f);
+  }
+  return s;
+}
+static __device__ __noinline__ float mm_avg_price_thread(const int* tr, int nt, int tid, bool want_buy, int Q, FictTrade f) {
+  float acc = 0.f;
+#pragma unroll 1
+  for (int r = 0; r < nt; ++r) {
+    const TradeRow t = classify_sub(tr, r, tid, f);
+    if (t.agent && (want_buy ? t.buy : t.sell)) acc = acc + (float)t.p / (float)Q * (float)abs(t.q);
+  }
+  return acc;
+}
+static __device__ __noinline__ MMCollect mm_collect_thread(const int* tr, int nt, const LobStepConfig& c,
+                                                           const LobAgentTypeConfig& ac, const StepOut& so, int inventory, int tid) {
+  MMCollect K;
+  const int tick = c.tick_size;
+  const float tickf = (float)tick;
+  const float last_mid = (float)(so.bb_last + so.ba_last) / 2.0f;
+  const bool ref_is_int = (ac.reference_price == LOB_REF_FAR_TOUCH || ac.reference_price == LOB_REF_NEAR_TOUCH);
+  const float ref_f = (ac.reference_price == LOB_REF_MID_AVG) ? so.avg_mid : last_mid;
+  int ref_buy_i = 0, ref_sell_i = 0;
+  if (ac.reference_price == LOB_REF_FAR_TOUCH) { ref_buy_i = so.ba_last; ref_sell_i = so.bb_last; }
+  else if (ac.reference_price == LOB_REF_NEAR_TOUCH) { ref_buy_i = so.bb_last; ref_sell_i = so.ba_last; }
+  FictTrade f = {-1, make_int4(0, 0, 0, 0), make_int4(0, 0, 0, 0)};
+  K.forced_unwind = 0;
+  if (so.ep_done) {   // mm:2294-2316 the inventory is unwound by a fictional trade at the unwind price
+    int buyQ = 0, sellQ = 0;
+#pragma unroll 1
+    for (int r = 0; r < nt; ++r) {
+      const TradeRow t = classify(tr, r, tid);
+      buyQ += (t.agent && t.buy) ? abs(t.q) : 0;
+      sellQ += (t.agent && t.sell) ? abs(t.q) : 0;
+    }
+    const int inv_before = inventory + buyQ - sellQ;
+    K.forced_unwind = inv_before;
+    if (abs(inv_before) > 0) {
+      int penalty = ac.unwind_price_penalty * tick;
+      penalty = (inv_before > 0) ? penalty : -penalty;
+      int unwind_price;
+      if (ac.unwind_price == LOB_REF_MID_AVG) unwind_price = f2i(so.avg_mid - (float)penalty);
+      else if (ac.unwind_price == LOB_REF_MID) unwind_price = f2i(last_mid - (float)penalty);
+      else unwind_price = ((inv_before > 0) ? so.bb_last : so.ba_last) - penalty;
+      f.row = first_flagged_trade_row_thread(tr, nt);
+      f.lo = make_int4(unwind_price, isign(inv_before) * abs(inv_before), c.artificial_order_id_end_episode, c.placeholder_order_id);
+      f.hi = make_int4(0, 0, c.artificial_trader_id_end_episode, tid);
+    }
+  }
+  K.s = mm_trade_sums_thread(tr, nt, tid, tickf, ref_is_int, ref_buy_i, ref_sell_i, ref_f, f);
+  K.avg_buy = 0.f; K.avg_sell = 0.f;
+  if (ac.reward_function == LOB_MM_REW_COMPLEX) {  // mm:2441-2442
+    K.avg_buy = (K.s.buyQ > 0) ? mm_avg_price_thread(tr, nt, tid, true, K.s.buyQ, f) : 0.f;
+    K.avg_sell = (K.s.sellQ > 0) ? mm_avg_price_thread(tr, nt, tid, false, K.s.sellQ, f) : 0.f;
+  }
+  return K;
+}
 static __device__ __noinline__ MMReward mm_finish(const MMCollect& K, const LobStepConfig& c, const LobAgentTypeConfig& ac,
                                                   const WorldIn& w, const StepOut& so, const MMState& st) {
   MMReward R;
@@ -835,6 +932,67 @@ static __device__ __noinline__ EXECollect exe_collect(int* tr, int nt, const Lob
   else K.p_vwap = exe_vwap(tr, nt, tid, tick, s.otherQ);
   if (fict) restore_trade(tr, frow, saved);
   K.s = s;
+  return K;
+}
+static __device__ __noinline__ EXECollect exe_collect_thread(const int* tr, int nt, const LobStepConfig& c,
+                                                             const LobAgentTypeConfig& ac, const WorldIn& w, const StepOut& so,
+                                                             const EXEState& st, int tid) {
+  EXECollect K;
+  const int tick = c.tick_size;
+  const float tickf = (float)tick;
+  FictTrade f = {-1, make_int4(0, 0, 0, 0), make_int4(0, 0, 0, 0)};
+  K.doom_quant = 0;
+  if (so.ep_done) {
+    int qsum = 0;
+#pragma unroll 1
+    for (int r = 0; r < nt; ++r) {
+      const TradeRow t = classify(tr, r, tid);
+      qsum += t.agent ? t.q : 0;
+    }
+    const int quant_left0 = st.task_to_execute - (st.quant_executed + abs(qsum));
+    K.doom_quant = quant_left0;
+    if (quant_left0 > 0) {   // exe:1564-1588 the remainder is executed by a fictional trade at the doom price
+      const int penalty = ac.doom_price_penalty * tick;
+      const int side_sign = st.is_sell_task * 2 - 1;
+      int reference_price;
+      if (ac.reference_price == LOB_REF_MID) {
+        const float x = st.is_sell_task ? (so.avg_mid - (float)penalty) : (so.avg_mid + (float)penalty);
+        reference_price = f2i(ffloordiv(x, tickf) * tickf);
+      } else {
+        const int x = st.is_sell_task ? (so.bb_last - penalty) : (so.ba_last + penalty);
+        reference_price = ifloordiv(x, tick) * tick;
+      }
+      f.row = first_flagged_trade_row_thread(tr, nt);
+      f.lo = make_int4(reference_price, side_sign * abs(quant_left0), c.artificial_order_id_end_episode, c.placeholder_order_id);
+      f.hi = make_int4(0, 0, c.artificial_trader_id_end_episode, tid);
+    }
+  }
+  EXESums s = {0, 0, 0, 0, 0.f, 0.f};
+#pragma unroll 1
+  for (int r = 0; r < nt; ++r) {
+    const TradeRow t = classify_sub(tr, r, tid, f);
+    const int aq = abs(t.q);
+    s.otherQ += t.agent ? 0 : aq;
+    if (!t.agent) continue;
+    s.qsum += t.q;
+    s.agentQ += aq;
+    s.QP += ifloordiv(t.p, tick) * aq;
+    s.tds = s.tds + (float)aq / (float)st.task_to_execute * (float)(t.ts - w.init_time0);
+    float slip = (float)t.p - st.init_price;   // exe:1744-1752
+    if (!st.is_sell_task) slip = -slip;
+    s.simplest = s.simplest + slip * (float)aq;
+  }
+  K.s = s;
+  if (s.otherQ == 0) K.p_vwap = ffloordiv(so.avg_mid, tickf);
+  else {   // exe:1630-1632
+    float acc = 0.f;
+#pragma unroll 1
+    for (int r = 0; r < nt; ++r) {
+      const TradeRow t = classify_sub(tr, r, tid, f);
+      if (!t.agent && t.q != 0) acc = acc + (float)ifloordiv(t.p, tick) * ((float)abs(t.q) / (float)s.otherQ);
+    }
+    K.p_vwap = acc;
+  }
   return K;
 }
 static __device__ __noinline__ EXEReward exe_finish(const EXECollect& K, const LobStepConfig& c, const LobAgentTypeConfig& ac,

@@ -378,16 +378,17 @@ __device__ __noinline__ ScanOut scan_messages(BookCtx ctx, int* msgs, int N, int
   return o;
 }
 
-// ---- SPLIT mode of the step (b.work_split != NULL): the step kernel only COLLECTS what reads the trade log and parks it, with
-// the old agent state and the step's world scalars, in the workspace; lob_agents_finish_kernel then does the agents' scalar
-// arithmetic (reward variants, new state, info row, observation) with ONE THREAD PER AGENT over the whole batch -- warps of
-// 32 same-type agents, coalesced leaves -- instead of 32 lanes repeating it for one agent after the other inside the
-// latency-bound phase 3.  Workspace words (32-bit), B = batch, A = agents per environment:
-//   env record   e            at  e * kSplitEnvWords
-//   agent record (e, slot)    at  B * kSplitEnvWords + (e * A + slot) * kSplitAgentWords     (slot = type-major index)
-constexpr int kSplitEnvWords = 24, kSplitAgentWords = 24;
+// ---- SPLIT mode of the step (b.work_split != NULL): the step kernel leaves the agents' whole reward / state / info /
+// observation work to lob_agents_finish_kernel, which does it with ONE THREAD PER AGENT over the whole batch -- warps of 32
+// same-type agents, coalesced leaves, each thread walking the (few) filled rows of its environment's trade log -- instead
+// of the warp doing it for one agent after the other inside the latency-bound phase 3.  The step kernel parks what that
+// needs in the workspace: the step's world scalars (one env record per environment).  A step that ends the episode is
+// finished by the step kernel itself (the fused auto-reset replaces the trade log and the agent leaves).  Workspace words
+// (32-bit), B = batch:
+//   env record e at e * kSplitEnvWords
+constexpr int kSplitEnvWords = 24, kSplitAgentWords = 0;
 enum { SE_MID = 0, SE_OLD_BA, SE_OLD_BB, SE_EXTREME, SE_STEP, SE_MAX_STEPS, SE_INIT0, SE_INIT1, SE_BA, SE_BB, SE_AVG_MID,
-       SE_EP_DONE, SE_NEW_MID, SE_NEW_STEP, SE_FT0, SE_FT1, SE_NEW_DT, SE_VOL_A, SE_VOL_B };
+       SE_EP_DONE, SE_NEW_MID, SE_NEW_STEP, SE_FT0, SE_FT1, SE_NEW_DT, SE_VOL_A, SE_VOL_B, SE_TRADE_ROWS };
 __device__ __forceinline__ int f2bits(float x) { return __float_as_int(x); }
 __device__ __forceinline__ float bits2f(int x) { return __int_as_float(x); }
 
@@ -666,7 +667,7 @@ lob_step_kernel(const __grid_constant__ LobStepConfig c, const __grid_constant__
       // takes the first row holding a -1 (job:886-889) -- work on nt_r rows: one more than the scan left non-blank.
       const int nt_r = min(nt, trade_rows + 1);
       int* trp = bk.c.tr;
-      if (nt_r <= N) {
+      if (nt_r <= N && !(split && !so.ep_done)) {
         const int4* g4 = reinterpret_cast<const int4*>(bk.c.tr);
         int4* s4 = reinterpret_cast<int4*>(msgs);
         for (int i = lane; i < nt_r * 2; i += 32) s4[i] = g4[i];
@@ -680,7 +681,7 @@ lob_step_kernel(const __grid_constant__ LobStepConfig c, const __grid_constant__
       // ---- (E)+(G)+(I)+(J)+(K) per agent: reward, state, done, info, obs ----
       const ObsTime ot = {c.ep_type_fixed_time, c.episode_time, ft0, ft1, w.init_time0, w.init_time1, new_dt};
       int flat = 0;
-      if (split) {   // collect only; lob_agents_finish_kernel does the rest (see kSplitEnvWords)
+      if (split) {   // lob_agents_finish_kernel does the agents' part (see kSplitEnvWords) ...
         int* er = b.work_split + e * kSplitEnvWords;
         if (lane == 0) {
           er[SE_MID] = f2bits(w.mid_price); er[SE_OLD_BA] = w.old_ba_last; er[SE_OLD_BB] = w.old_bb_last;
@@ -688,38 +689,12 @@ lob_step_kernel(const __grid_constant__ LobStepConfig c, const __grid_constant__
           er[SE_INIT0] = w.init_time0; er[SE_INIT1] = w.init_time1; er[SE_BA] = so.ba_last; er[SE_BB] = so.bb_last;
           er[SE_AVG_MID] = f2bits(so.avg_mid); er[SE_EP_DONE] = so.ep_done ? 1 : 0; er[SE_NEW_MID] = f2bits(new_mid);
           er[SE_NEW_STEP] = new_step; er[SE_FT0] = ft0; er[SE_FT1] = ft1; er[SE_NEW_DT] = f2bits(new_dt);
-          er[SE_VOL_A] = vol_a; er[SE_VOL_B] = vol_b;
+          er[SE_VOL_A] = vol_a; er[SE_VOL_B] = vol_b; er[SE_TRADE_ROWS] = nt_r;
         }
-        int* ar = b.work_split + batch_total * kSplitEnvWords + e * n_agents_total * kSplitAgentWords;
-        for (int t = 0; t < T; ++t) {
-          const LobAgentTypeConfig& ac = c.agent[t];
-          for (int a = 0; a < ac.n_agents; ++a, ++flat, ar += kSplitAgentWords) {
-            const long long idx = e * ac.n_agents + a;
-            const int tid = ac.trader_id_start - a;
-            if (ac.kind == LOB_AGENT_MM) {
-              MMState s; load_mm_state(b, t, idx, s);
-              const MMCollect K = mm_collect(trp, nt_r, c, ac, so, s.inventory, tid);
-              if (lane == 0) {
-                ar[0] = K.s.buyQ; ar[1] = K.s.sellQ; ar[2] = K.s.otherQ; ar[3] = f2bits(K.s.income); ar[4] = f2bits(K.s.outgoing);
-                ar[5] = f2bits(K.s.rebate_buy); ar[6] = f2bits(K.s.rebate_sell); ar[7] = f2bits(K.s.buyPnL);
-                ar[8] = f2bits(K.s.sellPnL); ar[9] = f2bits(K.avg_buy); ar[10] = f2bits(K.avg_sell); ar[11] = K.forced_unwind;
-                ar[12] = s.inventory; ar[13] = f2bits(s.total_PnL); ar[14] = f2bits(s.cash_balance);
-              }
-            } else {
-              EXEState s; load_exe_state(b, t, idx, s);
-              const EXECollect K = exe_collect(trp, nt_r, c, ac, w, so, s, tid);
-              if (lane == 0) {
-                ar[0] = K.s.qsum; ar[1] = K.s.agentQ; ar[2] = K.s.otherQ; ar[3] = K.s.QP; ar[4] = f2bits(K.s.tds);
-                ar[5] = f2bits(K.s.simplest); ar[6] = f2bits(K.p_vwap); ar[7] = K.doom_quant;
-                ar[8] = s.task_to_execute; ar[9] = s.quant_executed; ar[10] = s.is_sell_task; ar[11] = f2bits(s.init_price);
-                ar[12] = f2bits(s.p_vwap); ar[13] = f2bits(s.total_revenue); ar[14] = f2bits(s.drift_return);
-                ar[15] = f2bits(s.advantage_return); ar[16] = f2bits(s.slippage_rm); ar[17] = f2bits(s.price_adv_rm);
-                ar[18] = f2bits(s.price_drift_rm); ar[19] = f2bits(s.vwap_rm); ar[20] = f2bits(s.trade_duration);
-              }
-            }
-          }
-        }
-      } else
+      }
+      // ... except when the episode ended: the fused auto-reset below replaces the trade log and the agent leaves the finish
+      // kernel would read, so this (1 step in 64) is finished here, as without the split; the finish kernel skips the env
+      if (!(split && !so.ep_done))
       for (int t = 0; t < T; ++t) {
         const LobAgentTypeConfig& ac = c.agent[t];
         const int d = obs_dim_of(ac, c.ep_type_fixed_time);
@@ -853,13 +828,12 @@ static __global__ void __launch_bounds__(128)
 lob_agents_finish_kernel(const __grid_constant__ LobStepConfig c, const __grid_constant__ LobStepBuffers b, long long batch) {
   const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int T = c.n_agent_types;
-  int t = 0, slot0 = 0, n_agents_total = 0;
+  int t = 0;
   long long off = 0;
-  for (int k = 0; k < T; ++k) n_agents_total += c.agent[k].n_agents;
   for (; t < T; ++t) {
     const long long cnt = batch * c.agent[t].n_agents;
     if (g < off + cnt) break;
-    off += cnt; slot0 += c.agent[t].n_agents;
+    off += cnt;
   }
   if (t >= T) return;
   const LobAgentTypeConfig& ac = c.agent[t];
@@ -867,27 +841,25 @@ lob_agents_finish_kernel(const __grid_constant__ LobStepConfig c, const __grid_c
   const long long e = idx / ac.n_agents;
   const int a = (int)(idx - e * ac.n_agents);
   const int* er = b.work_split + e * kSplitEnvWords;
-  const int* ar = b.work_split + batch * kSplitEnvWords + (e * n_agents_total + slot0 + a) * kSplitAgentWords;
   WorldIn w;
   w.time0 = 0; w.time1 = 0;
   w.mid_price = bits2f(er[SE_MID]); w.old_ba_last = er[SE_OLD_BA]; w.old_bb_last = er[SE_OLD_BB];
   w.extreme_spread = er[SE_EXTREME] != 0; w.step_counter = er[SE_STEP]; w.max_steps = er[SE_MAX_STEPS];
   w.init_time0 = er[SE_INIT0]; w.init_time1 = er[SE_INIT1];
+  if (er[SE_EP_DONE] != 0) return;      // finished by the step kernel itself (see there)
   StepOut so;
-  so.ba_last = er[SE_BA]; so.bb_last = er[SE_BB]; so.avg_mid = bits2f(er[SE_AVG_MID]); so.ep_done = er[SE_EP_DONE] != 0;
+  so.ba_last = er[SE_BA]; so.bb_last = er[SE_BB]; so.avg_mid = bits2f(er[SE_AVG_MID]); so.ep_done = false;
   const float new_mid = bits2f(er[SE_NEW_MID]), new_dt = bits2f(er[SE_NEW_DT]);
   const int new_step = er[SE_NEW_STEP], vol_a = er[SE_VOL_A], vol_b = er[SE_VOL_B];
   const ObsTime ot = {c.ep_type_fixed_time, c.episode_time, er[SE_FT0], er[SE_FT1], w.init_time0, w.init_time1, new_dt};
   const int d = obs_dim_of(ac, c.ep_type_fixed_time);
   float* obs = b.obs[t] + idx * d;
+  const int* tr = b.trades + e * c.book.n_trades * 8;     // the step's trade log (global, L2): rows >= nt_r are blank
+  const int nt_r = er[SE_TRADE_ROWS];
+  const int tid = ac.trader_id_start - a;
   if (ac.kind == LOB_AGENT_MM) {
-    MMCollect K;
-    K.s.buyQ = ar[0]; K.s.sellQ = ar[1]; K.s.otherQ = ar[2]; K.s.income = bits2f(ar[3]); K.s.outgoing = bits2f(ar[4]);
-    K.s.rebate_buy = bits2f(ar[5]); K.s.rebate_sell = bits2f(ar[6]); K.s.buyPnL = bits2f(ar[7]); K.s.sellPnL = bits2f(ar[8]);
-    K.avg_buy = bits2f(ar[9]); K.avg_sell = bits2f(ar[10]); K.forced_unwind = ar[11];
-    MMState s;
-    s.posted_distance_bid = 0; s.posted_distance_ask = 0;
-    s.inventory = ar[12]; s.total_PnL = bits2f(ar[13]); s.cash_balance = bits2f(ar[14]);
+    MMState s; load_mm_state(b, t, idx, s);
+    const MMCollect K = mm_collect_thread(tr, nt_r, c, ac, so, s.inventory, tid);
     const MMReward R = mm_finish(K, c, ac, w, so, s);
     const int* x = b.info_agent_i32[t] + idx * LOB_MMINFO_I32_COLS + 3;   // the step kernel's phase 1 left them there
     MMState ns;   // mm:2677-2736
@@ -909,14 +881,8 @@ lob_agents_finish_kernel(const __grid_constant__ LobStepConfig c, const __grid_c
     if (!so.ep_done)
       mm_write_obs(ac, obs, ns.inventory, new_mid, so.ba_last, so.bb_last, vol_a, vol_b, new_step, false, ot);
   } else {
-    EXECollect K;
-    K.s.qsum = ar[0]; K.s.agentQ = ar[1]; K.s.otherQ = ar[2]; K.s.QP = ar[3]; K.s.tds = bits2f(ar[4]);
-    K.s.simplest = bits2f(ar[5]); K.p_vwap = bits2f(ar[6]); K.doom_quant = ar[7];
-    EXEState s;
-    s.task_to_execute = ar[8]; s.quant_executed = ar[9]; s.is_sell_task = ar[10]; s.init_price = bits2f(ar[11]);
-    s.p_vwap = bits2f(ar[12]); s.total_revenue = bits2f(ar[13]); s.drift_return = bits2f(ar[14]);
-    s.advantage_return = bits2f(ar[15]); s.slippage_rm = bits2f(ar[16]); s.price_adv_rm = bits2f(ar[17]);
-    s.price_drift_rm = bits2f(ar[18]); s.vwap_rm = bits2f(ar[19]); s.trade_duration = bits2f(ar[20]);
+    EXEState s; load_exe_state(b, t, idx, s);
+    const EXECollect K = exe_collect_thread(tr, nt_r, c, ac, w, so, s, tid);
     const EXEReward R = exe_finish(K, c, ac, w, s);
     EXEState ns = s;   // exe:1771-1839
     ns.quant_executed = s.quant_executed + R.agentQuant;
