@@ -615,7 +615,7 @@ static __device__ __noinline__ MMCollect mm_collect(int* tr, int nt, const LobSt
 static __device__ __noinline__ MMSums mm_trade_sums_thread(const int* tr, int nt, int tid, float tickf, bool ref_is_int,
                                                            int ref_buy_i, int ref_sell_i, float ref_f, FictTrade f) {
   MMSums s = {0, 0, 0, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-#pragma unroll 1
+#pragma unroll 4
   for (int r = 0; r < nt; ++r) {
     const TradeRow t = classify_sub(tr, r, tid, f);
     const int aq = abs(t.q);
@@ -639,7 +639,7 @@ static __device__ __noinline__ MMSums mm_trade_sums_thread(const int* tr, int nt
 }
 static __device__ __noinline__ float mm_avg_price_thread(const int* tr, int nt, int tid, bool want_buy, int Q, FictTrade f) {
   float acc = 0.f;
-#pragma unroll 1
+#pragma unroll 4
   for (int r = 0; r < nt; ++r) {
     const TradeRow t = classify_sub(tr, r, tid, f);
     if (t.agent && (want_buy ? t.buy : t.sell)) acc = acc + (float)t.p / (float)Q * (float)abs(t.q);
@@ -661,7 +661,7 @@ static __device__ __noinline__ MMCollect mm_collect_thread(const int* tr, int nt
   K.forced_unwind = 0;
   if (so.ep_done) {   // mm:2294-2316 the inventory is unwound by a fictional trade at the unwind price
     int buyQ = 0, sellQ = 0;
-#pragma unroll 1
+#pragma unroll 4
     for (int r = 0; r < nt; ++r) {
       const TradeRow t = classify(tr, r, tid);
       buyQ += (t.agent && t.buy) ? abs(t.q) : 0;
@@ -944,7 +944,7 @@ static __device__ __noinline__ EXECollect exe_collect_thread(const int* tr, int 
   K.doom_quant = 0;
   if (so.ep_done) {
     int qsum = 0;
-#pragma unroll 1
+#pragma unroll 4
     for (int r = 0; r < nt; ++r) {
       const TradeRow t = classify(tr, r, tid);
       qsum += t.agent ? t.q : 0;
@@ -968,7 +968,7 @@ static __device__ __noinline__ EXECollect exe_collect_thread(const int* tr, int 
     }
   }
   EXESums s = {0, 0, 0, 0, 0.f, 0.f};
-#pragma unroll 1
+#pragma unroll 4
   for (int r = 0; r < nt; ++r) {
     const TradeRow t = classify_sub(tr, r, tid, f);
     const int aq = abs(t.q);
@@ -986,7 +986,7 @@ static __device__ __noinline__ EXECollect exe_collect_thread(const int* tr, int 
   if (s.otherQ == 0) K.p_vwap = ffloordiv(so.avg_mid, tickf);
   else {   // exe:1630-1632
     float acc = 0.f;
-#pragma unroll 1
+#pragma unroll 4
     for (int r = 0; r < nt; ++r) {
       const TradeRow t = classify_sub(tr, r, tid, f);
       if (!t.agent && t.q != 0) acc = acc + (float)ifloordiv(t.p, tick) * ((float)abs(t.q) / (float)s.otherQ);

@@ -20,7 +20,7 @@ int launch_replay(const LobBookConfig* cfg, const LobReplayBuffers* bufs, int64_
 }
 
 // WIN: the shared-memory window pass of deep books (see lob_step_kernel); LIST: walk b->work_redo_list (second pass).
-template <int S, bool WIN, bool LIST>
+template <int S, bool WIN, bool LIST, int MAXW = lob::step_max_warps(S)>
 static int launch_step_impl(const LobStepConfig* c, const LobStepBuffers* b, int64_t batch, cudaStream_t st, const DevInfo& d,
                             const LobRolloutBuffers* roll = nullptr) {
   const int N = lob_num_msgs_per_step(c), n_act = lob_num_action_msgs(c), n_cnl = lob_num_cancel_msgs(c);
@@ -30,15 +30,15 @@ static int launch_step_impl(const LobStepConfig* c, const LobStepBuffers* b, int
   if (((n_cnl + n_act) * 8) % 4 != 0) return fail(LOB_E_INVALID, "internal: data slice misaligned");
   // one persistent CTA per SM; as many warps (= environments in flight) as shared memory and registers allow
   const size_t per_warp = (size_t)L.words * 4;
-  auto kernel = lob::lob_step_kernel<S, WIN>;
+  auto kernel = lob::lob_step_kernel<S, WIN, MAXW>;
   cudaFuncAttributes fa;
   cudaError_t e = cudaFuncGetAttributes(&fa, kernel);
   if (e != cudaSuccess) return fail(LOB_E_CUDA, "cudaFuncGetAttributes: %s", cudaGetErrorString(e));
   const int G = lob::kStepCtasPerSm;   // CTAs (phase-synchronous groups) per SM
   int warps = (int)((((size_t)d.max_smem_optin + 1024) / G - 1024 - fa.sharedSizeBytes) / per_warp);
-  const int by_regs = fa.numRegs > 0 ? 65536 / (fa.numRegs * 32) / G : lob::step_max_warps(S);
+  const int by_regs = fa.numRegs > 0 ? 65536 / (fa.numRegs * 32) / G : MAXW;
   if (warps > by_regs) warps = by_regs;
-  if (warps > lob::step_max_warps(S)) warps = lob::step_max_warps(S);
+  if (warps > MAXW) warps = MAXW;
   if (warps < 1)
     return fail(LOB_E_INVALID, "configuration needs %zu B of shared memory per environment (device limit %d)", per_warp,
                 d.max_smem_optin);
@@ -60,6 +60,11 @@ static int launch_step_impl(const LobStepConfig* c, const LobStepBuffers* b, int
 
 template <int S>
 int launch_step(const LobStepConfig* c, const LobStepBuffers* b, int64_t batch, cudaStream_t st, const DevInfo& d) {
+#if LOB_SLOTS == 4
+  int n_agents = 0;   // (see LOB_STEP_MAXW_HI)
+  for (int t = 0; t < c->n_agent_types; ++t) n_agents += c->agent[t].n_agents;
+  if (b->work_split && n_agents <= 2) return launch_step_impl<S, false, false, LOB_STEP_MAXW_HI>(c, b, batch, st, d);
+#endif
   return launch_step_impl<S, false, false>(c, b, batch, st, d);
 }
 template <int S>

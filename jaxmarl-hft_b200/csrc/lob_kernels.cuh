@@ -401,6 +401,13 @@ __device__ __forceinline__ float bits2f(int x) { return __int_as_float(x); }
 #ifndef LOB_STEP_MAXW
 #define LOB_STEP_MAXW 20
 #endif
+// A second instantiation of the 100-row class: 23 warps per SM at 80 registers (shared memory allows 23 x 10 KB).  Chosen at
+// launch for split-mode steps with at most two agents per environment, where it wins (2-player 0.535 -> 0.515 ms); with
+// more agents (more message-building code under the tighter register cap) or the in-kernel finish it loses (exec-only
+// 0.253 -> 0.278 ms, 10 + 10 agents 1.56 -> 1.59 ms), so everything else keeps 20 warps at 96 registers.
+#ifndef LOB_STEP_MAXW_HI
+#define LOB_STEP_MAXW_HI 23
+#endif
 #ifndef LOB_STEP_CTAS
 #define LOB_STEP_CTAS 1
 #endif
@@ -422,8 +429,8 @@ __host__ __device__ constexpr int step_max_warps(int slots) { return slots <= 4 
 // it is staged, or an order that has to rest beyond it during the scan -- writes nothing and is appended to
 // b.work_redo_list for the second pass: the same kernel with WIN = false at the book's full capacity class, walking that
 // list (env_list / env_count) instead of 0 .. batch-1.
-template <int SLOTS, bool WIN>
-__global__ void __launch_bounds__(step_max_warps(SLOTS) * 32, kStepCtasPerSm)
+template <int SLOTS, bool WIN, int MAXW = step_max_warps(SLOTS)>
+__global__ void __launch_bounds__(MAXW * 32, kStepCtasPerSm)
 lob_step_kernel(const __grid_constant__ LobStepConfig c, const __grid_constant__ LobStepBuffers b, long long batch,
                 WarpLayout L, int N, int n_act, int n_cnl, int need_extreme, const int* __restrict__ env_list,
                 const int* __restrict__ env_count, const __grid_constant__ LobRolloutBuffers rb) {
