@@ -31,6 +31,25 @@ constexpr int kBig = 0x3fffffff;
 constexpr unsigned kFull = 0xffffffffu;
 
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+// Warp-uniform by construction, but not provably so for ptxas: the warp's index (threadIdx.x >> 5).  Everything that steers
+// a scan derives from it (the address of the current message, hence its type / side / price / order id, hence every
+// branch), so without a hint ptxas treats every branch as divergent: a BSSY / BSYNC pair around each, a BRA.DIV + a
+// software fallback (WARPSYNC.COLLECTIVE) for every CREDUX, vector instead of uniform registers.  A shuffle from lane 0 --
+// once per kernel, outside the hot loop -- is the proof it accepts: lob_replay_kernel<4> shrinks from 3952 to 2968 SASS
+// instructions (57 -> 0 BRA.DIV, 127 -> 0 BSSY, 80 -> 70 registers, which is what lets 28 instead of 24 warps fit an SM).
+// The time per message does NOT change by itself (16.93 vs 16.91 ms: what disappears is fallback code that never ran and
+// ~3 of ~120 instructions per message); the gain is the occupancy the freed registers allow.  The proof does not carry
+// into lob_step_kernel: there ptxas' interprocedural analysis gives up on the calls into the agents' code (a callee that
+// may return non-converged poisons the whole persistent loop), measured in DESIGN.md section 6.
+__device__ __forceinline__ int uni(int v) { return __shfl_sync(kFull, v, 0); }
+__device__ __forceinline__ float uni(float v) { return __shfl_sync(kFull, v, 0); }
+template <class T>
+__device__ __forceinline__ T* uni(T* p) {
+  const unsigned long long a = (unsigned long long)p;
+  const unsigned lo = __shfl_sync(kFull, (unsigned)a, 0), hi = __shfl_sync(kFull, (unsigned)(a >> 32), 0);
+  return (T*)(((unsigned long long)hi << 32) | lo);
+}
+__device__ __forceinline__ int warp_id() { return uni((int)(threadIdx.x >> 5)); }
 __device__ __forceinline__ int wmin(int v) { return __reduce_min_sync(kFull, v); }
 __device__ __forceinline__ int wmax(int v) { return __reduce_max_sync(kFull, v); }
 __device__ __forceinline__ int wsum(int v) { return __reduce_add_sync(kFull, v); }

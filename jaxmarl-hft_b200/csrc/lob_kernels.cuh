@@ -18,10 +18,10 @@ namespace lob {
 
 constexpr int kWarps = 4;            // warps (= environments in flight) per CTA
 #ifndef LOB_REPLAY_CHUNK
-#define LOB_REPLAY_CHUNK 32
+#define LOB_REPLAY_CHUNK 24
 #endif
 #ifndef LOB_REPLAY_MINB
-#define LOB_REPLAY_MINB 6
+#define LOB_REPLAY_MINB 7
 #endif
 constexpr int kReplayChunk = LOB_REPLAY_CHUNK;   // messages per staged chunk of the replay kernel (double buffered)
 constexpr int kMaxAgents = 64;       // agents per environment, all types (validation bound; all per-agent storage is sized at launch)
@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(kWarps * 32, (SLOTS <= 4 ? LOB_REPLAY_MINB : S
 lob_replay_kernel(const __grid_constant__ LobBookConfig cfg, const __grid_constant__ LobReplayBuffers B,
                   long long n_books, WarpLayout L) {
   int* const smem = dyn_smem();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = warp_id(), lane = threadIdx.x & 31;
   int* ws = smem + warp * L.words;
   uint64_t* bar = reinterpret_cast<uint64_t*>(ws + L.bar);
   int* mbuf = ws + L.msgs;
@@ -435,7 +435,7 @@ lob_step_kernel(const __grid_constant__ LobStepConfig c, const __grid_constant__
                 WarpLayout L, int N, int n_act, int n_cnl, int need_extreme, const int* __restrict__ env_list,
                 const int* __restrict__ env_count, const __grid_constant__ LobRolloutBuffers rb) {
   int* const smem = dyn_smem();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = warp_id(), lane = threadIdx.x & 31;
   const int nwarps = blockDim.x >> 5;
   int* ws = smem + warp * L.words;
   uint64_t* bar = reinterpret_cast<uint64_t*>(ws + L.bar);
@@ -644,7 +644,9 @@ lob_step_kernel(const __grid_constant__ LobStepConfig c, const __grid_constant__
 #ifdef LOB_PHASE_TIMING
     const long long tp2 = clock64();
 #endif
+#ifndef LOB_NOSYNC2
     __syncthreads();
+#endif
 #ifdef LOB_PHASE_TIMING
     const long long tp2b = clock64();
 #endif
@@ -919,7 +921,7 @@ __global__ void __launch_bounds__(kWarps * 32)
 lob_reset_kernel(const __grid_constant__ LobStepConfig c, const __grid_constant__ LobStepBuffers b, long long batch,
                  WarpLayout L, int N) {
   int* const smem = dyn_smem();
-  const int warp = threadIdx.x >> 5;
+  const int warp = warp_id();
   int* ws = smem + warp * L.words;
   Book<SLOTS> bk;
   bk.init(c.book, ws + L.book);
@@ -940,7 +942,7 @@ template <int SLOTS>
 __global__ void __launch_bounds__(kWarps * 32)
 lob_l2_kernel(const __grid_constant__ LobBookConfig cfg, const int* __restrict__ asks, const int* __restrict__ bids,
               int* __restrict__ l2, int n_levels, long long n_books) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = warp_id(), lane = threadIdx.x & 31;
   const int no = cfg.n_orders, maxint = cfg.maxint;
   const long long stride = (long long)gridDim.x * kWarps;
   for (long long b = (long long)blockIdx.x * kWarps + warp; b < n_books; b += stride) {
