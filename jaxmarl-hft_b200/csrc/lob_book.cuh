@@ -515,11 +515,11 @@ struct Book {
   // blank one LIVE row (price rp != -1, quantity rq) and keep the summaries exact
   template <int S>
   __device__ __forceinline__ void blank_live(int r, int rp, int rq) {
-    if (lane_id() == (r & 31)) {
-      const unsigned a = row_sa(S, r);
-      sts64(a, -1, -1); sts64(a + 8, -1, -1); sts64(a + 16, -1, -1);
-      flag[S] |= 1u << (r >> 5);
-    }
+    // Row r and the words are warp-uniform: EVERY lane stores them (same address, same value: one wavefront, like the
+    // owner lane alone) -- no owner test, no branch, no BSSY / BSYNC around it; only the per-lane flag needs the owner.
+    const unsigned a = row_sa(S, r);
+    sts64(a, -1, -1); sts64(a + 8, -1, -1); sts64(a + 16, -1, -1);
+    flag[S] |= (lane_id() == (r & 31)) ? (1u << (r >> 5)) : 0u;
     nneg[S] += (rp >= 0);
     if (valid[S] && rp == bestp[S]) {
       bestq[S] = wsub(bestq[S], rq); bestn[S] -= 1;
@@ -593,7 +593,7 @@ struct Book {
       }
       if (ntr < c.nt && m.ts != -1) ntr += 1;
       if (newq > 0) {
-        if (lane == (top & 31)) sts32(oa + F_Q * 4, newq);
+        sts32(oa + F_Q * 4, newq);   // (all lanes, same word: see blank_live)
         bestq[OPP] = wadd(bestq[OPP], wsub(newq, oq));
       } else {
         blank_live<OPP>(top, tp, oq);
@@ -638,10 +638,10 @@ struct Book {
       scan_side(OWN);
       return;
     }
-    if (lane_id() == (r & 31)) {            // the blank row r takes the order
+    {                                       // the blank row r takes the order (all lanes store the same words: see blank_live)
       const unsigned a = row_sa(OWN, r);
       sts64(a, m.price, q); sts64(a + 8, m.oid, m.tid); sts64(a + 16, m.ts, m.tns);
-      flag[OWN] &= ~(1u << (r >> 5));
+      flag[OWN] &= ~((lane_id() == (r & 31)) ? (1u << (r >> 5)) : 0u);
     }
     nneg[OWN] -= 1;
     {   // keep the cached best level exact (branch-free: the scan is a latency chain, a select is cheaper than a branch)
@@ -700,7 +700,7 @@ struct Book {
     }
     const int nq = wsub(pq.y, m.qty);
     if (nq > 0) {
-      if (lane == (idx & 31)) sts32(row_sa(S, idx) + F_Q * 4, nq);
+      sts32(row_sa(S, idx) + F_Q * 4, nq);   // (all lanes, same word: see blank_live)
       if (valid[S] && pq.x == bestp[S]) bestq[S] = wsub(bestq[S], m.qty);
     } else {
       blank_live<S>(idx, pq.x, pq.y);

@@ -336,7 +336,7 @@ __device__ __noinline__ ScanOut scan_messages(BookCtx ctx, int* msgs, int N, int
     bk.process(m4[2 * i], m4[2 * i + 1]);
     if (WIN && bk.aborted()) break;   // the book left its shared-memory window: the full-size kernel redoes this step
     if (!(bk.valid[ASK] & bk.valid[BID])) { bk.ensure(ASK); bk.ensure(BID); }
-    if (lane == 0) m4[2 * i] = make_int4(bk.bestp[ASK], bk.bestq[ASK], bk.bestp[BID], bk.bestq[BID]);
+    m4[2 * i] = make_int4(bk.bestp[ASK], bk.bestq[ASK], bk.bestp[BID], bk.bestq[BID]);   // (all lanes, same words: no branch)
   }
   __syncwarp();
   if (WIN && bk.aborted()) {   // nothing of this step may reach global memory (the old best pairs are inputs of the redo)
@@ -453,7 +453,6 @@ lob_step_kernel(const __grid_constant__ LobStepConfig c, const __grid_constant__
   const int no = c.book.n_orders, nt = c.book.n_trades, Nd = c.n_data_msg_per_step, T = c.n_agent_types;
   int n_agents_total = 0;
   for (int t = 0; t < T; ++t) n_agents_total += c.agent[t].n_agents;
-  const long long batch_total = batch;                          // (the launch's batch: `batch` becomes the list length below)
   const bool split = b.work_split != nullptr && rb.n_steps == 0;   // see kSplitEnvWords (plain step only: a rollout launch,
                                                                    // n_steps >= 1, finishes in the kernel)
   const bool bulk_books = (no & 1) == 0;   // a side is no*24 bytes: 16-byte granular iff no is even (WIN: required)
