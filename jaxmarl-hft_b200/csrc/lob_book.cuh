@@ -512,6 +512,17 @@ struct Book {
     return wmin(m ? (__ffs(m) - 1) * 32 + lane_id() : kBig);
   }
 
+  // No warp barrier between messages on the fast paths: every shared-memory write of a fast path is an ALL-LANE store of
+  // warp-uniform words (see blank_live), so a lane that later reads a row -- its own rows in a search, a uniform row --
+  // reads what IT wrote, in its own program order; nothing depends on another lane's store.  (The trade row lane 0 appends
+  // in global memory is only read by the literal path, which starts with a __syncwarp, and after the scan.)  Saves
+  // WARPSYNC + its scheduling NOPs per message; -DLOB_FAST_SYNCWARP restores the barrier for A/B.
+  __device__ __forceinline__ void fast_sync() const {
+#ifdef LOB_FAST_SYNCWARP
+    __syncwarp();
+#endif
+  }
+
   // blank one LIVE row (price rp != -1, quantity rq) and keep the summaries exact
   template <int S>
   __device__ __forceinline__ void blank_live(int r, int rp, int rq) {
@@ -598,7 +609,7 @@ struct Book {
       } else {
         blank_live<OPP>(top, tp, oq);
       }
-      __syncwarp();
+      fast_sync();
     }
     return qtm;
   }
@@ -615,20 +626,35 @@ struct Book {
   template <int OWN>
   __device__ __forceinline__ void limit(const Msg& m) {
     constexpr int OPP = 1 - OWN;
-    const int qtm = match<OPP>(m, m.qty);
-    if (WIN && aborted()) return;
-    if (c.check_fill && nneg[OWN] == 0) {   // job:395-401: full side -> the worst price level is evicted
-      if (WIN) { oddm |= kAborted; return; }   // (unreachable: the rows beyond the window are blank)
-      drop_best();
-      g_evict(c, OWN);
-      scan_side(OWN);
+    int qtm = m.qty;
+    {   // job:285-331: nothing to match while the cached best level does not cross -- the common case, decided without
+        // entering the loop (match() would come to the same test after ensure())
+      const int tp = bestp[OPP];
+      const bool cross = (OPP == BID) ? (tp >= m.price) : (tp <= m.price);
+      const bool quiet = valid[OPP] & !(cross & (qtm > 0) & (tp != -1));
+      if (!quiet) {
+        qtm = match<OPP>(m, m.qty);
+        if (WIN && aborted()) return;
+      }
     }
-    if (m.type == 4 && c.t4 != 1) return;   // IOC remainder dropped, eviction kept
+    if ((c.check_fill & (nneg[OWN] == 0)) | (m.type == 4)) {   // the two rare turns behind ONE test
+      if (c.check_fill && nneg[OWN] == 0) {   // job:395-401: full side -> the worst price level is evicted
+        if (WIN) { oddm |= kAborted; return; }   // (unreachable: the rows beyond the window are blank)
+        drop_best();
+        g_evict(c, OWN);
+        scan_side(OWN);
+      }
+      if (m.type == 4 && c.t4 != 1) return;   // IOC remainder dropped, eviction kept
+    }
     const int q = max(0, qtm);
     const int r = first_flagged(OWN);
     if (q == 0 && r != kBig && !odd(OWN)) return;   // written into a blank row and blanked again (job:83): no-op
-    const bool neg1 = (m.price == -1) | (m.oid == -1) | (m.tid == -1) | (m.ts == -1) | (m.tns == -1);
-    if (q == 0 || r == kBig || odd(OWN) || neg1 || m.price <= 0 || m.price == c.maxint) {   // (an ask AT maxint reads as "empty", job:940)
+    // Fields the fast path does not model, as two unsigned tests: a -1 in any of oid / tid / ts / tns (the unsigned maximum is
+    // 0xffffffff), a price outside [1, maxint - 1] (-1, <= 0, == maxint: an ask AT maxint reads as "empty", job:940 -- and
+    // anything beyond maxint, which the literal path handles just as exactly)
+    const unsigned umax4 = max(max((unsigned)m.oid, (unsigned)m.tid), max((unsigned)m.ts, (unsigned)m.tns));
+    const bool unmodelled = (umax4 == 0xffffffffu) | ((unsigned)m.price - 1u >= (unsigned)c.maxint - 1u);
+    if (q == 0 || r == kBig || odd(OWN) || unmodelled) {
       if (WIN) { oddm |= kAborted; return; }   // in particular r == kBig: the window is full, the order rests beyond it
       Msg a = m;
       a.qty = qtm;
@@ -730,7 +756,7 @@ struct Book {
       if (s == 0 && t == 0) return;                        // doNothing
       limit<ASK>(m);
     }
-    __syncwarp();
+    fast_sync();
   }
 };
 
