@@ -46,7 +46,7 @@
 extern "C" {
 #endif
 
-#define LOB_ABI_VERSION 10
+#define LOB_ABI_VERSION 11
 #define LOB_MAX_AGENT_TYPES 8
 #define LOB_MAX_AGENT_I32 4  /* int32 state leaves per agent type */
 #define LOB_MAX_AGENT_F32 10 /* float32 state leaves per agent type */

@@ -5,7 +5,7 @@ Field order and types follow the header exactly; ``check_sizes`` compares ``ctyp
 """
 import ctypes as C
 
-LOB_ABI_VERSION = 10
+LOB_ABI_VERSION = 11
 LOB_MAX_AGENT_TYPES = 8
 LOB_MAX_AGENT_I32 = 4
 LOB_MAX_AGENT_F32 = 10
@@ -153,7 +153,9 @@ SPLIT_ENV_WORDS, SPLIT_AGENT_WORDS = 24, 0     # csrc/lob_kernels.cuh kSplitEnvW
 def split_workspace_words(cfg, batch: int) -> int:
     """== lob_split_workspace_words: 32-bit words of ``LobStepBuffers.work_split``."""
     n = sum(cfg.agent[t].n_agents for t in range(cfg.n_agent_types))
-    return int(batch) * (SPLIT_ENV_WORDS + SPLIT_AGENT_WORDS * n)
+    n_am = sum(cfg.agent[t].n_agents * cfg.agent[t].num_messages_by_agent for t in range(cfg.n_agent_types))
+    # env records, then (the piped step, csrc/lob_pipe.cuh) the agents' cancel + action messages of every environment
+    return int(batch) * (SPLIT_ENV_WORDS + SPLIT_AGENT_WORDS * n) + int(batch) * n_am * 8
 
 
 def action_width(a) -> int:

@@ -67,6 +67,60 @@ int launch_step(const LobStepConfig* c, const LobStepBuffers* b, int64_t batch, 
 #endif
   return launch_step_impl<S, false, false>(c, b, batch, st, d);
 }
+// The piped step (lob_pipe.cuh): message building -> scan -> [finish: lobstep.cu] -> auto-reset, as kernels of their own.
+// Launches the first two; lob_step_launch adds the finish kernel and then calls launch_step_piped_reset.
+template <int S>
+int launch_step_piped(const LobStepConfig* c, const LobStepBuffers* b, int64_t batch, cudaStream_t st, const DevInfo& d) {
+  const int N = lob_num_msgs_per_step(c), n_act = lob_num_action_msgs(c), n_cnl = lob_num_cancel_msgs(c);
+  int n_agents = 0, need_extreme = 0;
+  for (int t = 0; t < c->n_agent_types; ++t) {
+    n_agents += c->agent[t].n_agents;
+    if (c->agent[t].kind == LOB_AGENT_MM && c->agent[t].exclude_extreme_spreads) need_extreme = 1;
+  }
+  {   // (C) the agents' messages: one warp per environment, as many CTAs per SM as fit
+    const lob::WarpLayout L = lob::make_layout(S * 32, (n_cnl + n_act) * 8, n_act, n_agents);
+    const size_t smem = (size_t)L.words * 4 * lob::kWarps;
+    int per_sm = 1;
+    int rc = prepare(lob::lob_step_prep_kernel<S>, smem, d, &per_sm);
+    if (rc) return rc;
+    lob::lob_step_prep_kernel<S><<<grid_for(batch, d.sms, per_sm), lob::kWarps * 32, smem, st>>>(*c, *b, batch, L, N, n_act, n_cnl,
+                                                                                                   need_extreme);
+    if ((rc = launched("lob_step_prep_kernel"))) return rc;
+  }
+  {   // (D) the scan: one persistent CTA per SM, as many warps as shared memory and registers allow
+    const lob::WarpLayout L = lob::make_layout(S * 32, N * 8, 0, 0);
+    const size_t per_warp = (size_t)L.words * 4;
+    auto kernel = lob::lob_step_scan_kernel<S>;
+    cudaFuncAttributes fa;
+    cudaError_t e = cudaFuncGetAttributes(&fa, kernel);
+    if (e != cudaSuccess) return fail(LOB_E_CUDA, "cudaFuncGetAttributes: %s", cudaGetErrorString(e));
+    int warps = (int)(((size_t)d.max_smem_optin - fa.sharedSizeBytes) / per_warp);
+    const int by_regs = fa.numRegs > 0 ? 65536 / (fa.numRegs * 32) : lob::kScanMaxWarps;
+    if (warps > by_regs) warps = by_regs;
+    if (warps > lob::kScanMaxWarps) warps = lob::kScanMaxWarps;
+    if (warps < 1)
+      return fail(LOB_E_INVALID, "configuration needs %zu B of shared memory per environment (device limit %d)", per_warp,
+                  d.max_smem_optin);
+    const size_t smem = per_warp * warps;
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return fail(LOB_E_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    long long ctas = (batch + warps - 1) / warps;
+    if (ctas > (long long)d.sms) ctas = d.sms;
+    kernel<<<(int)ctas, warps * 32, smem, st>>>(*c, *b, batch, L, N, n_act, n_cnl);
+    return launched("lob_step_scan_kernel");
+  }
+}
+template <int S>
+int launch_step_piped_reset(const LobStepConfig* c, const LobStepBuffers* b, int64_t batch, cudaStream_t st, const DevInfo& d) {
+  const int N = lob_num_msgs_per_step(c);
+  const lob::WarpLayout L = lob::make_layout(S * 32, 0, 0, 0);
+  const size_t smem = (size_t)L.words * 4 * lob::kWarps;
+  int per_sm = 1;
+  int rc = prepare(lob::lob_step_reset_done_kernel<S>, smem, d, &per_sm);
+  if (rc) return rc;
+  lob::lob_step_reset_done_kernel<S><<<grid_for(batch, d.sms, per_sm), lob::kWarps * 32, smem, st>>>(*c, *b, batch, L, N);
+  return launched("lob_step_reset_done_kernel");
+}
 template <int S>
 int launch_rollout(const LobStepConfig* c, const LobStepBuffers* b, const LobRolloutBuffers* roll, int64_t batch, cudaStream_t st,
                    const DevInfo& d) {
@@ -104,6 +158,8 @@ int launch_l2(const LobBookConfig* cfg, const int32_t* asks, const int32_t* bids
 
 template int launch_replay<LOB_SLOTS>(const LobBookConfig*, const LobReplayBuffers*, int64_t, cudaStream_t, const DevInfo&);
 template int launch_step<LOB_SLOTS>(const LobStepConfig*, const LobStepBuffers*, int64_t, cudaStream_t, const DevInfo&);
+template int launch_step_piped<LOB_SLOTS>(const LobStepConfig*, const LobStepBuffers*, int64_t, cudaStream_t, const DevInfo&);
+template int launch_step_piped_reset<LOB_SLOTS>(const LobStepConfig*, const LobStepBuffers*, int64_t, cudaStream_t, const DevInfo&);
 template int launch_step_redo<LOB_SLOTS>(const LobStepConfig*, const LobStepBuffers*, int64_t, cudaStream_t, const DevInfo&);
 template int launch_rollout<LOB_SLOTS>(const LobStepConfig*, const LobStepBuffers*, const LobRolloutBuffers*, int64_t, cudaStream_t,
                                        const DevInfo&);

@@ -317,8 +317,8 @@ __device__ __forceinline__ void ffill32(int& price, int& qty, int& carry, bool i
 }
 
 template <int SLOTS, bool WIN>
-__device__ __noinline__ ScanOut scan_messages(BookCtx ctx, int* msgs, int N, int* best_asks, int* best_bids,
-                                              int prev_a, int prev_b) {
+__device__ __forceinline__ ScanOut scan_messages_inl(BookCtx ctx, int* msgs, int N, int* best_asks, int* best_bids,
+                                                     int prev_a, int prev_b) {
   Book<SLOTS, WIN> bk;
   bk.c = ctx;
   bk.bind();
@@ -376,6 +376,13 @@ __device__ __noinline__ ScanOut scan_messages(BookCtx ctx, int* msgs, int N, int
   o.sum_a = wsumf(pa); o.sum_b = wsumf(pb);
   o.prev_a = prev_a; o.prev_b = prev_b;
   return o;
+}
+// (the fused step kernel calls the scan as a function of its own: own register allocation, see above; the piped step's scan
+//  kernel inlines it)
+template <int SLOTS, bool WIN>
+__device__ __noinline__ ScanOut scan_messages(BookCtx ctx, int* msgs, int N, int* best_asks, int* best_bids,
+                                              int prev_a, int prev_b) {
+  return scan_messages_inl<SLOTS, WIN>(ctx, msgs, N, best_asks, best_bids, prev_a, prev_b);
 }
 
 // ---- SPLIT mode of the step (b.work_split != NULL): the step kernel leaves the agents' whole reward / state / info /
@@ -833,7 +840,8 @@ lob_step_kernel(const __grid_constant__ LobStepConfig c, const __grid_constant__
 // step kernel left in b.work_split; writes what the in-kernel path writes: reward, done, info row, and -- unless the
 // episode ended (then reset_env already wrote the reset state and observation) -- the new agent state and observation.
 static __global__ void __launch_bounds__(128)
-lob_agents_finish_kernel(const __grid_constant__ LobStepConfig c, const __grid_constant__ LobStepBuffers b, long long batch) {
+lob_agents_finish_kernel(const __grid_constant__ LobStepConfig c, const __grid_constant__ LobStepBuffers b, long long batch,
+                         int finish_done /* piped step: the episode-ending steps are finished here too */) {
   const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int T = c.n_agent_types;
   int t = 0;
@@ -854,9 +862,10 @@ lob_agents_finish_kernel(const __grid_constant__ LobStepConfig c, const __grid_c
   w.mid_price = bits2f(er[SE_MID]); w.old_ba_last = er[SE_OLD_BA]; w.old_bb_last = er[SE_OLD_BB];
   w.extreme_spread = er[SE_EXTREME] != 0; w.step_counter = er[SE_STEP]; w.max_steps = er[SE_MAX_STEPS];
   w.init_time0 = er[SE_INIT0]; w.init_time1 = er[SE_INIT1];
-  if (er[SE_EP_DONE] != 0) return;      // finished by the step kernel itself (see there)
+  const bool ep_done = er[SE_EP_DONE] != 0;
+  if (ep_done && !finish_done) return;      // finished by the fused step kernel itself (see there)
   StepOut so;
-  so.ba_last = er[SE_BA]; so.bb_last = er[SE_BB]; so.avg_mid = bits2f(er[SE_AVG_MID]); so.ep_done = false;
+  so.ba_last = er[SE_BA]; so.bb_last = er[SE_BB]; so.avg_mid = bits2f(er[SE_AVG_MID]); so.ep_done = ep_done;
   const float new_mid = bits2f(er[SE_NEW_MID]), new_dt = bits2f(er[SE_NEW_DT]);
   const int new_step = er[SE_NEW_STEP], vol_a = er[SE_VOL_A], vol_b = er[SE_VOL_B];
   const ObsTime ot = {c.ep_type_fixed_time, c.episode_time, er[SE_FT0], er[SE_FT1], w.init_time0, w.init_time1, new_dt};

@@ -7,6 +7,7 @@
 
 #include "lob_glaunch.h"
 #include "lob_kernels.cuh"
+#include "lob_pipe.cuh"
 
 namespace lobhost {
 
@@ -34,6 +35,8 @@ int prepare(K kernel, size_t smem_bytes, const DevInfo& d, int* ctas_per_sm) {
 
 template <int S> int launch_replay(const LobBookConfig* cfg, const LobReplayBuffers* bufs, int64_t n_books, cudaStream_t st, const DevInfo& d);
 template <int S> int launch_step(const LobStepConfig* c, const LobStepBuffers* b, int64_t batch, cudaStream_t st, const DevInfo& d);
+template <int S> int launch_step_piped(const LobStepConfig* c, const LobStepBuffers* b, int64_t batch, cudaStream_t st, const DevInfo& d);
+template <int S> int launch_step_piped_reset(const LobStepConfig* c, const LobStepBuffers* b, int64_t batch, cudaStream_t st, const DevInfo& d);
 // deep books: the window pass (Book<LOB_WINDOW_SLOTS, true>) and the second pass over b->work_redo_list at full capacity
 #define LOB_WINDOW_SLOTS 4
 int launch_step_window(const LobStepConfig* c, const LobStepBuffers* b, int64_t batch, cudaStream_t st, const DevInfo& d);

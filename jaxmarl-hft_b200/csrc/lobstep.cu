@@ -165,13 +165,13 @@ int slots_for(int n_orders) {
   return p;
 }
 
-int launch_agents_finish(const LobStepConfig* c, const LobStepBuffers* b, int64_t batch, cudaStream_t st) {
+int launch_agents_finish(const LobStepConfig* c, const LobStepBuffers* b, int64_t batch, cudaStream_t st, int finish_done) {
   long long n = 0;
   for (int t = 0; t < c->n_agent_types; ++t) n += c->agent[t].n_agents;
   n *= batch;
   if (n == 0) return LOB_OK;
   if (reinterpret_cast<uintptr_t>(b->work_split) & 15u) return fail(LOB_E_INVALID, "work_split must be 16-byte aligned");
-  lob::lob_agents_finish_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(*c, *b, batch);
+  lob::lob_agents_finish_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(*c, *b, batch, finish_done);
   return launched("lob_agents_finish_kernel");
 }
 
@@ -231,7 +231,8 @@ int32_t lob_num_cancel_msgs(const LobStepConfig* c) {
 int64_t lob_split_workspace_words(const LobStepConfig* c, int64_t batch) {
   int64_t n = 0;
   for (int t = 0; t < c->n_agent_types; ++t) n += c->agent[t].n_agents;
-  return batch * (lob::kSplitEnvWords + lob::kSplitAgentWords * n);
+  // env records, then (the piped step) the agents' messages of every environment: lob_pipe.cuh
+  return batch * (lob::kSplitEnvWords + lob::kSplitAgentWords * n) + batch * (int64_t)(lob_num_action_msgs(c) + lob_num_cancel_msgs(c)) * 8;
 }
 int32_t lob_num_msgs_per_step(const LobStepConfig* c) {
   return c->n_data_msg_per_step + lob_num_action_msgs(c) + lob_num_cancel_msgs(c);
@@ -312,6 +313,17 @@ int lob_step_launch(const LobStepConfig* cfg, const LobStepBuffers* bufs, int64_
   // first 32 * LOB_WINDOW_SLOTS rows (the reference keeps the live orders in the lowest rows, job:73); pass 2 redoes, at
   // full capacity, the environments whose book did not fit.  Needs the workspace buffers; LOB_NO_WINDOW=1 disables it.
   static const bool no_window = [] { const char* e = getenv("LOB_NO_WINDOW"); return e && e[0] == '1'; }();
+  // The piped step (lob_pipe.cuh: message building, scan, finish and auto-reset as kernels of their own) whenever the split
+  // workspace is there and the book fits its capacity class's shared memory without the window; LOB_NO_PIPE=1 keeps the
+  // fused kernel (A/B).
+  static const bool no_pipe = [] { const char* e = getenv("LOB_NO_PIPE"); return e && e[0] == '1'; }();
+  if (bufs->work_split && slots <= LOB_WINDOW_SLOTS && (cfg->book.n_orders & 1) == 0 && !no_pipe) {
+    if (reinterpret_cast<uintptr_t>(bufs->work_split) & 15u) return fail(LOB_E_INVALID, "work_split must be 16-byte aligned");
+    DISPATCH_SLOTS(slots, rc = launch_step_piped<S>(cfg, bufs, batch, st, d));
+    if (!rc) rc = launch_agents_finish(cfg, bufs, batch, st, 1);
+    if (!rc) { DISPATCH_SLOTS(slots, rc = launch_step_piped_reset<S>(cfg, bufs, batch, st, d)); }
+    return rc;
+  }
   if (slots > LOB_WINDOW_SLOTS && bufs->work_redo_list && bufs->work_redo_count && (cfg->book.n_orders & 1) == 0 && !no_window) {
     cudaError_t e = cudaMemsetAsync(bufs->work_redo_count, 0, sizeof(int32_t), st);
     if (e != cudaSuccess) return fail(LOB_E_CUDA, "cudaMemsetAsync: %s", cudaGetErrorString(e));
@@ -320,7 +332,7 @@ int lob_step_launch(const LobStepConfig* cfg, const LobStepBuffers* bufs, int64_
   } else {
     DISPATCH_SLOTS(slots, rc = launch_step<S>(cfg, bufs, batch, st, d));
   }
-  if (!rc && bufs->work_split) rc = launch_agents_finish(cfg, bufs, batch, st);   // split mode: one thread per agent
+  if (!rc && bufs->work_split) rc = launch_agents_finish(cfg, bufs, batch, st, 0);   // split mode: one thread per agent
   return rc;
 }
 
