@@ -134,17 +134,21 @@ __device__ __forceinline__ void restore_trade(int* tr, int e, int saved) {
 static __device__ __noinline__ void cancel_msgs(BookCtx bk, int s, int agent, int size, int side_sign, int t, int tns,
                                                int* out /* smem [size][8] */) {
   const int lane = lane_id();
-  int prev = -1;
+  // one pass over the side: bit j of `mine` <-> row lane + 32 j carries the agent's trader id; the k-th message then takes
+  // the lowest row still set anywhere in the warp (== the k-th match in row order, job:843-846), one REDUX per message
+  unsigned mine = 0u;
+#pragma unroll 1
+  for (int r = lane, j = 0; r < bk.no; r += 32, ++j)
+    if (rowp(bk, s, r)[F_TID] == agent) mine |= 1u << j;
 #pragma unroll 1
   for (int k = 0; k < size; ++k) {
-    int idx = kBig;
-#pragma unroll 1
-    for (int r = lane; r < bk.no; r += 32)
-      if (r > prev && rowp(bk, s, r)[F_TID] == agent) idx = min(idx, r);
-    idx = wmin(idx);
-    int q = 0, p = 0, o = 0, ti = 0;
-    if (idx != kBig) { const int* rw = rowp(bk, s, idx); q = rw[F_Q]; p = rw[F_P]; o = rw[F_OID]; ti = rw[F_TID]; prev = idx; }
-    else prev = bk.no;  // nothing further: zeros from the appended row
+    const int cand = mine ? (__ffs(mine) - 1) * 32 + lane : kBig;
+    const int idx = wmin(cand);
+    int q = 0, p = 0, o = 0, ti = 0;   // nothing further: zeros from the appended row
+    if (idx != kBig) {
+      const int* rw = rowp(bk, s, idx); q = rw[F_Q]; p = rw[F_P]; o = rw[F_OID]; ti = rw[F_TID];
+      if (cand == idx) mine &= mine - 1u;
+    }
     if (lane == 0) {
       int4* m = reinterpret_cast<int4*>(out + k * 8);
       m[0] = make_int4(2, side_sign, q, p);

@@ -38,12 +38,24 @@ lob_step_prep_kernel(const __grid_constant__ LobStepConfig c, const __grid_const
   int* ws = smem + warp * L.words;
   int* msgs = ws + L.msgs;        // [cancels | permuted actions]
   int* act_all = ws + L.act;      // the actions before the permutation
+  uint64_t* bar = reinterpret_cast<uint64_t*>(ws + L.bar);
+  if (lane == 0) mbar_init(&bar[0], 1);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  unsigned phase = 0u;
   Book<SLOTS, false> bk;
   bk.init(c.book, ws + L.book);
   const int no = c.book.n_orders, T = c.n_agent_types;
   const int n_am = n_cnl + n_act;
+  const unsigned side_bytes = (unsigned)no * 24u;   // (the launcher checked: no even -> 16-byte granular)
   const long long stride = (long long)gridDim.x * kWarps;
   for (long long e = (long long)blockIdx.x * kWarps + warp; e < batch; e += stride) {
+    __syncwarp();   // (the previous environment's readers of this warp's shared memory are done)
+    if (lane == 0) {   // both sides by the bulk-copy engine, under the scalar loads below
+      fence_async_smem();
+      mbar_expect_tx(&bar[0], 2u * side_bytes);
+      bulk_g2s(bk.side_base(ASK), b.asks + e * no * 6, side_bytes, &bar[0]);
+      bulk_g2s(bk.side_base(BID), b.bids + e * no * 6, side_bytes, &bar[0]);
+    }
     WorldIn w;
     w.time0 = b.time[e * 2]; w.time1 = b.time[e * 2 + 1];
     w.init_time0 = b.init_time[e * 2]; w.init_time1 = b.init_time[e * 2 + 1];
@@ -53,9 +65,6 @@ lob_step_prep_kernel(const __grid_constant__ LobStepConfig c, const __grid_const
     w.old_ba_last = b.best_asks[(e * N + N - 1) * 2];
     w.old_bb_last = b.best_bids[(e * N + N - 1) * 2];
     const int oid_counter = b.order_id_counter[e];
-    __syncwarp();   // (the previous environment's readers of this warp's shared memory are done)
-    bk.load_side(ASK, b.asks + e * no * 6);
-    bk.load_side(BID, b.bids + e * no * 6);
     w.extreme_spread = false;
     if (need_extreme) {   // mm:2545-2553 over the OLD per-message bests (the scan kernel overwrites them)
       bool any = false;
@@ -67,6 +76,8 @@ lob_step_prep_kernel(const __grid_constant__ LobStepConfig c, const __grid_const
       w.extreme_spread = __any_sync(kFull, any);
     }
     if (lane == 0) b.work_split[e * kSplitEnvWords + SE_EXTREME] = w.extreme_spread ? 1 : 0;
+    mbar_wait(&bar[0], phase);
+    phase ^= 1u;
     __syncwarp();
     // ---- (C) marl:254-315 agent messages: [cancels | permuted actions] ----
     int ci = 0, ai = 0;
