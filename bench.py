@@ -440,14 +440,14 @@ def run_native(args):
         full_rate = args.total_envs * K * max(1, s_inner // 2) / (f_ms * 1e-3)     # env-steps/s of ONE GPU on all envs
     else:
         full_rate, f_kern = strong_value, s_kern
-    warps_per_pass = 148 * 20      # lob_step_kernel<4>: one persistent CTA of 20 warps (= environments) per SM
+    warps_per_pass = 148 * 23      # lob_step_scan_kernel<4>: one persistent CTA of 23 warps (= environments) per SM
     strong = {"total_envs": args.total_envs, "envs_per_gpu": shard.count, "value": strong_value, "unit": "env-steps/s",
               "ms_per_step": s_kern, "one_gpu_all_envs_value": full_rate,
               "efficiency": strong_value / (ws * full_rate),
               "grid_passes": {"exact": shard.count / warps_per_pass, "run": -(-shard.count // warps_per_pass),
                               "quantisation_efficiency": (shard.count / warps_per_pass) / (-(-shard.count // warps_per_pass))},
-              "note": "per-GPU batch shrinks with N: the last pass of the persistent grid (148 SMs x 20 environments) runs "
-                      "partly empty -- e.g. 8192 envs = 2.77 passes run as 3"}
+              "note": "per-GPU batch shrinks with N: the last pass of the scan kernel's persistent grid (148 SMs x 23 "
+                      "environments) runs partly empty -- e.g. 8192 envs = 2.41 passes run as 3"}
 
     # ---- (3b) the other env.step configurations of BASELINE.json, kernel-only (same timing rules) ----
     others = []
@@ -517,8 +517,12 @@ def run_native(args):
                          "config": {"workload": "MARLEnv.step 2_player_fq_fqc (MM fixed_quants + EXE fixed_quants_complex), "
                                                 "BASELINE configs[3] shapes", "envs_per_gpu": args.envs, "msgs_per_env_step": N,
                                     "launches_per_bench_step": inner},
-                         "roofline": {"bound": "hbm", "kernel": "lob_step_kernel", "achieved": step_achieved,
-                                      "peak": hbm_peak, "unit": "GB/s", "frac": step_achieved / hbm_peak, "traffic": _traffic("lob_step_kernel"),
+                         "roofline": {"bound": "hbm", "kernel": "lob_step_scan_kernel (dominant: ~75 % of the step) + "
+                                                                   "lob_step_prep_kernel + lob_agents_finish_kernel + "
+                                                                   "lob_step_reset_done_kernel: the four launches of ONE "
+                                                                   "lob_step_launch call, timed together",
+                                      "achieved": step_achieved,
+                                      "peak": hbm_peak, "unit": "GB/s", "frac": step_achieved / hbm_peak, "traffic": _traffic("lob_step_piped"),
                                       "algorithmic_bytes_per_env_step": step_bytes, "kernel_ms": step_kern_ms},
                          "e2e": {"value": step_e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": step_h2d,
                                  "d2h_bytes_per_step": step_d2h,

@@ -258,14 +258,18 @@ typedef struct LobStepBuffers {
   int32_t* work_redo_list;                   /* [B] environment indices of the second pass */
   int32_t* work_redo_count;                  /* [4] word 0: environments in the second pass of the LAST call; word 1: running
                                                 total over all calls (statistics); 16-byte aligned */
-  /* optional workspace of lob_step_launch (NULL = not used): lob_split_workspace_words(cfg, B) 32-bit words.  With it the
-   * step kernel only collects what reads the trade log, and the agents' scalar arithmetic (rewards, new agent state, info
-   * rows, observations) runs as a second launch with ONE THREAD PER AGENT over the whole batch.  Same results. */
+  /* optional workspace of lob_step_launch (NULL = not used): lob_split_workspace_words(cfg, B) 32-bit words, 16-byte
+   * aligned; contents are scratch, not state.  With it the step runs PIPED, as four launches of the same call -- the
+   * agents' messages (one warp per environment), the message scan (books resident in shared memory), the agents' rewards /
+   * state / info / observations (one thread per agent over the whole batch) and the auto-reset of the environments whose
+   * episode ended -- instead of one fused kernel; books deeper than 128 rows per side keep the fused kernel and only move
+   * the agents' scalar arithmetic to the per-agent launch.  Same results either way (LOB_NO_PIPE=1 forces the fused kernel). */
   int32_t* work_split;
 } LobStepBuffers;
 
-/* ---- rollout: n_steps consecutive steps of every environment in ONE launch (lob_rollout_launch), the books resident in
- *      shared memory in between -- the trainer's jit(lax.scan(vmap(env.step))) with the actions given up front
+/* ---- rollout: n_steps consecutive steps of every environment in ONE call (lob_rollout_launch) -- with the work_split
+ *      workspace as n_steps piped steps (4 launches each, the faster schedule), without it as ONE launch of the fused kernel,
+ *      the books resident in shared memory in between -- the trainer's jit(lax.scan(vmap(env.step))) with the actions given up front
  *      (ippo_rnn_JAXMARL.py:616-661 with a pre-sampled policy, Speed_test.py:165-214).  Step ts reads row ts of the
  *      trajectory inputs and writes row ts of the trajectory outputs; a NULL input falls back to the LobStepBuffers field
  *      (the same values every step), a NULL output is not recorded.  T = n_steps, B = batch.                          */

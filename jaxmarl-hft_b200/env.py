@@ -358,8 +358,9 @@ class MARLEnv:
         return obs, view, rewards, dones, info
 
     def rollout(self, state: MultiAgentState, actions, n_steps: int, params: MultiAgentParams = None, draw=True):
-        """``n_steps`` env steps in ONE kernel launch (``lob_rollout_launch``): every environment's books stay in shared
-        memory for the whole rollout -- the trainer's ``jit(lax.scan(vmap(env.step)))`` (ippo_rnn_JAXMARL.py:616-661) with
+        """``n_steps`` env steps in ONE call of the C ABI (``lob_rollout_launch``: the piped step ``n_steps`` times over,
+        trajectory rows written in place; for deep books one launch of the fused kernel with the books resident in shared
+        memory for the whole rollout) -- the trainer's ``jit(lax.scan(vmap(env.step)))`` (ippo_rnn_JAXMARL.py:616-661) with
         the actions given up front (a pre-sampled / open-loop policy: Speed_test.py:165-214).  ``actions``: one int32 CUDA
         tensor ``[T, B, n_i]`` per agent type.  Equal, leaf for leaf, to ``n_steps`` calls of ``step`` (same PRNG counter
         sequence).  Returns (traj, state) with ``traj = {"obs": [[T,B,n_i,d_i] per type], "reward": [[T,B,n_i]],

@@ -312,9 +312,11 @@ def test_loader_preprocessing_on_the_device_matches_the_host_loader(seed):
         lobster.preprocess_day_cuda(bad, device="cuda:0")
 
 
-@pytest.mark.parametrize("config,kw", [("2_player_fq_fqc", {}), ("2_player_fq_fqc", {"cancel_mode": 3, "nOrders": 48, "nTrades": 20}),
-                                       ("hetero_deep_book", {})])
-def test_rollout_kernel_equals_eager_steps(config, kw):
+@pytest.mark.parametrize("config,kw,fused", [("2_player_fq_fqc", {}, False), ("2_player_fq_fqc", {}, True),
+                                             ("2_player_fq_fqc", {"cancel_mode": 3, "nOrders": 48, "nTrades": 20}, False),
+                                             ("2_player_fq_fqc", {"cancel_mode": 3, "nOrders": 48, "nTrades": 20}, True),
+                                             ("hetero_deep_book", {}, False)])
+def test_rollout_kernel_equals_eager_steps(config, kw, fused):
     """MARLEnv.rollout (lob_rollout_launch: T steps per environment in one launch, books resident in shared memory) == T
     calls of MARLEnv.step on a twin env with the same seed: trajectory outputs row by row, every state / output / info
     leaf at the end.  70 steps cross the auto-reset."""
@@ -329,6 +331,9 @@ def test_rollout_kernel_equals_eager_steps(config, kw):
     g = torch.Generator(device="cuda"); g.manual_seed(3)
     acts = [torch.randint(0, envs[0].action_spaces[t].n, (T,) + tuple(states_[0].arrays[f"actions{t}"].shape), generator=g,
                           device="cuda", dtype=torch.int32) for t in range(nt)]
+    if fused:   # without the split workspace lob_rollout_launch is ONE launch of the fused kernel (the books stay in shared
+        states_[0].arrays.pop("work_split")   # memory from the first to the last step); with it, T piped steps (lob_pipe.cuh)
+        envs[0]._cache = {}                   # (the packed buffer struct of these arrays was cached with the workspace pointer)
     traj, _ = envs[0].rollout(states_[0], acts, T, params[0])
     ref = {"obs": [[] for _ in range(nt)], "reward": [[] for _ in range(nt)], "done": []}
     for k in range(T):

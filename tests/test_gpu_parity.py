@@ -98,10 +98,12 @@ def test_l2_on_sparse_and_empty_books(oracle):
         np.testing.assert_array_equal(got, oracle.l2(bc, asks, bids, n_levels))
 
 
-def _rollout_parity(oracle, mac, day, B, steps, seed, stress_actions=False):
+def _rollout_parity(oracle, mac, day, B, steps, seed, stress_actions=False, fused=False):
     ld = H.load_for(mac, day)
     ref = H.OracleEnv(oracle, mac, ld, B)
     gpu = H.CudaEnv(mac, ld, B, ref.params)
+    if fused:   # no split workspace -> lob_step_launch runs the ONE fused kernel instead of the piped step (lob_pipe.cuh)
+        gpu.arrays.pop("work_split")
     rng = np.random.default_rng(seed)
     H.draw_prng(rng, ref.cfg, ref.arrays)
     gpu.set_inputs(ref.arrays)
@@ -131,6 +133,15 @@ def test_step_2_player_rollout_with_auto_reset(oracle):
     ref, n_done = _rollout_parity(oracle, mac, H.small_day(n_events=30000), B=96, steps=70, seed=1, stress_actions=True)
     assert n_done == 96
     assert (ref.arrays["info_i32_1"][..., 0] >= 0).all()
+
+
+@pytest.mark.parametrize("config,B,steps", [("2_player_fq_fqc", 96, 70), ("exec_longrun_fixed_quants_complex", 64, 70)])
+def test_step_fused_kernel_without_workspace(oracle, config, B, steps):
+    """The same rollouts through the FUSED step kernel (a caller that passes no workspace): the piped step -- four launches,
+    what every other test of this file runs -- and the fused kernel are two schedules of the same device functions."""
+    mac = H.load_mac(config)
+    _, n_done = _rollout_parity(oracle, mac, H.small_day(n_events=30000), B=B, steps=steps, seed=11, stress_actions=True, fused=True)
+    assert n_done == B
 
 
 def test_step_exec_only(oracle):
