@@ -421,10 +421,13 @@ struct Book {
     bind();
   }
   unsigned book_sa, lane_sa;   // shared-window byte address of row 0 of the ASK side / of this lane's first row
+  int lane_k;                  // this lane's index, opaque like the two addresses: the fast paths' owner tests and row numbers use
+                               // it, so ptxas keeps ONE register instead of re-reading %tid (an S2R per message in ncu)
   __device__ __forceinline__ void bind() {   // after c.rows_off is known
     const unsigned base = (unsigned)__cvta_generic_to_shared(dyn_smem() + c.rows_off);
     book_sa = keep(base);
     lane_sa = keep(base + (unsigned)lane_id() * 24u);
+    lane_k = (int)keep((unsigned)lane_id());
   }
   // byte address of row r (any r, warp-uniform or not) / of this lane's row k*32+lane of side s
   __device__ __forceinline__ unsigned row_sa(int s, int r) const { return book_sa + (unsigned)((s * kRows + r) * 24); }
@@ -509,7 +512,7 @@ struct Book {
   // first flagged row (== first blank row when !odd), else kBig
   __device__ __forceinline__ int first_flagged(int s) const {
     const unsigned m = flag[s];
-    return wmin(m ? (__ffs(m) - 1) * 32 + lane_id() : kBig);
+    return wmin(m ? (__ffs(m) - 1) * 32 + lane_k : kBig);
   }
 
   // No warp barrier between messages on the fast paths: every shared-memory write of a fast path is an ALL-LANE store of
@@ -530,7 +533,7 @@ struct Book {
     // owner lane alone) -- no owner test, no branch, no BSSY / BSYNC around it; only the per-lane flag needs the owner.
     const unsigned a = row_sa(S, r);
     sts64(a, -1, -1); sts64(a + 8, -1, -1); sts64(a + 16, -1, -1);
-    flag[S] |= (lane_id() == (r & 31)) ? (1u << (r >> 5)) : 0u;
+    flag[S] |= (lane_k == (r & 31)) ? (1u << (r >> 5)) : 0u;
     nneg[S] += (rp >= 0);
     if (valid[S] && rp == bestp[S]) {
       bestq[S] = wsub(bestq[S], rq); bestn[S] -= 1;
@@ -541,7 +544,7 @@ struct Book {
   // job:285-331 against the cached best level of side OPP; returns the remaining quantity
   template <int OPP>
   __device__ __forceinline__ int match(const Msg& m, int qtm) {
-    const int lane = lane_id();
+    const int lane = lane_k;
     while (true) {
       ensure(OPP);
       const int tp = bestp[OPP];
@@ -667,7 +670,7 @@ struct Book {
     {                                       // the blank row r takes the order (all lanes store the same words: see blank_live)
       const unsigned a = row_sa(OWN, r);
       sts64(a, m.price, q); sts64(a + 8, m.oid, m.tid); sts64(a + 16, m.ts, m.tns);
-      flag[OWN] &= ~((lane_id() == (r & 31)) ? (1u << (r >> 5)) : 0u);
+      flag[OWN] &= ~((lane_k == (r & 31)) ? (1u << (r >> 5)) : 0u);
     }
     nneg[OWN] -= 1;
     {   // keep the cached best level exact (branch-free: the scan is a latency chain, a select is cheaper than a branch)
@@ -685,7 +688,7 @@ struct Book {
   // (JAX normalises the index -1: quirk Q2)
   template <int S>
   __device__ __forceinline__ void cancel(const Msg& m) {
-    const int lane = lane_id();
+    const int lane = lane_k;
     int idx = kBig;
 #pragma unroll
     for (int k = SLOTS - 1; k >= 0; --k) if (lds32(lane_row_sa(S, k) + F_OID * 4) == m.oid) idx = k * 32 + lane;
