@@ -111,7 +111,8 @@ def ffi_step(cfg: abi.LobStepConfig, state_leaves: dict, inputs: dict, params: d
     operands = [{**state_leaves, **inputs, **params}[n] for n in tab.names_in]
     n_state = len(tab.aliases)
     out_specs = [jax.ShapeDtypeStruct(operands[i].shape, operands[i].dtype) for i in range(n_state)] + \
-                [jax.ShapeDtypeStruct(specs[n][0][1:], specs[n][1]) for n in tab.names_out[n_state:]]
+                [jax.ShapeDtypeStruct((4,) if n == "work_redo_count" else specs[n][0][1:], specs[n][1])   # (per env: vmap adds B)
+                 for n in tab.names_out[n_state:]]
     batch = int(np.prod(operands[0].shape[:-2])) if operands[0].ndim > 2 else 1     # asks [..., No, 6]
     outs = jax.ffi.ffi_call("lob_step", out_specs, vmap_method="expand_dims", input_output_aliases=tab.aliases)(
         *operands, cfg=np.frombuffer(bytes(cfg), np.uint8), batch=np.int64(batch), reset_only=bool(reset_only),

@@ -36,7 +36,9 @@ def leaf_specs(cfg: abi.LobStepConfig, batch: int):
         "info_world_i32": ((B, len(abi.WINFO_I32)), np.int32, "o"),
         "info_world_f32": ((B, len(abi.WINFO_F32)), np.float32, "o"),
     }
-    sp["work_split"] = ((max(abi.split_workspace_words(cfg, B), 4),), np.int32, "w")   # collect / finish split of the step
+    # the piped step's workspace (env records, then the agents' messages: csrc/lob_pipe.cuh); a flat buffer of
+    # lob_split_workspace_words(cfg, B) words, declared [B, words per env] so that a vmapped custom call sizes it right
+    sp["work_split"] = ((B, max(abi.split_workspace_words(cfg, 1), 4)), np.int32, "w")
     if No > 128:   # workspace of lob_step_launch's window pass for deep books (scratch, not state; see include/lobstep.h)
         sp["work_redo_list"] = ((B,), np.int32, "w")
         sp["work_redo_count"] = ((4,), np.int32, "w")
