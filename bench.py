@@ -526,7 +526,7 @@ def run_native(args):
                                       "algorithmic_bytes_per_env_step": step_bytes, "kernel_ms": step_kern_ms},
                          "e2e": {"value": step_e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": step_h2d,
                                  "d2h_bytes_per_step": step_d2h,
-                                 "api": "MARLEnv.capture_step: actions from pinned host memory, PRNG draw, step kernel, "
+                                 "api": "MARLEnv.capture_step: actions from pinned host memory, PRNG draw, the piped step (4 launches), "
                                         "obs / rewards / done read back -- one CUDA graph launch per step",
                                  "eager_value": step_e2e_eager_value,
                                  "rollout_value": rollout_value,

@@ -421,7 +421,7 @@ class MARLEnv:
         return traj, view
 
     def capture_step(self, state: MultiAgentState, actions, params: MultiAgentParams = None, pre=None, post=None):
-        """One step as a CUDA graph: [pre()] + actions copy + PRNG draw + step kernel [+ post()] captured on the current
+        """One step as a CUDA graph: [pre()] + actions copy + PRNG draw + step launches [+ post()] captured on the current
         stream (the rollout-fusion row of SURVEY 8f-4: one graph launch per step instead of 4+ launches and their Python).
         ``actions`` are the device tensors the graph reads every replay; ``pre`` / ``post`` are optional callables that
         enqueue copies (e.g. pinned host -> ``actions``, results -> pinned host).  Returns (graph, outputs) where outputs
